@@ -1,0 +1,598 @@
+// LEGM::formNormalEq / formNormalEqIRLS + applyL2Reg on the device (reference src/emba/model.cpp:316-719).
+//
+//   1. active set: pixels with num_ev_map >= thres in ascending index (the std::set order) -> mask + scan
+//   2. k_asm_pose: one CTA per work item (a run of measurements touching the same control-pose pair, static
+//      per window). Each thread forms one Jacobian row [Jc(6) Jp(6) | dp(2) | e]; the 13x13 outer products
+//      [Jc Jp e]^T [Jc Jp e] (A11 blocks, b1) are accumulated in registers from a shared-memory tile and
+//      reduced with warp shuffles; per-item partials are combined in a fixed order (deterministic).
+//      The row is also written out (128-byte record) for the map side.
+//   3. map side: rows are ordered by target pixel with a stable radix sort of (active index, row id); one warp
+//      per active pixel then reduces its rows in that fixed order into A22 / b2 and the pixel's A12 strip
+//      (3x2 block per control pose in the pixel's pose window) -- a deterministic segmented reduction.
+#include <climits>
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include "emba_internal.cuh"
+
+namespace emba {
+
+PanoCam make_cam(const Handle* h);
+int comm_allreduce(Handle* h, void* buf, int64_t count, int dtype);
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_active_flags(const int32_t* __restrict__ hist, int64_t P, int thres, int32_t* __restrict__ flag) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  flag[p] = hist[p] >= thres ? 1 : 0;  // model.cpp:333
+}
+
+__global__ void k_active_fill(const int32_t* __restrict__ flag, const int32_t* __restrict__ aidx, int64_t P,
+                              int32_t* __restrict__ amap, int32_t* __restrict__ apix, int32_t* __restrict__ winlo,
+                              int32_t* __restrict__ winhi) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  if (flag[p]) {
+    const int32_t a = aidx[p];
+    amap[p] = a;
+    apix[a] = (int32_t)p;
+    winlo[a] = INT_MAX;
+    winhi[a] = -1;
+  } else {
+    amap[p] = -1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+constexpr int kAsmThreads = 256;
+constexpr int kTileStride = kAsmThreads + 1;
+
+// accumulates rows I0..I1-1 of the upper triangle of v v^T (13 x 13) into a[0..]; both halves of the CTA use
+// the same 46 registers (rows 0..3 -> 46 entries, rows 4..12 -> 45 entries)
+template <int I0, int I1>
+__device__ __forceinline__ void tri_add(double (&a)[46], const double* v) {
+  int k = 0;
+#pragma unroll
+  for (int i = I0; i < I1; i++)
+#pragma unroll
+    for (int j = i; j < 13; j++) a[k++] += v[i] * v[j];
+}
+
+template <int COST>
+__global__ void __launch_bounds__(kAsmThreads)
+k_asm_pose(const WorkItem* __restrict__ items, const MeasRec* __restrict__ rec, const double* __restrict__ lut,
+           const double* __restrict__ Rtab, const double* __restrict__ Atab, const double2* __restrict__ G2,
+           const double4* __restrict__ H3, const double2* __restrict__ dp_in, const double* __restrict__ e_in,
+           const int32_t* __restrict__ pix_in, const int32_t* __restrict__ amap, PanoCam cam, double eta,
+           uint32_t invalid_key, double* __restrict__ jrec, uint32_t* __restrict__ skey, uint32_t* __restrict__ sval,
+           int32_t* __restrict__ winlo, int32_t* __restrict__ winhi, double* __restrict__ acc_part) {
+  __shared__ double tile[13][kTileStride];
+  __shared__ double red[2][4][46];
+  const WorkItem it = items[blockIdx.x];
+  const int tid = threadIdx.x;
+  const int half = tid >> 7, idx = tid & 127;
+  double acc[46];
+#pragma unroll
+  for (int k = 0; k < 46; k++) acc[k] = 0.0;
+  for (int t0 = 0; t0 < it.count; t0 += kAsmThreads) {
+    const int j = t0 + tid;
+    double row[13];
+#pragma unroll
+    for (int k = 0; k < 13; k++) row[k] = 0.0;
+    if (j < it.count) {
+      const int64_t m = (int64_t)it.start + j;
+      const int32_t pix = pix_in[m];
+      const int32_t a = pix >= 0 ? amap[pix] : -1;  // model.cpp:396-412: outliers and inactive pixels are skipped
+      skey[m] = a >= 0 ? (uint32_t)a : invalid_key;
+      sval[m] = (uint32_t)m;
+      if (a >= 0) {
+        const uint4 rr = reinterpret_cast<const uint4*>(rec)[m];
+        const uint32_t spix = rr.x, bc = rr.y & 0x7FFFFFFFu, bp = rr.z;
+        const double bx = lut[3 * (size_t)spix], by = lut[3 * (size_t)spix + 1], bz = lut[3 * (size_t)spix + 2];
+        const double2 dpv = dp_in[m];
+        double e = e_in[m];
+        const double2 g = G2[pix];
+        const double4 Hh = H3[pix];
+        // temp = Gpm + dp^T * G2pm (model.cpp:233-238)
+        const double h0 = g.x + dpv.x * Hh.x + dpv.y * Hh.y;
+        const double h1 = g.y + dpv.x * Hh.y + dpv.y * Hh.z;
+        double vc[3], vp[3], wc[3], wp[3];
+        {
+          const double* R = Rtab + (size_t)bc * kPoseStride;
+          const double X = R[0] * bx + R[1] * by + R[2] * bz;
+          const double Y = R[3] * bx + R[4] * by + R[5] * bz;
+          const double Z = R[6] * bx + R[7] * by + R[8] * bz;
+          double M[6];
+          project_jac(cam, X, Y, Z, M);
+#pragma unroll
+          for (int k = 0; k < 3; k++) vc[k] = h0 * M[k] + h1 * M[3 + k];  // temp * dpm_ddrot (model.cpp:449)
+          const double* A = Atab + (size_t)bc * kPoseStride;
+#pragma unroll
+          for (int k = 0; k < 3; k++) wc[k] = vc[0] * A[k] + vc[1] * A[3 + k] + vc[2] * A[6 + k];
+        }
+        {
+          const double* R = Rtab + (size_t)bp * kPoseStride;
+          const double X = R[0] * bx + R[1] * by + R[2] * bz;
+          const double Y = R[3] * bx + R[4] * by + R[5] * bz;
+          const double Z = R[6] * bx + R[7] * by + R[8] * bz;
+          double M[6];
+          project_jac(cam, X, Y, Z, M);
+#pragma unroll
+          for (int k = 0; k < 3; k++) vp[k] = -(g.x * M[k] + g.y * M[3 + k]);  // -Gpm * dpm_ddrot (model.cpp:459)
+          const double* A = Atab + (size_t)bp * kPoseStride;
+#pragma unroll
+          for (int k = 0; k < 3; k++) wp[k] = vp[0] * A[k] + vp[1] * A[3 + k] + vp[2] * A[6 + k];
+        }
+        // IRLS weight (model.cpp:599-618), applied as sqrt(w) on the whole row and on e
+        double sw = 1.0;
+        if (COST == EMBA_COST_CAUCHY) sw = sqrt(1.0 / (1.0 + eta * e * e));
+        if (COST == EMBA_COST_HUBER) { const double ab = fabs(e); sw = ab < eta ? 1.0 : sqrt(eta / ab); }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          row[k] = sw * (vc[k] - wc[k]);   // d/d(pose cp_c)   : [I - A | A] (so3_spline.h:254-269)
+          row[3 + k] = sw * wc[k];         // d/d(pose cp_c+1)
+          row[6 + k] = sw * (vp[k] - wp[k]);
+          row[9 + k] = sw * wp[k];
+        }
+        e *= sw;
+        row[12] = e;
+        double* out = jrec + (size_t)m * kRecDoubles;
+        double2* o2 = reinterpret_cast<double2*>(out);
+#pragma unroll
+        for (int k = 0; k < 6; k++) o2[k] = make_double2(row[2 * k], row[2 * k + 1]);
+        o2[6] = make_double2(sw * dpv.x, sw * dpv.y);
+        const unsigned long long meta = (unsigned long long)((uint32_t)it.cp_c | ((uint32_t)it.cp_p << 16)) |
+                                        ((unsigned long long)(uint32_t)m << 32);
+        o2[7] = make_double2(e, __longlong_as_double((long long)meta));
+        atomicMin(&winlo[a], it.cp_p);
+        atomicMax(&winhi[a], it.cp_c + 1);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 13; k++) tile[k][tid] = row[k];
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const int c = idx + 128 * q;
+      double v[13];
+      if (half == 0) {
+#pragma unroll
+        for (int k = 0; k < 13; k++) v[k] = tile[k][c];
+        tri_add<0, 4>(acc, v);
+      } else {
+#pragma unroll
+        for (int k = 4; k < 13; k++) v[k] = tile[k][c];
+        tri_add<4, 13>(acc, v);
+      }
+    }
+    __syncthreads();
+  }
+  // reduce the accumulators over the 128 threads of each half: warp shuffles, then 4 warps through shared memory
+  const int lane = tid & 31, wq = (tid >> 5) & 3;
+#pragma unroll
+  for (int k = 0; k < 46; k++) {
+    double x = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if (lane == 0) red[half][wq][k] = x;
+  }
+  __syncthreads();
+  if (tid < kAccN) {
+    const int hh = tid < 46 ? 0 : 1, k = tid < 46 ? tid : tid - 46;
+    acc_part[(size_t)blockIdx.x * kAccN + tid] = (red[hh][0][k] + red[hh][1][k]) + (red[hh][2][k] + red[hh][3][k]);
+  }
+}
+
+// per-group sums of the item partials, fixed order
+__global__ void k_group_sum(const double* __restrict__ acc_part, const int32_t* __restrict__ item0, int n_groups,
+                            double* __restrict__ gsum) {
+  const int g = blockIdx.x;
+  const int k = threadIdx.x;
+  if (g >= n_groups || k >= kAccN) return;
+  double s = 0;
+  for (int i = item0[g]; i < item0[g + 1]; i++) s += acc_part[(size_t)i * kAccN + k];
+  gsum[(size_t)g * kAccN + k] = s;
+}
+
+// Dense A11 / b1 from the group sums (model.cpp:453-477): one CTA per control pose `a` owns rows 3a..3a+2 and
+// gathers, in a fixed order, every group whose pose set {c, c+1, p, p+1} contains a.
+__global__ void k_a11_gather(int n, int dmax, const int32_t* __restrict__ gid, const double* __restrict__ gsum,
+                             double* __restrict__ A11, double* __restrict__ b1) {
+  extern __shared__ double rowbuf[];  // [3][3n] + [3]
+  const int a = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int d3 = 3 * n;
+  for (int i = tid; i < 3 * d3 + 3; i += blockDim.x) rowbuf[i] = 0.0;
+  __syncthreads();
+  auto visit = [&](int c, int d) {
+    if (c < 0 || c > n - 2 || d < 0 || d > dmax || d > c) return;
+    const int g = gid[(size_t)c * (dmax + 1) + d];
+    if (g < 0) return;
+    const int p = c - d;
+    const int S[4] = {c, c + 1, p, p + 1};
+    const double* Z = gsum + (size_t)g * kAccN;
+    if (tid < 12) {
+      const int r = tid < 9 ? tid / 3 : tid - 9;
+      const int k = tid % 3;
+      for (int s = 0; s < 4; s++) {
+        if (S[s] != a) continue;
+        const int i = 3 * s + r;
+        if (tid < 9) {
+          for (int t = 0; t < 4; t++) {
+            const int j = 3 * t + k;
+            const double z = i <= j ? Z[tri13(i, j)] : Z[tri13(j, i)];
+            rowbuf[r * d3 + 3 * S[t] + k] += z;
+          }
+        } else {
+          rowbuf[3 * d3 + r] += Z[tri13(i, 12)];
+        }
+      }
+    }
+  };
+  for (int c = a - 1; c <= a; c++)
+    for (int d = 0; d <= dmax; d++) visit(c, d);
+  for (int p = a - 1; p <= a; p++) {
+    if (p < 0) continue;
+    for (int c = max(p, a + 1); c <= min(n - 2, p + dmax); c++) visit(c, c - p);
+  }
+  __syncthreads();
+  for (int i = tid; i < 3 * d3; i += blockDim.x) A11[(size_t)(3 * a + i / d3) * d3 + (i % d3)] = rowbuf[i];
+  if (tid < 3) b1[3 * a + tid] = rowbuf[3 * d3 + tid];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pose windows -> strip lengths
+__global__ void k_strip_len(const int32_t* __restrict__ winlo, const int32_t* __restrict__ winhi, int64_t Np,
+                            int64_t* __restrict__ len) {
+  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= Np) return;
+  const int32_t lo = winlo[a], hi = winhi[a];
+  len[a] = hi >= lo ? (int64_t)(hi - lo + 1) : 0;
+}
+
+// segment [segoff[a], segoff[a+1]) of the rows of active pixel a in the sorted key array; segoff[Np] = number of
+// valid rows (rows of outliers / inactive pixels carry key Np and sort to the end)
+__global__ void k_seg_bounds(const uint32_t* __restrict__ keys, int64_t M, int64_t Np, int32_t* __restrict__ segoff) {
+  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a > Np) return;
+  int64_t lo = 0, hi = M;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (keys[mid] < (uint32_t)a) lo = mid + 1;
+    else hi = mid;
+  }
+  segoff[a] = (int32_t)lo;
+}
+
+// Map side: one warp per active pixel, rows in fixed (sorted) order.
+constexpr int kPixWarps = 8;
+constexpr int kStripCap = 64;  // poses per shared-memory strip
+constexpr int kPixTile = 16;   // rows staged per step
+
+__global__ void __launch_bounds__(kPixWarps * 32)
+k_pix(int64_t Np, const int32_t* __restrict__ segoff, const uint32_t* __restrict__ sval,
+      const double* __restrict__ jrec, const int32_t* __restrict__ winlo, const int32_t* __restrict__ winhi,
+      const int64_t* __restrict__ stripoff, double* __restrict__ strip, const int32_t* __restrict__ apix,
+      const double* __restrict__ Gx, const double* __restrict__ Gy, double alpha, double* __restrict__ A22,
+      double* __restrict__ b2) {
+  __shared__ double s_tile[kPixWarps][kPixTile][kRecDoubles];
+  __shared__ double s_strip[kPixWarps][kStripCap * 6];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t nw = (int64_t)gridDim.x * kPixWarps;
+  // lane roles: 0..23 -> A12 component (slot s, row r, col c); 24..28 -> A22 xx, xy, yy, b2 x, y
+  const int s = lane / 6, r = (lane % 6) >> 1, c = lane & 1;
+  int ia = 0, ib = 0;
+  if (lane < 24) { ia = 3 * s + r; ib = 12 + c; }
+  else if (lane == 24) { ia = 12; ib = 12; }
+  else if (lane == 25) { ia = 12; ib = 13; }
+  else if (lane == 26) { ia = 13; ib = 13; }
+  else if (lane == 27) { ia = 12; ib = 14; }
+  else if (lane == 28) { ia = 13; ib = 14; }
+  for (int64_t a = (int64_t)blockIdx.x * kPixWarps + warp; a < Np; a += nw) {
+    const int64_t seg0 = segoff[a];
+    const int64_t seg1 = segoff[a + 1];
+    const int qlo = winlo[a];
+    const int len = winhi[a] - qlo + 1;
+    double* gs = strip + stripoff[a] * 6;
+    double* sp = (len <= kStripCap) ? s_strip[warp] : gs;
+    for (int i = lane; i < len * 6; i += 32) sp[i] = 0.0;
+    __syncwarp();
+    double acc = 0.0, acc22 = 0.0;
+    uint32_t runkey = 0xFFFFFFFFu;
+    bool have = false;
+    auto flush = [&]() {
+      const int cpc = (int)(runkey & 0xFFFFu), cpp = (int)(runkey >> 16);
+      const int pose = (s == 0) ? cpc : (s == 1) ? cpc + 1 : (s == 2) ? cpp : cpp + 1;
+      if (lane < 12) sp[(pose - qlo) * 6 + r * 2 + c] += acc;
+      __syncwarp();
+      if (lane >= 12 && lane < 24) sp[(pose - qlo) * 6 + r * 2 + c] += acc;
+      __syncwarp();
+    };
+    for (int64_t base = seg0; base < seg1; base += kPixTile) {
+      const int cnt = (int)min((int64_t)kPixTile, seg1 - base);
+      for (int i = lane >> 4; i < cnt; i += 2) {
+        const uint32_t m = sval[base + i];
+        s_tile[warp][i][lane & 15] = jrec[(size_t)m * kRecDoubles + (lane & 15)];
+      }
+      __syncwarp();
+      for (int i = 0; i < cnt; i++) {
+        const uint32_t key = (uint32_t)(unsigned long long)__double_as_longlong(s_tile[warp][i][15]);
+        if (key != runkey) {
+          if (have) flush();
+          runkey = key;
+          have = true;
+          acc = 0.0;
+        }
+        const double p = s_tile[warp][i][ia] * s_tile[warp][i][ib];
+        if (lane < 24) acc += p;
+        else acc22 += p;
+      }
+      __syncwarp();
+    }
+    if (have) flush();
+    if (sp != gs) {
+      for (int i = lane; i < len * 6; i += 32) gs[i] = sp[i];
+    }
+    // applyL2Reg (model.cpp:689-719): A22 += alpha*I, b2 -= alpha * (Gx, Gy)[pixel]
+    const int32_t pix = apix[a];
+    if (lane == 24) A22[3 * a] = acc22 + alpha;
+    if (lane == 25) A22[3 * a + 1] = acc22;
+    if (lane == 26) A22[3 * a + 2] = acc22 + alpha;
+    if (lane == 27) b2[2 * a] = acc22 - alpha * Gx[pix];
+    if (lane == 28) b2[2 * a + 1] = acc22 - alpha * Gy[pix];
+    __syncwarp();
+  }
+}
+
+// dense copy of A12 for emba_get_normal_eq (parity only)
+__global__ void k_a12_dense(int64_t Np, int n, const int32_t* __restrict__ winlo, const int32_t* __restrict__ winhi,
+                            const int64_t* __restrict__ stripoff, const double* __restrict__ strip,
+                            double* __restrict__ out) {
+  const int64_t a = blockIdx.x;
+  if (a >= Np) return;
+  const int lo = winlo[a], hi = winhi[a];
+  const double* sp = strip + stripoff[a] * 6;
+  for (int i = threadIdx.x; i < (hi - lo + 1) * 6; i += blockDim.x) {
+    const int q = lo + i / 6, rr = (i % 6) >> 1, cc = i & 1;
+    out[(size_t)(3 * q + rr) * (2 * Np) + 2 * a + cc] = sp[i];
+  }
+}
+__global__ void k_a22_expand(int64_t Np, const double* __restrict__ A22, double* __restrict__ out) {
+  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= Np) return;
+  out[4 * a] = A22[3 * a];
+  out[4 * a + 1] = A22[3 * a + 1];
+  out[4 * a + 2] = A22[3 * a + 1];
+  out[4 * a + 3] = A22[3 * a + 2];
+}
+__global__ void k_i32_to_i64(const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+
+template <typename T>
+static int cub_exclusive_sum(Handle* h, const T* in, T* out, int64_t count) {
+  size_t tb = 0;
+  EMBA_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, (int)count, h->stream));
+  if (tb > h->cub_tmp_bytes) {
+    if (h->d_cub_tmp) cudaFree(h->d_cub_tmp);
+    h->d_cub_tmp = nullptr;
+    EMBA_CUDA(cudaMalloc(&h->d_cub_tmp, tb));
+    h->cub_tmp_bytes = tb;
+  }
+  EMBA_CUDA(cub::DeviceScan::ExclusiveSum(h->d_cub_tmp, tb, in, out, (int)count, h->stream));
+  h->launches += 2;
+  return EMBA_OK;
+}
+
+int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha) {
+  StateSlot& s = h->st[h->cur];
+  const int64_t P = h->P;
+  const int T = 256;
+  const int n = h->n;
+  h->thres = thres;
+  h->formed = false;
+  EMBA_CUDA(cudaEventRecord(h->ev[4], h->stream));
+  // ---- 1. active set (model.cpp:324-379): mask + exclusive scan reproduces the ascending std::set order
+  int32_t *d_flag = nullptr, *d_aidx = nullptr;
+  int64_t* d_len = nullptr;
+  auto cleanup = [&]() { cudaFree(d_flag); cudaFree(d_aidx); cudaFree(d_len); };
+#define EMBA_TRYC(x) do { int _r = (x); if (_r != EMBA_OK) { cleanup(); return _r; } } while (0)
+#define EMBA_CUDAC(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { h->err = std::string(#x) + ": " + cudaGetErrorString(_e); cleanup(); return EMBA_E_CUDA; } } while (0)
+  EMBA_TRYC(dev_alloc(h, &d_flag, P));
+  EMBA_TRYC(dev_alloc(h, &d_aidx, P));
+  k_active_flags<<<ceil_div64(P, T), T, 0, h->stream>>>(s.hist, P, thres, d_flag);
+  h->launches++;
+  EMBA_TRYC(cub_exclusive_sum(h, d_flag, d_aidx, P));
+  int32_t tail[2];
+  EMBA_CUDAC(cudaMemcpyAsync(&tail[0], d_aidx + (P - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  EMBA_CUDAC(cudaMemcpyAsync(&tail[1], d_flag + (P - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  EMBA_CUDAC(cudaStreamSynchronize(h->stream));
+  const int64_t Np = (int64_t)tail[0] + tail[1];
+  h->Np = Np;
+  EMBA_TRYC(dev_alloc(h, &h->d_apix, Np));
+  EMBA_TRYC(dev_alloc(h, &h->d_segoff, Np + 1));
+  EMBA_TRYC(dev_alloc(h, &h->d_winlo, Np));
+  EMBA_TRYC(dev_alloc(h, &h->d_winhi, Np));
+  EMBA_TRYC(dev_alloc(h, &h->d_stripoff, Np + 1));
+  EMBA_TRYC(dev_alloc(h, &h->d_A22, 3 * Np));
+  EMBA_TRYC(dev_alloc(h, &h->d_b2, 2 * Np));
+  EMBA_TRYC(dev_alloc(h, &h->d_C, 3 * Np));
+  EMBA_TRYC(dev_alloc(h, &h->d_x2, 2 * Np));
+  k_active_fill<<<ceil_div64(P, T), T, 0, h->stream>>>(d_flag, d_aidx, P, h->d_amap, h->d_apix, h->d_winlo, h->d_winhi);
+  h->launches++;
+  // ---- 2. pose side + Jacobian rows
+  const int64_t Mc = h->Mc;
+  EMBA_TRYC(dev_reserve(h, &h->d_jrec, &h->jrec_cap, Mc * kRecDoubles));
+  if (h->sort_cap < Mc) {
+    EMBA_TRYC(dev_alloc(h, &h->d_skey, Mc)); EMBA_TRYC(dev_alloc(h, &h->d_sval, Mc));
+    EMBA_TRYC(dev_alloc(h, &h->d_skey2, Mc)); EMBA_TRYC(dev_alloc(h, &h->d_sval2, Mc));
+    h->sort_cap = Mc;
+  }
+  const PanoCam cam = make_cam(h);
+  EMBA_CUDAC(cudaEventRecord(h->ev[5], h->stream));
+  if (h->n_items > 0) {
+#define EMBA_ASM_LAUNCH(C)                                                                                         \
+  k_asm_pose<C><<<h->n_items, kAsmThreads, 0, h->stream>>>(h->d_items, h->d_rec, h->d_lut, s.Rtab, s.Atab, s.G2,   \
+                                                           s.H3, s.dp, s.e, s.pix, h->d_amap, cam, eta,            \
+                                                           (uint32_t)Np, h->d_jrec, h->d_skey, h->d_sval,          \
+                                                           h->d_winlo, h->d_winhi, h->d_acc_part)
+    if (cost_type == EMBA_COST_QUADRATIC) EMBA_ASM_LAUNCH(EMBA_COST_QUADRATIC);
+    else if (cost_type == EMBA_COST_CAUCHY) EMBA_ASM_LAUNCH(EMBA_COST_CAUCHY);
+    else EMBA_ASM_LAUNCH(EMBA_COST_HUBER);
+#undef EMBA_ASM_LAUNCH
+    h->launches++;
+    EMBA_CUDAC(cudaGetLastError());
+  }
+  EMBA_CUDAC(cudaEventRecord(h->ev[6], h->stream));
+  EMBA_CUDAC(cudaMemsetAsync(h->d_A11, 0, sizeof(double) * 9 * n * n, h->stream));
+  EMBA_CUDAC(cudaMemsetAsync(h->d_b1, 0, sizeof(double) * 3 * n, h->stream));
+  if (h->n_groups > 0) {
+    k_group_sum<<<h->n_groups, 96, 0, h->stream>>>(h->d_acc_part, h->d_group_item0, h->n_groups, h->d_gsum);
+    h->launches++;
+    const size_t shm = sizeof(double) * (9 * (size_t)n + 3);
+    if (shm > 48 * 1024) EMBA_CUDAC(cudaFuncSetAttribute(k_a11_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+    k_a11_gather<<<n, 64, shm, h->stream>>>(n, h->dmax, h->d_gid, h->d_gsum, h->d_A11, h->d_b1);
+    h->launches++;
+    EMBA_CUDAC(cudaGetLastError());
+  }
+  if (h->world > 1) {
+    // partial (H, g) of the time slices are combined over NVLink
+    EMBA_TRYC(comm_allreduce(h, h->d_A11, (int64_t)9 * n * n, 1));
+    EMBA_TRYC(comm_allreduce(h, h->d_b1, (int64_t)3 * n, 1));
+    EMBA_TRYC(comm_allreduce(h, h->d_winlo, Np, 2));  // min
+    EMBA_TRYC(comm_allreduce(h, h->d_winhi, Np, 3));  // max
+  }
+  // ---- 3. map side: pose windows -> strip offsets
+  EMBA_TRYC(dev_alloc(h, &d_len, Np + 1));
+  EMBA_CUDAC(cudaMemsetAsync(d_len, 0, sizeof(int64_t) * (Np + 1), h->stream));
+  if (Np) { k_strip_len<<<ceil_div64(Np, T), T, 0, h->stream>>>(h->d_winlo, h->d_winhi, Np, d_len); h->launches++; }
+  EMBA_TRYC(cub_exclusive_sum(h, d_len, h->d_stripoff, Np + 1));
+  int64_t tot = 0;
+  EMBA_CUDAC(cudaMemcpyAsync(&tot, h->d_stripoff + Np, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+  EMBA_CUDAC(cudaStreamSynchronize(h->stream));
+  h->strip_total = tot;
+  EMBA_TRYC(dev_reserve(h, &h->d_strip, &h->strip_cap, tot * 6));
+  // stable radix sort of the rows by active pixel index (rows of outliers / inactive pixels carry key Np)
+  uint32_t* vs = h->d_sval;
+  if (Mc > 0) {
+    int bits = 1;
+    while (bits < 32 && ((uint64_t)Np >> bits)) bits++;
+    cub::DoubleBuffer<uint32_t> dk(h->d_skey, h->d_skey2), dv(h->d_sval, h->d_sval2);
+    size_t tb = 0;
+    EMBA_CUDAC(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int)Mc, 0, bits, h->stream));
+    if (tb > h->cub_tmp_bytes) {
+      if (h->d_cub_tmp) cudaFree(h->d_cub_tmp);
+      h->d_cub_tmp = nullptr;
+      h->cub_tmp_bytes = 0;
+      EMBA_CUDAC(cudaMalloc(&h->d_cub_tmp, tb));
+      h->cub_tmp_bytes = tb;
+    }
+    EMBA_CUDAC(cub::DeviceRadixSort::SortPairs(h->d_cub_tmp, tb, dk, dv, (int)Mc, 0, bits, h->stream));
+    h->launches += 1 + 2 * ((bits + 7) / 8);
+    vs = dv.Current();
+    k_seg_bounds<<<ceil_div64(Np + 1, T), T, 0, h->stream>>>(dk.Current(), Mc, Np, h->d_segoff);
+    h->launches++;
+  } else {
+    EMBA_CUDAC(cudaMemsetAsync(h->d_segoff, 0, sizeof(int32_t) * (Np + 1), h->stream));
+  }
+  if (Np > 0) {
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((Np + kPixWarps - 1) / kPixWarps, (int64_t)h->sm_count * 16));
+    k_pix<<<grid, kPixWarps * 32, 0, h->stream>>>(Np, h->d_segoff, vs, h->d_jrec, h->d_winlo, h->d_winhi,
+                                                  h->d_stripoff, h->d_strip, h->d_apix, s.Gx, s.Gy,
+                                                  h->rank == 0 ? alpha : 0.0, h->d_A22, h->d_b2);
+    h->launches++;
+    EMBA_CUDAC(cudaGetLastError());
+  }
+  if (h->world > 1 && Np > 0) {
+    EMBA_TRYC(comm_allreduce(h, h->d_A22, 3 * Np, 1));
+    EMBA_TRYC(comm_allreduce(h, h->d_b2, 2 * Np, 1));
+    EMBA_TRYC(comm_allreduce(h, h->d_strip, tot * 6, 1));
+  }
+  EMBA_CUDAC(cudaEventRecord(h->ev[7], h->stream));
+  EMBA_CUDAC(cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[4], h->ev[7]); h->t_ms[2] = ms;
+  cudaEventElapsedTime(&ms, h->ev[5], h->ev[6]); h->t_ms[3] = ms;
+  cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]); h->t_ms[4] = ms;
+  cleanup();
+#undef EMBA_TRYC
+#undef EMBA_CUDAC
+  h->formed = true;
+  h->solved = false;
+  return EMBA_OK;
+}
+
+}  // namespace emba
+
+using namespace emba;
+
+extern "C" {
+
+int emba_form_normal_eq(emba_handle_t hh, int32_t thres, int32_t cost_type, double eta, double alpha,
+                        int64_t* Np_out) {
+  Handle* h = (Handle*)hh;
+  if (!h) return EMBA_E_ARG;
+  if (!h->st[h->cur].evaluated) { h->err = "emba_form_normal_eq: evaluate the current state first"; return EMBA_E_ARG; }
+  if (cost_type < 0 || cost_type > 2) { h->err = "bad cost type"; return EMBA_E_ARG; }
+  EMBA_CUDA(cudaSetDevice(h->device));
+  EMBA_TRY(form_normal_eq(h, thres, cost_type, eta, alpha));
+  if (Np_out) *Np_out = h->Np;
+  return EMBA_OK;
+}
+
+int emba_get_normal_eq(emba_handle_t hh, double* A11, double* b1, double* A22, double* b2, int64_t* active,
+                       double* A12_dense) {
+  Handle* h = (Handle*)hh;
+  if (!h) return EMBA_E_ARG;
+  if (!h->formed) { h->err = "emba_get_normal_eq: no normal equations formed"; return EMBA_E_ARG; }
+  EMBA_CUDA(cudaSetDevice(h->device));
+  const int n = h->n;
+  const int64_t Np = h->Np;
+  if (A11) EMBA_CUDA(cudaMemcpyAsync(A11, h->d_A11, sizeof(double) * 9 * n * n, cudaMemcpyDeviceToHost, h->stream));
+  if (b1) EMBA_CUDA(cudaMemcpyAsync(b1, h->d_b1, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, h->stream));
+  if (b2 && Np) EMBA_CUDA(cudaMemcpyAsync(b2, h->d_b2, sizeof(double) * 2 * Np, cudaMemcpyDeviceToHost, h->stream));
+  EMBA_CUDA(cudaStreamSynchronize(h->stream));
+  if (A22 && Np) {
+    double* tmp = nullptr;
+    EMBA_TRY(dev_alloc(h, &tmp, 4 * Np));
+    k_a22_expand<<<ceil_div64(Np, 256), 256, 0, h->stream>>>(Np, h->d_A22, tmp);
+    h->launches++;
+    cudaError_t e = cudaMemcpyAsync(A22, tmp, sizeof(double) * 4 * Np, cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) { h->err = "emba_get_normal_eq: A22 copy failed"; return EMBA_E_CUDA; }
+  }
+  if (active && Np) {
+    int64_t* tmp = nullptr;
+    EMBA_TRY(dev_alloc(h, &tmp, Np));
+    k_i32_to_i64<<<ceil_div64(Np, 256), 256, 0, h->stream>>>(h->d_apix, Np, tmp);
+    h->launches++;
+    cudaError_t e = cudaMemcpyAsync(active, tmp, sizeof(int64_t) * Np, cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) { h->err = "emba_get_normal_eq: active copy failed"; return EMBA_E_CUDA; }
+  }
+  if (A12_dense && Np) {
+    double* tmp = nullptr;
+    const int64_t cnt = (int64_t)3 * n * 2 * Np;
+    EMBA_TRY(dev_alloc(h, &tmp, cnt));
+    cudaMemsetAsync(tmp, 0, sizeof(double) * cnt, h->stream);
+    k_a12_dense<<<(unsigned)Np, 64, 0, h->stream>>>(Np, n, h->d_winlo, h->d_winhi, h->d_stripoff, h->d_strip, tmp);
+    h->launches++;
+    cudaError_t e = cudaMemcpyAsync(A12_dense, tmp, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) { h->err = "emba_get_normal_eq: A12 copy failed"; return EMBA_E_CUDA; }
+  }
+  return EMBA_OK;
+}
+
+int emba_a12_entries(emba_handle_t hh, int64_t* out) {
+  Handle* h = (Handle*)hh;
+  if (!h || !out) return EMBA_E_ARG;
+  *out = h->formed ? h->strip_total * 6 : 0;
+  return EMBA_OK;
+}
+
+}  // extern "C"

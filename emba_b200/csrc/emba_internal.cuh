@@ -1,0 +1,341 @@
+// emba_b200 internal declarations: handle layout, error macros, device math.
+// All arithmetic on the measurement path is fp64 (the reference is fp64 throughout and its
+// cost function is discontinuous: SURVEY.md "five facts" #4).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/emba_b200.h"
+
+namespace emba {
+
+constexpr int kBatch = 100;         // hard-coded event batch size (reference src/emba/model.cpp:78)
+constexpr int kPoseStride = 10;     // doubles per 3x3 table entry (9 + 1 pad -> 16-byte aligned rows)
+constexpr int kItemMax = 8192;      // measurements per pose-block assembly work item
+constexpr int kAccN = 91;           // upper triangle of the 13x13 outer product of [Jc Jp e]
+constexpr int kRecDoubles = 16;     // Jacobian-row record: Jc[6] Jp[6] dp[2] e meta  (128 bytes)
+constexpr double kSophusEps = 1e-10;  // Sophus::Constants<double>::epsilon()
+
+// static per-measurement record, canonical order (sorted by (cp_c, cp_p), then time of the current event)
+struct __align__(16) MeasRec {
+  uint32_t spix;     // sensor pixel index y*W_s + x (both events of a pair share it)
+  uint32_t bc_pol;   // batch of the current event | polarity << 31
+  uint32_t bp;       // batch of the previous event
+  uint32_t refpos;   // rank of this pair in the reference's order (sensor pixel row-major, then time)
+};
+
+struct WorkItem {
+  int32_t cp_c, cp_p;  // control-pose indices of the group
+  int32_t start, count;  // measurement range in canonical order (local to the shard)
+  int32_t group;       // group id
+};
+
+// device-resident optimisation state + outputs of its last evaluation
+struct StateSlot {
+  double* quat = nullptr;    // [n*4] xyzw
+  double* Gx = nullptr;      // [P]
+  double* Gy = nullptr;      // [P]
+  double2* G2 = nullptr;     // [P] interleaved (Gx, Gy)
+  double4* H3 = nullptr;     // [P] (Gxx, Gxy, Gyy, 0)
+  double* Rtab = nullptr;    // [B*kPoseStride] batch rotation matrices, row-major
+  double* Atab = nullptr;    // [B*kPoseStride] batch A = u*R_s*Jl(u d)*Jl^-1(d)*R_s^T
+  double2* dp = nullptr;     // [Mc] displacement pm_c - pm_p
+  double* e = nullptr;       // [Mc] residual
+  int32_t* pix = nullptr;    // [Mc] pano pixel index of the current event, -1 = outlier
+  int32_t* hist = nullptr;   // [P] num_ev_map
+  double cost_data = 0, cost_reg = 0;
+  int64_t M = 0;
+  bool evaluated = false;
+};
+
+struct Handle {
+  std::string err;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  int64_t launches = 0;
+  // config
+  int Ws = 0, Hs = 0, Wp = 0, Hp = 0;
+  int64_t P = 0;
+  double C_th = 0;
+  double* d_lut = nullptr;  // [Ws*Hs*3]
+  // events
+  int64_t N = 0, Nuse = 0, B = 0;
+  std::vector<int64_t> h_tmid;
+  int64_t* d_tmid = nullptr;     // [B]
+  uint32_t* d_spix_ev = nullptr; // [Nuse] sensor pixel per event
+  uint8_t* d_pol = nullptr;      // [Nuse]
+  int32_t* d_prev = nullptr;     // [Nuse] previous event at the same sensor pixel, -1 if none
+  uint32_t* d_refrank = nullptr; // [Nuse] rank of the pair (as current event) in reference order
+  int64_t Mc_total = 0;          // pairs in the window
+  // spline time base and everything that depends on it
+  int64_t t0_ns = -1, dt_ns = -1;
+  int n = 0;
+  int32_t* d_bs = nullptr;    // [B] knot index s of the batch mid-time
+  double* d_bu = nullptr;     // [B] u in [0,1)
+  MeasRec* d_rec = nullptr;   // [Mc] canonical order, this shard only
+  int64_t Mc = 0;             // measurements of this shard
+  std::vector<WorkItem> h_items;
+  WorkItem* d_items = nullptr;
+  int n_items = 0, n_groups = 0, dmax = 0;
+  int32_t* d_gid = nullptr;         // [n*(dmax+1)] group id of (cp_c, d) or -1
+  int32_t* d_group_item0 = nullptr; // [n_groups+1] first item of each group
+  // shard
+  int rank = 0, world = 1;
+  void* nccl_comm = nullptr;
+  // states
+  StateSlot st[2];
+  int cur = 0;  // index of the CURRENT slot; candidate = 1-cur
+  // scratch for reductions
+  double* d_part = nullptr;  // per-block partial sums
+  int64_t part_cap = 0;
+  double* d_scal = nullptr;  // small device scalars
+  int32_t* d_flags = nullptr;  // error flags
+  // normal equations (device)
+  int thres = 0;
+  int64_t Np = 0;
+  int32_t* d_amap = nullptr;    // [P] active index or -1
+  int32_t* d_apix = nullptr;    // [Np] pixel index of each active pixel
+  int32_t* d_segoff = nullptr;  // [Np+1] offsets of the per-pixel row segments in the sorted row list
+  int64_t Ma = 0;               // measurements on active pixels
+  double* d_jrec = nullptr;     // [Mc*16] Jacobian rows
+  int64_t jrec_cap = 0;
+  int64_t sort_cap = 0;
+  uint32_t* d_skey = nullptr;   // sort keys/values (double-buffered)
+  uint32_t* d_sval = nullptr;
+  uint32_t* d_skey2 = nullptr;
+  uint32_t* d_sval2 = nullptr;
+  void* d_cub_tmp = nullptr;
+  size_t cub_tmp_bytes = 0;
+  int32_t* d_winlo = nullptr;   // [Np] first control pose touching the pixel
+  int32_t* d_winhi = nullptr;   // [Np] last control pose touching the pixel
+  int64_t* d_stripoff = nullptr;  // [Np+1] offsets (in poses) of the per-pixel A12 strips
+  int64_t strip_total = 0;
+  double* d_strip = nullptr;    // [strip_total*6] A12, per pixel per pose: 3 rows x 2 cols
+  int64_t strip_cap = 0;
+  double* d_A22 = nullptr;      // [Np*3] xx, xy, yy
+  double* d_b2 = nullptr;       // [Np*2]
+  double* d_acc_part = nullptr; // [n_items*91]
+  double* d_gsum = nullptr;     // [n_groups*91]
+  double* d_A11 = nullptr;      // [3n*3n]
+  double* d_b1 = nullptr;       // [3n]
+  bool formed = false;
+  // solve
+  double* d_C = nullptr;        // [Np*3] inverse of damped A22
+  double* d_S = nullptr;        // [d*d]
+  double* d_rhs = nullptr;      // [d]
+  double* d_x1 = nullptr;       // [3n]
+  double* d_x2 = nullptr;       // [2Np]
+  double* d_Spart = nullptr;
+  int64_t Spart_cap = 0;
+  double* d_cg = nullptr;       // PCG vectors
+  int64_t cg_cap = 0;
+  int solved_fix = 0;
+  bool solved = false;
+  // timing
+  cudaEvent_t ev[8];
+  double t_ms[6] = {0, 0, 0, 0, 0, 0};
+};
+
+#define EMBA_CUDA(call)                                                                     \
+  do {                                                                                      \
+    cudaError_t _e = (call);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + ":" + \
+               std::to_string(__LINE__);                                                    \
+      return EMBA_E_CUDA;                                                                   \
+    }                                                                                       \
+  } while (0)
+
+#define EMBA_TRY(call)        \
+  do {                        \
+    int _r = (call);          \
+    if (_r != EMBA_OK) return _r; \
+  } while (0)
+
+#define EMBA_LAUNCH_CHECK()      \
+  do {                           \
+    h->launches++;               \
+    EMBA_CUDA(cudaGetLastError()); \
+  } while (0)
+
+template <typename T>
+inline int dev_alloc(Handle* h, T** p, int64_t count) {
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  if (count <= 0) count = 1;
+  EMBA_CUDA(cudaMalloc((void**)p, sizeof(T) * (size_t)count));
+  return EMBA_OK;
+}
+template <typename T>
+inline int dev_reserve(Handle* h, T** p, int64_t* cap, int64_t count) {
+  if (*p && *cap >= count) return EMBA_OK;
+  int64_t want = count + count / 8 + 16;
+  EMBA_TRY(dev_alloc(h, p, want));
+  *cap = want;
+  return EMBA_OK;
+}
+
+inline int ceil_div64(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------
+// device math
+// ------------------------------------------------------------------------------------------------
+struct Vec3 { double x, y, z; };
+struct Mat3 { double m[9]; };  // row-major
+
+__device__ __forceinline__ Mat3 mat_mul(const Mat3& a, const Mat3& b) {
+  Mat3 c;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) c.m[3 * i + j] = a.m[3 * i] * b.m[j] + a.m[3 * i + 1] * b.m[3 + j] + a.m[3 * i + 2] * b.m[6 + j];
+  return c;
+}
+__device__ __forceinline__ Mat3 mat_T(const Mat3& a) {
+  Mat3 c;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) c.m[3 * i + j] = a.m[3 * j + i];
+  return c;
+}
+__device__ __forceinline__ Mat3 hat(const Vec3& v) {
+  Mat3 c = {{0, -v.z, v.y, v.z, 0, -v.x, -v.y, v.x, 0}};
+  return c;
+}
+
+// Hamilton product, xyzw (Sophus SO3::operator*)
+__device__ __forceinline__ double4 quat_mul(const double4& a, const double4& b) {
+  double4 r;
+  r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+  r.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
+  r.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
+  r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+  return r;
+}
+
+// Eigen::Quaternion::toRotationMatrix
+__device__ __forceinline__ Mat3 quat_to_R(const double4& q) {
+  const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
+  const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+  const double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+  const double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+  Mat3 R = {{1 - (tyy + tzz), txy - twz, txz + twy, txy + twz, 1 - (txx + tzz), tyz - twx, txz - twy, tyz + twx,
+             1 - (txx + tyy)}};
+  return R;
+}
+
+// Sophus SO3::logAndTheta (reference thirdparty/basalt-headers/thirdparty/Sophus/sophus/so3.hpp:247-290)
+__device__ __forceinline__ Vec3 so3_log(const double4& q) {
+  const double sq = q.x * q.x + q.y * q.y + q.z * q.z;
+  const double w = q.w;
+  double f;
+  if (sq < kSophusEps * kSophusEps) {
+    f = 2.0 / w - (2.0 / 3.0) * sq / (w * w * w);
+  } else {
+    const double n = sqrt(sq);
+    if (fabs(w) < kSophusEps) f = (w > 0 ? 3.14159265358979323846 : -3.14159265358979323846) / n;
+    else f = 2.0 * atan(n / w) / n;
+  }
+  Vec3 r = {f * q.x, f * q.y, f * q.z};
+  return r;
+}
+
+// Sophus SO3::expAndTheta (so3.hpp:583-619)
+__device__ __forceinline__ double4 so3_exp(const Vec3& o) {
+  const double th2 = o.x * o.x + o.y * o.y + o.z * o.z;
+  double imag, real;
+  if (th2 < kSophusEps * kSophusEps) {
+    const double th4 = th2 * th2;
+    imag = 0.5 - (1.0 / 48.0) * th2 + (1.0 / 3840.0) * th4;
+    real = 1.0 - (1.0 / 8.0) * th2 + (1.0 / 384.0) * th4;
+  } else {
+    const double th = sqrt(th2);
+    const double half = 0.5 * th;
+    imag = sin(half) / th;
+    real = cos(half);
+  }
+  double4 q = {imag * o.x, imag * o.y, imag * o.z, real};
+  return q;
+}
+
+// Sophus::leftJacobianSO3 (reference thirdparty/basalt-headers/include/basalt/utils/sophus_utils.hpp:333-362)
+__device__ __forceinline__ Mat3 left_jacobian(const Vec3& p) {
+  const double n2 = p.x * p.x + p.y * p.y + p.z * p.z;
+  const Mat3 H = hat(p);
+  const Mat3 H2 = mat_mul(H, H);
+  double a, b;
+  if (n2 > kSophusEps) {
+    const double n = sqrt(n2);
+    a = (1 - cos(n)) / n2;
+    b = (n - sin(n)) / (n2 * n);
+  } else {
+    a = 0.5;
+    b = 1.0 / 6.0;
+  }
+  Mat3 J;
+#pragma unroll
+  for (int i = 0; i < 9; i++) J.m[i] = H.m[i] * a + H2.m[i] * b;
+  J.m[0] += 1; J.m[4] += 1; J.m[8] += 1;
+  return J;
+}
+
+// Sophus::leftJacobianInvSO3 (sophus_utils.hpp:373-414)
+__device__ __forceinline__ Mat3 left_jacobian_inv(const Vec3& p) {
+  const double n2 = p.x * p.x + p.y * p.y + p.z * p.z;
+  const Mat3 H = hat(p);
+  const Mat3 H2 = mat_mul(H, H);
+  double c;
+  if (n2 > kSophusEps) {
+    const double n = sqrt(n2);
+    if (n < 3.14159265358979323846 - 1e-5) c = 1 / n2 - (1 + cos(n)) / (2 * n * sin(n));
+    else c = 1.0 / (3.14159265358979323846 * 3.14159265358979323846);
+  } else {
+    c = 1.0 / 12.0;
+  }
+  Mat3 J;
+#pragma unroll
+  for (int i = 0; i < 9; i++) J.m[i] = -0.5 * H.m[i] + H2.m[i] * c;
+  J.m[0] += 1; J.m[4] += 1; J.m[8] += 1;
+  return J;
+}
+
+struct PanoCam {
+  double fx, fy, cx, cy;  // fx = W/(2 pi), fy = H/pi, centre (W/2, H/2) (equirectangular_camera.h:11-16,64-67)
+};
+
+// EquirectangularCamera::projectToImage without the Jacobian (include/utils/equirectangular_camera.h:18-45)
+__device__ __forceinline__ void project_pm(const PanoCam& c, double X, double Y, double Z, double& px, double& py) {
+  const double phi = atan2(X, Z);
+  const double rho = sqrt(X * X + Y * Y + Z * Z);
+  const double theta = asin(Y / rho);
+  px = c.cx + phi * c.fx;
+  py = c.cy + theta * c.fy;
+}
+
+// M = dpm_drb * drb_ddrot (2x3): projection Jacobian (equirectangular_camera.h:31-43) times -[rb]x
+// (src/utils/event_pano_warper.cpp:62-65)
+__device__ __forceinline__ void project_jac(const PanoCam& c, double X, double Y, double Z, double M[6]) {
+  const double rho = sqrt(X * X + Y * Y + Z * Z);
+  const double Ydivrho = Y / rho;
+  const double XdivZ = X / Z;
+  const double tmp1 = c.fx / ((1 + XdivZ * XdivZ) * Z);
+  const double tmp2 = -c.fy / sqrt(1 - Ydivrho * Ydivrho);
+  const double tmp3 = Ydivrho / (rho * rho);
+  const double j00 = tmp1, j02 = -tmp1 * XdivZ;
+  const double j10 = tmp2 * tmp3 * X, j11 = tmp2 * (tmp3 * Y - 1 / rho), j12 = tmp2 * tmp3 * Z;
+  // -[r]x = [[0, Z, -Y], [-Z, 0, X], [Y, -X, 0]]
+  M[0] = j02 * Y;
+  M[1] = j00 * Z - j02 * X;
+  M[2] = -j00 * Y;
+  M[3] = -j11 * Z + j12 * Y;
+  M[4] = j10 * Z - j12 * X;
+  M[5] = -j10 * Y + j11 * X;
+}
+
+// index into the packed upper triangle of a symmetric 13x13 (i <= j)
+__host__ __device__ __forceinline__ int tri13(int i, int j) { return i * 13 - (i * (i - 1)) / 2 + (j - i); }
+
+}  // namespace emba

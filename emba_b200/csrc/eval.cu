@@ -1,0 +1,422 @@
+// LEGM::evaluateDataError on the device (reference src/emba/model.cpp:72-258): second-order maps, per-batch
+// spline poses, and the per-measurement residual kernel.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include "emba_internal.cuh"
+
+namespace emba {
+
+int rebuild_static(Handle* h);
+int comm_allreduce(Handle* h, void* buf, int64_t count, int dtype);  // dtype: 0 = int32, 1 = fp64
+
+// ---------------------------------------------------------------------------------------------------
+// Second-order gradient maps (model.cpp:87-97): 0.125 * 3x3 Sobel (cv::Sobel defaults: scale 1,
+// BORDER_REFLECT_101), Gxy = 0.5 * (dGx/dy + dGy/dx). Also interleaves (Gx, Gy) for single 16-byte gathers.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect101(int p, int len) {
+  if (len == 1) return 0;
+  if (p < 0) p = -p;
+  if (p >= len) p = 2 * (len - 1) - p;
+  return p;
+}
+
+__global__ void k_map_prepare(const double* __restrict__ Gx, const double* __restrict__ Gy, int W, int H,
+                              double2* __restrict__ G2, double4* __restrict__ H3) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W || y >= H) return;
+  const int xm = reflect101(x - 1, W), xp = reflect101(x + 1, W);
+  const int ym = reflect101(y - 1, H), yp = reflect101(y + 1, H);
+  const int64_t r0 = (int64_t)ym * W, r1 = (int64_t)y * W, r2 = (int64_t)yp * W;
+  // d/dx: derivative [-1 0 1] along x, smoothing [1 2 1] along y; d/dy the transpose
+  auto ddx = [&](const double* A) {
+    return (A[r0 + xp] - A[r0 + xm]) + 2.0 * (A[r1 + xp] - A[r1 + xm]) + (A[r2 + xp] - A[r2 + xm]);
+  };
+  auto ddy = [&](const double* A) {
+    return (A[r2 + xm] + 2.0 * A[r2 + x] + A[r2 + xp]) - (A[r0 + xm] + 2.0 * A[r0 + x] + A[r0 + xp]);
+  };
+  const double gxx = 0.125 * ddx(Gx);
+  const double gxy = 0.125 * ddy(Gx);
+  const double gyx = 0.125 * ddx(Gy);
+  const double gyy = 0.125 * ddy(Gy);
+  const int64_t i = r1 + x;
+  G2[i] = make_double2(Gx[i], Gy[i]);
+  H3[i] = make_double4(gxx, 0.5 * (gxy + gyx), gyy, 0.0);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Per-batch pose and Jacobian factor (model.cpp:115-136 -> src/utils/trajectory.cpp:122-147 ->
+// basalt So3Spline<2>::evaluate, so3_spline.h:218-274). For the linear spline
+//   R = R_s * Exp(u * Log(R_s^-1 R_{s+1})),   d_val_d_knot = [I - A | A],
+//   A = u * R_s * Jl(u delta) * Jl^-1(delta) * R_s^T          (so3_spline.h:254-265)
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_pose_table(const double* __restrict__ quat, const int32_t* __restrict__ bs,
+                             const double* __restrict__ bu, int64_t B, double* __restrict__ Rtab,
+                             double* __restrict__ Atab) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int s = bs[b];
+  const double u = bu[b];
+  const double4 q0 = reinterpret_cast<const double4*>(quat)[s];
+  const double4 q1 = reinterpret_cast<const double4*>(quat)[s + 1];
+  const double4 q0inv = make_double4(-q0.x, -q0.y, -q0.z, q0.w);
+  const double4 r01 = quat_mul(q0inv, q1);
+  const Vec3 delta = so3_log(r01);
+  const Vec3 kdelta = {delta.x * u, delta.y * u, delta.z * u};
+  const Mat3 Jli = left_jacobian_inv(delta);
+  const Mat3 Jlk = left_jacobian(kdelta);
+  const Mat3 R0 = quat_to_R(q0);
+  Mat3 A = mat_mul(mat_mul(mat_mul(R0, Jlk), Jli), mat_T(R0));
+  const double4 qr = quat_mul(q0, so3_exp(kdelta));
+  const Mat3 R = quat_to_R(qr);
+  double* Ro = Rtab + b * kPoseStride;
+  double* Ao = Atab + b * kPoseStride;
+#pragma unroll
+  for (int i = 0; i < 9; i++) { Ro[i] = R.m[i]; Ao[i] = u * A.m[i]; }
+  Ro[9] = 0; Ao[9] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The per-measurement residual kernel (model.cpp:140-246). One thread per event pair:
+//   rb_c = R(batch_c) b, rb_p = R(batch_p) b      (same sensor pixel -> same bearing b)
+//   pm = equirectangular(rb); dp = pm_c - pm_p; outlier iff |dp| > 10
+//   pix = round(pm_c); e = +-C_th - G(pix).dp; num_ev_map[pix]++
+// Outputs dp, e, pix per measurement; cost and inlier count as per-block partial sums (fixed grid ->
+// deterministic summation order).
+// ---------------------------------------------------------------------------------------------------
+template <int COST>
+__device__ __forceinline__ double rho_of(double e, double a) {
+  if (COST == EMBA_COST_QUADRATIC) return 0.5 * e * e;
+  if (COST == EMBA_COST_CAUCHY) return (0.5 / a) * log1p(a * e * e);  // model.cpp:283-290
+  const double ab = fabs(e);                                           // model.cpp:294-312
+  return ab < a ? 0.5 * ab * ab : a * ab - 0.5 * a * a;
+}
+
+constexpr int kEvalThreads = 256;
+
+template <int COST>
+__global__ void __launch_bounds__(kEvalThreads)
+k_eval(const MeasRec* __restrict__ rec, int64_t Mc, const double* __restrict__ lut, const double* __restrict__ Rtab,
+       const double2* __restrict__ G2, PanoCam cam, int W, int H, double C_th, double eta,
+       double2* __restrict__ dp_out, double* __restrict__ e_out, int32_t* __restrict__ pix_out,
+       int32_t* __restrict__ hist, double* __restrict__ part, int32_t* __restrict__ flags) {
+  double cost = 0.0;
+  double cnt = 0.0;
+  for (int64_t m = (int64_t)blockIdx.x * kEvalThreads + threadIdx.x; m < Mc; m += (int64_t)gridDim.x * kEvalThreads) {
+    const uint4 rr = reinterpret_cast<const uint4*>(rec)[m];
+    const uint32_t spix = rr.x, bc = rr.y & 0x7FFFFFFFu, bp = rr.z;
+    const double pol = (rr.y >> 31) ? 1.0 : 0.0;
+    const double bx = lut[3 * (size_t)spix], by = lut[3 * (size_t)spix + 1], bz = lut[3 * (size_t)spix + 2];
+    const double2* Rc = reinterpret_cast<const double2*>(Rtab + (size_t)bc * kPoseStride);
+    const double2* Rp = reinterpret_cast<const double2*>(Rtab + (size_t)bp * kPoseStride);
+    double pcx, pcy, ppx, ppy;
+    {
+      const double2 a0 = Rc[0], a1 = Rc[1], a2 = Rc[2], a3 = Rc[3], a4 = Rc[4];
+      const double X = a0.x * bx + a0.y * by + a1.x * bz;
+      const double Y = a1.y * bx + a2.x * by + a2.y * bz;
+      const double Z = a3.x * bx + a3.y * by + a4.x * bz;
+      project_pm(cam, X, Y, Z, pcx, pcy);
+    }
+    {
+      const double2 a0 = Rp[0], a1 = Rp[1], a2 = Rp[2], a3 = Rp[3], a4 = Rp[4];
+      const double X = a0.x * bx + a0.y * by + a1.x * bz;
+      const double Y = a1.y * bx + a2.x * by + a2.y * bz;
+      const double Z = a3.x * bx + a3.y * by + a4.x * bz;
+      project_pm(cam, X, Y, Z, ppx, ppy);
+    }
+    const double dx = pcx - ppx, dy = pcy - ppy;
+    // dp.norm() > 10 (model.cpp:199-200), evaluated without FMA contraction like the CPU build
+    const double nrm = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+    int32_t pix = -1;
+    double e = 0.0;
+    if (!(nrm > 10.0)) {
+      const int px = (int)round(pcx), py = (int)round(pcy);  // std::round, model.cpp:209-210
+      if (px < 0 || px >= W || py < 0 || py >= H) {
+        atomicOr(flags, 4);  // the reference reads out of bounds here
+      } else {
+        pix = py * W + px;
+        const double2 g = G2[pix];
+        const double C_pred = g.x * dx + g.y * dy;        // model.cpp:217
+        const double C_meas = 2.0 * (pol - 0.5) * C_th;   // model.cpp:219
+        e = C_meas - C_pred;
+        atomicAdd(&hist[pix], 1);                         // model.cpp:227
+        cost += rho_of<COST>(e, eta);
+        cnt += 1.0;
+      }
+    }
+    dp_out[m] = make_double2(dx, dy);
+    e_out[m] = e;
+    pix_out[m] = pix;
+  }
+  // block reduction, fixed tree
+  __shared__ double s_cost[kEvalThreads / 32], s_cnt[kEvalThreads / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cost += __shfl_down_sync(0xffffffffu, cost, o);
+    cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+  }
+  if ((threadIdx.x & 31) == 0) { s_cost[threadIdx.x >> 5] = cost; s_cnt[threadIdx.x >> 5] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double c = 0, k = 0;
+#pragma unroll
+    for (int w = 0; w < kEvalThreads / 32; w++) { c += s_cost[w]; k += s_cnt[w]; }
+    part[2 * blockIdx.x] = c;
+    part[2 * blockIdx.x + 1] = k;
+  }
+}
+
+// sum of squares of both maps over all pixels (evaluateRegError, model.cpp:260-277 + solver.cpp:90)
+__global__ void __launch_bounds__(256) k_reg_partial(const double* __restrict__ Gx, const double* __restrict__ Gy,
+                                                     int64_t P, double* __restrict__ part) {
+  double s = 0;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < P; i += (int64_t)gridDim.x * 256) {
+    const double a = Gx[i], b = Gy[i];
+    s += a * a + b * b;
+  }
+  __shared__ double sh[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) t += sh[w];
+    part[blockIdx.x] = t;
+  }
+}
+
+// final fixed-order sum of `nblk` partial rows of width `stride`; out[j] = sum_b part[b*stride + j]
+__global__ void k_sum_partials(const double* __restrict__ part, int nblk, int stride, double* __restrict__ out) {
+  const int j = blockIdx.x;
+  __shared__ double sh[256];
+  double s = 0;
+  for (int b = threadIdx.x; b < nblk; b += 256) s += part[(size_t)b * stride + j];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[j] = sh[0];
+}
+
+// scatter residuals to the reference's measurement order for emba_get_evaluation
+__global__ void k_scatter_ref(const MeasRec* __restrict__ rec, const int32_t* __restrict__ pix,
+                              const double* __restrict__ e, int64_t Mc, double* __restrict__ tmp_e,
+                              int32_t* __restrict__ tmp_flag) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= Mc) return;
+  if (pix[m] >= 0) {
+    const uint32_t r = rec[m].refpos;
+    tmp_e[r] = e[m];
+    tmp_flag[r] = 1;
+  }
+}
+__global__ void k_compact_ref(const double* __restrict__ tmp_e, const int32_t* __restrict__ flag,
+                              const int32_t* __restrict__ pos, int64_t Mt, double* __restrict__ out) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= Mt) return;
+  if (flag[r]) out[pos[r]] = tmp_e[r];
+}
+
+PanoCam make_cam(const Handle* h) {
+  PanoCam c;
+  // focalFromFOV(imageSize, 360, 180) (include/utils/equirectangular_camera.h:64-67)
+  c.fx = ((double)h->Wp / 360.0) * 180.0 / 3.1415926535897932384626433832795;
+  c.fy = ((double)h->Hp / 180.0) * 180.0 / 3.1415926535897932384626433832795;
+  c.cx = (double)h->Wp / 2.0;
+  c.cy = (double)h->Hp / 2.0;
+  return c;
+}
+
+int prepare_state_tables(Handle* h, StateSlot& s) {
+  dim3 blk(32, 8), grd((h->Wp + 31) / 32, (h->Hp + 7) / 8);
+  k_map_prepare<<<grd, blk, 0, h->stream>>>(s.Gx, s.Gy, h->Wp, h->Hp, s.G2, s.H3);
+  EMBA_LAUNCH_CHECK();
+  if (h->B) {
+    k_pose_table<<<ceil_div64(h->B, 128), 128, 0, h->stream>>>(s.quat, h->d_bs, h->d_bu, h->B, s.Rtab, s.Atab);
+    EMBA_LAUNCH_CHECK();
+  }
+  return EMBA_OK;
+}
+
+int evaluate_slot(Handle* h, int slot, int cost_type, double eta, double alpha) {
+  StateSlot& s = h->st[slot];
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((h->Mc + kEvalThreads - 1) / kEvalThreads, (int64_t)h->sm_count * 8));
+  const int rgrid = h->sm_count * 4;
+  EMBA_TRY(dev_reserve(h, &h->d_part, &h->part_cap, (int64_t)2 * grid + rgrid + 16));
+  EMBA_CUDA(cudaEventRecord(h->ev[0], h->stream));
+  EMBA_TRY(prepare_state_tables(h, s));
+  EMBA_CUDA(cudaMemsetAsync(s.hist, 0, sizeof(int32_t) * h->P, h->stream));
+  EMBA_CUDA(cudaMemsetAsync(h->d_flags, 0, sizeof(int32_t) * 16, h->stream));
+  const PanoCam cam = make_cam(h);
+  EMBA_CUDA(cudaEventRecord(h->ev[1], h->stream));
+  if (h->Mc > 0) {
+#define EMBA_EVAL_LAUNCH(C)                                                                                       \
+  k_eval<C><<<grid, kEvalThreads, 0, h->stream>>>(h->d_rec, h->Mc, h->d_lut, s.Rtab, s.G2, cam, h->Wp, h->Hp,     \
+                                                  h->C_th, eta, s.dp, s.e, s.pix, s.hist, h->d_part, h->d_flags)
+    if (cost_type == EMBA_COST_QUADRATIC) EMBA_EVAL_LAUNCH(EMBA_COST_QUADRATIC);
+    else if (cost_type == EMBA_COST_CAUCHY) EMBA_EVAL_LAUNCH(EMBA_COST_CAUCHY);
+    else EMBA_EVAL_LAUNCH(EMBA_COST_HUBER);
+#undef EMBA_EVAL_LAUNCH
+    EMBA_LAUNCH_CHECK();
+  }
+  EMBA_CUDA(cudaEventRecord(h->ev[2], h->stream));
+  if (h->Mc > 0) {
+    k_sum_partials<<<2, 256, 0, h->stream>>>(h->d_part, grid, 2, h->d_scal);
+    EMBA_LAUNCH_CHECK();
+  } else {
+    EMBA_CUDA(cudaMemsetAsync(h->d_scal, 0, sizeof(double) * 2, h->stream));
+  }
+  k_reg_partial<<<rgrid, 256, 0, h->stream>>>(s.Gx, s.Gy, h->P, h->d_part + 2 * grid);
+  EMBA_LAUNCH_CHECK();
+  k_sum_partials<<<1, 256, 0, h->stream>>>(h->d_part + 2 * grid, rgrid, 1, h->d_scal + 2);
+  EMBA_LAUNCH_CHECK();
+  if (h->world > 1) {
+    // the active-pixel decision is global: combine the histogram and the scalars
+    EMBA_TRY(comm_allreduce(h, s.hist, h->P, 0));
+    EMBA_TRY(comm_allreduce(h, h->d_scal, 2, 1));
+  }
+  EMBA_CUDA(cudaEventRecord(h->ev[3], h->stream));
+  double sc[3];
+  int32_t fl = 0;
+  EMBA_CUDA(cudaMemcpyAsync(sc, h->d_scal, sizeof(double) * 3, cudaMemcpyDeviceToHost, h->stream));
+  EMBA_CUDA(cudaMemcpyAsync(&fl, h->d_flags, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  EMBA_CUDA(cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[3]); h->t_ms[0] = ms;
+  cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->t_ms[1] = ms;
+  s.cost_data = sc[0];
+  s.M = (int64_t)llround(sc[1]);
+  s.cost_reg = 0.5 * alpha * sc[2];
+  s.evaluated = true;
+  if (fl & 4) {
+    h->err = "a warped event rounds outside the panorama (out-of-bounds read in the reference, model.cpp:213)";
+    return EMBA_E_RANGE;
+  }
+  return EMBA_OK;
+}
+
+}  // namespace emba
+
+using namespace emba;
+
+extern "C" {
+
+int emba_set_state(emba_handle_t hh, int32_t which, int64_t t0_ns, int64_t dt_ns, int32_t n_poses,
+                   const double* quat, const double* Gx, const double* Gy) {
+  Handle* h = (Handle*)hh;
+  if (!h) return EMBA_E_ARG;
+  if ((which != 0 && which != 1) || !quat || !Gx || !Gy || n_poses < 2 || dt_ns <= 0) {
+    h->err = "emba_set_state: bad argument";
+    return EMBA_E_ARG;
+  }
+  EMBA_CUDA(cudaSetDevice(h->device));
+  if (t0_ns != h->t0_ns || dt_ns != h->dt_ns || n_poses != h->n) {
+    h->t0_ns = t0_ns; h->dt_ns = dt_ns; h->n = n_poses;
+    int rc = rebuild_static(h);
+    if (rc != EMBA_OK) { h->t0_ns = -1; return rc; }
+  }
+  StateSlot& s = h->st[which ? 1 - h->cur : h->cur];
+  EMBA_CUDA(cudaMemcpyAsync(s.quat, quat, sizeof(double) * 4 * n_poses, cudaMemcpyHostToDevice, h->stream));
+  EMBA_CUDA(cudaMemcpyAsync(s.Gx, Gx, sizeof(double) * h->P, cudaMemcpyHostToDevice, h->stream));
+  EMBA_CUDA(cudaMemcpyAsync(s.Gy, Gy, sizeof(double) * h->P, cudaMemcpyHostToDevice, h->stream));
+  EMBA_CUDA(cudaStreamSynchronize(h->stream));
+  s.evaluated = false;
+  if (which == EMBA_STATE_CURRENT) h->formed = h->solved = false;
+  return EMBA_OK;
+}
+
+int emba_get_state(emba_handle_t hh, int32_t which, double* quat, double* Gx, double* Gy) {
+  Handle* h = (Handle*)hh;
+  if (!h || (which != 0 && which != 1) || h->n <= 0) return EMBA_E_ARG;
+  EMBA_CUDA(cudaSetDevice(h->device));
+  StateSlot& s = h->st[which ? 1 - h->cur : h->cur];
+  if (quat) EMBA_CUDA(cudaMemcpyAsync(quat, s.quat, sizeof(double) * 4 * h->n, cudaMemcpyDeviceToHost, h->stream));
+  if (Gx) EMBA_CUDA(cudaMemcpyAsync(Gx, s.Gx, sizeof(double) * h->P, cudaMemcpyDeviceToHost, h->stream));
+  if (Gy) EMBA_CUDA(cudaMemcpyAsync(Gy, s.Gy, sizeof(double) * h->P, cudaMemcpyDeviceToHost, h->stream));
+  EMBA_CUDA(cudaStreamSynchronize(h->stream));
+  return EMBA_OK;
+}
+
+int emba_evaluate(emba_handle_t hh, int32_t which, int32_t cost_type, double eta, double alpha, double* cost_data,
+                  double* cost_reg, int64_t* M) {
+  Handle* h = (Handle*)hh;
+  if (!h) return EMBA_E_ARG;
+  if ((which != 0 && which != 1) || h->t0_ns < 0 || cost_type < 0 || cost_type > 2) {
+    h->err = "emba_evaluate: set events and state first";
+    return EMBA_E_ARG;
+  }
+  EMBA_CUDA(cudaSetDevice(h->device));
+  const int slot = which ? 1 - h->cur : h->cur;
+  int rc = evaluate_slot(h, slot, cost_type, eta, alpha);
+  if (which == EMBA_STATE_CURRENT) h->formed = h->solved = false;
+  if (cost_data) *cost_data = h->st[slot].cost_data;
+  if (cost_reg) *cost_reg = h->st[slot].cost_reg;
+  if (M) *M = h->st[slot].M;
+  return rc;
+}
+
+int emba_get_evaluation(emba_handle_t hh, int32_t which, double* ep_out, int32_t* num_out) {
+  Handle* h = (Handle*)hh;
+  if (!h || (which != 0 && which != 1)) return EMBA_E_ARG;
+  EMBA_CUDA(cudaSetDevice(h->device));
+  StateSlot& s = h->st[which ? 1 - h->cur : h->cur];
+  if (!s.evaluated) { h->err = "emba_get_evaluation: state not evaluated"; return EMBA_E_ARG; }
+  if (num_out) EMBA_CUDA(cudaMemcpyAsync(num_out, s.hist, sizeof(int32_t) * h->P, cudaMemcpyDeviceToHost, h->stream));
+  if (ep_out && h->Mc_total > 0) {
+    const int64_t Mt = h->Mc_total;
+    double *tmp_e = nullptr, *d_out = nullptr;
+    int32_t *flag = nullptr, *pos = nullptr;
+    int rc = EMBA_OK;
+    if ((rc = dev_alloc(h, &tmp_e, Mt)) || (rc = dev_alloc(h, &d_out, Mt)) || (rc = dev_alloc(h, &flag, Mt)) ||
+        (rc = dev_alloc(h, &pos, Mt))) {
+      cudaFree(tmp_e); cudaFree(d_out); cudaFree(flag); cudaFree(pos);
+      return rc;
+    }
+    cudaMemsetAsync(flag, 0, sizeof(int32_t) * Mt, h->stream);
+    if (h->Mc) k_scatter_ref<<<ceil_div64(h->Mc, 256), 256, 0, h->stream>>>(h->d_rec, s.pix, s.e, h->Mc, tmp_e, flag);
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, flag, pos, (int)Mt, h->stream);
+    void* d_tmp = nullptr;
+    cudaMalloc(&d_tmp, tb ? tb : 1);
+    cub::DeviceScan::ExclusiveSum(d_tmp, tb, flag, pos, (int)Mt, h->stream);
+    k_compact_ref<<<ceil_div64(Mt, 256), 256, 0, h->stream>>>(tmp_e, flag, pos, Mt, d_out);
+    h->launches += 4;
+    int32_t lp = 0, lf = 0;
+    cudaMemcpyAsync(&lp, pos + Mt - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(&lf, flag + Mt - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess && lp + lf > 0)
+      e = cudaMemcpy(ep_out, d_out, sizeof(double) * (size_t)(lp + lf), cudaMemcpyDeviceToHost);
+    cudaFree(tmp_e); cudaFree(d_out); cudaFree(flag); cudaFree(pos); cudaFree(d_tmp);
+    if (e != cudaSuccess) { h->err = std::string("emba_get_evaluation: ") + cudaGetErrorString(e); return EMBA_E_CUDA; }
+  }
+  EMBA_CUDA(cudaStreamSynchronize(h->stream));
+  return EMBA_OK;
+}
+
+int emba_last_timings_ms(emba_handle_t hh, double* out6) {
+  Handle* h = (Handle*)hh;
+  if (!h || !out6) return EMBA_E_ARG;
+  for (int i = 0; i < 6; i++) out6[i] = h->t_ms[i];
+  return EMBA_OK;
+}
+int emba_launch_count(emba_handle_t hh, int64_t* out) {
+  Handle* h = (Handle*)hh;
+  if (!h || !out) return EMBA_E_ARG;
+  *out = h->launches;
+  return EMBA_OK;
+}
+int emba_synchronize(emba_handle_t hh) {
+  Handle* h = (Handle*)hh;
+  if (!h) return EMBA_E_ARG;
+  EMBA_CUDA(cudaSetDevice(h->device));
+  EMBA_CUDA(cudaStreamSynchronize(h->stream));
+  return EMBA_OK;
+}
+
+}  // extern "C"

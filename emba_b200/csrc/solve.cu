@@ -1,0 +1,623 @@
+// LEGM::solveNormalEq (Schur complement onto the control poses, reference src/emba/model.cpp:721-792) and
+// LEGM::solveNormalEqCG (Jacobi-preconditioned CG on the full system, model.cpp:794-840; iteration as in
+// Eigen/src/IterativeLinearSolvers/ConjugateGradient.h:26-96), plus the state update
+// (Model::updateTraj model.cpp:22-53, LEGM::updateMap model.cpp:863-903).
+//
+// A12 lives on the device as per-pixel strips (3x2 block per control pose inside the pixel's pose window), so
+//   S   = A11m - sum_a U_a C_a U_a^T,   C_a = (A22_a + lambda diag A22_a)^-1
+//   rhs = b1   - sum_a U_a C_a b2_a
+// is a block-sparse SYRK: tiles of S are accumulated in registers over the pixels whose window meets the tile.
+#include <algorithm>
+#include "emba_internal.cuh"
+
+namespace emba {
+
+int comm_allreduce(Handle* h, void* buf, int64_t count, int dtype);
+
+// C_a = inverse of the damped 2x2 block (model.cpp:743-759)
+__global__ void k_a22_inv(int64_t Np, const double* __restrict__ A22, double lambda, double* __restrict__ C) {
+  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= Np) return;
+  const double xx = A22[3 * a], xy = A22[3 * a + 1], yy = A22[3 * a + 2];
+  const double mxx = xx + lambda * xx, myy = yy + lambda * yy;
+  const double det = mxx * myy - xy * xy;
+  const double inv = 1.0 / det;
+  C[3 * a] = myy * inv;
+  C[3 * a + 1] = -xy * inv;
+  C[3 * a + 2] = mxx * inv;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Schur tiles. Extended index space [0, d]: rows 0..d-1 are pose unknowns (row = 3*(pose - fix) + r), row d is
+// the right-hand-side "row" (value C_a b2_a per pixel). Tile = 48 rows (16 poses). One CTA accumulates one
+// (I <= J) tile pair over one chunk of pixels; 16x16 threads, 3x3 outputs each, K step = 8 pixels x 2 columns.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kST = 48;
+constexpr int kSK = 16;
+
+__global__ void __launch_bounds__(256)
+k_schur_tiles(int64_t Np, int d, int fix, int nt, int Z, const int32_t* __restrict__ winlo,
+              const int32_t* __restrict__ winhi, const int64_t* __restrict__ stripoff,
+              const double* __restrict__ strip, const double* __restrict__ C, const double* __restrict__ b2,
+              double* __restrict__ Spart) {
+  // decode (I, J) from the linear pair index
+  int pair = blockIdx.x, I = 0;
+  while (pair >= nt - I) { pair -= nt - I; I++; }
+  const int J = I + pair;
+  const int z = blockIdx.y;
+  const int64_t a0 = Np * z / Z, a1 = Np * (z + 1) / Z;
+  const int rowI0 = I * kST, rowJ0 = J * kST;
+  const bool Jhas_rhs = (d >= rowJ0 && d < rowJ0 + kST);
+  // pose ranges covered by the tiles (poses are >= fix)
+  const int pI0 = rowI0 / 3 + fix, pI1 = min(d - 1, rowI0 + kST - 1) / 3 + fix;
+  const int pJ0 = rowJ0 / 3 + fix, pJ1 = min(d - 1, rowJ0 + kST - 1) / 3 + fix;
+  __shared__ double VI[kSK][kST];
+  __shared__ double VJ[kSK][kST];
+  __shared__ int32_t list[256];
+  __shared__ int32_t nlist;
+  const int tid = threadIdx.x, ti = tid & 15, tj = tid >> 4;
+  double acc[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) acc[r][c] = 0.0;
+
+  for (int64_t base = a0; base < a1; base += 256) {
+    // compact the pixels of this block of 256 whose window meets both tiles (ballot order -> deterministic)
+    if (tid == 0) nlist = 0;
+    __syncthreads();
+    const int64_t a = base + tid;
+    bool ok = false;
+    if (a < a1) {
+      const int lo = winlo[a], hi = winhi[a];
+      const bool mI = (rowI0 < d) && hi >= pI0 && lo <= pI1;
+      const bool mJ = ((rowJ0 < d) && hi >= pJ0 && lo <= pJ1) || Jhas_rhs;
+      ok = mI && mJ && hi >= lo;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    __shared__ int32_t wcount[8];
+    if ((tid & 31) == 0) wcount[tid >> 5] = __popc(bal);
+    __syncthreads();
+    int off = 0;
+    for (int w = 0; w < (tid >> 5); w++) off += wcount[w];
+    if (ok) list[off + __popc(bal & ((1u << (tid & 31)) - 1))] = (int32_t)(a - base);
+    if (tid == 255) nlist = off + __popc(bal);
+    __syncthreads();
+    const int nl = nlist;
+    for (int l0 = 0; l0 < nl; l0 += kSK / 2) {
+      // stage 8 pixels: thread -> (pixel slot pl = tid / 32, 32 lanes cover 48 rows x {I, J} in 3 passes)
+      for (int e = tid; e < (kSK / 2) * kST * 2; e += 256) {
+        const int pl = e / (kST * 2);
+        const int rem = e % (kST * 2);
+        const int side = rem / kST;  // 0: I rows, 1: J rows
+        const int rr = rem % kST;
+        double u0 = 0.0, u1 = 0.0;
+        if (l0 + pl < nl) {
+          const int64_t ap = base + list[l0 + pl];
+          const int grow = (side ? rowJ0 : rowI0) + rr;
+          if (grow < d) {
+            const int pose = grow / 3 + fix, comp = grow % 3;
+            const int lo = winlo[ap], hi = winhi[ap];
+            if (pose >= lo && pose <= hi) {
+              const double* sp = strip + (stripoff[ap] + (pose - lo)) * 6 + comp * 2;
+              u0 = sp[0];
+              u1 = sp[1];
+            }
+            if (side) {  // J side carries C_a: (u0, u1) <- (u0, u1) C_a
+              const double c00 = C[3 * ap], c01 = C[3 * ap + 1], c11 = C[3 * ap + 2];
+              const double t0 = u0 * c00 + u1 * c01, t1 = u0 * c01 + u1 * c11;
+              u0 = t0; u1 = t1;
+            }
+          } else if (grow == d && side) {  // right-hand-side row: C_a b2_a
+            const double c00 = C[3 * ap], c01 = C[3 * ap + 1], c11 = C[3 * ap + 2];
+            const double bx = b2[2 * ap], by = b2[2 * ap + 1];
+            u0 = c00 * bx + c01 * by;
+            u1 = c01 * bx + c11 * by;
+          }
+        }
+        if (side) { VJ[2 * pl][rr] = u0; VJ[2 * pl + 1][rr] = u1; }
+        else { VI[2 * pl][rr] = u0; VI[2 * pl + 1][rr] = u1; }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < kSK; k++) {
+        double av[3], bv[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) { av[r] = VI[k][3 * ti + r]; bv[r] = VJ[k][3 * tj + r]; }
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+          for (int c = 0; c < 3; c++) acc[r][c] += av[r] * bv[c];
+      }
+      __syncthreads();
+    }
+  }
+  double* out = Spart + ((size_t)z * gridDim.x + blockIdx.x) * (kST * kST);
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) out[(3 * ti + r) * kST + 3 * tj + c] = acc[r][c];
+}
+
+// S = A11m - sum_z partial tiles (fixed order); rhs = b1 - (...). A11m = A11 + lambda*diag(A11) (model.cpp:728-730).
+__global__ void k_schur_finish(int d, int fix, int n, int nt, int npairs, int Z, const double* __restrict__ Spart,
+                               const double* __restrict__ A11, const double* __restrict__ b1, double lambda,
+                               double* __restrict__ S, double* __restrict__ rhs) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)d * (d + 1);
+  if (idx >= total) return;
+  const int i = (int)(idx / (d + 1)), j = (int)(idx % (d + 1));  // j == d -> rhs
+  int ii = i, jj = j;
+  if (jj != d && ii > jj) { const int t = ii; ii = jj; jj = t; }
+  const int I = ii / kST, J = jj / kST;
+  // pair index of (I, J), I <= J
+  int pair = 0;
+  for (int k = 0; k < I; k++) pair += nt - k;
+  pair += J - I;
+  const int ri = ii % kST, rj = jj % kST;
+  double s = 0.0;
+  for (int z = 0; z < Z; z++) s += Spart[((size_t)z * npairs + pair) * (kST * kST) + ri * kST + rj];
+  const int d3 = 3 * n;
+  if (j == d) {
+    rhs[i] = b1[3 * fix + i] - s;
+  } else {
+    double a = A11[(size_t)(3 * fix + i) * d3 + 3 * fix + j];
+    if (i == j) a += lambda * a;
+    S[(size_t)i * d + j] = a - s;
+  }
+}
+
+// In-place LDL^T (no pivoting) of the dense symmetric S and solution of S x = rhs, one CTA.
+// The reference uses Eigen's LDLT (model.cpp:789); S is the Schur complement of a damped SPD system.
+__global__ void __launch_bounds__(1024) k_ldlt_solve(int d, double* __restrict__ S, double* __restrict__ x,
+                                                     int32_t* __restrict__ flags) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  __shared__ double dk_sh;
+  for (int k = 0; k < d; k++) {
+    if (tid == 0) {
+      const double dk = S[(size_t)k * d + k];
+      if (dk == 0.0 || !isfinite(dk)) atomicOr(flags, 8);
+      dk_sh = dk;
+    }
+    __syncthreads();
+    const double dk = dk_sh;
+    // column k of L (stored in the lower triangle); the upper triangle row k keeps d_k * l_ik for the update
+    for (int i = k + 1 + tid; i < d; i += nt) {
+      const double v = S[(size_t)i * d + k];
+      S[(size_t)k * d + i] = v;          // d_k * l_ik
+      S[(size_t)i * d + k] = v / dk;     // l_ik
+    }
+    __syncthreads();
+    // trailing update of the lower triangle: S_ij -= l_ik * (d_k l_jk), j <= i
+    const int m = d - k - 1;
+    for (int64_t e = tid; e < (int64_t)m * m; e += nt) {
+      const int i = k + 1 + (int)(e / m), j = k + 1 + (int)(e % m);
+      if (j <= i) S[(size_t)i * d + j] -= S[(size_t)i * d + k] * S[(size_t)k * d + j];
+    }
+    __syncthreads();
+  }
+  // forward: L y = b
+  for (int k = 0; k < d; k++) {
+    const double yk = x[k];
+    for (int i = k + 1 + tid; i < d; i += nt) x[i] -= S[(size_t)i * d + k] * yk;
+    __syncthreads();
+  }
+  for (int i = tid; i < d; i += nt) x[i] /= S[(size_t)i * d + i];
+  __syncthreads();
+  // backward: L^T x = z
+  for (int k = d - 1; k >= 0; k--) {
+    const double xk = x[k];
+    for (int i = tid; i < k; i += nt) x[i] -= S[(size_t)k * d + i] * xk;
+    __syncthreads();
+  }
+}
+
+// x2_a = C_a (b2_a - U_a^T x1) (model.cpp:791); x1full has 3n entries (zeros for a fixed first pose)
+__global__ void k_solve_x2(int64_t Np, const int32_t* __restrict__ winlo, const int32_t* __restrict__ winhi,
+                           const int64_t* __restrict__ stripoff, const double* __restrict__ strip,
+                           const double* __restrict__ C, const double* __restrict__ b2,
+                           const double* __restrict__ x1full, double* __restrict__ x2) {
+  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= Np) return;
+  const int lo = winlo[a], hi = winhi[a];
+  const double* sp = strip + stripoff[a] * 6;
+  double t0 = 0.0, t1 = 0.0;
+  for (int q = lo; q <= hi; q++) {
+    const double* u = sp + (size_t)(q - lo) * 6;
+    const double xa = x1full[3 * q], xb = x1full[3 * q + 1], xc = x1full[3 * q + 2];
+    t0 += u[0] * xa + u[2] * xb + u[4] * xc;
+    t1 += u[1] * xa + u[3] * xb + u[5] * xc;
+  }
+  const double r0 = b2[2 * a] - t0, r1 = b2[2 * a + 1] - t1;
+  const double c00 = C[3 * a], c01 = C[3 * a + 1], c11 = C[3 * a + 2];
+  x2[2 * a] = c00 * r0 + c01 * r1;
+  x2[2 * a + 1] = c01 * r0 + c11 * r1;
+}
+
+__global__ void k_expand_x1(int n, int fix, const double* __restrict__ rhs_x, double* __restrict__ x1full) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * n) return;
+  x1full[i] = i < 3 * fix ? 0.0 : rhs_x[i - 3 * fix];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Jacobi-PCG on [[A11m, A12], [A12^T, A22m]] (model.cpp:794-840). Vectors are laid out [x1 (d) | x2 (2Np)].
+// ---------------------------------------------------------------------------------------------------
+// y1 = A11m p1 (+ A12 p2 accumulated by k_cg_a12), one thread per row
+__global__ void k_cg_a11(int d, int fix, int n, const double* __restrict__ A11, double lambda,
+                         const double* __restrict__ p, double* __restrict__ y) {
+  const int i = blockIdx.x;
+  const int d3 = 3 * n;
+  const double* row = A11 + (size_t)(3 * fix + i) * d3 + 3 * fix;
+  double s = 0.0;
+  for (int j = threadIdx.x; j < d; j += blockDim.x) {
+    double a = row[j];
+    if (j == i) a += lambda * a;
+    s += a * p[j];
+  }
+  __shared__ double sh[128];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) y[i] = sh[0];
+}
+
+// per pixel: y2_a = U_a^T p1 + A22m_a p2_a ; and the pixel's contribution U_a p2_a to y1, written to a
+// per-pixel-chunk partial buffer part[chunk][d] that k_cg_y1 sums in a fixed order
+constexpr int kCgChunks = 64;
+__global__ void __launch_bounds__(256)
+k_cg_pix(int64_t Np, int d, int fix, const int32_t* __restrict__ winlo, const int32_t* __restrict__ winhi,
+         const int64_t* __restrict__ stripoff, const double* __restrict__ strip, const double* __restrict__ A22,
+         double lambda, const double* __restrict__ p, double* __restrict__ y, double* __restrict__ part) {
+  extern __shared__ double y1s[];  // [d]
+  const int chunk = blockIdx.x;
+  const int64_t a0 = Np * chunk / gridDim.x, a1 = Np * (chunk + 1) / gridDim.x;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) y1s[i] = 0.0;
+  __syncthreads();
+  const double* p1 = p;
+  const double* p2 = p + d;
+  // sequential over pixels inside the chunk, threads parallel over the strip rows -> fixed summation order
+  for (int64_t a = a0; a < a1; a++) {
+    const int lo = winlo[a], hi = winhi[a];
+    const double* sp = strip + stripoff[a] * 6;
+    const double pa = p2[2 * a], pb = p2[2 * a + 1];
+    const int rows = (hi - lo + 1) * 3;
+    double t0 = 0.0, t1 = 0.0;
+    for (int rr = threadIdx.x; rr < rows; rr += blockDim.x) {
+      const int grow = 3 * (lo - fix) + rr;  // row in the reduced system
+      if (grow < 0) continue;
+      const double u0 = sp[2 * rr], u1 = sp[2 * rr + 1];
+      y1s[grow] += u0 * pa + u1 * pb;
+      const double x = p1[grow];
+      t0 += u0 * x;
+      t1 += u1 * x;
+    }
+    // block reduce (t0, t1)
+    __shared__ double r0[256], r1[256];
+    r0[threadIdx.x] = t0; r1[threadIdx.x] = t1;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) { r0[threadIdx.x] += r0[threadIdx.x + o]; r1[threadIdx.x] += r1[threadIdx.x + o]; }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      const double xx = A22[3 * a], xy = A22[3 * a + 1], yy = A22[3 * a + 2];
+      y[d + 2 * a] = r0[0] + (xx + lambda * xx) * pa + xy * pb;
+      y[d + 2 * a + 1] = r1[0] + xy * pa + (yy + lambda * yy) * pb;
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < d; i += blockDim.x) part[(size_t)chunk * d + i] = y1s[i];
+}
+
+__global__ void k_cg_y1(int d, int chunks, const double* __restrict__ part, double* __restrict__ y) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d) return;
+  double s = y[i];
+  for (int c = 0; c < chunks; c++) s += part[(size_t)c * d + i];
+  y[i] = s;
+}
+
+// deterministic dot products: out[0] = a.b with fixed-grid partials
+__global__ void __launch_bounds__(256) k_dot_partial(int64_t n, const double* __restrict__ a,
+                                                     const double* __restrict__ b, double* __restrict__ part) {
+  double s = 0;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) s += a[i] * b[i];
+  __shared__ double sh[256];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+}
+__global__ void k_dot_final(int nblk, const double* __restrict__ part, double* __restrict__ out) {
+  __shared__ double sh[256];
+  double s = 0;
+  for (int b = threadIdx.x; b < nblk; b += 256) s += part[b];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sh[0];
+}
+// y = a*x + y ; z = inv_diag .* r etc.
+__global__ void k_axpy(int64_t n, double a, const double* __restrict__ x, double* __restrict__ y) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] += a * x[i];
+}
+__global__ void k_xpby(int64_t n, const double* __restrict__ x, double b, double* __restrict__ y) {  // y = x + b*y
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = x[i] + b * y[i];
+}
+__global__ void k_mul(int64_t n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ c) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) c[i] = a[i] * b[i];
+}
+// rhs vector b = [b1(fixed) | b2] and the inverse Jacobi diagonal (Eigen DiagonalPreconditioner: 1/diag, 1 if 0)
+__global__ void k_cg_setup(int d, int fix, int n, int64_t Np, const double* __restrict__ A11,
+                           const double* __restrict__ b1, const double* __restrict__ A22,
+                           const double* __restrict__ b2, double lambda, double* __restrict__ b,
+                           double* __restrict__ invd) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t tot = d + 2 * Np;
+  if (i >= tot) return;
+  double dg, bv;
+  if (i < d) {
+    const double a = A11[(size_t)(3 * fix + i) * (3 * n) + 3 * fix + i];
+    dg = a + lambda * a;
+    bv = b1[3 * fix + i];
+  } else {
+    const int64_t k = i - d, a = k >> 1;
+    const double v = (k & 1) ? A22[3 * a + 2] : A22[3 * a];
+    dg = v + lambda * v;
+    bv = b2[k];
+  }
+  b[i] = bv;
+  invd[i] = dg != 0.0 ? 1.0 / dg : 1.0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// state update
+__global__ void k_update_quat(int n, int fix, const double* __restrict__ qin, const double* __restrict__ x1full,
+                              double* __restrict__ qout) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double4 q = reinterpret_cast<const double4*>(qin)[i];
+  double4 r = q;
+  if (i >= fix) {
+    // R_i <- Exp(dphi_i) * R_i, left perturbation (src/utils/trajectory.cpp:296-304); Sophus renormalises
+    const Vec3 w = {x1full[3 * i], x1full[3 * i + 1], x1full[3 * i + 2]};
+    r = quat_mul(so3_exp(w), q);
+    const double nrm = sqrt(r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w);
+    r.x /= nrm; r.y /= nrm; r.z /= nrm; r.w /= nrm;
+  }
+  reinterpret_cast<double4*>(qout)[i] = r;
+}
+
+// active pixels += damping * x2, inactive pixels <- 0 (model.cpp:863-903)
+__global__ void k_update_map(int64_t P, const int32_t* __restrict__ amap, const double* __restrict__ x2,
+                             double damping, const double* __restrict__ Gx, const double* __restrict__ Gy,
+                             double* __restrict__ Gxo, double* __restrict__ Gyo) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const int32_t a = amap[p];
+  if (a >= 0) {
+    Gxo[p] = Gx[p] + damping * x2[2 * (int64_t)a];
+    Gyo[p] = Gy[p] + damping * x2[2 * (int64_t)a + 1];
+  } else {
+    Gxo[p] = 0.0;
+    Gyo[p] = 0.0;
+  }
+}
+
+static int dot(Handle* h, int64_t n, const double* a, const double* b, double* out_dev, int slot) {
+  const int grid = h->sm_count * 2;
+  double* part = h->d_part;
+  k_dot_partial<<<grid, 256, 0, h->stream>>>(n, a, b, part + 4096 * slot);
+  k_dot_final<<<1, 256, 0, h->stream>>>(grid, part + 4096 * slot, out_dev);
+  h->launches += 2;
+  return EMBA_OK;
+}
+
+int solve_schur(Handle* h, double lambda, int fix) {
+  const int n = h->n;
+  const int d = 3 * (n - fix);
+  const int64_t Np = h->Np;
+  const int T = 256;
+  if (Np > 0) { k_a22_inv<<<ceil_div64(Np, T), T, 0, h->stream>>>(Np, h->d_A22, lambda, h->d_C); EMBA_LAUNCH_CHECK(); }
+  const int nt = (d + 1 + kST - 1) / kST;
+  const int npairs = nt * (nt + 1) / 2;
+  int Z = std::max(1, (h->sm_count * 4) / npairs);
+  Z = (int)std::min<int64_t>(Z, std::max<int64_t>(1, (Np + 255) / 256));
+  EMBA_TRY(dev_reserve(h, &h->d_Spart, &h->Spart_cap, (int64_t)Z * npairs * kST * kST));
+  dim3 grid(npairs, Z);
+  k_schur_tiles<<<grid, 256, 0, h->stream>>>(Np, d, fix, nt, Z, h->d_winlo, h->d_winhi, h->d_stripoff, h->d_strip,
+                                             h->d_C, h->d_b2, h->d_Spart);
+  EMBA_LAUNCH_CHECK();
+  const int64_t tot = (int64_t)d * (d + 1);
+  k_schur_finish<<<ceil_div64(tot, T), T, 0, h->stream>>>(d, fix, n, nt, npairs, Z, h->d_Spart, h->d_A11, h->d_b1,
+                                                         lambda, h->d_S, h->d_rhs);
+  EMBA_LAUNCH_CHECK();
+  EMBA_CUDA(cudaMemsetAsync(h->d_flags, 0, sizeof(int32_t) * 16, h->stream));
+  k_ldlt_solve<<<1, 1024, 0, h->stream>>>(d, h->d_S, h->d_rhs, h->d_flags);
+  EMBA_LAUNCH_CHECK();
+  k_expand_x1<<<ceil_div64(3 * n, T), T, 0, h->stream>>>(n, fix, h->d_rhs, h->d_x1);
+  EMBA_LAUNCH_CHECK();
+  if (Np > 0) {
+    k_solve_x2<<<ceil_div64(Np, 128), 128, 0, h->stream>>>(Np, h->d_winlo, h->d_winhi, h->d_stripoff, h->d_strip,
+                                                           h->d_C, h->d_b2, h->d_x1, h->d_x2);
+    EMBA_LAUNCH_CHECK();
+  }
+  int32_t fl = 0;
+  EMBA_CUDA(cudaMemcpyAsync(&fl, h->d_flags, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  EMBA_CUDA(cudaStreamSynchronize(h->stream));
+  if (fl & 8) { h->err = "zero or non-finite pivot in the LDL^T factorisation of the Schur complement"; return EMBA_E_NUMERIC; }
+  return EMBA_OK;
+}
+
+int solve_pcg(Handle* h, double lambda, int fix, int* iters_out, double* err_out) {
+  const int n = h->n;
+  const int d = 3 * (n - fix);
+  const int64_t Np = h->Np;
+  const int64_t tot = d + 2 * Np;
+  const int T = 256;
+  const int G = ceil_div64(tot, T);
+  const int max_iter = 100;
+  const double tol = 1e-6;  // model.cpp:828-831
+  // vectors: b, invd, x, r, p, z, tmp + per-chunk y1 partials
+  EMBA_TRY(dev_reserve(h, &h->d_cg, &h->cg_cap, 7 * tot + (int64_t)kCgChunks * d + 64));
+  EMBA_TRY(dev_reserve(h, &h->d_part, &h->part_cap, 4096 * 4));
+  double* b = h->d_cg;
+  double* invd = b + tot;
+  double* x = invd + tot;
+  double* r = x + tot;
+  double* p = r + tot;
+  double* z = p + tot;
+  double* tmp = z + tot;
+  double* ypart = tmp + tot;
+  double* sc = h->d_scal + 8;
+  k_cg_setup<<<G, T, 0, h->stream>>>(d, fix, n, Np, h->d_A11, h->d_b1, h->d_A22, h->d_b2, lambda, b, invd);
+  EMBA_LAUNCH_CHECK();
+  EMBA_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * tot, h->stream));
+  EMBA_CUDA(cudaMemcpyAsync(r, b, sizeof(double) * tot, cudaMemcpyDeviceToDevice, h->stream));  // x0 = 0
+  auto hdot = [&](const double* a, const double* c, double* out) -> int {
+    EMBA_TRY(dot(h, tot, a, c, sc, 0));
+    EMBA_CUDA(cudaMemcpyAsync(out, sc, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    EMBA_CUDA(cudaStreamSynchronize(h->stream));
+    return EMBA_OK;
+  };
+  auto matvec = [&](const double* v, double* y) -> int {
+    k_cg_a11<<<d, 128, 0, h->stream>>>(d, fix, n, h->d_A11, lambda, v, y);
+    h->launches++;
+    if (Np > 0) {
+      const size_t shm = sizeof(double) * d;
+      if (shm > 40 * 1024) EMBA_CUDA(cudaFuncSetAttribute(k_cg_pix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+      k_cg_pix<<<kCgChunks, 256, shm, h->stream>>>(Np, d, fix, h->d_winlo, h->d_winhi, h->d_stripoff, h->d_strip,
+                                                   h->d_A22, lambda, v, y, ypart);
+      k_cg_y1<<<ceil_div64(d, 128), 128, 0, h->stream>>>(d, kCgChunks, ypart, y);
+      h->launches += 2;
+    }
+    EMBA_CUDA(cudaGetLastError());
+    return EMBA_OK;
+  };
+  double rhs2 = 0, rn2 = 0;
+  EMBA_TRY(hdot(b, b, &rhs2));
+  int it = 0;
+  double err = 0;
+  if (rhs2 == 0) {
+    it = 0; err = 0;
+  } else {
+    const double thr = std::max(tol * tol * rhs2, 2.2250738585072014e-308);
+    rn2 = rhs2;
+    if (rn2 < thr) {
+      err = sqrt(rn2 / rhs2);
+    } else {
+      k_mul<<<G, T, 0, h->stream>>>(tot, invd, r, p);
+      h->launches++;
+      double absNew = 0;
+      EMBA_TRY(hdot(r, p, &absNew));
+      while (it < max_iter) {
+        EMBA_TRY(matvec(p, tmp));
+        double ptmp = 0;
+        EMBA_TRY(hdot(p, tmp, &ptmp));
+        const double alpha = absNew / ptmp;
+        k_axpy<<<G, T, 0, h->stream>>>(tot, alpha, p, x);
+        k_axpy<<<G, T, 0, h->stream>>>(tot, -alpha, tmp, r);
+        h->launches += 2;
+        EMBA_TRY(hdot(r, r, &rn2));
+        if (rn2 < thr) break;
+        k_mul<<<G, T, 0, h->stream>>>(tot, invd, r, z);
+        h->launches++;
+        const double absOld = absNew;
+        EMBA_TRY(hdot(r, z, &absNew));
+        const double beta = absNew / absOld;
+        k_xpby<<<G, T, 0, h->stream>>>(tot, z, beta, p);
+        h->launches++;
+        it++;
+      }
+      err = sqrt(rn2 / rhs2);
+    }
+  }
+  k_expand_x1<<<ceil_div64(3 * n, T), T, 0, h->stream>>>(n, fix, x, h->d_x1);
+  EMBA_LAUNCH_CHECK();
+  if (Np > 0) EMBA_CUDA(cudaMemcpyAsync(h->d_x2, x + d, sizeof(double) * 2 * Np, cudaMemcpyDeviceToDevice, h->stream));
+  EMBA_CUDA(cudaStreamSynchronize(h->stream));
+  if (iters_out) *iters_out = it;
+  if (err_out) *err_out = err;
+  return EMBA_OK;
+}
+
+int make_candidate(Handle* h, double damping, int fix) {
+  StateSlot& c = h->st[h->cur];
+  StateSlot& k = h->st[1 - h->cur];
+  k_update_quat<<<ceil_div64(h->n, 128), 128, 0, h->stream>>>(h->n, fix, c.quat, h->d_x1, k.quat);
+  EMBA_LAUNCH_CHECK();
+  k_update_map<<<ceil_div64(h->P, 256), 256, 0, h->stream>>>(h->P, h->d_amap, h->d_x2, damping, c.Gx, c.Gy, k.Gx, k.Gy);
+  EMBA_LAUNCH_CHECK();
+  k.evaluated = false;
+  return EMBA_OK;
+}
+
+}  // namespace emba
+
+using namespace emba;
+
+extern "C" {
+
+int emba_solve(emba_handle_t hh, double lambda, int32_t use_cg, int32_t fix, double* x1_out, double* x2_out,
+               int32_t* cg_iters, double* cg_error) {
+  Handle* h = (Handle*)hh;
+  if (!h) return EMBA_E_ARG;
+  if (!h->formed) { h->err = "emba_solve: form the normal equations first"; return EMBA_E_ARG; }
+  fix = fix ? 1 : 0;
+  EMBA_CUDA(cudaSetDevice(h->device));
+  EMBA_CUDA(cudaEventRecord(h->ev[0], h->stream));
+  if (use_cg) {
+    int it = 0; double er = 0;
+    EMBA_TRY(solve_pcg(h, lambda, fix, &it, &er));
+    if (cg_iters) *cg_iters = it;
+    if (cg_error) *cg_error = er;
+  } else {
+    EMBA_TRY(solve_schur(h, lambda, fix));
+  }
+  EMBA_CUDA(cudaEventRecord(h->ev[1], h->stream));
+  h->solved = true;
+  h->solved_fix = fix;
+  const int d = 3 * (h->n - fix);
+  if (x1_out) EMBA_CUDA(cudaMemcpyAsync(x1_out, h->d_x1 + 3 * fix, sizeof(double) * d, cudaMemcpyDeviceToHost, h->stream));
+  if (x2_out && h->Np) EMBA_CUDA(cudaMemcpyAsync(x2_out, h->d_x2, sizeof(double) * 2 * h->Np, cudaMemcpyDeviceToHost, h->stream));
+  EMBA_CUDA(cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+  h->t_ms[5] = ms;
+  return EMBA_OK;
+}
+
+int emba_make_candidate(emba_handle_t hh, double damping, int32_t fix) {
+  Handle* h = (Handle*)hh;
+  if (!h) return EMBA_E_ARG;
+  if (!h->solved) { h->err = "emba_make_candidate: solve first"; return EMBA_E_ARG; }
+  EMBA_CUDA(cudaSetDevice(h->device));
+  EMBA_TRY(make_candidate(h, damping, fix ? 1 : 0));
+  EMBA_CUDA(cudaStreamSynchronize(h->stream));
+  return EMBA_OK;
+}
+
+int emba_accept_candidate(emba_handle_t hh) {
+  Handle* h = (Handle*)hh;
+  if (!h) return EMBA_E_ARG;
+  if (!h->st[1 - h->cur].evaluated) { h->err = "emba_accept_candidate: candidate not evaluated"; return EMBA_E_ARG; }
+  h->cur = 1 - h->cur;  // solver.cpp:299-317: the candidate (state, residuals, num_ev_map) becomes current
+  h->formed = false;
+  h->solved = false;
+  return EMBA_OK;
+}
+
+}  // extern "C"

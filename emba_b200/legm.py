@@ -1,0 +1,290 @@
+"""Host-side mirror of the reference's optimiser interface for the LM hot path.
+
+`Engine` is a thin numpy-in / numpy-out wrapper of the C ABI (include/emba_b200.h).
+`LEGM` re-creates the method names, argument meaning and call order of the reference's
+`EMBA::LEGM` (include/emba/model.h:72-133) and `Trajectory` the part of
+`LinearTrajectory` (include/utils/trajectory.h:106-191) that the LM loop touches, so that
+`solveTimeWindow` below reads like the reference's `EMBA::solveTimeWindow`
+(src/emba/solver.cpp:11-368) and the parity tests read like tests of the reference.
+
+All numerics run in the CUDA library; nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import EmbaError, LMLog, LMSettings, ptr
+
+
+def spline_base_ns(t_beg: float, dt_knots: float):
+    """int64_t(1e9*t_beg), int64_t(1e9*dt_knots): the truncating expression of
+    LinearTrajectory(double, double, cps) (src/utils/trajectory.cpp:61-70)."""
+    return int(np.int64(np.float64(1e9) * np.float64(t_beg))), int(np.int64(np.float64(1e9) * np.float64(dt_knots)))
+
+
+class Engine:
+    def __init__(self, sensor_w, sensor_h, bearing_lut, C_th, pano_w, pano_h, device=0):
+        self.L = capi.load()
+        self.sensor_w, self.sensor_h, self.pano_w, self.pano_h = sensor_w, sensor_h, pano_w, pano_h
+        self.P = pano_w * pano_h
+        lut = np.ascontiguousarray(bearing_lut, dtype=np.float64).reshape(-1)
+        assert lut.size == 3 * sensor_w * sensor_h
+        cfg = capi.Config(sensor_w, sensor_h, pano_w, pano_h, float(C_th), ptr(lut), device)
+        self.h = C.c_void_p()
+        rc = self.L.emba_create(C.byref(cfg), C.byref(self.h))
+        if rc != 0:
+            raise EmbaError(rc, "emba_create failed (no CUDA device? there is no CPU fallback)")
+        self.n = 0
+        self.N = 0
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.L.emba_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise EmbaError(rc, self.L.emba_last_error(self.h).decode())
+
+    # -- events / shard -------------------------------------------------------------------------
+    def set_events(self, x, y, t_ns, pol):
+        x = np.ascontiguousarray(x, dtype=np.uint16)
+        y = np.ascontiguousarray(y, dtype=np.uint16)
+        t = np.ascontiguousarray(t_ns, dtype=np.int64)
+        p = np.ascontiguousarray(pol, dtype=np.uint8)
+        self.N = x.size
+        self._chk(self.L.emba_set_events(self.h, x.size, ptr(x, C.c_uint16), ptr(y, C.c_uint16), ptr(t, C.c_int64),
+                                         ptr(p, C.c_uint8)))
+
+    def num_pairs(self):
+        v = C.c_int64(0)
+        self._chk(self.L.emba_num_pairs(self.h, C.byref(v)))
+        return v.value
+
+    def set_shard(self, rank, world):
+        self._chk(self.L.emba_set_shard(self.h, rank, world))
+
+    def comm_init(self, uid_bytes, rank, world):
+        buf = C.create_string_buffer(bytes(uid_bytes), 128)
+        self._chk(self.L.emba_comm_init(self.h, buf, rank, world))
+
+    def comm_unique_id(self):
+        buf = C.create_string_buffer(128)
+        rc = self.L.emba_comm_unique_id(buf)
+        if rc != 0:
+            raise EmbaError(rc, "emba_comm_unique_id")
+        return buf.raw
+
+    # -- state -----------------------------------------------------------------------------------
+    def set_state(self, which, t0_ns, dt_ns, quat, Gx, Gy):
+        q = np.ascontiguousarray(quat, dtype=np.float64)
+        gx = np.ascontiguousarray(Gx, dtype=np.float64)
+        gy = np.ascontiguousarray(Gy, dtype=np.float64)
+        assert gx.size == self.P and gy.size == self.P
+        self.n = q.shape[0]
+        self._chk(self.L.emba_set_state(self.h, which, int(t0_ns), int(dt_ns), self.n, ptr(q), ptr(gx), ptr(gy)))
+
+    def get_state(self, which=capi.STATE_CURRENT):
+        q = np.empty((self.n, 4))
+        gx = np.empty((self.pano_h, self.pano_w))
+        gy = np.empty((self.pano_h, self.pano_w))
+        self._chk(self.L.emba_get_state(self.h, which, ptr(q), ptr(gx), ptr(gy)))
+        return q, gx, gy
+
+    # -- evaluate ----------------------------------------------------------------------------------
+    def evaluate(self, which=capi.STATE_CURRENT, cost_type=0, eta=1.0, alpha=0.0):
+        cd, cr, M = C.c_double(0), C.c_double(0), C.c_int64(0)
+        self._chk(self.L.emba_evaluate(self.h, which, cost_type, float(eta), float(alpha), C.byref(cd), C.byref(cr),
+                                       C.byref(M)))
+        return cd.value, cr.value, M.value
+
+    def get_evaluation(self, which=capi.STATE_CURRENT, M=None, want_ep=True, want_num=True):
+        ep = np.empty(max(self.num_pairs(), 1)) if want_ep else None
+        num = np.empty((self.pano_h, self.pano_w), dtype=np.int32) if want_num else None
+        self._chk(self.L.emba_get_evaluation(self.h, which, ptr(ep), ptr(num, C.c_int32)))
+        if ep is not None and M is not None:
+            ep = ep[:M].copy()
+        return ep, num
+
+    # -- normal equations ----------------------------------------------------------------------------
+    def form_normal_eq(self, thres, cost_type=0, eta=1.0, alpha=0.0):
+        Np = C.c_int64(0)
+        self._chk(self.L.emba_form_normal_eq(self.h, thres, cost_type, float(eta), float(alpha), C.byref(Np)))
+        self.Np = Np.value
+        return self.Np
+
+    def get_normal_eq(self, want_A12=True):
+        n, Np = self.n, self.Np
+        A11 = np.empty((3 * n, 3 * n))
+        b1 = np.empty(3 * n)
+        A22 = np.empty((Np, 2, 2))
+        b2 = np.empty(2 * Np)
+        act = np.empty(Np, dtype=np.int64)
+        A12 = np.empty((3 * n, 2 * Np)) if want_A12 else None
+        self._chk(self.L.emba_get_normal_eq(self.h, ptr(A11), ptr(b1), ptr(A22), ptr(b2), ptr(act, C.c_int64),
+                                            ptr(A12)))
+        return A11, A12, A22, b1, b2, act
+
+    def a12_entries(self):
+        v = C.c_int64(0)
+        self._chk(self.L.emba_a12_entries(self.h, C.byref(v)))
+        return v.value
+
+    def solve(self, lam, use_cg=False, fix_first=True, want=True):
+        d = 3 * (self.n - (1 if fix_first else 0))
+        x1 = np.empty(d) if want else None
+        x2 = np.empty(2 * self.Np) if want else None
+        it, err = C.c_int32(0), C.c_double(0)
+        self._chk(self.L.emba_solve(self.h, float(lam), int(use_cg), int(fix_first), ptr(x1), ptr(x2), C.byref(it),
+                                    C.byref(err)))
+        return x1, x2, it.value, err.value
+
+    def make_candidate(self, damping, fix_first=True):
+        self._chk(self.L.emba_make_candidate(self.h, float(damping), int(fix_first)))
+
+    def accept_candidate(self):
+        self._chk(self.L.emba_accept_candidate(self.h))
+
+    def solve_time_window(self, *, max_num_iter=50, tol_fun=1e-3, num_times_tol_fun_sat=2, use_cg=False, cost_type=0,
+                          eta=1.0, thres=5, damping=1.0, alpha=5.0, first_window=True):
+        s = LMSettings(max_num_iter, tol_fun, num_times_tol_fun_sat, int(use_cg), cost_type, eta, thres, damping,
+                       alpha, int(first_window))
+        cap = max_num_iter + 8
+        log = (LMLog * cap)()
+        nlog, fc = C.c_int32(0), C.c_double(0)
+        self._chk(self.L.emba_solve_time_window(self.h, C.byref(s), log, cap, C.byref(nlog), C.byref(fc)))
+        rows = np.array([[r.iter, r.lambda_, r.cost_min, r.cost_new, r.accepted, r.num_active_pixels,
+                          r.num_measurements] for r in log[: nlog.value]], dtype=np.float64).reshape(-1, 7)
+        return rows, fc.value
+
+    def timings_ms(self):
+        out = np.zeros(6)
+        self._chk(self.L.emba_last_timings_ms(self.h, ptr(out)))
+        return dict(evaluate=out[0], eval_kernel=out[1], form=out[2], asm_pose_kernel=out[3], map_side=out[4],
+                    solve=out[5])
+
+    def launch_count(self):
+        v = C.c_int64(0)
+        self._chk(self.L.emba_launch_count(self.h, C.byref(v)))
+        return v.value
+
+    def synchronize(self):
+        self._chk(self.L.emba_synchronize(self.h))
+
+
+# ------------------------------------------------------------------------------------------------
+# reference-shaped interface
+# ------------------------------------------------------------------------------------------------
+class Trajectory:
+    """The part of the reference's LinearTrajectory the LM loop uses (include/utils/trajectory.h:106-191):
+    size(), getControlPose(), begTime(), getDtCtrlPoses(), clone(). Control poses are xyzw unit quaternions."""
+
+    def __init__(self, t_beg, dt_knots, quat_xyzw):
+        self.t_beg_ = float(t_beg)
+        self.dt_knots_ = float(dt_knots)
+        self.quat = np.array(quat_xyzw, dtype=np.float64, copy=True)
+
+    def size(self):
+        return self.quat.shape[0]
+
+    def getControlPose(self, i):
+        return self.quat[i]
+
+    def begTime(self):
+        return self.t_beg_
+
+    def getDtCtrlPoses(self):
+        return self.dt_knots_
+
+    def clone(self):
+        return Trajectory(self.t_beg_, self.dt_knots_, self.quat)
+
+
+class EventPacket:
+    """std::vector<dvs_msgs::Event> as flat arrays (include/emba/model.h:15)."""
+
+    def __init__(self, x, y, t_ns, polarity):
+        self.x, self.y, self.t_ns, self.polarity = x, y, t_ns, polarity
+
+    def size(self):
+        return int(np.asarray(self.t_ns).size)
+
+
+class LEGM:
+    """Drop-in shaped like EMBA::LEGM (include/emba/model.h:72-133), running on the GPU.
+
+    Like the reference, the model keeps hidden state between calls: the per-measurement data of the LAST
+    evaluated point (the reference's event_map_, model.h:131-132). evaluateDataError() evaluates into the device's
+    candidate slot; formNormalEq() promotes that slot to current first, which is exactly the reference's rule that
+    the normal equations are formed from the last evaluated point (solver.cpp:96-130)."""
+
+    def __init__(self, sensor_w, sensor_h, bearing_lut, C_th, pano_width, pano_height, device=0):
+        self.eng = Engine(sensor_w, sensor_h, bearing_lut, C_th, pano_width, pano_height, device)
+        self._events_id = None
+        self._pending = False
+        self._M = 0
+        self._fix = 1
+
+    def _sync_events(self, events: EventPacket):
+        key = (id(events.t_ns), events.size())
+        if key != self._events_id:
+            self.eng.set_events(events.x, events.y, events.t_ns, events.polarity)
+            self._events_id = key
+
+    def evaluateDataError(self, traj: Trajectory, Gx, Gy, events: EventPacket, eval_deriv=True, num_ev_map=None,
+                          cost_type=0, eta=1.0):
+        """model.cpp:72-258. Returns ep (reference order); fills num_ev_map in place if given."""
+        self._sync_events(events)
+        t0, dt = spline_base_ns(traj.begTime(), traj.getDtCtrlPoses())
+        self.eng.set_state(capi.STATE_CANDIDATE, t0, dt, traj.quat, Gx, Gy)
+        cd, _, M = self.eng.evaluate(capi.STATE_CANDIDATE, cost_type, eta, 0.0)
+        self._pending, self._M, self._cost_data = True, M, cd
+        ep, num = self.eng.get_evaluation(capi.STATE_CANDIDATE, M, True, num_ev_map is not None)
+        if num_ev_map is not None:
+            num_ev_map[...] = num
+        return ep
+
+    def evaluateRegError(self, Gx, Gy):
+        """model.cpp:260-277 (a plain reshuffle of the map values; host side like the reference)."""
+        return np.stack([np.asarray(Gx).reshape(-1), np.asarray(Gy).reshape(-1)], -1).reshape(-1)
+
+    def lastDataCost(self):
+        """0.5*ep.ep (or the robust cost) of the last evaluateDataError, reduced on the device."""
+        return self._cost_data
+
+    def formNormalEq(self, num_ctrl_poses, thres_valid_pixel, cost_type=0, eta=1.0, want_A12=True):
+        """model.cpp:316-491 (IRLS: 493-687). Returns A11, A12, A22_blocks, b1, b2, active_pix_idxes."""
+        if self._pending:
+            self.eng.accept_candidate()
+            self._pending = False
+        assert num_ctrl_poses == self.eng.n
+        self.eng.form_normal_eq(thres_valid_pixel, cost_type, eta, 0.0)
+        return self.eng.get_normal_eq(want_A12)
+
+    def solveNormalEq(self, lam, fix_first=True):
+        """model.cpp:721-792."""
+        x1, x2, _, _ = self.eng.solve(lam, False, fix_first)
+        self._fix = fix_first
+        return x1, x2
+
+    def solveNormalEqCG(self, lam, fix_first=True):
+        """model.cpp:794-840. Returns x1, x2, (iterations, error)."""
+        x1, x2, it, err = self.eng.solve(lam, True, fix_first)
+        self._fix = fix_first
+        return x1, x2, (it, err)
+
+    def updateTrajAndMap(self, traj: Trajectory, damping_factor):
+        """Model::updateTraj (model.cpp:22-53) + LEGM::updateMap (model.cpp:863-903) applied to clones of the
+        current state with the last solution; returns (traj_new, Gx_new, Gy_new)."""
+        self.eng.make_candidate(damping_factor, self._fix)
+        q, gx, gy = self.eng.get_state(capi.STATE_CANDIDATE)
+        return Trajectory(traj.begTime(), traj.getDtCtrlPoses(), q), gx, gy

@@ -1,0 +1,178 @@
+/*
+ * emba_b200 C ABI -- B200 (sm_100a) drop-in for EMBA's per-iteration
+ * Levenberg-Marquardt hot path.
+ *
+ * Each entry point replaces one member of the reference's measurement-model
+ * class `EMBA::LEGM : Model` (reference: include/emba/model.h:26-133), whose
+ * only caller is `EMBA::solveTimeWindow` (reference: src/emba/solver.cpp:11-368).
+ * The reference-side binding (a header-only adapter with LEGM's signatures on
+ * top of these calls) is shown in INTEGRATION.md.
+ *
+ * Conventions (identical to the reference so results compare 1:1):
+ *  - events are time-sorted; only the first 100*floor(N/100) are used
+ *    (src/emba/model.cpp:78-79,102);
+ *  - maps are row-major fp64, index = x + y*pano_w (include/emba/model.h:42-43);
+ *  - control poses are unit quaternions, (x, y, z, w) per pose;
+ *  - pose unknowns are 3-vector LEFT perturbations stacked in pose order
+ *    (src/emba/model.cpp:25-35); map unknowns are (Gx, Gy) interleaved per ACTIVE
+ *    pixel in ascending pixel index (src/emba/model.cpp:438-439,874-875);
+ *  - the spline time base is passed as the two int64 nanosecond values the
+ *    reference forms with int64_t(1e9*t_beg), int64_t(1e9*dt_knots)
+ *    (src/utils/trajectory.cpp:61-70) -- the adapter must use that expression.
+ *
+ * All functions return 0 on success and a negative EMBA_E_* code on failure;
+ * emba_last_error() gives a message. Nothing aborts or throws across the ABI
+ * (the reference aborts through glog CHECK / basalt asserts instead).
+ * A handle is not thread-safe; one host thread drives one handle = one GPU.
+ * There is no CPU fallback: without a CUDA device emba_create fails.
+ * All pointers are HOST pointers unless a parameter name ends in `_dev`.
+ */
+#ifndef EMBA_B200_H_
+#define EMBA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define EMBA_API __attribute__((visibility("default")))
+#else
+#define EMBA_API
+#endif
+
+typedef struct emba_handle_s* emba_handle_t;
+
+enum {
+  EMBA_OK = 0,
+  EMBA_E_ARG = -1,      /* bad argument / call order */
+  EMBA_E_CUDA = -2,     /* CUDA runtime error */
+  EMBA_E_SUPPORT = -3,  /* batch time outside the spline support (basalt so3_spline.h:221-230 asserts) */
+  EMBA_E_RANGE = -4,    /* warped event rounds outside the panorama (UB in the reference, model.cpp:213) */
+  EMBA_E_NCCL = -5,     /* collective error */
+  EMBA_E_NUMERIC = -6   /* zero pivot in the Schur factorisation */
+};
+
+/* which device-resident state a call refers to (solver.cpp keeps traj_ptr/Gx/Gy and traj_new_ptr/Gx_new/Gy_new) */
+enum { EMBA_STATE_CURRENT = 0, EMBA_STATE_CANDIDATE = 1 };
+
+/* robust cost (formNormalEqIRLS / evaluateRobustDataCost, model.cpp:279-314,493-687) */
+enum { EMBA_COST_QUADRATIC = 0, EMBA_COST_CAUCHY = 1, EMBA_COST_HUBER = 2 };
+
+typedef struct {
+  int32_t sensor_w, sensor_h;   /* camera_info width/height (model.cpp:67-68) */
+  int32_t pano_w, pano_h;       /* panorama size (model.cpp:64) */
+  double C_th;                  /* contrast threshold (model.cpp:60) */
+  const double* bearing_lut;    /* [sensor_h*sensor_w*3] rays b[y*W+x], computed by the host exactly as
+                                   EventWarper::precomputeBearingVectors does (event_pano_warper.cpp:27-41) */
+  int32_t device;               /* CUDA device ordinal */
+} emba_config_t;
+
+/* BASettings / LMSettings subset that drives the path (include/emba/params.h:4-61) */
+typedef struct {
+  int32_t max_num_iter;            /* LMSettings::max_num_iter */
+  double tol_fun;                  /* LMSettings::tol_fun */
+  int32_t num_times_tol_fun_sat;   /* LMSettings::num_times_tol_fun_sat */
+  int32_t use_cg;                  /* BASettings::use_CG */
+  int32_t cost_type;               /* EMBA_COST_*; != QUADRATIC means use_IRLS */
+  double eta;                      /* BASettings::eta */
+  int32_t thres_valid_pixel;       /* BASettings::thres_valid_pixel */
+  double damping_factor;           /* BASettings::damping_factor */
+  double alpha;                    /* BASettings::alpha */
+  int32_t first_time_window;       /* EMBA::first_time_window_: fix the first control pose (solver.cpp:156-165) */
+} emba_lm_settings_t;
+
+/* one row per LM solve, the content of the reference's iteration log line (solver.cpp:170-171) */
+typedef struct {
+  int32_t iter;
+  double lambda;
+  double cost_min;   /* before the step */
+  double cost_new;   /* at the candidate */
+  int32_t accepted;
+  int64_t num_active_pixels;
+  int64_t num_measurements;  /* inlier measurements M at the candidate */
+} emba_lm_log_t;
+
+/* ---- lifetime: replaces LEGM::LEGM / ~LEGM (model.cpp:56-70, model.h:80) ---- */
+EMBA_API int emba_create(const emba_config_t* cfg, emba_handle_t* out);
+EMBA_API int emba_destroy(emba_handle_t h);
+EMBA_API const char* emba_last_error(emba_handle_t h);
+
+/* ---- events: replaces the `const EventPacket& events` argument of evaluateDataError (model.h:83-84) and the
+ * per-pixel EventMap pairing structure (include/emba/event_map.h:22-113). Called once per time window: uploads
+ * the events, computes batch mid-times (model.cpp:115-119) and the static pair links. */
+EMBA_API int emba_set_events(emba_handle_t h, int64_t n_events, const uint16_t* x, const uint16_t* y, const int64_t* t_ns,
+                    const uint8_t* polarity);
+/* number of event pairs (candidate measurements, before the outlier gate) */
+EMBA_API int emba_num_pairs(emba_handle_t h, int64_t* out);
+
+/* ---- time-sharding across GPUs: this handle evaluates the measurements of shard `rank`
+ * of `world` (contiguous control-pose / time slices). Call before emba_set_state. Partial results are combined
+ * by emba_comm_* below when a communicator is attached; with world == 1 it is a no-op. */
+EMBA_API int emba_set_shard(emba_handle_t h, int32_t rank, int32_t world);
+/* attach an NCCL communicator: `nccl_unique_id` is the 128-byte ncclUniqueId created by rank 0 and broadcast by
+ * the host (e.g. torch.distributed); collectives run over NVLink/NVSwitch inside the handle's stream. */
+EMBA_API int emba_comm_unique_id(void* nccl_unique_id_out128);
+EMBA_API int emba_comm_init(emba_handle_t h, const void* nccl_unique_id128, int32_t rank, int32_t world);
+
+/* ---- state: replaces the (Trajectory*, cv::Mat Gx, cv::Mat Gy) arguments. Reads what the adapter gets through
+ * Trajectory::size/getControlPose/begTime/getDtCtrlPoses (include/utils/trajectory.h:30-47). */
+EMBA_API int emba_set_state(emba_handle_t h, int32_t which, int64_t t0_ns, int64_t dt_ns, int32_t n_poses,
+                   const double* quat_xyzw, const double* Gx, const double* Gy);
+EMBA_API int emba_get_state(emba_handle_t h, int32_t which, double* quat_xyzw_out, double* Gx_out, double* Gy_out);
+
+/* ---- LEGM::evaluateDataError (model.cpp:72-258) + evaluateRegError (:260-277) + the cost of solver.cpp:82-91,
+ * 257-268. cost_data = 0.5*sum(e^2) or the robust cost; cost_reg = 0.5*alpha*sum(Gx^2+Gy^2) over ALL pixels.
+ * Per-measurement residuals, displacements and target pixels stay on the device for emba_form_normal_eq. */
+EMBA_API int emba_evaluate(emba_handle_t h, int32_t which, int32_t cost_type, double eta, double alpha, double* cost_data,
+                  double* cost_reg, int64_t* num_measurements);
+/* optional downloads of the last evaluation of `which` (parity / the adapter's VecXd return value):
+ * ep_out [M] in the reference's order (sensor pixel row-major, then time; model.cpp:179-246),
+ * num_ev_map_out [pano_h*pano_w] int32 (model.cpp:227). Either may be NULL. */
+EMBA_API int emba_get_evaluation(emba_handle_t h, int32_t which, double* ep_out, int32_t* num_ev_map_out);
+
+/* ---- LEGM::formNormalEq / formNormalEqIRLS (model.cpp:316-687) fused with applyL2Reg (:689-719), on the last
+ * evaluation of the CURRENT state. */
+EMBA_API int emba_form_normal_eq(emba_handle_t h, int32_t thres_valid_pixel, int32_t cost_type, double eta, double alpha,
+                        int64_t* num_active_pixels);
+/* parity / adapter download. A11 [3n*3n] row-major, b1 [3n], A22 [Np*4] (2x2 row-major blocks), b2 [2Np],
+ * active [Np] ascending pixel indices (the std::set order, model.cpp:370-377). A12 is returned dense row-major
+ * [3n * 2Np] exactly like the reference's MatXd (model.cpp:358) -- only for small problems. Any may be NULL. */
+EMBA_API int emba_get_normal_eq(emba_handle_t h, double* A11, double* b1, double* A22, double* b2, int64_t* active,
+                       double* A12_dense);
+/* number of structurally non-zero A12 entries held on the device (windowed per-pixel strips) */
+EMBA_API int emba_a12_entries(emba_handle_t h, int64_t* out);
+
+/* ---- LEGM::solveNormalEq (model.cpp:721-792, Schur complement onto the control poses) or
+ * LEGM::solveNormalEqCG (:794-840, Jacobi-PCG, <=100 iterations, tolerance 1e-6). fix_first_pose applies the
+ * gauge shrink of solver.cpp:156-165. x1_out [3(n - fix)] and x2_out [2Np] may be NULL. */
+EMBA_API int emba_solve(emba_handle_t h, double lambda, int32_t use_cg, int32_t fix_first_pose, double* x1_out,
+               double* x2_out, int32_t* cg_iters, double* cg_error);
+
+/* ---- Model::updateTraj (model.cpp:22-53) + LEGM::updateMap (:863-903): candidate <- current (+) last solution */
+EMBA_API int emba_make_candidate(emba_handle_t h, double damping_factor, int32_t fix_first_pose);
+/* solver.cpp:299-317: candidate becomes current (state, residuals, num_ev_map) */
+EMBA_API int emba_accept_candidate(emba_handle_t h);
+
+/* ---- EMBA::solveTimeWindow (solver.cpp:11-368): the whole LM loop with all state resident on the device.
+ * Starts from the CURRENT state; on return the CURRENT state is the refined one. log may be NULL. */
+EMBA_API int emba_solve_time_window(emba_handle_t h, const emba_lm_settings_t* s, emba_lm_log_t* log, int32_t log_cap,
+                           int32_t* n_log, double* final_cost);
+
+/* ---- measurement hooks used by bench.py (CUDA events on the handle's stream) */
+/* elapsed device time of the kernels launched by the last emba_evaluate / emba_form_normal_eq / emba_solve, ms:
+ * out[0]=evaluate total, out[1]=per-measurement residual kernel, out[2]=form total, out[3]=pose-block assembly
+ * kernel, out[4]=map-block assembly kernel, out[5]=solve total */
+EMBA_API int emba_last_timings_ms(emba_handle_t h, double* out6);
+/* number of kernel launches issued by this handle so far */
+EMBA_API int emba_launch_count(emba_handle_t h, int64_t* out);
+EMBA_API int emba_synchronize(emba_handle_t h);
+
+/* library / build identification ("emba_b200 <version> sm_100a") */
+EMBA_API const char* emba_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMBA_B200_H_ */

@@ -1,0 +1,235 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and with the golden outputs of the
+reference library, stage by stage: residuals / num_ev_map / cost, Jacobian-derived normal equations, the Schur
+and PCG solves, the state update and the full LM run.
+
+Tolerances are BASELINE.json's: per-measurement residuals 1e-6 relative (we get ~1e-12), assembled H/g 1e-9
+relative, refined rotations 1e-5 rad, refined map 1e-4 relative. Integer outputs (num_ev_map, active set, M,
+accept/reject sequence) must be identical.
+"""
+import numpy as np
+import pytest
+
+from conftest import rel
+
+pytestmark = pytest.mark.gpu
+
+ALPHA, THRES, LAM = 5.0, 5, 1e-3
+
+
+def _engine(sc):
+    from emba_b200.legm import Engine
+
+    eng = Engine(sc.sensor_w, sc.sensor_h, sc.bearing_lut(), sc.C_th, sc.pano_w, sc.pano_h)
+    eng.set_events(sc.x, sc.y, sc.t_ns, sc.pol)
+    return eng
+
+
+def _oracle(sc):
+    from oracle import emba_oracle as O
+
+    orc = O.Oracle(sc.sensor_w, sc.sensor_h, sc.bearing_lut(), sc.pano_w, sc.pano_h, sc.C_th)
+    orc.set_events(sc.x, sc.y, sc.t_ns, sc.pol)
+    return orc
+
+
+def _base(sc):
+    from emba_b200.legm import spline_base_ns
+
+    return spline_base_ns(sc.t_beg, sc.dt_knots)
+
+
+@pytest.fixture(scope="module", params=["tiny", "small"])
+def case(request):
+    from conftest import GoldenScene, load_golden_ref
+
+    sc = GoldenScene(request.param)
+    ref = load_golden_ref(request.param)
+    eng = _engine(sc)
+    t0, dt = _base(sc)
+    eng.set_state(0, t0, dt, sc.quat_init, sc.Gx_init, sc.Gy_init)
+    yield sc, ref, eng
+    eng.close()
+
+
+def test_pairs_and_evaluate_vs_golden(case):
+    sc, ref, eng = case
+    cd, cr, M = eng.evaluate(0, 0, 1.0, ALPHA)
+    assert M == ref["ep"].size
+    assert eng.num_pairs() == ref["ep"].size + int(ref["n_outliers"])
+    ep, num = eng.get_evaluation(0, M)
+    assert np.array_equal(num, ref["num_ev_map"])  # integer work: bit-exact
+    assert rel(ref["ep"], ep) < 1e-10  # spec 1e-6
+    assert np.max(np.abs(ref["ep"] - ep)) < 1e-9
+    assert abs(cd - float(ref["cost_data"])) <= 1e-11 * float(ref["cost_data"])
+    assert abs(cr - float(ref["cost_reg"])) <= 1e-12 * float(ref["cost_reg"])
+
+
+def test_robust_costs_vs_golden(case):
+    sc, ref, eng = case
+    cd, _, _ = eng.evaluate(0, 1, 0.1, ALPHA)
+    assert abs(cd - float(ref["cost_cauchy"])) <= 1e-11 * float(ref["cost_cauchy"])
+    cd, _, _ = eng.evaluate(0, 2, 0.1, ALPHA)
+    assert abs(cd - float(ref["cost_huber"])) <= 1e-11 * float(ref["cost_huber"])
+
+
+def test_normal_equations_vs_golden_and_oracle(case):
+    sc, ref, eng = case
+    eng.evaluate(0, 0, 1.0, ALPHA)
+    Np = eng.form_normal_eq(THRES, 0, 1.0, ALPHA)
+    A11, A12, A22, b1, b2, act = eng.get_normal_eq(True)
+    assert Np == ref["active"].size
+    assert np.array_equal(act, ref["active"])
+    # H/g within 1e-9 relative (spec); measured ~1e-13
+    assert rel(ref["A11"], A11) < 1e-9
+    assert rel(ref["b1"], b1) < 1e-9
+    assert rel(ref["A22"], A22) < 1e-9
+    assert rel(ref["b2"], b2) < 1e-9
+    assert rel(ref["A12_rowsum"], A12.sum(1)) < 1e-9
+    assert rel(ref["A12_colsum"], A12.sum(0)) < 1e-9
+    assert abs(np.linalg.norm(A12) - float(ref["A12_fro"])) < 1e-9 * float(ref["A12_fro"])
+    assert np.allclose(A11, A11.T, rtol=0, atol=1e-9 * np.abs(A11).max())
+    # element-wise A12 against the oracle on the same inputs
+    orc = _oracle(sc)
+    t0, dt = _base(sc)
+    orc.evaluate(sc.quat_init, t0, dt, sc.Gx_init, sc.Gy_init, True)
+    B11, B12, B22, c1, c2, act2 = orc.form_normal_eq(sc.n_poses, THRES)
+    B22, c2 = orc.apply_l2_reg(B22, c2, act2, ALPHA, sc.Gx_init, sc.Gy_init)
+    assert rel(B12, A12) < 1e-9
+    assert rel(B11, A11) < 1e-9
+    # the device keeps A12 only inside each pixel's pose window: nothing outside may be non-zero in the reference
+    assert np.count_nonzero(A12) <= eng.a12_entries()
+    assert np.count_nonzero(B12) == np.count_nonzero((A12 != 0) | (B12 != 0))
+
+
+def test_irls_normal_equations_vs_golden(case):
+    sc, ref, eng = case
+    eng.evaluate(0, 1, 0.1, ALPHA)
+    eng.form_normal_eq(THRES, 1, 0.1, ALPHA)
+    A11, A12, A22, b1, b2, act = eng.get_normal_eq(True)
+    assert rel(ref["irls_A11"], A11) < 1e-9
+    assert rel(ref["irls_b1"], b1) < 1e-9
+    assert rel(ref["irls_A22"], A22) < 1e-9
+    assert rel(ref["irls_b2"], b2) < 1e-9
+    assert rel(ref["irls_A12_rowsum"], A12.sum(1)) < 1e-9
+
+
+def test_schur_solve_vs_golden(case):
+    sc, ref, eng = case
+    eng.evaluate(0, 0, 1.0, ALPHA)
+    eng.form_normal_eq(THRES, 0, 1.0, ALPHA)
+    x1, x2, _, _ = eng.solve(LAM, False, True)
+    assert rel(ref["x1"], x1) < 1e-7
+    assert rel(ref["x2"], x2) < 1e-7
+    x1n, x2n, _, _ = eng.solve(LAM, False, False)
+    assert x1n.size == 3 * sc.n_poses
+    assert rel(ref["x1_nofix"], x1n) < 1e-6
+    assert rel(ref["x2_nofix"], x2n) < 1e-6
+
+
+def test_pcg_solve_vs_golden(case):
+    sc, ref, eng = case
+    eng.evaluate(0, 0, 1.0, ALPHA)
+    eng.form_normal_eq(THRES, 0, 1.0, ALPHA)
+    x1, x2, it, err = eng.solve(LAM, True, True)
+    assert it == int(ref["cg_iters"])
+    assert abs(err - float(ref["cg_err"])) < 1e-3 * float(ref["cg_err"])
+    assert rel(ref["x1_cg"], x1) < 1e-6
+    assert rel(ref["x2_cg"], x2) < 1e-6
+
+
+def test_candidate_update_vs_oracle(case):
+    sc, ref, eng = case
+    from oracle import emba_oracle as O
+
+    eng.evaluate(0, 0, 1.0, ALPHA)
+    eng.form_normal_eq(THRES, 0, 1.0, ALPHA)
+    x1, x2, _, _ = eng.solve(LAM, False, True)
+    eng.make_candidate(1.0, True)
+    q, gx, gy = eng.get_state(1)
+    q_ref = O.Oracle.update_traj(sc.quat_init, x1, True)
+    gx_ref, gy_ref = O.Oracle.update_map(sc.Gx_init, sc.Gy_init, x2, 1.0, ref["active"])
+    assert np.max(np.abs(q - q_ref)) < 1e-14
+    assert np.max(np.abs(gx - gx_ref)) < 1e-13 and np.max(np.abs(gy - gy_ref)) < 1e-13
+    assert np.array_equal(q[0], sc.quat_init[0])  # gauge: first pose untouched
+
+
+def test_full_lm_vs_golden(case):
+    sc, ref, eng = case
+    t0, dt = _base(sc)
+    eng.set_state(0, t0, dt, sc.quat_init, sc.Gx_init, sc.Gy_init)
+    log, fcost = eng.solve_time_window(alpha=ALPHA, thres=THRES)
+    rlog = ref["lm_log"]
+    assert log.shape[0] == rlog.shape[0]
+    assert np.array_equal(log[:, 4], rlog[:, 4])  # identical accept/reject sequence
+    assert np.array_equal(log[:, 5], rlog[:, 5])  # identical active-pixel counts
+    assert np.allclose(log[:, 1], rlog[:, 1], rtol=1e-12)  # lambda schedule
+    assert np.max(np.abs(log[:, 3] - rlog[:, 3]) / rlog[:, 3]) < 1e-8
+    assert abs(fcost - float(ref["lm_final_cost"])) < 1e-8 * float(ref["lm_final_cost"])
+    q, gx, gy = eng.get_state(0)
+    qr = ref["q_final"]
+    dots = np.abs(np.sum(q * qr, -1)).clip(0, 1)
+    ang = 2 * np.arccos(dots)
+    assert np.max(ang) < 1e-5  # rad
+    assert rel(ref["Gx_final"], gx) < 1e-4 and rel(ref["Gy_final"], gy) < 1e-4
+
+
+def test_reference_shaped_interface(tiny, tiny_ref):
+    """The LEGM-shaped host mirror: same call order as solver.cpp for one LM step."""
+    from emba_b200.legm import LEGM, EventPacket, Trajectory
+
+    sc, ref = tiny, tiny_ref
+    model = LEGM(sc.sensor_w, sc.sensor_h, sc.bearing_lut(), sc.C_th, sc.pano_w, sc.pano_h)
+    events = EventPacket(sc.x, sc.y, sc.t_ns, sc.pol)
+    traj = Trajectory(sc.t_beg, sc.dt_knots, sc.quat_init)
+    num = np.zeros((sc.pano_h, sc.pano_w), dtype=np.int32)
+    ep = model.evaluateDataError(traj, sc.Gx_init, sc.Gy_init, events, True, num)
+    assert rel(ref["ep"], ep) < 1e-10 and np.array_equal(num, ref["num_ev_map"])
+    ep_reg = model.evaluateRegError(sc.Gx_init, sc.Gy_init)
+    assert abs(0.5 * ALPHA * ep_reg @ ep_reg - float(ref["cost_reg"])) < 1e-9 * float(ref["cost_reg"])
+    A11, A12, A22, b1, b2, act = model.formNormalEq(traj.size(), THRES)
+    # applyL2Reg is a separate call in the reference; the fixture has it applied
+    assert rel(ref["A11"], A11) < 1e-9 and np.array_equal(act, ref["active"])
+    A22 = A22 + ALPHA * np.eye(2)[None]
+    assert rel(ref["A22"], A22) < 1e-9
+    model.eng.close()
+
+
+def test_error_paths(tiny):
+    from emba_b200.capi import EmbaError
+    from emba_b200.legm import Engine
+
+    sc = tiny
+    eng = _engine(sc)
+    t0, dt = _base(sc)
+    with pytest.raises(EmbaError):  # evaluate before any state
+        eng.evaluate(0)
+    with pytest.raises(EmbaError) as ei:  # spline too short: the reference aborts in basalt (so3_spline.h:228)
+        eng.set_state(0, t0, dt, sc.quat_init[:4], sc.Gx_init, sc.Gy_init)
+    assert ei.value.code == -3
+    eng.set_state(0, t0, dt, sc.quat_init, sc.Gx_init, sc.Gy_init)
+    with pytest.raises(EmbaError):  # form before evaluate
+        eng.form_normal_eq(THRES)
+    eng.close()
+
+
+def test_empty_and_ragged_events(tiny):
+    """Edge cases: no events, fewer than one batch (all dropped by the integer division at model.cpp:79), and a
+    ragged tail (N % 100 != 0: the tail is ignored)."""
+    from emba_b200.legm import Engine
+
+    sc = tiny
+    t0, dt = _base(sc)
+    eng = Engine(sc.sensor_w, sc.sensor_h, sc.bearing_lut(), sc.C_th, sc.pano_w, sc.pano_h)
+    for n_ev in (0, 57):
+        eng.set_events(sc.x[:n_ev], sc.y[:n_ev], sc.t_ns[:n_ev], sc.pol[:n_ev])
+        eng.set_state(0, t0, dt, sc.quat_init, sc.Gx_init, sc.Gy_init)
+        cd, cr, M = eng.evaluate(0, 0, 1.0, ALPHA)
+        assert M == 0 and cd == 0.0 and cr > 0
+    n_full, n_rag = 5000, 5057
+    res = []
+    for n_ev in (n_full, n_rag):
+        eng.set_events(sc.x[:n_ev], sc.y[:n_ev], sc.t_ns[:n_ev], sc.pol[:n_ev])
+        eng.set_state(0, t0, dt, sc.quat_init, sc.Gx_init, sc.Gy_init)
+        res.append(eng.evaluate(0, 0, 1.0, ALPHA))
+    assert res[0] == res[1]
+    eng.close()
