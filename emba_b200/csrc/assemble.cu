@@ -394,13 +394,11 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   h->formed = false;
   EMBA_CUDA(cudaEventRecord(h->ev[4], h->stream));
   // ---- 1. active set (model.cpp:324-379): mask + exclusive scan reproduces the ascending std::set order
-  int32_t *d_flag = nullptr, *d_aidx = nullptr;
-  int64_t* d_len = nullptr;
-  auto cleanup = [&]() { cudaFree(d_flag); cudaFree(d_aidx); cudaFree(d_len); };
+  int32_t *d_flag = h->d_pflag, *d_aidx = h->d_paidx;
+  int64_t* d_len = h->d_len;
+  auto cleanup = [&]() {};
 #define EMBA_TRYC(x) do { int _r = (x); if (_r != EMBA_OK) { cleanup(); return _r; } } while (0)
 #define EMBA_CUDAC(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { h->err = std::string(#x) + ": " + cudaGetErrorString(_e); cleanup(); return EMBA_E_CUDA; } } while (0)
-  EMBA_TRYC(dev_alloc(h, &d_flag, P));
-  EMBA_TRYC(dev_alloc(h, &d_aidx, P));
   k_active_flags<<<ceil_div64(P, T), T, 0, h->stream>>>(s.hist, P, thres, d_flag);
   h->launches++;
   EMBA_TRYC(cub_exclusive_sum(h, d_flag, d_aidx, P));
@@ -410,25 +408,10 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   EMBA_CUDAC(cudaStreamSynchronize(h->stream));
   const int64_t Np = (int64_t)tail[0] + tail[1];
   h->Np = Np;
-  EMBA_TRYC(dev_alloc(h, &h->d_apix, Np));
-  EMBA_TRYC(dev_alloc(h, &h->d_segoff, Np + 1));
-  EMBA_TRYC(dev_alloc(h, &h->d_winlo, Np));
-  EMBA_TRYC(dev_alloc(h, &h->d_winhi, Np));
-  EMBA_TRYC(dev_alloc(h, &h->d_stripoff, Np + 1));
-  EMBA_TRYC(dev_alloc(h, &h->d_A22, 3 * Np));
-  EMBA_TRYC(dev_alloc(h, &h->d_b2, 2 * Np));
-  EMBA_TRYC(dev_alloc(h, &h->d_C, 3 * Np));
-  EMBA_TRYC(dev_alloc(h, &h->d_x2, 2 * Np));
   k_active_fill<<<ceil_div64(P, T), T, 0, h->stream>>>(d_flag, d_aidx, P, h->d_amap, h->d_apix, h->d_winlo, h->d_winhi);
   h->launches++;
   // ---- 2. pose side + Jacobian rows
   const int64_t Mc = h->Mc;
-  EMBA_TRYC(dev_reserve(h, &h->d_jrec, &h->jrec_cap, Mc * kRecDoubles));
-  if (h->sort_cap < Mc) {
-    EMBA_TRYC(dev_alloc(h, &h->d_skey, Mc)); EMBA_TRYC(dev_alloc(h, &h->d_sval, Mc));
-    EMBA_TRYC(dev_alloc(h, &h->d_skey2, Mc)); EMBA_TRYC(dev_alloc(h, &h->d_sval2, Mc));
-    h->sort_cap = Mc;
-  }
   const PanoCam cam = make_cam(h);
   EMBA_CUDAC(cudaEventRecord(h->ev[5], h->stream));
   if (h->n_items > 0) {
@@ -464,7 +447,6 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
     EMBA_TRYC(comm_allreduce(h, h->d_winhi, Np, 3));  // max
   }
   // ---- 3. map side: pose windows -> strip offsets
-  EMBA_TRYC(dev_alloc(h, &d_len, Np + 1));
   EMBA_CUDAC(cudaMemsetAsync(d_len, 0, sizeof(int64_t) * (Np + 1), h->stream));
   if (Np) { k_strip_len<<<ceil_div64(Np, T), T, 0, h->stream>>>(h->d_winlo, h->d_winhi, Np, d_len); h->launches++; }
   EMBA_TRYC(cub_exclusive_sum(h, d_len, h->d_stripoff, Np + 1));
@@ -554,13 +536,12 @@ int emba_get_normal_eq(emba_handle_t hh, double* A11, double* b1, double* A22, d
   if (b2 && Np) EMBA_CUDA(cudaMemcpyAsync(b2, h->d_b2, sizeof(double) * 2 * Np, cudaMemcpyDeviceToHost, h->stream));
   EMBA_CUDA(cudaStreamSynchronize(h->stream));
   if (A22 && Np) {
-    double* tmp = nullptr;
-    EMBA_TRY(dev_alloc(h, &tmp, 4 * Np));
+    EMBA_TRY(dev_reserve(h, &h->d_cg, &h->cg_cap, 4 * Np));
+    double* tmp = h->d_cg;
     k_a22_expand<<<ceil_div64(Np, 256), 256, 0, h->stream>>>(Np, h->d_A22, tmp);
     h->launches++;
     cudaError_t e = cudaMemcpyAsync(A22, tmp, sizeof(double) * 4 * Np, cudaMemcpyDeviceToHost, h->stream);
     cudaStreamSynchronize(h->stream);
-    cudaFree(tmp);
     if (e != cudaSuccess) { h->err = "emba_get_normal_eq: A22 copy failed"; return EMBA_E_CUDA; }
   }
   if (active && Np) {

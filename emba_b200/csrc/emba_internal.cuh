@@ -97,6 +97,9 @@ struct Handle {
   int thres = 0;
   int64_t Np = 0;
   int32_t* d_amap = nullptr;    // [P] active index or -1
+  int32_t* d_pflag = nullptr;   // [P] scratch: active flag
+  int32_t* d_paidx = nullptr;   // [P] scratch: exclusive scan of the flags
+  int64_t* d_len = nullptr;     // [P+1] scratch: strip lengths
   int32_t* d_apix = nullptr;    // [Np] pixel index of each active pixel
   int32_t* d_segoff = nullptr;  // [Np+1] offsets of the per-pixel row segments in the sorted row list
   int64_t Ma = 0;               // measurements on active pixels

@@ -231,7 +231,22 @@ int emba_create(const emba_config_t* cfg, emba_handle_t* out) {
          cudaMalloc((void**)&st.H3, sizeof(double4) * h->P) == cudaSuccess &&
          cudaMalloc((void**)&st.hist, sizeof(int32_t) * h->P) == cudaSuccess;
   }
-  ok = ok && cudaMalloc((void**)&h->d_amap, sizeof(int32_t) * h->P) == cudaSuccess;
+  // per-pixel buffers of the normal equations are sized for the worst case (every pixel active) once, so that
+  // forming the equations never allocates
+  const size_t P1 = (size_t)h->P + 1;
+  ok = ok && cudaMalloc((void**)&h->d_amap, sizeof(int32_t) * P1) == cudaSuccess &&
+       cudaMalloc((void**)&h->d_pflag, sizeof(int32_t) * P1) == cudaSuccess &&
+       cudaMalloc((void**)&h->d_paidx, sizeof(int32_t) * P1) == cudaSuccess &&
+       cudaMalloc((void**)&h->d_len, sizeof(int64_t) * P1) == cudaSuccess &&
+       cudaMalloc((void**)&h->d_apix, sizeof(int32_t) * P1) == cudaSuccess &&
+       cudaMalloc((void**)&h->d_segoff, sizeof(int32_t) * P1) == cudaSuccess &&
+       cudaMalloc((void**)&h->d_winlo, sizeof(int32_t) * P1) == cudaSuccess &&
+       cudaMalloc((void**)&h->d_winhi, sizeof(int32_t) * P1) == cudaSuccess &&
+       cudaMalloc((void**)&h->d_stripoff, sizeof(int64_t) * P1) == cudaSuccess &&
+       cudaMalloc((void**)&h->d_A22, sizeof(double) * 3 * P1) == cudaSuccess &&
+       cudaMalloc((void**)&h->d_b2, sizeof(double) * 2 * P1) == cudaSuccess &&
+       cudaMalloc((void**)&h->d_C, sizeof(double) * 3 * P1) == cudaSuccess &&
+       cudaMalloc((void**)&h->d_x2, sizeof(double) * 2 * P1) == cudaSuccess;
   if (!ok) { emba_destroy((emba_handle_t)h); return EMBA_E_CUDA; }
   *out = (emba_handle_t)h;
   return EMBA_OK;
@@ -245,7 +260,7 @@ int emba_destroy(emba_handle_t hh) {
   comm_destroy(h);
   free_state(h->st[0]); free_state(h->st[1]);
   void* ptrs[] = {h->d_lut, h->d_tmid, h->d_spix_ev, h->d_pol, h->d_prev, h->d_refrank, h->d_bs, h->d_bu, h->d_rec,
-                  h->d_items, h->d_gid, h->d_group_item0, h->d_part, h->d_scal, h->d_flags, h->d_amap, h->d_apix,
+                  h->d_items, h->d_gid, h->d_group_item0, h->d_part, h->d_scal, h->d_flags, h->d_amap, h->d_pflag, h->d_paidx, h->d_len, h->d_apix,
                   h->d_segoff, h->d_jrec, h->d_skey, h->d_sval, h->d_skey2, h->d_sval2, h->d_cub_tmp, h->d_winlo,
                   h->d_winhi, h->d_stripoff, h->d_strip, h->d_A22, h->d_b2, h->d_acc_part, h->d_gsum, h->d_A11,
                   h->d_b1, h->d_C, h->d_S, h->d_rhs, h->d_x1, h->d_x2, h->d_Spart, h->d_cg};
@@ -465,6 +480,9 @@ int rebuild_static(Handle* h) {
       if ((rc = dev_alloc(h, &h->d_items, h->n_items)) || (rc = dev_alloc(h, &h->d_gid, (int64_t)gid.size())) ||
           (rc = dev_alloc(h, &h->d_group_item0, (int64_t)item0.size())) || (rc = dev_alloc(h, &h->d_rec, h->Mc)) ||
           (rc = dev_alloc(h, &h->d_acc_part, (int64_t)h->n_items * kAccN)) ||
+          (rc = dev_alloc(h, &h->d_skey, h->Mc)) || (rc = dev_alloc(h, &h->d_sval, h->Mc)) ||
+          (rc = dev_alloc(h, &h->d_skey2, h->Mc)) || (rc = dev_alloc(h, &h->d_sval2, h->Mc)) ||
+          (rc = dev_reserve(h, &h->d_jrec, &h->jrec_cap, h->Mc * kRecDoubles)) ||
           (rc = dev_alloc(h, &h->d_gsum, (int64_t)h->n_groups * kAccN)))
         break;
       for (int s = 0; s < 2 && rc == EMBA_OK; s++) {

@@ -202,6 +202,57 @@ def simulate_events(L, scene: Scene, t_start, t_stop, *, dt_sim=0.25e-3, yaw_rat
             p.cpu().numpy().astype(np.uint8))
 
 
+def _exp_so3_np(phi):
+    th = np.linalg.norm(phi, axis=-1, keepdims=True).clip(1e-300)
+    k = phi / th
+    K = np.zeros(phi.shape[:-1] + (3, 3))
+    K[..., 0, 1], K[..., 0, 2] = -k[..., 2], k[..., 1]
+    K[..., 1, 0], K[..., 1, 2] = k[..., 2], -k[..., 0]
+    K[..., 2, 0], K[..., 2, 1] = -k[..., 1], k[..., 0]
+    s = np.sin(th)[..., None]
+    c = np.cos(th)[..., None]
+    return np.eye(3) + s * K + (1 - c) * (K @ K)
+
+
+def simulate_events_cuda(L, scene: Scene, t_start, t_stop, *, dt_sim=0.25e-3, yaw_rate=0.35, periodic=False,
+                         device_index=0):
+    """Same event model as simulate_events, one CUDA thread per sensor pixel (emba_b200/csrc/synth.cu through
+    include/emba_synth.h). Used for the large benchmark configurations."""
+    import ctypes as C
+    import os
+
+    lib = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "libemba_synth.so"))
+    dp = C.POINTER(C.c_double)
+    lib.emba_synth_simulate.argtypes = [C.c_int, C.c_int, C.c_int, dp, C.c_int, C.c_int, dp, C.c_double, C.c_int, dp,
+                                        C.c_double, C.c_double, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    lib.emba_synth_fetch.argtypes = [C.c_void_p, C.POINTER(C.c_uint16), C.POINTER(C.c_uint16), C.POINTER(C.c_int64),
+                                     C.POINTER(C.c_uint8)]
+    lib.emba_synth_free.argtypes = [C.c_void_p]
+    n_steps = int(round((t_stop - t_start) / dt_sim))
+    ts = t_start + dt_sim * np.arange(n_steps + 1)
+    Rs = np.ascontiguousarray(_exp_so3_np(gt_rotvec(ts, yaw_rate, periodic)).reshape(-1, 9))
+    lut = np.ascontiguousarray(scene.bearing_lut())
+    Lc = np.ascontiguousarray(L, dtype=np.float64)
+    h = C.c_void_p()
+    n = C.c_int64(0)
+    rc = lib.emba_synth_simulate(device_index, scene.sensor_w, scene.sensor_h, lut.ctypes.data_as(dp), scene.pano_w,
+                                 scene.pano_h, Lc.ctypes.data_as(dp), float(scene.C_th), n_steps,
+                                 Rs.ctypes.data_as(dp), float(t_start), float(dt_sim), C.byref(h), C.byref(n))
+    if rc != 0:
+        raise RuntimeError(f"emba_synth_simulate failed ({rc})")
+    N = n.value
+    x = np.empty(N, dtype=np.uint16)
+    y = np.empty(N, dtype=np.uint16)
+    t = np.empty(N, dtype=np.int64)
+    p = np.empty(N, dtype=np.uint8)
+    rc = lib.emba_synth_fetch(h, x.ctypes.data_as(C.POINTER(C.c_uint16)), y.ctypes.data_as(C.POINTER(C.c_uint16)),
+                              t.ctypes.data_as(C.POINTER(C.c_int64)), p.ctypes.data_as(C.POINTER(C.c_uint8)))
+    lib.emba_synth_free(h)
+    if rc != 0:
+        raise RuntimeError(f"emba_synth_fetch failed ({rc})")
+    return x, y, t, p
+
+
 def make_scene(sensor_w=128, sensor_h=128, fx=91.4014729896821, fy=None, cx=None, cy=None, pano_w=1024, pano_h=512,
                C_th=0.45, t_beg=0.1, t_end=2.4, dt_knots=0.05, texture_std=1.5, seed=1, dt_sim=0.25e-3,
                yaw_rate=0.35, periodic=False, device="cpu", pose_noise_deg=0.3, map_scale=0.7, map_noise=0.02,
@@ -217,8 +268,13 @@ def make_scene(sensor_w=128, sensor_h=128, fx=91.4014729896821, fy=None, cx=None
     sc.Gx_gt, sc.Gy_gt = _sobel8(L)
     # events strictly inside the spline support, like EMBA::getEventSubset's 1 ms guard
     # (src/emba/emba.cpp:476-478)
-    x, y, t_ns, pol = simulate_events(L, sc, t_beg + guard, t_end - guard, dt_sim=dt_sim, yaw_rate=yaw_rate,
-                                      periodic=periodic, device=device, max_events=max_events)
+    if str(device).startswith("cuda"):
+        dev_idx = int(str(device).split(":")[1]) if ":" in str(device) else 0
+        x, y, t_ns, pol = simulate_events_cuda(L, sc, t_beg + guard, t_end - guard, dt_sim=dt_sim, yaw_rate=yaw_rate,
+                                               periodic=periodic, device_index=dev_idx)
+    else:
+        x, y, t_ns, pol = simulate_events(L, sc, t_beg + guard, t_end - guard, dt_sim=dt_sim, yaw_rate=yaw_rate,
+                                          periodic=periodic, device=device, max_events=max_events)
     if max_events is not None and t_ns.size > max_events:
         x, y, t_ns, pol = x[:max_events], y[:max_events], t_ns[:max_events], pol[:max_events]
     n_keep = (t_ns.size // 100) * 100  # the reference drops the tail batch (model.cpp:78-79)
@@ -246,16 +302,16 @@ CONFIGS = {
                   dt_knots=0.05, texture_std=1.5, dt_sim=0.5e-3),
     # C1: playroom.launch (128x128 DVS-playroom.yaml, 1024x512, n=47, C_th=0.45), ~1M events
     "C1": dict(sensor_w=128, sensor_h=128, fx=91.4014729896821, pano_w=1024, pano_h=512, C_th=0.45, t_beg=0.1,
-               t_end=2.4, dt_knots=0.05, texture_std=3.3),
+               t_end=2.4, dt_knots=0.05, texture_std=1.5),
     # C2: bay.launch-style 240x180, f=200, 1024x512, t in [0.1,4.9], n=97, C_th=0.2, ~10M events
     "C2": dict(sensor_w=240, sensor_h=180, fx=200.0, pano_w=1024, pano_h=512, C_th=0.2, t_beg=0.1, t_end=4.9,
-               dt_knots=0.05, texture_std=1.0),
+               dt_knots=0.05, texture_std=1.25),
     # C3: shapes.launch-style, 2048x1024, t in [1,11], n=201, ~30M events
     "C3": dict(sensor_w=240, sensor_h=180, fx=200.0, pano_w=2048, pano_h=1024, C_th=0.2, t_beg=1.0, t_end=11.0,
-               dt_knots=0.05, texture_std=1.0),
+               dt_knots=0.05, texture_std=1.9),
     # C4: as C3 with ~100M events
     "C4": dict(sensor_w=240, sensor_h=180, fx=200.0, pano_w=2048, pano_h=1024, C_th=0.2, t_beg=1.0, t_end=11.0,
-               dt_knots=0.05, texture_std=3.3),
+               dt_knots=0.05, texture_std=6.3),
 }
 
 
