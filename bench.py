@@ -145,7 +145,7 @@ def run_reference(args, workload, rank, world):
         dev = "cpu"
     sc = synth.make_scene(**kw, device=dev)
     # bounded sample per step: a prefix of the window sized for ~3 s of CPU work
-    n_sample = min(sc.n_events, 2_000_000)
+    n_sample = min(sc.n_events, max(200_000, min(2_000_000, int(1.4e8 / max(1, args.steps + args.warmup)))))
     times = []
     for i in range(args.warmup + args.steps):
         v, kind, cores, sec = cpu_reference_pass(sc, n_sample)

@@ -47,10 +47,10 @@ __global__ void k_active_fill(const int32_t* __restrict__ flag, const int32_t* _
 constexpr int kAsmThreads = 256;
 constexpr int kTileStride = kAsmThreads + 1;
 
-// accumulates rows I0..I1-1 of the upper triangle of v v^T (13 x 13) into a[0..]; both halves of the CTA use
-// the same 46 registers (rows 0..3 -> 46 entries, rows 4..12 -> 45 entries)
+// Rows I0..I1-1 of the upper triangle of v v^T (13 x 13), accumulated into a[0..]. The CTA is split into four
+// 64-thread roles that own rows {0,1}, {2,3}, {4,5,6}, {7..12}: 25 / 21 / 24 / 21 accumulators per thread.
 template <int I0, int I1>
-__device__ __forceinline__ void tri_add(double (&a)[46], const double* v) {
+__device__ __forceinline__ void tri_add(double (&a)[25], const double* v) {
   int k = 0;
 #pragma unroll
   for (int i = I0; i < I1; i++)
@@ -58,29 +58,44 @@ __device__ __forceinline__ void tri_add(double (&a)[46], const double* v) {
     for (int j = i; j < 13; j++) a[k++] += v[i] * v[j];
 }
 
+template <int I0, int I1>
+__device__ __forceinline__ void tri_tile(double (&a)[25], const double (*tile)[kTileStride], int idx) {
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const int c = idx + 64 * q;
+    double v[13];
+#pragma unroll
+    for (int k = I0; k < 13; k++) v[k] = tile[k][c];
+    tri_add<I0, I1>(a, v);
+  }
+}
+
 template <int COST>
-__global__ void __launch_bounds__(kAsmThreads)
+__global__ void __launch_bounds__(kAsmThreads, 2)
 k_asm_pose(const WorkItem* __restrict__ items, const MeasRec* __restrict__ rec, const double* __restrict__ lut,
            const double* __restrict__ Rtab, const double* __restrict__ Atab, const double2* __restrict__ G2,
            const double4* __restrict__ H3, const double2* __restrict__ dp_in, const double* __restrict__ e_in,
            const int32_t* __restrict__ pix_in, const int32_t* __restrict__ amap, PanoCam cam, double eta,
            uint32_t invalid_key, double* __restrict__ jrec, uint32_t* __restrict__ skey, uint32_t* __restrict__ sval,
            int32_t* __restrict__ winlo, int32_t* __restrict__ winhi, double* __restrict__ acc_part) {
-  __shared__ double tile[13][kTileStride];
-  __shared__ double red[2][4][46];
+  // rows 0..11: Jc, Jp; 12: e; 13,14: dp; 15: meta  (row-major [field][measurement], padded against conflicts)
+  __shared__ double tile[kRecDoubles][kTileStride];
+  __shared__ double red[8][25];
   const WorkItem it = items[blockIdx.x];
   const int tid = threadIdx.x;
-  const int half = tid >> 7, idx = tid & 127;
-  double acc[46];
+  const int role = tid >> 6, idx = tid & 63;
+  double acc[25];
 #pragma unroll
-  for (int k = 0; k < 46; k++) acc[k] = 0.0;
+  for (int k = 0; k < 25; k++) acc[k] = 0.0;
+  const unsigned long long meta_lo = (unsigned long long)((uint32_t)it.cp_c | ((uint32_t)it.cp_p << 16));
   for (int t0 = 0; t0 < it.count; t0 += kAsmThreads) {
     const int j = t0 + tid;
     double row[13];
 #pragma unroll
     for (int k = 0; k < 13; k++) row[k] = 0.0;
+    double d0 = 0.0, d1 = 0.0;
+    const int64_t m = (int64_t)it.start + j;
     if (j < it.count) {
-      const int64_t m = (int64_t)it.start + j;
       const int32_t pix = pix_in[m];
       const int32_t a = pix >= 0 ? amap[pix] : -1;  // model.cpp:396-412: outliers and inactive pixels are skipped
       skey[m] = a >= 0 ? (uint32_t)a : invalid_key;
@@ -98,30 +113,38 @@ k_asm_pose(const WorkItem* __restrict__ items, const MeasRec* __restrict__ rec, 
         const double h1 = g.y + dpv.x * Hh.y + dpv.y * Hh.z;
         double vc[3], vp[3], wc[3], wp[3];
         {
-          const double* R = Rtab + (size_t)bc * kPoseStride;
-          const double X = R[0] * bx + R[1] * by + R[2] * bz;
-          const double Y = R[3] * bx + R[4] * by + R[5] * bz;
-          const double Z = R[6] * bx + R[7] * by + R[8] * bz;
+          const double2* R = reinterpret_cast<const double2*>(Rtab + (size_t)bc * kPoseStride);
+          const double2 a0 = R[0], a1 = R[1], a2 = R[2], a3 = R[3], a4 = R[4];
+          const double X = a0.x * bx + a0.y * by + a1.x * bz;
+          const double Y = a1.y * bx + a2.x * by + a2.y * bz;
+          const double Z = a3.x * bx + a3.y * by + a4.x * bz;
           double M[6];
           project_jac(cam, X, Y, Z, M);
-#pragma unroll
-          for (int k = 0; k < 3; k++) vc[k] = h0 * M[k] + h1 * M[3 + k];  // temp * dpm_ddrot (model.cpp:449)
-          const double* A = Atab + (size_t)bc * kPoseStride;
-#pragma unroll
-          for (int k = 0; k < 3; k++) wc[k] = vc[0] * A[k] + vc[1] * A[3 + k] + vc[2] * A[6 + k];
+          vc[0] = h0 * M[0] + h1 * M[3];  // temp * dpm_ddrot (model.cpp:449)
+          vc[1] = h0 * M[1];
+          vc[2] = h0 * M[2] + h1 * M[5];
+          const double2* A = reinterpret_cast<const double2*>(Atab + (size_t)bc * kPoseStride);
+          const double2 b0 = A[0], b1 = A[1], b2 = A[2], b3 = A[3], b4 = A[4];
+          wc[0] = vc[0] * b0.x + vc[1] * b1.y + vc[2] * b3.x;
+          wc[1] = vc[0] * b0.y + vc[1] * b2.x + vc[2] * b3.y;
+          wc[2] = vc[0] * b1.x + vc[1] * b2.y + vc[2] * b4.x;
         }
         {
-          const double* R = Rtab + (size_t)bp * kPoseStride;
-          const double X = R[0] * bx + R[1] * by + R[2] * bz;
-          const double Y = R[3] * bx + R[4] * by + R[5] * bz;
-          const double Z = R[6] * bx + R[7] * by + R[8] * bz;
+          const double2* R = reinterpret_cast<const double2*>(Rtab + (size_t)bp * kPoseStride);
+          const double2 a0 = R[0], a1 = R[1], a2 = R[2], a3 = R[3], a4 = R[4];
+          const double X = a0.x * bx + a0.y * by + a1.x * bz;
+          const double Y = a1.y * bx + a2.x * by + a2.y * bz;
+          const double Z = a3.x * bx + a3.y * by + a4.x * bz;
           double M[6];
           project_jac(cam, X, Y, Z, M);
-#pragma unroll
-          for (int k = 0; k < 3; k++) vp[k] = -(g.x * M[k] + g.y * M[3 + k]);  // -Gpm * dpm_ddrot (model.cpp:459)
-          const double* A = Atab + (size_t)bp * kPoseStride;
-#pragma unroll
-          for (int k = 0; k < 3; k++) wp[k] = vp[0] * A[k] + vp[1] * A[3 + k] + vp[2] * A[6 + k];
+          vp[0] = -(g.x * M[0] + g.y * M[3]);  // -Gpm * dpm_ddrot (model.cpp:459)
+          vp[1] = -(g.x * M[1]);
+          vp[2] = -(g.x * M[2] + g.y * M[5]);
+          const double2* A = reinterpret_cast<const double2*>(Atab + (size_t)bp * kPoseStride);
+          const double2 b0 = A[0], b1 = A[1], b2 = A[2], b3 = A[3], b4 = A[4];
+          wp[0] = vp[0] * b0.x + vp[1] * b1.y + vp[2] * b3.x;
+          wp[1] = vp[0] * b0.y + vp[1] * b2.x + vp[2] * b3.y;
+          wp[2] = vp[0] * b1.x + vp[1] * b2.y + vp[2] * b4.x;
         }
         // IRLS weight (model.cpp:599-618), applied as sqrt(w) on the whole row and on e
         double sw = 1.0;
@@ -134,52 +157,47 @@ k_asm_pose(const WorkItem* __restrict__ items, const MeasRec* __restrict__ rec, 
           row[6 + k] = sw * (vp[k] - wp[k]);
           row[9 + k] = sw * wp[k];
         }
-        e *= sw;
-        row[12] = e;
-        double* out = jrec + (size_t)m * kRecDoubles;
-        double2* o2 = reinterpret_cast<double2*>(out);
-#pragma unroll
-        for (int k = 0; k < 6; k++) o2[k] = make_double2(row[2 * k], row[2 * k + 1]);
-        o2[6] = make_double2(sw * dpv.x, sw * dpv.y);
-        const unsigned long long meta = (unsigned long long)((uint32_t)it.cp_c | ((uint32_t)it.cp_p << 16)) |
-                                        ((unsigned long long)(uint32_t)m << 32);
-        o2[7] = make_double2(e, __longlong_as_double((long long)meta));
+        row[12] = sw * e;
+        d0 = sw * dpv.x;
+        d1 = sw * dpv.y;
         atomicMin(&winlo[a], it.cp_p);
         atomicMax(&winhi[a], it.cp_c + 1);
       }
     }
 #pragma unroll
     for (int k = 0; k < 13; k++) tile[k][tid] = row[k];
+    tile[13][tid] = d0;
+    tile[14][tid] = d1;
+    tile[15][tid] = __longlong_as_double((long long)(meta_lo | ((unsigned long long)(uint32_t)m << 32)));
     __syncthreads();
-#pragma unroll
-    for (int q = 0; q < 2; q++) {
-      const int c = idx + 128 * q;
-      double v[13];
-      if (half == 0) {
-#pragma unroll
-        for (int k = 0; k < 13; k++) v[k] = tile[k][c];
-        tri_add<0, 4>(acc, v);
-      } else {
-#pragma unroll
-        for (int k = 4; k < 13; k++) v[k] = tile[k][c];
-        tri_add<4, 13>(acc, v);
-      }
+    // Jacobian rows -> global, coalesced: 16 consecutive threads write one 128-byte record
+    {
+      const int nrec = min(kAsmThreads, it.count - t0);
+      double* out = jrec + ((size_t)it.start + t0) * kRecDoubles;
+      const int f = tid & 15;
+      for (int r = tid >> 4; r < nrec; r += kAsmThreads / 16) out[(size_t)r * kRecDoubles + f] = tile[f][r];
     }
+    if (role == 0) tri_tile<0, 2>(acc, tile, idx);
+    else if (role == 1) tri_tile<2, 4>(acc, tile, idx);
+    else if (role == 2) tri_tile<4, 7>(acc, tile, idx);
+    else tri_tile<7, 13>(acc, tile, idx);
     __syncthreads();
   }
-  // reduce the accumulators over the 128 threads of each half: warp shuffles, then 4 warps through shared memory
-  const int lane = tid & 31, wq = (tid >> 5) & 3;
+  // reduce the accumulators over the 64 threads of each role: warp shuffles, then 2 warps through shared memory
+  const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
-  for (int k = 0; k < 46; k++) {
+  for (int k = 0; k < 25; k++) {
     double x = acc[k];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-    if (lane == 0) red[half][wq][k] = x;
+    if (lane == 0) red[warp][k] = x;
   }
   __syncthreads();
   if (tid < kAccN) {
-    const int hh = tid < 46 ? 0 : 1, k = tid < 46 ? tid : tid - 46;
-    acc_part[(size_t)blockIdx.x * kAccN + tid] = (red[hh][0][k] + red[hh][1][k]) + (red[hh][2][k] + red[hh][3][k]);
+    // tri13 order is row-major: rows {0,1} -> 0..24, {2,3} -> 25..45, {4,5,6} -> 46..69, {7..12} -> 70..90
+    const int r = tid < 25 ? 0 : tid < 46 ? 1 : tid < 70 ? 2 : 3;
+    const int k = tid - (r == 0 ? 0 : r == 1 ? 25 : r == 2 ? 46 : 70);
+    acc_part[(size_t)blockIdx.x * kAccN + tid] = red[2 * r][k] + red[2 * r + 1][k];
   }
 }
 
@@ -282,12 +300,13 @@ k_pix(int64_t Np, const int32_t* __restrict__ segoff, const uint32_t* __restrict
   // lane roles: 0..23 -> A12 component (slot s, row r, col c); 24..28 -> A22 xx, xy, yy, b2 x, y
   const int s = lane / 6, r = (lane % 6) >> 1, c = lane & 1;
   int ia = 0, ib = 0;
-  if (lane < 24) { ia = 3 * s + r; ib = 12 + c; }
-  else if (lane == 24) { ia = 12; ib = 12; }
-  else if (lane == 25) { ia = 12; ib = 13; }
-  else if (lane == 26) { ia = 13; ib = 13; }
-  else if (lane == 27) { ia = 12; ib = 14; }
-  else if (lane == 28) { ia = 13; ib = 14; }
+  // record fields: 0..11 Jc|Jp, 12 e, 13..14 dp, 15 meta
+  if (lane < 24) { ia = 3 * s + r; ib = 13 + c; }
+  else if (lane == 24) { ia = 13; ib = 13; }
+  else if (lane == 25) { ia = 13; ib = 14; }
+  else if (lane == 26) { ia = 14; ib = 14; }
+  else if (lane == 27) { ia = 13; ib = 12; }
+  else if (lane == 28) { ia = 14; ib = 12; }
   for (int64_t a = (int64_t)blockIdx.x * kPixWarps + warp; a < Np; a += nw) {
     const int64_t seg0 = segoff[a];
     const int64_t seg1 = segoff[a + 1];

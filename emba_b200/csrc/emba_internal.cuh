@@ -15,7 +15,7 @@ constexpr int kBatch = 100;         // hard-coded event batch size (reference sr
 constexpr int kPoseStride = 10;     // doubles per 3x3 table entry (9 + 1 pad -> 16-byte aligned rows)
 constexpr int kItemMax = 8192;      // measurements per pose-block assembly work item
 constexpr int kAccN = 91;           // upper triangle of the 13x13 outer product of [Jc Jp e]
-constexpr int kRecDoubles = 16;     // Jacobian-row record: Jc[6] Jp[6] dp[2] e meta  (128 bytes)
+constexpr int kRecDoubles = 16;     // Jacobian-row record: Jc[6] Jp[6] e dp[2] meta  (128 bytes)
 constexpr double kSophusEps = 1e-10;  // Sophus::Constants<double>::epsilon()
 
 // static per-measurement record, canonical order (sorted by (cp_c, cp_p), then time of the current event)
@@ -319,23 +319,21 @@ __device__ __forceinline__ void project_pm(const PanoCam& c, double X, double Y,
 }
 
 // M = dpm_drb * drb_ddrot (2x3): projection Jacobian (equirectangular_camera.h:31-43) times -[rb]x
-// (src/utils/event_pano_warper.cpp:62-65)
+// (src/utils/event_pano_warper.cpp:62-65). With rb = (X, Y, Z), s = X^2 + Z^2 the product of the reference's
+// two matrices simplifies exactly to
+//   [ -fx X Y / s,  fx,  -fx Y Z / s ]
+//   [ -fy Z / sqrt(s),  0,  fy X / sqrt(s) ]
+// (the norm of rb cancels), which needs one reciprocal square root and no division. M[4] == 0 is dropped.
 __device__ __forceinline__ void project_jac(const PanoCam& c, double X, double Y, double Z, double M[6]) {
-  const double rho = sqrt(X * X + Y * Y + Z * Z);
-  const double Ydivrho = Y / rho;
-  const double XdivZ = X / Z;
-  const double tmp1 = c.fx / ((1 + XdivZ * XdivZ) * Z);
-  const double tmp2 = -c.fy / sqrt(1 - Ydivrho * Ydivrho);
-  const double tmp3 = Ydivrho / (rho * rho);
-  const double j00 = tmp1, j02 = -tmp1 * XdivZ;
-  const double j10 = tmp2 * tmp3 * X, j11 = tmp2 * (tmp3 * Y - 1 / rho), j12 = tmp2 * tmp3 * Z;
-  // -[r]x = [[0, Z, -Y], [-Z, 0, X], [Y, -X, 0]]
-  M[0] = j02 * Y;
-  M[1] = j00 * Z - j02 * X;
-  M[2] = -j00 * Y;
-  M[3] = -j11 * Z + j12 * Y;
-  M[4] = j10 * Z - j12 * X;
-  M[5] = -j10 * Y + j11 * X;
+  const double i1 = rsqrt(X * X + Z * Z);
+  const double i2 = i1 * i1;
+  const double fxy = c.fx * Y * i2;
+  M[0] = -fxy * X;
+  M[1] = c.fx;
+  M[2] = -fxy * Z;
+  M[3] = -c.fy * Z * i1;
+  M[4] = 0.0;
+  M[5] = c.fy * X * i1;
 }
 
 // index into the packed upper triangle of a symmetric 13x13 (i <= j)
