@@ -73,7 +73,8 @@ __device__ __forceinline__ void tri_tile(double (&a)[25], const double (*tile)[k
 template <int COST>
 __global__ void __launch_bounds__(kAsmThreads, 2)
 k_asm_pose(const WorkItem* __restrict__ items, const MeasRec* __restrict__ rec, const double* __restrict__ lut,
-           const double* __restrict__ Rtab, const double* __restrict__ Atab, const double2* __restrict__ G2,
+           const double* __restrict__ Ktab, const double4* __restrict__ RotTab, const double4* __restrict__ JacTab,
+           const double2* __restrict__ G2,
            const double4* __restrict__ H3, const double2* __restrict__ dp_in, const double* __restrict__ e_in,
            const int32_t* __restrict__ pix_in, const int32_t* __restrict__ amap, PanoCam cam, double eta,
            uint32_t invalid_key, double* __restrict__ jrec, uint32_t* __restrict__ skey, uint32_t* __restrict__ sval,
@@ -81,8 +82,14 @@ k_asm_pose(const WorkItem* __restrict__ items, const MeasRec* __restrict__ rec, 
   // rows 0..11: Jc, Jp; 12: e; 13,14: dp; 15: meta  (row-major [field][measurement], padded against conflicts)
   __shared__ double tile[kRecDoubles][kTileStride];
   __shared__ double red[8][25];
+  __shared__ double knots[2 * kKnotStride];  // knot-interval data of cp_c and cp_p: uniform over the work item
   const WorkItem it = items[blockIdx.x];
   const int tid = threadIdx.x;
+  if (tid < 2 * kKnotStride)
+    knots[tid] = Ktab[(size_t)(tid < kKnotStride ? it.cp_c : it.cp_p) * kKnotStride + (tid % kKnotStride)];
+  __syncthreads();
+  const double* knot_c = knots;
+  const double* knot_p = knots + kKnotStride;
   const int role = tid >> 6, idx = tid & 63;
   double acc[25];
 #pragma unroll
@@ -113,38 +120,26 @@ k_asm_pose(const WorkItem* __restrict__ items, const MeasRec* __restrict__ rec, 
         const double h1 = g.y + dpv.x * Hh.y + dpv.y * Hh.z;
         double vc[3], vp[3], wc[3], wp[3];
         {
-          const double2* R = reinterpret_cast<const double2*>(Rtab + (size_t)bc * kPoseStride);
-          const double2 a0 = R[0], a1 = R[1], a2 = R[2], a3 = R[3], a4 = R[4];
-          const double X = a0.x * bx + a0.y * by + a1.x * bz;
-          const double Y = a1.y * bx + a2.x * by + a2.y * bz;
-          const double Z = a3.x * bx + a3.y * by + a4.x * bz;
-          double M[6];
+          const double4 rt = RotTab[bc];
+          const double4 jt = JacTab[bc];
+          double X, Y, Z, M[6];
+          rotate_bearing(knot_c, rt.x, rt.y, bx, by, bz, X, Y, Z);
           project_jac(cam, X, Y, Z, M);
           vc[0] = h0 * M[0] + h1 * M[3];  // temp * dpm_ddrot (model.cpp:449)
           vc[1] = h0 * M[1];
           vc[2] = h0 * M[2] + h1 * M[5];
-          const double2* A = reinterpret_cast<const double2*>(Atab + (size_t)bc * kPoseStride);
-          const double2 b0 = A[0], b1 = A[1], b2 = A[2], b3 = A[3], b4 = A[4];
-          wc[0] = vc[0] * b0.x + vc[1] * b1.y + vc[2] * b3.x;
-          wc[1] = vc[0] * b0.y + vc[1] * b2.x + vc[2] * b3.y;
-          wc[2] = vc[0] * b1.x + vc[1] * b2.y + vc[2] * b4.x;
+          row_times_A(knot_c, jt.x, jt.y, jt.z, vc, wc);
         }
         {
-          const double2* R = reinterpret_cast<const double2*>(Rtab + (size_t)bp * kPoseStride);
-          const double2 a0 = R[0], a1 = R[1], a2 = R[2], a3 = R[3], a4 = R[4];
-          const double X = a0.x * bx + a0.y * by + a1.x * bz;
-          const double Y = a1.y * bx + a2.x * by + a2.y * bz;
-          const double Z = a3.x * bx + a3.y * by + a4.x * bz;
-          double M[6];
+          const double4 rt = RotTab[bp];
+          const double4 jt = JacTab[bp];
+          double X, Y, Z, M[6];
+          rotate_bearing(knot_p, rt.x, rt.y, bx, by, bz, X, Y, Z);
           project_jac(cam, X, Y, Z, M);
           vp[0] = -(g.x * M[0] + g.y * M[3]);  // -Gpm * dpm_ddrot (model.cpp:459)
           vp[1] = -(g.x * M[1]);
           vp[2] = -(g.x * M[2] + g.y * M[5]);
-          const double2* A = reinterpret_cast<const double2*>(Atab + (size_t)bp * kPoseStride);
-          const double2 b0 = A[0], b1 = A[1], b2 = A[2], b3 = A[3], b4 = A[4];
-          wp[0] = vp[0] * b0.x + vp[1] * b1.y + vp[2] * b3.x;
-          wp[1] = vp[0] * b0.y + vp[1] * b2.x + vp[2] * b3.y;
-          wp[2] = vp[0] * b1.x + vp[1] * b2.y + vp[2] * b4.x;
+          row_times_A(knot_p, jt.x, jt.y, jt.z, vp, wp);
         }
         // IRLS weight (model.cpp:599-618), applied as sqrt(w) on the whole row and on e
         double sw = 1.0;
@@ -435,7 +430,8 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   EMBA_CUDAC(cudaEventRecord(h->ev[5], h->stream));
   if (h->n_items > 0) {
 #define EMBA_ASM_LAUNCH(C)                                                                                         \
-  k_asm_pose<C><<<h->n_items, kAsmThreads, 0, h->stream>>>(h->d_items, h->d_rec, h->d_lut, s.Rtab, s.Atab, s.G2,   \
+  k_asm_pose<C><<<h->n_items, kAsmThreads, 0, h->stream>>>(h->d_items, h->d_rec, h->d_lut, s.Ktab, s.RotTab,      \
+                                                           s.JacTab, s.G2,                                        \
                                                            s.H3, s.dp, s.e, s.pix, h->d_amap, cam, eta,            \
                                                            (uint32_t)Np, h->d_jrec, h->d_skey, h->d_sval,          \
                                                            h->d_winlo, h->d_winhi, h->d_acc_part)

@@ -12,7 +12,7 @@
 namespace emba {
 
 constexpr int kBatch = 100;         // hard-coded event batch size (reference src/emba/model.cpp:78)
-constexpr int kPoseStride = 10;     // doubles per 3x3 table entry (9 + 1 pad -> 16-byte aligned rows)
+constexpr int kKnotStride = 12;     // doubles per knot-interval entry: R_s (9) + delta_w (3)
 constexpr int kItemMax = 8192;      // measurements per pose-block assembly work item
 constexpr int kAccN = 91;           // upper triangle of the 13x13 outer product of [Jc Jp e]
 constexpr int kRecDoubles = 16;     // Jacobian-row record: Jc[6] Jp[6] e dp[2] meta  (128 bytes)
@@ -39,8 +39,9 @@ struct StateSlot {
   double* Gy = nullptr;      // [P]
   double2* G2 = nullptr;     // [P] interleaved (Gx, Gy)
   double4* H3 = nullptr;     // [P] (Gxx, Gxy, Gyy, 0)
-  double* Rtab = nullptr;    // [B*kPoseStride] batch rotation matrices, row-major
-  double* Atab = nullptr;    // [B*kPoseStride] batch A = u*R_s*Jl(u d)*Jl^-1(d)*R_s^T
+  double* Ktab = nullptr;    // [n*kKnotStride] per knot interval s: R_s (9, row-major), delta_w = Log(R_{s+1} R_s^-1) (3)
+  double4* RotTab = nullptr; // [B] per batch: (s1, s2, knot index s, 0): R_batch = (I + s1 K + s2 K^2) R_s, K = [delta_w]x
+  double4* JacTab = nullptr; // [B] per batch: (alpha, beta, gamma, 0): A = alpha I + beta K + gamma K^2
   double2* dp = nullptr;     // [Mc] displacement pm_c - pm_p
   double* e = nullptr;       // [Mc] residual
   int32_t* pix = nullptr;    // [Mc] pano pixel index of the current event, -1 = outlier
@@ -303,6 +304,34 @@ __device__ __forceinline__ Mat3 left_jacobian_inv(const Vec3& p) {
   for (int i = 0; i < 9; i++) J.m[i] = -0.5 * H.m[i] + H2.m[i] * c;
   J.m[0] += 1; J.m[4] += 1; J.m[8] += 1;
   return J;
+}
+
+// Batch pose applied to a bearing vector. The linear SO(3) spline gives R_batch = Exp(u delta_w) R_s with
+// delta_w = Log(R_{s+1} R_s^-1) (so3_spline.h:218-274 in world-frame form), i.e. Rodrigues with the per-batch
+// scalars s1 = sin(u th)/th, s2 = (1 - cos(u th))/th^2 and the per-knot-interval matrix K = [delta_w]x:
+//   rb = r0 + s1 (delta x r0) + s2 (delta x (delta x r0)),  r0 = R_s b
+__device__ __forceinline__ void rotate_bearing(const double* __restrict__ kt, double s1, double s2, double bx,
+                                               double by, double bz, double& X, double& Y, double& Z) {
+  const double x0 = kt[0] * bx + kt[1] * by + kt[2] * bz;
+  const double y0 = kt[3] * bx + kt[4] * by + kt[5] * bz;
+  const double z0 = kt[6] * bx + kt[7] * by + kt[8] * bz;
+  const double dx = kt[9], dy = kt[10], dz = kt[11];
+  const double x1 = dy * z0 - dz * y0, y1 = dz * x0 - dx * z0, z1 = dx * y0 - dy * x0;
+  const double x2 = dy * z1 - dz * y1, y2 = dz * x1 - dx * z1, z2 = dx * y1 - dy * x1;
+  X = x0 + s1 * x1 + s2 * x2;
+  Y = y0 + s1 * y1 + s2 * y2;
+  Z = z0 + s1 * z1 + s2 * z2;
+}
+
+// w = v A for a row vector v, A = alpha I + beta K + gamma K^2, K = [delta]x:  v K = v x delta
+__device__ __forceinline__ void row_times_A(const double* __restrict__ kt, double al, double be, double ga,
+                                            const double v[3], double w[3]) {
+  const double dx = kt[9], dy = kt[10], dz = kt[11];
+  const double a0 = v[1] * dz - v[2] * dy, a1 = v[2] * dx - v[0] * dz, a2 = v[0] * dy - v[1] * dx;
+  const double b0 = a1 * dz - a2 * dy, b1 = a2 * dx - a0 * dz, b2 = a0 * dy - a1 * dx;
+  w[0] = al * v[0] + be * a0 + ga * b0;
+  w[1] = al * v[1] + be * a1 + ga * b1;
+  w[2] = al * v[2] + be * a2 + ga * b2;
 }
 
 struct PanoCam {

@@ -51,30 +51,67 @@ __global__ void k_map_prepare(const double* __restrict__ Gx, const double* __res
 //   R = R_s * Exp(u * Log(R_s^-1 R_{s+1})),   d_val_d_knot = [I - A | A],
 //   A = u * R_s * Jl(u delta) * Jl^-1(delta) * R_s^T          (so3_spline.h:254-265)
 // ---------------------------------------------------------------------------------------------------
-__global__ void k_pose_table(const double* __restrict__ quat, const int32_t* __restrict__ bs,
-                             const double* __restrict__ bu, int64_t B, double* __restrict__ Rtab,
-                             double* __restrict__ Atab) {
+__global__ void k_knot_table(const double* __restrict__ quat, int n, double* __restrict__ Ktab) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n - 1) return;
+  const double4 q0 = reinterpret_cast<const double4*>(quat)[s];
+  const double4 q1 = reinterpret_cast<const double4*>(quat)[s + 1];
+  const double4 q0inv = make_double4(-q0.x, -q0.y, -q0.z, q0.w);
+  const Vec3 db = so3_log(quat_mul(q0inv, q1));  // delta = Log(R_s^-1 R_{s+1}) (so3_spline.h:249-250)
+  const Mat3 R0 = quat_to_R(q0);
+  double* o = Ktab + (size_t)s * kKnotStride;
+#pragma unroll
+  for (int i = 0; i < 9; i++) o[i] = R0.m[i];
+  // world-frame increment delta_w = R_s delta: R_s Exp(u delta) = Exp(u delta_w) R_s
+  o[9] = R0.m[0] * db.x + R0.m[1] * db.y + R0.m[2] * db.z;
+  o[10] = R0.m[3] * db.x + R0.m[4] * db.y + R0.m[5] * db.z;
+  o[11] = R0.m[6] * db.x + R0.m[7] * db.y + R0.m[8] * db.z;
+}
+
+// Per batch: Rodrigues scalars of Exp(u delta_w) and the three coefficients of
+//   A = u Jl(u delta_w) Jl^-1(delta_w) = alpha I + beta K + gamma K^2
+// (both Jacobians are polynomials in K = [delta_w]x, K^3 = -th^2 K), with the small-angle branches of
+// leftJacobianSO3 / leftJacobianInvSO3 (sophus_utils.hpp:333-414).
+__global__ void k_batch_table(const double* __restrict__ Ktab, const int32_t* __restrict__ bs,
+                              const double* __restrict__ bu, int64_t B, double4* __restrict__ RotTab,
+                              double4* __restrict__ JacTab) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int s = bs[b];
   const double u = bu[b];
-  const double4 q0 = reinterpret_cast<const double4*>(quat)[s];
-  const double4 q1 = reinterpret_cast<const double4*>(quat)[s + 1];
-  const double4 q0inv = make_double4(-q0.x, -q0.y, -q0.z, q0.w);
-  const double4 r01 = quat_mul(q0inv, q1);
-  const Vec3 delta = so3_log(r01);
-  const Vec3 kdelta = {delta.x * u, delta.y * u, delta.z * u};
-  const Mat3 Jli = left_jacobian_inv(delta);
-  const Mat3 Jlk = left_jacobian(kdelta);
-  const Mat3 R0 = quat_to_R(q0);
-  Mat3 A = mat_mul(mat_mul(mat_mul(R0, Jlk), Jli), mat_T(R0));
-  const double4 qr = quat_mul(q0, so3_exp(kdelta));
-  const Mat3 R = quat_to_R(qr);
-  double* Ro = Rtab + b * kPoseStride;
-  double* Ao = Atab + b * kPoseStride;
-#pragma unroll
-  for (int i = 0; i < 9; i++) { Ro[i] = R.m[i]; Ao[i] = u * A.m[i]; }
-  Ro[9] = 0; Ao[9] = 0;
+  const double* kt = Ktab + (size_t)s * kKnotStride;
+  const double th2 = kt[9] * kt[9] + kt[10] * kt[10] + kt[11] * kt[11];
+  const double th = sqrt(th2);
+  const double ut = u * th, ut2 = ut * ut;
+  double s1, s2;
+  if (th2 < kSophusEps * kSophusEps) {
+    s1 = u * (1.0 - ut2 / 6.0);
+    s2 = 0.5 * u * u * (1.0 - ut2 / 12.0);
+  } else {
+    s1 = sin(ut) / th;
+    s2 = (1.0 - cos(ut)) / th2;
+  }
+  // Jl(u delta) = I + p K + q K^2
+  double p, q;
+  if (ut2 > kSophusEps) {
+    p = u * (1.0 - cos(ut)) / ut2;
+    q = u * u * (ut - sin(ut)) / (ut2 * ut);
+  } else {
+    p = 0.5 * u;
+    q = u * u / 6.0;
+  }
+  // Jl^-1(delta) = I - K/2 + c K^2
+  double c;
+  if (th2 > kSophusEps) {
+    if (th < 3.14159265358979323846 - 1e-5) c = 1.0 / th2 - (1.0 + cos(th)) / (2.0 * th * sin(th));
+    else c = 1.0 / (3.14159265358979323846 * 3.14159265358979323846);
+  } else {
+    c = 1.0 / 12.0;
+  }
+  const double beta = p - 0.5 - th2 * (p * c - 0.5 * q);
+  const double gamma = q + c - 0.5 * p - th2 * q * c;
+  RotTab[b] = make_double4(s1, s2, __longlong_as_double((long long)s), 0.0);
+  JacTab[b] = make_double4(u, u * beta, u * gamma, 0.0);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -97,8 +134,8 @@ constexpr int kEvalThreads = 256;
 
 template <int COST>
 __global__ void __launch_bounds__(kEvalThreads)
-k_eval(const MeasRec* __restrict__ rec, int64_t Mc, const double* __restrict__ lut, const double* __restrict__ Rtab,
-       const double2* __restrict__ G2, PanoCam cam, int W, int H, double C_th, double eta,
+k_eval(const MeasRec* __restrict__ rec, int64_t Mc, const double* __restrict__ lut, const double* __restrict__ Ktab,
+       const double4* __restrict__ RotTab, const double2* __restrict__ G2, PanoCam cam, int W, int H, double C_th, double eta,
        double2* __restrict__ dp_out, double* __restrict__ e_out, int32_t* __restrict__ pix_out,
        int32_t* __restrict__ hist, double* __restrict__ part, int32_t* __restrict__ flags) {
   double cost = 0.0;
@@ -108,21 +145,19 @@ k_eval(const MeasRec* __restrict__ rec, int64_t Mc, const double* __restrict__ l
     const uint32_t spix = rr.x, bc = rr.y & 0x7FFFFFFFu, bp = rr.z;
     const double pol = (rr.y >> 31) ? 1.0 : 0.0;
     const double bx = lut[3 * (size_t)spix], by = lut[3 * (size_t)spix + 1], bz = lut[3 * (size_t)spix + 2];
-    const double2* Rc = reinterpret_cast<const double2*>(Rtab + (size_t)bc * kPoseStride);
-    const double2* Rp = reinterpret_cast<const double2*>(Rtab + (size_t)bp * kPoseStride);
     double pcx, pcy, ppx, ppy;
     {
-      const double2 a0 = Rc[0], a1 = Rc[1], a2 = Rc[2], a3 = Rc[3], a4 = Rc[4];
-      const double X = a0.x * bx + a0.y * by + a1.x * bz;
-      const double Y = a1.y * bx + a2.x * by + a2.y * bz;
-      const double Z = a3.x * bx + a3.y * by + a4.x * bz;
+      const double4 rt = RotTab[bc];
+      const int sk = (int)__double_as_longlong(rt.z);
+      double X, Y, Z;
+      rotate_bearing(Ktab + (size_t)sk * kKnotStride, rt.x, rt.y, bx, by, bz, X, Y, Z);
       project_pm(cam, X, Y, Z, pcx, pcy);
     }
     {
-      const double2 a0 = Rp[0], a1 = Rp[1], a2 = Rp[2], a3 = Rp[3], a4 = Rp[4];
-      const double X = a0.x * bx + a0.y * by + a1.x * bz;
-      const double Y = a1.y * bx + a2.x * by + a2.y * bz;
-      const double Z = a3.x * bx + a3.y * by + a4.x * bz;
+      const double4 rt = RotTab[bp];
+      const int sk = (int)__double_as_longlong(rt.z);
+      double X, Y, Z;
+      rotate_bearing(Ktab + (size_t)sk * kKnotStride, rt.x, rt.y, bx, by, bz, X, Y, Z);
       project_pm(cam, X, Y, Z, ppx, ppy);
     }
     const double dx = pcx - ppx, dy = pcy - ppy;
@@ -236,8 +271,10 @@ int prepare_state_tables(Handle* h, StateSlot& s) {
   dim3 blk(32, 8), grd((h->Wp + 31) / 32, (h->Hp + 7) / 8);
   k_map_prepare<<<grd, blk, 0, h->stream>>>(s.Gx, s.Gy, h->Wp, h->Hp, s.G2, s.H3);
   EMBA_LAUNCH_CHECK();
+  k_knot_table<<<ceil_div64(h->n, 64), 64, 0, h->stream>>>(s.quat, h->n, s.Ktab);
+  EMBA_LAUNCH_CHECK();
   if (h->B) {
-    k_pose_table<<<ceil_div64(h->B, 128), 128, 0, h->stream>>>(s.quat, h->d_bs, h->d_bu, h->B, s.Rtab, s.Atab);
+    k_batch_table<<<ceil_div64(h->B, 128), 128, 0, h->stream>>>(s.Ktab, h->d_bs, h->d_bu, h->B, s.RotTab, s.JacTab);
     EMBA_LAUNCH_CHECK();
   }
   return EMBA_OK;
@@ -256,7 +293,7 @@ int evaluate_slot(Handle* h, int slot, int cost_type, double eta, double alpha) 
   EMBA_CUDA(cudaEventRecord(h->ev[1], h->stream));
   if (h->Mc > 0) {
 #define EMBA_EVAL_LAUNCH(C)                                                                                       \
-  k_eval<C><<<grid, kEvalThreads, 0, h->stream>>>(h->d_rec, h->Mc, h->d_lut, s.Rtab, s.G2, cam, h->Wp, h->Hp,     \
+  k_eval<C><<<grid, kEvalThreads, 0, h->stream>>>(h->d_rec, h->Mc, h->d_lut, s.Ktab, s.RotTab, s.G2, cam, h->Wp, h->Hp,     \
                                                   h->C_th, eta, s.dp, s.e, s.pix, s.hist, h->d_part, h->d_flags)
     if (cost_type == EMBA_COST_QUADRATIC) EMBA_EVAL_LAUNCH(EMBA_COST_QUADRATIC);
     else if (cost_type == EMBA_COST_CAUCHY) EMBA_EVAL_LAUNCH(EMBA_COST_CAUCHY);

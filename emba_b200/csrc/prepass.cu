@@ -165,8 +165,8 @@ static int exclusive_sum(Handle* h, const int32_t* in, int32_t* out, int64_t cou
 }
 
 static void free_state(StateSlot& s) {
-  cudaFree(s.quat); cudaFree(s.Gx); cudaFree(s.Gy); cudaFree(s.G2); cudaFree(s.H3); cudaFree(s.Rtab);
-  cudaFree(s.Atab); cudaFree(s.dp); cudaFree(s.e); cudaFree(s.pix); cudaFree(s.hist);
+  cudaFree(s.quat); cudaFree(s.Gx); cudaFree(s.Gy); cudaFree(s.G2); cudaFree(s.H3); cudaFree(s.Ktab);
+  cudaFree(s.RotTab); cudaFree(s.JacTab); cudaFree(s.dp); cudaFree(s.e); cudaFree(s.pix); cudaFree(s.hist);
   s = StateSlot();
 }
 
@@ -370,8 +370,9 @@ int rebuild_static(Handle* h) {
   EMBA_TRY(dev_alloc(h, &h->d_bu, B));
   for (int s = 0; s < 2; s++) {
     EMBA_TRY(dev_alloc(h, &h->st[s].quat, (int64_t)n * 4));
-    EMBA_TRY(dev_alloc(h, &h->st[s].Rtab, B * kPoseStride));
-    EMBA_TRY(dev_alloc(h, &h->st[s].Atab, B * kPoseStride));
+    EMBA_TRY(dev_alloc(h, &h->st[s].Ktab, (int64_t)n * kKnotStride));
+    EMBA_TRY(dev_alloc(h, &h->st[s].RotTab, B));
+    EMBA_TRY(dev_alloc(h, &h->st[s].JacTab, B));
     h->st[s].evaluated = false;
   }
   h->formed = h->solved = false;
