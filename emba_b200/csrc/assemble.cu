@@ -358,6 +358,18 @@ k_pix(int64_t Np, const int32_t* __restrict__ segoff, const uint32_t* __restrict
   }
 }
 
+__global__ void k_l2_reg(int64_t Np, const int32_t* __restrict__ apix, const double* __restrict__ Gx,
+                         const double* __restrict__ Gy, double alpha, double* __restrict__ A22,
+                         double* __restrict__ b2) {
+  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= Np) return;
+  const int32_t pix = apix[a];
+  A22[3 * a] += alpha;
+  A22[3 * a + 2] += alpha;
+  b2[2 * a] -= alpha * Gx[pix];
+  b2[2 * a + 1] -= alpha * Gy[pix];
+}
+
 // dense copy of A12 for emba_get_normal_eq (parity only)
 __global__ void k_a12_dense(int64_t Np, int n, const int32_t* __restrict__ winlo, const int32_t* __restrict__ winhi,
                             const int64_t* __restrict__ stripoff, const double* __restrict__ strip,
@@ -535,6 +547,21 @@ int emba_form_normal_eq(emba_handle_t hh, int32_t thres, int32_t cost_type, doub
   EMBA_CUDA(cudaSetDevice(h->device));
   EMBA_TRY(form_normal_eq(h, thres, cost_type, eta, alpha));
   if (Np_out) *Np_out = h->Np;
+  return EMBA_OK;
+}
+
+int emba_apply_l2_reg(emba_handle_t hh, double alpha) {
+  Handle* h = (Handle*)hh;
+  if (!h) return EMBA_E_ARG;
+  if (!h->formed) { h->err = "emba_apply_l2_reg: no normal equations formed"; return EMBA_E_ARG; }
+  EMBA_CUDA(cudaSetDevice(h->device));
+  if (h->Np > 0) {
+    StateSlot& s = h->st[h->cur];
+    k_l2_reg<<<ceil_div64(h->Np, 256), 256, 0, h->stream>>>(h->Np, h->d_apix, s.Gx, s.Gy, alpha, h->d_A22, h->d_b2);
+    EMBA_LAUNCH_CHECK();
+  }
+  EMBA_CUDA(cudaStreamSynchronize(h->stream));
+  h->solved = false;
   return EMBA_OK;
 }
 

@@ -122,6 +122,9 @@ class Engine:
         self.Np = Np.value
         return self.Np
 
+    def apply_l2_reg(self, alpha):
+        self._chk(self.L.emba_apply_l2_reg(self.h, float(alpha)))
+
     def get_normal_eq(self, want_A12=True):
         n, Np = self.n, self.Np
         A11 = np.empty((3 * n, 3 * n))
@@ -269,6 +272,12 @@ class LEGM:
         assert num_ctrl_poses == self.eng.n
         self.eng.form_normal_eq(thres_valid_pixel, cost_type, eta, 0.0)
         return self.eng.get_normal_eq(want_A12)
+
+    def applyL2Reg(self, alpha):
+        """model.cpp:689-719 on the device-resident A22 / b2; returns the updated (A22_blocks, b2)."""
+        self.eng.apply_l2_reg(alpha)
+        _, _, A22, _, b2, _ = self.eng.get_normal_eq(False)
+        return A22, b2
 
     def solveNormalEq(self, lam, fix_first=True):
         """model.cpp:721-792."""

@@ -136,6 +136,9 @@ EMBA_API int emba_get_evaluation(emba_handle_t h, int32_t which, double* ep_out,
  * evaluation of the CURRENT state. */
 EMBA_API int emba_form_normal_eq(emba_handle_t h, int32_t thres_valid_pixel, int32_t cost_type, double eta, double alpha,
                         int64_t* num_active_pixels);
+/* ---- LEGM::applyL2Reg (model.cpp:689-719) as a separate step, for callers that form with alpha = 0 (the
+ * reference calls it right after formNormalEq, solver.cpp:130): A22 += alpha*I, b2 -= alpha*(Gx,Gy)[active]. */
+EMBA_API int emba_apply_l2_reg(emba_handle_t h, double alpha);
 /* parity / adapter download. A11 [3n*3n] row-major, b1 [3n], A22 [Np*4] (2x2 row-major blocks), b2 [2Np],
  * active [Np] ascending pixel indices (the std::set order, model.cpp:370-377). A12 is returned dense row-major
  * [3n * 2Np] exactly like the reference's MatXd (model.cpp:358) -- only for small problems. Any may be NULL. */

@@ -118,6 +118,8 @@ public:
   template <typename T> const T& at(int r, int c) const {
     return reinterpret_cast<const T*>(data)[(size_t)r * cols + c];
   }
+  template <typename T> T* ptr(int r = 0) { return reinterpret_cast<T*>(data) + (size_t)r * cols; }
+  template <typename T> const T* ptr(int r = 0) const { return reinterpret_cast<const T*>(data) + (size_t)r * cols; }
   template <typename T> T& at(Point2i p) { return at<T>(p.y, p.x); }
   template <typename T> const T& at(Point2i p) const { return at<T>(p.y, p.x); }
 

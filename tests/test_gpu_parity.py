@@ -189,8 +189,12 @@ def test_reference_shaped_interface(tiny, tiny_ref):
     A11, A12, A22, b1, b2, act = model.formNormalEq(traj.size(), THRES)
     # applyL2Reg is a separate call in the reference; the fixture has it applied
     assert rel(ref["A11"], A11) < 1e-9 and np.array_equal(act, ref["active"])
-    A22 = A22 + ALPHA * np.eye(2)[None]
-    assert rel(ref["A22"], A22) < 1e-9
+    A22, b2 = model.applyL2Reg(ALPHA)
+    assert rel(ref["A22"], A22) < 1e-9 and rel(ref["b2"], b2) < 1e-9
+    x1, x2 = model.solveNormalEq(LAM, True)
+    assert rel(ref["x1"], x1) < 1e-7 and rel(ref["x2"], x2) < 1e-7
+    traj_new, gx_new, gy_new = model.updateTrajAndMap(traj, 1.0)
+    assert traj_new.size() == traj.size() and np.array_equal(traj_new.quat[0], traj.quat[0])
     model.eng.close()
 
 
