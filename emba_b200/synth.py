@@ -89,10 +89,13 @@ def make_texture(pano_w, pano_h, seed=1, std=1.5):
 
 def gt_rotvec(t, yaw_rate=0.35, periodic=False):
     """Ground-truth rotation vector phi(t) = (0.25 sin 1.3t, 0.35 t, 0.08 cos 0.7t) rad; with
-    periodic=True the yaw is a bounded sinusoid (for spans > 10 s)."""
+    periodic=True the yaw is a bounded triangle wave with the same rate (for spans > 10 s)."""
     t = np.asarray(t, dtype=np.float64)
     if periodic:
-        yaw = 1.6 * np.sin(yaw_rate / 1.6 * t)
+        # triangle wave: constant |yaw rate|, bounded to +-1.6 rad (keeps the view away from the seam for any span)
+        A = 1.6
+        ph = (yaw_rate * t + A) % (4 * A)
+        yaw = np.where(ph < 2 * A, ph - A, 3 * A - ph)
     else:
         yaw = yaw_rate * t
     return np.stack([0.25 * np.sin(1.3 * t), yaw, 0.08 * np.cos(0.7 * t)], -1)
