@@ -29,9 +29,13 @@ __global__ void k_active_flags(const int32_t* __restrict__ hist, int64_t P, int 
 
 __global__ void k_active_fill(const int32_t* __restrict__ flag, const int32_t* __restrict__ aidx, int64_t P,
                               int32_t* __restrict__ amap, int32_t* __restrict__ apix, int32_t* __restrict__ winlo,
-                              int32_t* __restrict__ winhi) {
+                              int32_t* __restrict__ winhi, double4* __restrict__ H3) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
+  // the active index also rides in the spare lane of the Hessian entry, so the assembly kernel gets it with the
+  // gather it does anyway
+  const int32_t av = flag[p] ? aidx[p] : -1;
+  reinterpret_cast<double*>(H3 + p)[3] = __longlong_as_double((long long)av);
   if (flag[p]) {
     const int32_t a = aidx[p];
     amap[p] = a;
@@ -104,17 +108,23 @@ k_asm_pose(const WorkItem* __restrict__ items, const MeasRec* __restrict__ rec, 
     const int64_t m = (int64_t)it.start + j;
     if (j < it.count) {
       const int32_t pix = pix_in[m];
-      const int32_t a = pix >= 0 ? amap[pix] : -1;  // model.cpp:396-412: outliers and inactive pixels are skipped
+      double4 Hh = make_double4(0.0, 0.0, 0.0, 0.0);
+      int32_t a = -1;  // model.cpp:396-412: outliers and inactive pixels are skipped
+      if (pix >= 0) {
+        Hh = H3[pix];
+        a = (int32_t)__double_as_longlong(Hh.w);
+      }
       skey[m] = a >= 0 ? (uint32_t)a : invalid_key;
       sval[m] = (uint32_t)m;
       if (a >= 0) {
-        const uint4 rr = reinterpret_cast<const uint4*>(rec)[m];
-        const uint32_t spix = rr.x, bc = rr.y & 0x7FFFFFFFu, bp = rr.z;
-        const double bx = lut[3 * (size_t)spix], by = lut[3 * (size_t)spix + 1], bz = lut[3 * (size_t)spix + 2];
+        const double2 r0 = reinterpret_cast<const double2*>(rec)[2 * m];
+        const double2 r1 = reinterpret_cast<const double2*>(rec)[2 * m + 1];
+        const double bx = r0.x, by = r0.y, bz = r1.x;
+        const unsigned long long rw = (unsigned long long)__double_as_longlong(r1.y);
+        const uint32_t bc = (uint32_t)rw & 0x7FFFFFFFu, bp = (uint32_t)(rw >> 32);
         const double2 dpv = dp_in[m];
         double e = e_in[m];
         const double2 g = G2[pix];
-        const double4 Hh = H3[pix];
         // temp = Gpm + dp^T * G2pm (model.cpp:233-238)
         const double h0 = g.x + dpv.x * Hh.x + dpv.y * Hh.y;
         const double h1 = g.y + dpv.x * Hh.y + dpv.y * Hh.z;
@@ -277,10 +287,24 @@ __global__ void k_seg_bounds(const uint32_t* __restrict__ keys, int64_t M, int64
   segoff[a] = (int32_t)lo;
 }
 
-// Map side: one warp per active pixel, rows in fixed (sorted) order.
+// Map side: one warp per active pixel, rows in fixed (sorted) order. The 128-byte rows are gathered with cp.async
+// (16 B per lane, 4 rows per instruction) into a 3-stage shared-memory ring, so the DRAM latency of the gather
+// overlaps the reduction of the previous tiles. Lanes 0..23 own one A12 component (slot, row, col), lanes 24..28
+// own A22 xx, xy, yy and b2 x, y. A12 components are accumulated per run of equal (cp_c, cp_p) -- rows are sorted
+// by row id, i.e. grouped by control-pose pair -- and flushed into the pixel's strip in shared memory.
 constexpr int kPixWarps = 8;
 constexpr int kStripCap = 64;  // poses per shared-memory strip
-constexpr int kPixTile = 16;   // rows staged per step
+constexpr int kPixTile = 16;   // rows per stage
+constexpr int kPixStages = 3;
+constexpr int kPixSmemPerWarp = (kPixStages * kPixTile * kRecDoubles + kStripCap * 6) * 8;  // bytes
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(kPixWarps * 32)
 k_pix(int64_t Np, const int32_t* __restrict__ segoff, const uint32_t* __restrict__ sval,
@@ -288,30 +312,48 @@ k_pix(int64_t Np, const int32_t* __restrict__ segoff, const uint32_t* __restrict
       const int64_t* __restrict__ stripoff, double* __restrict__ strip, const int32_t* __restrict__ apix,
       const double* __restrict__ Gx, const double* __restrict__ Gy, double alpha, double* __restrict__ A22,
       double* __restrict__ b2) {
-  __shared__ double s_tile[kPixWarps][kPixTile][kRecDoubles];
-  __shared__ double s_strip[kPixWarps][kStripCap * 6];
+  extern __shared__ __align__(16) unsigned char pix_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* s_tile = reinterpret_cast<double*>(pix_smem + (size_t)warp * kPixSmemPerWarp);  // [stage][row][16]
+  double* s_strip = s_tile + kPixStages * kPixTile * kRecDoubles;
   const int64_t nw = (int64_t)gridDim.x * kPixWarps;
-  // lane roles: 0..23 -> A12 component (slot s, row r, col c); 24..28 -> A22 xx, xy, yy, b2 x, y
   const int s = lane / 6, r = (lane % 6) >> 1, c = lane & 1;
-  int ia = 0, ib = 0;
   // record fields: 0..11 Jc|Jp, 12 e, 13..14 dp, 15 meta
+  int ia = 15, ib = 15;
   if (lane < 24) { ia = 3 * s + r; ib = 13 + c; }
   else if (lane == 24) { ia = 13; ib = 13; }
   else if (lane == 25) { ia = 13; ib = 14; }
   else if (lane == 26) { ia = 14; ib = 14; }
   else if (lane == 27) { ia = 13; ib = 12; }
   else if (lane == 28) { ia = 14; ib = 12; }
+  const int lrow = lane >> 3, lchunk = lane & 7;  // cp.async role: 4 rows per instruction, 8 x 16 B per row
   for (int64_t a = (int64_t)blockIdx.x * kPixWarps + warp; a < Np; a += nw) {
     const int64_t seg0 = segoff[a];
     const int64_t seg1 = segoff[a + 1];
     const int qlo = winlo[a];
     const int len = winhi[a] - qlo + 1;
     double* gs = strip + stripoff[a] * 6;
-    double* sp = (len <= kStripCap) ? s_strip[warp] : gs;
+    double* sp = (len <= kStripCap) ? s_strip : gs;
     for (int i = lane; i < len * 6; i += 32) sp[i] = 0.0;
-    __syncwarp();
-    double acc = 0.0, acc22 = 0.0;
+    const int ntiles = (int)((seg1 - seg0 + kPixTile - 1) / kPixTile);
+    auto issue = [&](int t) {
+      if (t < ntiles) {
+        const int64_t base = seg0 + (int64_t)t * kPixTile;
+        const int cnt = (int)min((int64_t)kPixTile, seg1 - base);
+        const uint32_t mine = (lane < cnt) ? sval[base + lane] : 0u;
+        double* dst = s_tile + (size_t)(t % kPixStages) * kPixTile * kRecDoubles;
+#pragma unroll
+        for (int k = 0; k < kPixTile / 4; k++) {
+          const int row = 4 * k + lrow;
+          const uint32_t m = __shfl_sync(0xffffffffu, mine, row);
+          if (row < cnt) cp_async16(dst + row * kRecDoubles + 2 * lchunk, jrec + (size_t)m * kRecDoubles + 2 * lchunk);
+        }
+      }
+      cp_async_commit();
+    };
+    issue(0);
+    issue(1);
+    double acc = 0.0;
     uint32_t runkey = 0xFFFFFFFFu;
     bool have = false;
     auto flush = [&]() {
@@ -321,39 +363,61 @@ k_pix(int64_t Np, const int32_t* __restrict__ segoff, const uint32_t* __restrict
       __syncwarp();
       if (lane >= 12 && lane < 24) sp[(pose - qlo) * 6 + r * 2 + c] += acc;
       __syncwarp();
+      if (lane < 24) acc = 0.0;
     };
-    for (int64_t base = seg0; base < seg1; base += kPixTile) {
-      const int cnt = (int)min((int64_t)kPixTile, seg1 - base);
-      for (int i = lane >> 4; i < cnt; i += 2) {
-        const uint32_t m = sval[base + i];
-        s_tile[warp][i][lane & 15] = jrec[(size_t)m * kRecDoubles + (lane & 15)];
-      }
+    for (int t = 0; t < ntiles; t++) {
+      issue(t + 2);
+      cp_async_wait<2>();
       __syncwarp();
-      for (int i = 0; i < cnt; i++) {
-        const uint32_t key = (uint32_t)(unsigned long long)__double_as_longlong(s_tile[warp][i][15]);
-        if (key != runkey) {
-          if (have) flush();
-          runkey = key;
-          have = true;
-          acc = 0.0;
+      const int cnt = (int)min((int64_t)kPixTile, seg1 - (seg0 + (int64_t)t * kPixTile));
+      const double* tl = s_tile + (size_t)(t % kPixStages) * kPixTile * kRecDoubles;
+      const double* pa = tl + ia;
+      const double* pb = tl + ib;
+      const uint32_t* pk = reinterpret_cast<const uint32_t*>(tl + 15);
+      int i = 0;
+      for (; i + 4 <= cnt; i += 4) {
+        const uint32_t k0 = pk[(i + 0) * 2 * kRecDoubles], k1 = pk[(i + 1) * 2 * kRecDoubles];
+        const uint32_t k2 = pk[(i + 2) * 2 * kRecDoubles], k3 = pk[(i + 3) * 2 * kRecDoubles];
+        const double a0 = pa[(i + 0) * kRecDoubles], b0 = pb[(i + 0) * kRecDoubles];
+        const double a1 = pa[(i + 1) * kRecDoubles], b1 = pb[(i + 1) * kRecDoubles];
+        const double a2 = pa[(i + 2) * kRecDoubles], b2v = pb[(i + 2) * kRecDoubles];
+        const double a3 = pa[(i + 3) * kRecDoubles], b3 = pb[(i + 3) * kRecDoubles];
+        if (have && k0 == runkey && k1 == runkey && k2 == runkey && k3 == runkey) {
+          acc = fma(a0, b0, acc);
+          acc = fma(a1, b1, acc);
+          acc = fma(a2, b2v, acc);
+          acc = fma(a3, b3, acc);
+        } else {
+          if (k0 != runkey || !have) { if (have) flush(); runkey = k0; have = true; }
+          acc = fma(a0, b0, acc);
+          if (k1 != runkey) { flush(); runkey = k1; }
+          acc = fma(a1, b1, acc);
+          if (k2 != runkey) { flush(); runkey = k2; }
+          acc = fma(a2, b2v, acc);
+          if (k3 != runkey) { flush(); runkey = k3; }
+          acc = fma(a3, b3, acc);
         }
-        const double p = s_tile[warp][i][ia] * s_tile[warp][i][ib];
-        if (lane < 24) acc += p;
-        else acc22 += p;
+      }
+      for (; i < cnt; i++) {
+        const uint32_t k0 = pk[i * 2 * kRecDoubles];
+        if (k0 != runkey || !have) { if (have) flush(); runkey = k0; have = true; }
+        acc = fma(pa[i * kRecDoubles], pb[i * kRecDoubles], acc);
       }
       __syncwarp();
     }
+    cp_async_wait<0>();
     if (have) flush();
+    __syncwarp();
     if (sp != gs) {
       for (int i = lane; i < len * 6; i += 32) gs[i] = sp[i];
     }
     // applyL2Reg (model.cpp:689-719): A22 += alpha*I, b2 -= alpha * (Gx, Gy)[pixel]
     const int32_t pix = apix[a];
-    if (lane == 24) A22[3 * a] = acc22 + alpha;
-    if (lane == 25) A22[3 * a + 1] = acc22;
-    if (lane == 26) A22[3 * a + 2] = acc22 + alpha;
-    if (lane == 27) b2[2 * a] = acc22 - alpha * Gx[pix];
-    if (lane == 28) b2[2 * a + 1] = acc22 - alpha * Gy[pix];
+    if (lane == 24) A22[3 * a] = acc + alpha;
+    if (lane == 25) A22[3 * a + 1] = acc;
+    if (lane == 26) A22[3 * a + 2] = acc + alpha;
+    if (lane == 27) b2[2 * a] = acc - alpha * Gx[pix];
+    if (lane == 28) b2[2 * a + 1] = acc - alpha * Gy[pix];
     __syncwarp();
   }
 }
@@ -434,7 +498,7 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   EMBA_CUDAC(cudaStreamSynchronize(h->stream));
   const int64_t Np = (int64_t)tail[0] + tail[1];
   h->Np = Np;
-  k_active_fill<<<ceil_div64(P, T), T, 0, h->stream>>>(d_flag, d_aidx, P, h->d_amap, h->d_apix, h->d_winlo, h->d_winhi);
+  k_active_fill<<<ceil_div64(P, T), T, 0, h->stream>>>(d_flag, d_aidx, P, h->d_amap, h->d_apix, h->d_winlo, h->d_winhi, s.H3);
   h->launches++;
   // ---- 2. pose side + Jacobian rows
   const int64_t Mc = h->Mc;
@@ -481,7 +545,7 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   EMBA_CUDAC(cudaMemcpyAsync(&tot, h->d_stripoff + Np, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
   EMBA_CUDAC(cudaStreamSynchronize(h->stream));
   h->strip_total = tot;
-  EMBA_TRYC(dev_reserve(h, &h->d_strip, &h->strip_cap, tot * 6));
+  EMBA_TRYC(dev_reserve(h, &h->d_strip, &h->strip_cap, tot * 6 + tot * 3));  // +50 %: windows drift between iterations
   // stable radix sort of the rows by active pixel index (rows of outliers / inactive pixels carry key Np)
   uint32_t* vs = h->d_sval;
   if (Mc > 0) {
@@ -507,7 +571,9 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   }
   if (Np > 0) {
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((Np + kPixWarps - 1) / kPixWarps, (int64_t)h->sm_count * 16));
-    k_pix<<<grid, kPixWarps * 32, 0, h->stream>>>(Np, h->d_segoff, vs, h->d_jrec, h->d_winlo, h->d_winhi,
+    const int pix_smem = kPixWarps * kPixSmemPerWarp;
+    EMBA_CUDAC(cudaFuncSetAttribute(k_pix, cudaFuncAttributeMaxDynamicSharedMemorySize, pix_smem));
+    k_pix<<<grid, kPixWarps * 32, pix_smem, h->stream>>>(Np, h->d_segoff, vs, h->d_jrec, h->d_winlo, h->d_winhi,
                                                   h->d_stripoff, h->d_strip, h->d_apix, s.Gx, s.Gy,
                                                   h->rank == 0 ? alpha : 0.0, h->d_A22, h->d_b2);
     h->launches++;

@@ -20,10 +20,9 @@ constexpr double kSophusEps = 1e-10;  // Sophus::Constants<double>::epsilon()
 
 // static per-measurement record, canonical order (sorted by (cp_c, cp_p), then time of the current event)
 struct __align__(16) MeasRec {
-  uint32_t spix;     // sensor pixel index y*W_s + x (both events of a pair share it)
-  uint32_t bc_pol;   // batch of the current event | polarity << 31
-  uint32_t bp;       // batch of the previous event
-  uint32_t refpos;   // rank of this pair in the reference's order (sensor pixel row-major, then time)
+  double bx, by, bz;  // bearing vector of the sensor pixel (both events of a pair share it): saves a LUT gather
+  uint32_t bc_pol;    // batch of the current event | polarity << 31
+  uint32_t bp;        // batch of the previous event
 };
 
 struct WorkItem {
@@ -76,7 +75,8 @@ struct Handle {
   int n = 0;
   int32_t* d_bs = nullptr;    // [B] knot index s of the batch mid-time
   double* d_bu = nullptr;     // [B] u in [0,1)
-  MeasRec* d_rec = nullptr;   // [Mc] canonical order, this shard only
+  MeasRec* d_rec = nullptr;   // [Mc] canonical order, this shard only (32 B, read as two coalesced 16 B loads)
+  uint32_t* d_refpos = nullptr;  // [Mc] rank of the pair in the reference's order (sensor pixel row-major, then time)
   int64_t Mc = 0;             // measurements of this shard
   std::vector<WorkItem> h_items;
   WorkItem* d_items = nullptr;
@@ -132,6 +132,8 @@ struct Handle {
   double* d_rhs = nullptr;      // [d]
   double* d_x1 = nullptr;       // [3n]
   double* d_x2 = nullptr;       // [2Np]
+  double* d_ldlt_w = nullptr;   // [d*32] panel scratch of the blocked LDL^T
+  int64_t ldlt_w_cap = 0;
   double* d_Spart = nullptr;
   int64_t Spart_cap = 0;
   double* d_cg = nullptr;       // PCG vectors

@@ -141,10 +141,13 @@ k_eval(const MeasRec* __restrict__ rec, int64_t Mc, const double* __restrict__ l
   double cost = 0.0;
   double cnt = 0.0;
   for (int64_t m = (int64_t)blockIdx.x * kEvalThreads + threadIdx.x; m < Mc; m += (int64_t)gridDim.x * kEvalThreads) {
-    const uint4 rr = reinterpret_cast<const uint4*>(rec)[m];
-    const uint32_t spix = rr.x, bc = rr.y & 0x7FFFFFFFu, bp = rr.z;
-    const double pol = (rr.y >> 31) ? 1.0 : 0.0;
-    const double bx = lut[3 * (size_t)spix], by = lut[3 * (size_t)spix + 1], bz = lut[3 * (size_t)spix + 2];
+    const double2 r0 = reinterpret_cast<const double2*>(rec)[2 * m];
+    const double2 r1 = reinterpret_cast<const double2*>(rec)[2 * m + 1];
+    const double bx = r0.x, by = r0.y, bz = r1.x;
+    const unsigned long long w = (unsigned long long)__double_as_longlong(r1.y);
+    const uint32_t bcp = (uint32_t)w, bp = (uint32_t)(w >> 32);
+    const uint32_t bc = bcp & 0x7FFFFFFFu;
+    const double pol = (bcp >> 31) ? 1.0 : 0.0;
     double pcx, pcy, ppx, ppy;
     {
       const double4 rt = RotTab[bc];
@@ -239,13 +242,13 @@ __global__ void k_sum_partials(const double* __restrict__ part, int nblk, int st
 }
 
 // scatter residuals to the reference's measurement order for emba_get_evaluation
-__global__ void k_scatter_ref(const MeasRec* __restrict__ rec, const int32_t* __restrict__ pix,
+__global__ void k_scatter_ref(const uint32_t* __restrict__ refpos, const int32_t* __restrict__ pix,
                               const double* __restrict__ e, int64_t Mc, double* __restrict__ tmp_e,
                               int32_t* __restrict__ tmp_flag) {
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= Mc) return;
   if (pix[m] >= 0) {
-    const uint32_t r = rec[m].refpos;
+    const uint32_t r = refpos[m];
     tmp_e[r] = e[m];
     tmp_flag[r] = 1;
   }
@@ -415,7 +418,7 @@ int emba_get_evaluation(emba_handle_t hh, int32_t which, double* ep_out, int32_t
       return rc;
     }
     cudaMemsetAsync(flag, 0, sizeof(int32_t) * Mt, h->stream);
-    if (h->Mc) k_scatter_ref<<<ceil_div64(h->Mc, 256), 256, 0, h->stream>>>(h->d_rec, s.pix, s.e, h->Mc, tmp_e, flag);
+    if (h->Mc) k_scatter_ref<<<ceil_div64(h->Mc, 256), 256, 0, h->stream>>>(h->d_refpos, s.pix, s.e, h->Mc, tmp_e, flag);
     size_t tb = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tb, flag, pos, (int)Mt, h->stream);
     void* d_tmp = nullptr;

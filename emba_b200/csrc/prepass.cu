@@ -109,16 +109,18 @@ __global__ void k_head_scatter(const uint32_t* __restrict__ key, const int32_t* 
 __global__ void k_build_recs(const uint32_t* __restrict__ sev, int64_t m_lo, int64_t Mloc,
                              const uint32_t* __restrict__ spix, const uint8_t* __restrict__ pol,
                              const int32_t* __restrict__ prev, const uint32_t* __restrict__ refrank,
-                             MeasRec* __restrict__ rec) {
+                             const double* __restrict__ lut, MeasRec* __restrict__ rec,
+                             uint32_t* __restrict__ refpos) {
   int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= Mloc) return;
   const uint32_t ev = sev[m_lo + j];
   MeasRec r;
-  r.spix = spix[ev];
+  const size_t sp = spix[ev];
+  r.bx = lut[3 * sp]; r.by = lut[3 * sp + 1]; r.bz = lut[3 * sp + 2];
   r.bc_pol = (ev / kBatch) | ((uint32_t)(pol[ev] ? 1u : 0u) << 31);
   r.bp = (uint32_t)prev[ev] / kBatch;
-  r.refpos = refrank[ev];
   rec[j] = r;
+  refpos[j] = refrank[ev];
 }
 
 static int bits_for(uint64_t maxval) {
@@ -259,11 +261,11 @@ int emba_destroy(emba_handle_t hh) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   comm_destroy(h);
   free_state(h->st[0]); free_state(h->st[1]);
-  void* ptrs[] = {h->d_lut, h->d_tmid, h->d_spix_ev, h->d_pol, h->d_prev, h->d_refrank, h->d_bs, h->d_bu, h->d_rec,
+  void* ptrs[] = {h->d_lut, h->d_tmid, h->d_spix_ev, h->d_pol, h->d_prev, h->d_refrank, h->d_bs, h->d_bu, h->d_rec, h->d_refpos,
                   h->d_items, h->d_gid, h->d_group_item0, h->d_part, h->d_scal, h->d_flags, h->d_amap, h->d_pflag, h->d_paidx, h->d_len, h->d_apix,
                   h->d_segoff, h->d_jrec, h->d_skey, h->d_sval, h->d_skey2, h->d_sval2, h->d_cub_tmp, h->d_winlo,
                   h->d_winhi, h->d_stripoff, h->d_strip, h->d_A22, h->d_b2, h->d_acc_part, h->d_gsum, h->d_A11,
-                  h->d_b1, h->d_C, h->d_S, h->d_rhs, h->d_x1, h->d_x2, h->d_Spart, h->d_cg};
+                  h->d_b1, h->d_C, h->d_S, h->d_rhs, h->d_x1, h->d_x2, h->d_Spart, h->d_cg, h->d_ldlt_w};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -386,6 +388,7 @@ int rebuild_static(Handle* h) {
       EMBA_TRY(dev_alloc(h, &h->st[s].dp, 1)); EMBA_TRY(dev_alloc(h, &h->st[s].e, 1)); EMBA_TRY(dev_alloc(h, &h->st[s].pix, 1));
     }
     EMBA_TRY(dev_alloc(h, &h->d_rec, 1));
+    EMBA_TRY(dev_alloc(h, &h->d_refpos, 1));
     EMBA_TRY(dev_alloc(h, &h->d_gid, (int64_t)n));
     EMBA_CUDA(cudaMemset(h->d_gid, 0xFF, sizeof(int32_t) * n));
     return EMBA_OK;
@@ -480,6 +483,7 @@ int rebuild_static(Handle* h) {
     do {
       if ((rc = dev_alloc(h, &h->d_items, h->n_items)) || (rc = dev_alloc(h, &h->d_gid, (int64_t)gid.size())) ||
           (rc = dev_alloc(h, &h->d_group_item0, (int64_t)item0.size())) || (rc = dev_alloc(h, &h->d_rec, h->Mc)) ||
+          (rc = dev_alloc(h, &h->d_refpos, h->Mc)) ||
           (rc = dev_alloc(h, &h->d_acc_part, (int64_t)h->n_items * kAccN)) ||
           (rc = dev_alloc(h, &h->d_skey, h->Mc)) || (rc = dev_alloc(h, &h->d_sval, h->Mc)) ||
           (rc = dev_alloc(h, &h->d_skey2, h->Mc)) || (rc = dev_alloc(h, &h->d_sval2, h->Mc)) ||
@@ -497,7 +501,7 @@ int rebuild_static(Handle* h) {
       cudaMemcpyAsync(h->d_group_item0, item0.data(), sizeof(int32_t) * item0.size(), cudaMemcpyHostToDevice, h->stream);
       if (h->Mc) {
         k_build_recs<<<ceil_div64(h->Mc, T), T, 0, h->stream>>>(vs, m_lo, h->Mc, h->d_spix_ev, h->d_pol, h->d_prev,
-                                                                h->d_refrank, h->d_rec);
+                                                                h->d_refrank, h->d_lut, h->d_rec, h->d_refpos);
         h->launches++;
       }
       cudaError_t e = cudaStreamSynchronize(h->stream);

@@ -167,47 +167,157 @@ __global__ void k_schur_finish(int d, int fix, int n, int nt, int npairs, int Z,
   }
 }
 
-// In-place LDL^T (no pivoting) of the dense symmetric S and solution of S x = rhs, one CTA.
+// Blocked right-looking LDL^T (no pivoting) of the dense symmetric Schur complement, lower triangle in place.
 // The reference uses Eigen's LDLT (model.cpp:789); S is the Schur complement of a damped SPD system.
-__global__ void __launch_bounds__(1024) k_ldlt_solve(int d, double* __restrict__ S, double* __restrict__ x,
-                                                     int32_t* __restrict__ flags) {
-  const int tid = threadIdx.x, nt = blockDim.x;
-  __shared__ double dk_sh;
-  for (int k = 0; k < d; k++) {
-    if (tid == 0) {
-      const double dk = S[(size_t)k * d + k];
-      if (dk == 0.0 || !isfinite(dk)) atomicOr(flags, 8);
-      dk_sh = dk;
-    }
-    __syncthreads();
-    const double dk = dk_sh;
-    // column k of L (stored in the lower triangle); the upper triangle row k keeps d_k * l_ik for the update
-    for (int i = k + 1 + tid; i < d; i += nt) {
-      const double v = S[(size_t)i * d + k];
-      S[(size_t)k * d + i] = v;          // d_k * l_ik
-      S[(size_t)i * d + k] = v / dk;     // l_ik
-    }
-    __syncthreads();
-    // trailing update of the lower triangle: S_ij -= l_ik * (d_k l_jk), j <= i
-    const int m = d - k - 1;
-    for (int64_t e = tid; e < (int64_t)m * m; e += nt) {
-      const int i = k + 1 + (int)(e / m), j = k + 1 + (int)(e % m);
-      if (j <= i) S[(size_t)i * d + j] -= S[(size_t)i * d + k] * S[(size_t)k * d + j];
-    }
-    __syncthreads();
+// Per 32-column panel two launches:
+//   k_ldlt_panel : every CTA factors the 32x32 diagonal block in shared memory (redundantly -- it is tiny), then one
+//                  thread per row of its 64-row slab solves the panel row: y = L_row D (scratch W), L_row in place;
+//   k_ldlt_update: trailing update A_ij -= sum_m y_im L_jm over 64x64 lower-triangular tiles, 4x4 register tiles.
+// Then k_ldlt_subst (one CTA): blocked forward / diagonal / backward substitution.
+constexpr int kNB = 32;
+
+__global__ void __launch_bounds__(256)
+k_ldlt_panel(int d, int k0, int nb, double* __restrict__ S, double* __restrict__ W, int32_t* __restrict__ flags) {
+  __shared__ double Dk[kNB][kNB + 1];
+  const int tid = threadIdx.x;
+  for (int e = tid; e < nb * nb; e += 256) {
+    const int i = e / nb, j = e % nb;
+    Dk[i][j] = (j <= i) ? S[(size_t)(k0 + i) * d + k0 + j] : 0.0;
   }
-  // forward: L y = b
-  for (int k = 0; k < d; k++) {
-    const double yk = x[k];
-    for (int i = k + 1 + tid; i < d; i += nt) x[i] -= S[(size_t)i * d + k] * yk;
-    __syncthreads();
-  }
-  for (int i = tid; i < d; i += nt) x[i] /= S[(size_t)i * d + i];
   __syncthreads();
-  // backward: L^T x = z
-  for (int k = d - 1; k >= 0; k--) {
-    const double xk = x[k];
-    for (int i = tid; i < k; i += nt) x[i] -= S[(size_t)k * d + i] * xk;
+  for (int j = 0; j < nb; j++) {
+    const double dj = Dk[j][j];
+    if (tid == 0 && blockIdx.x == 0 && (dj == 0.0 || !isfinite(dj))) atomicOr(flags, 8);
+    __syncthreads();
+    // column j: l_ij = a_ij / d_j ; keep y_ij = a_ij in the upper triangle slot for the update below
+    if (tid > j && tid < nb) {
+      const double a = Dk[tid][j];
+      Dk[j][tid] = a;        // y_ij (upper slot)
+      Dk[tid][j] = a / dj;   // l_ij
+    }
+    __syncthreads();
+    // trailing update inside the block: a_im -= l_ij * y_mj for j < m <= i
+    for (int e = tid; e < nb * nb; e += 256) {
+      const int i = e / nb, m = e % nb;
+      if (m > j && i >= m) Dk[i][m] -= Dk[i][j] * Dk[j][m];
+    }
+    __syncthreads();
+  }
+  if (blockIdx.x == 0) {
+    for (int e = tid; e < nb * nb; e += 256) {
+      const int i = e / nb, j = e % nb;
+      if (j <= i) S[(size_t)(k0 + i) * d + k0 + j] = Dk[i][j];
+    }
+  }
+  // rows below the diagonal block: one thread per row
+  const int r = k0 + nb + blockIdx.x * 64 + tid;
+  if (tid < 64 && r < d) {
+    double y[kNB];
+    double* row = S + (size_t)r * d + k0;
+#pragma unroll 4
+    for (int j = 0; j < nb; j++) {
+      double a = row[j];
+      for (int m = 0; m < j; m++) a -= y[m] * Dk[j][m];
+      y[j] = a;
+    }
+    double* w = W + (size_t)r * kNB;
+    for (int j = 0; j < nb; j++) {
+      w[j] = y[j];
+      row[j] = y[j] / Dk[j][j];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_ldlt_update(int d, int k0, int nb, double* __restrict__ S, const double* __restrict__ W) {
+  // lower-triangular tile pair (I >= J) of the trailing matrix starting at k1 = k0 + nb
+  const int k1 = k0 + nb;
+  int pair = blockIdx.x, I = 0;
+  while (pair > I) { pair -= I + 1; I++; }
+  const int J = pair;
+  const int i0 = k1 + I * 64, j0 = k1 + J * 64;
+  __shared__ double Yt[64][kNB + 1];
+  __shared__ double Lt[64][kNB + 1];
+  const int tid = threadIdx.x;
+  for (int e = tid; e < 64 * kNB; e += 256) {
+    const int rr = e / kNB, m = e % kNB;
+    const int gi = i0 + rr, gj = j0 + rr;
+    Yt[rr][m] = (gi < d && m < nb) ? W[(size_t)gi * kNB + m] : 0.0;
+    Lt[rr][m] = (gj < d && m < nb) ? S[(size_t)gj * d + k0 + m] : 0.0;
+  }
+  __syncthreads();
+  const int ti = tid >> 4, tj = tid & 15;
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+#pragma unroll 8
+  for (int m = 0; m < kNB; m++) {
+    double av[4], bv[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) { av[a] = Yt[ti * 4 + a][m]; bv[a] = Lt[tj * 4 + a][m]; }
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) acc[a][b] += av[a] * bv[b];
+  }
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      const int gi = i0 + ti * 4 + a, gj = j0 + tj * 4 + b;
+      if (gi < d && gj <= gi) S[(size_t)gi * d + gj] -= acc[a][b];
+    }
+}
+
+// x <- S^-1 x with S = L D L^T from above (unit lower L below the diagonal, D on the diagonal)
+__global__ void __launch_bounds__(1024) k_ldlt_subst(int d, const double* __restrict__ S, double* __restrict__ x) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ double xb[kNB];
+  // forward: L y = b, blocks of 32 rows
+  for (int k0 = 0; k0 < d; k0 += kNB) {
+    const int nb = min(kNB, d - k0);
+    // dot products with the already solved part: warp w handles row k0 + w
+    if (warp < nb) {
+      const double* row = S + (size_t)(k0 + warp) * d;
+      double s = 0.0;
+      for (int j = lane; j < k0; j += 32) s += row[j] * x[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+      if (lane == 0) xb[warp] = x[k0 + warp] - s;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double v = lane < nb ? xb[lane] : 0.0;
+      for (int j = 0; j < nb; j++) {
+        const double vj = __shfl_sync(0xffffffffu, v, j);
+        if (lane > j && lane < nb) v -= S[(size_t)(k0 + lane) * d + k0 + j] * vj;
+      }
+      if (lane < nb) x[k0 + lane] = v;
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < d; i += blockDim.x) x[i] /= S[(size_t)i * d + i];
+  __syncthreads();
+  // backward: L^T z = y, blocks from the end
+  for (int k0 = ((d - 1) / kNB) * kNB; k0 >= 0; k0 -= kNB) {
+    const int nb = min(kNB, d - k0);
+    if (warp == 0) {
+      double v = lane < nb ? x[k0 + lane] : 0.0;
+      for (int j = nb - 1; j >= 0; j--) {
+        const double vj = __shfl_sync(0xffffffffu, v, j);
+        if (lane < j) v -= S[(size_t)(k0 + j) * d + k0 + lane] * vj;
+      }
+      if (lane < nb) { x[k0 + lane] = v; xb[lane] = v; }
+    }
+    __syncthreads();
+    // x_i -= sum_{k in block} L_ki x_k for i < k0 (row k of L is contiguous in i)
+    for (int i = tid; i < k0; i += blockDim.x) {
+      double s = 0.0;
+      for (int kk = 0; kk < nb; kk++) s += S[(size_t)(k0 + kk) * d + i] * xb[kk];
+      x[i] -= s;
+    }
     __syncthreads();
   }
 }
@@ -446,7 +556,20 @@ int solve_schur(Handle* h, double lambda, int fix) {
                                                          lambda, h->d_S, h->d_rhs);
   EMBA_LAUNCH_CHECK();
   EMBA_CUDA(cudaMemsetAsync(h->d_flags, 0, sizeof(int32_t) * 16, h->stream));
-  k_ldlt_solve<<<1, 1024, 0, h->stream>>>(d, h->d_S, h->d_rhs, h->d_flags);
+  EMBA_TRY(dev_reserve(h, &h->d_ldlt_w, &h->ldlt_w_cap, (int64_t)d * kNB));
+  for (int k0 = 0; k0 < d; k0 += kNB) {
+    const int nb = std::min(kNB, d - k0);
+    const int rows_below = d - (k0 + nb);
+    const int slabs = std::max(1, (rows_below + 63) / 64);
+    k_ldlt_panel<<<slabs, 256, 0, h->stream>>>(d, k0, nb, h->d_S, h->d_ldlt_w, h->d_flags);
+    h->launches++;
+    if (rows_below > 0) {
+      const int nt = (rows_below + 63) / 64;
+      k_ldlt_update<<<nt * (nt + 1) / 2, 256, 0, h->stream>>>(d, k0, nb, h->d_S, h->d_ldlt_w);
+      h->launches++;
+    }
+  }
+  k_ldlt_subst<<<1, 1024, 0, h->stream>>>(d, h->d_S, h->d_rhs);
   EMBA_LAUNCH_CHECK();
   k_expand_x1<<<ceil_div64(3 * n, T), T, 0, h->stream>>>(n, fix, h->d_rhs, h->d_x1);
   EMBA_LAUNCH_CHECK();
