@@ -19,6 +19,7 @@ namespace emba {
 
 PanoCam make_cam(const Handle* h);
 int comm_allreduce(Handle* h, void* buf, int64_t count, int dtype);
+int comm_exchange_strips(Handle* h);
 
 // ---------------------------------------------------------------------------------------------------
 __global__ void k_active_flags(const int32_t* __restrict__ hist, int64_t P, int thres, int32_t* __restrict__ flag) {
@@ -331,7 +332,7 @@ k_pix(int64_t Np, const int32_t* __restrict__ segoff, const uint32_t* __restrict
     const int64_t seg0 = segoff[a];
     const int64_t seg1 = segoff[a + 1];
     const int qlo = winlo[a];
-    const int len = winhi[a] - qlo + 1;
+    const int len = winhi[a] >= qlo ? winhi[a] - qlo + 1 : 0;  // empty window: no local rows (multi-GPU)
     double* gs = strip + stripoff[a] * 6;
     double* sp = (len <= kStripCap) ? s_strip : gs;
     for (int i = lane; i < len * 6; i += 32) sp[i] = 0.0;
@@ -441,6 +442,7 @@ __global__ void k_a12_dense(int64_t Np, int n, const int32_t* __restrict__ winlo
   const int64_t a = blockIdx.x;
   if (a >= Np) return;
   const int lo = winlo[a], hi = winhi[a];
+  if (hi < lo) return;
   const double* sp = strip + stripoff[a] * 6;
   for (int i = threadIdx.x; i < (hi - lo + 1) * 6; i += blockDim.x) {
     const int q = lo + i / 6, rr = (i % 6) >> 1, cc = i & 1;
@@ -534,8 +536,6 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
     // partial (H, g) of the time slices are combined over NVLink
     EMBA_TRYC(comm_allreduce(h, h->d_A11, (int64_t)9 * n * n, 1));
     EMBA_TRYC(comm_allreduce(h, h->d_b1, (int64_t)3 * n, 1));
-    EMBA_TRYC(comm_allreduce(h, h->d_winlo, Np, 2));  // min
-    EMBA_TRYC(comm_allreduce(h, h->d_winhi, Np, 3));  // max
   }
   // ---- 3. map side: pose windows -> strip offsets
   EMBA_CUDAC(cudaMemsetAsync(d_len, 0, sizeof(int64_t) * (Np + 1), h->stream));
@@ -579,10 +579,15 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
     h->launches++;
     EMBA_CUDAC(cudaGetLastError());
   }
+  h->sv_winlo = h->d_winlo; h->sv_winhi = h->d_winhi; h->sv_stripoff = h->d_stripoff; h->sv_strip = h->d_strip;
+  h->sv_strip_total = tot;
   if (h->world > 1 && Np > 0) {
+    // A22 / b2 are small: all-reduce. A12: every rank's strips cover (almost) disjoint pose ranges, so they are not
+    // summed everywhere; each rank becomes the owner of a contiguous range of pixels and receives only the
+    // sub-strips of those pixels (1/world of the volume), see comm.cu
     EMBA_TRYC(comm_allreduce(h, h->d_A22, 3 * Np, 1));
     EMBA_TRYC(comm_allreduce(h, h->d_b2, 2 * Np, 1));
-    EMBA_TRYC(comm_allreduce(h, h->d_strip, tot * 6, 1));
+    EMBA_TRYC(comm_exchange_strips(h));
   }
   EMBA_CUDAC(cudaEventRecord(h->ev[7], h->stream));
   EMBA_CUDAC(cudaStreamSynchronize(h->stream));
@@ -667,7 +672,7 @@ int emba_get_normal_eq(emba_handle_t hh, double* A11, double* b1, double* A22, d
     const int64_t cnt = (int64_t)3 * n * 2 * Np;
     EMBA_TRY(dev_alloc(h, &tmp, cnt));
     cudaMemsetAsync(tmp, 0, sizeof(double) * cnt, h->stream);
-    k_a12_dense<<<(unsigned)Np, 64, 0, h->stream>>>(Np, n, h->d_winlo, h->d_winhi, h->d_stripoff, h->d_strip, tmp);
+    k_a12_dense<<<(unsigned)Np, 64, 0, h->stream>>>(Np, n, h->sv_winlo, h->sv_winhi, h->sv_stripoff, h->sv_strip, tmp);
     h->launches++;
     cudaError_t e = cudaMemcpyAsync(A12_dense, tmp, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->stream);
     cudaStreamSynchronize(h->stream);
@@ -680,7 +685,7 @@ int emba_get_normal_eq(emba_handle_t hh, double* A11, double* b1, double* A22, d
 int emba_a12_entries(emba_handle_t hh, int64_t* out) {
   Handle* h = (Handle*)hh;
   if (!h || !out) return EMBA_E_ARG;
-  *out = h->formed ? h->strip_total * 6 : 0;
+  *out = h->formed ? h->sv_strip_total * 6 : 0;
   return EMBA_OK;
 }
 

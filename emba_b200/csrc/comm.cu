@@ -2,6 +2,8 @@
 // num_ev_map histogram, the cost scalars, A11/b1, A22/b2 and the A12 strips on the handle's stream. NCCL is
 // loaded lazily (dlopen) so that the library has no hard dependency on it for single-GPU use.
 #include <dlfcn.h>
+#include <climits>
+#include <vector>
 
 #include <cstring>
 
@@ -13,6 +15,9 @@ typedef struct { char internal[128]; } nccl_uid_t;
 typedef int (*fn_get_uid)(nccl_uid_t*);
 typedef int (*fn_init_rank)(void**, int, nccl_uid_t, int);
 typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_allgather)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef int (*fn_sendrecv)(void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_group)(void);
 typedef int (*fn_destroy)(void*);
 typedef const char* (*fn_errstr)(int);
 
@@ -21,6 +26,11 @@ struct NcclApi {
   fn_get_uid get_uid = nullptr;
   fn_init_rank init_rank = nullptr;
   fn_allreduce allreduce = nullptr;
+  fn_allgather allgather = nullptr;
+  fn_sendrecv send = nullptr;
+  fn_sendrecv recv = nullptr;
+  fn_group group_start = nullptr;
+  fn_group group_end = nullptr;
   fn_destroy destroy = nullptr;
   fn_errstr errstr = nullptr;
 };
@@ -37,9 +47,18 @@ static NcclApi* nccl_api() {
   api.get_uid = (fn_get_uid)dlsym(api.lib, "ncclGetUniqueId");
   api.init_rank = (fn_init_rank)dlsym(api.lib, "ncclCommInitRank");
   api.allreduce = (fn_allreduce)dlsym(api.lib, "ncclAllReduce");
+  api.allgather = (fn_allgather)dlsym(api.lib, "ncclAllGather");
+  api.send = (fn_sendrecv)dlsym(api.lib, "ncclSend");
+  api.recv = (fn_sendrecv)dlsym(api.lib, "ncclRecv");
+  api.group_start = (fn_group)dlsym(api.lib, "ncclGroupStart");
+  api.group_end = (fn_group)dlsym(api.lib, "ncclGroupEnd");
   api.destroy = (fn_destroy)dlsym(api.lib, "ncclCommDestroy");
   api.errstr = (fn_errstr)dlsym(api.lib, "ncclGetErrorString");
-  if (!api.get_uid || !api.init_rank || !api.allreduce || !api.destroy) { api.lib = nullptr; return nullptr; }
+  if (!api.get_uid || !api.init_rank || !api.allreduce || !api.destroy || !api.allgather || !api.send || !api.recv ||
+      !api.group_start || !api.group_end) {
+    api.lib = nullptr;
+    return nullptr;
+  }
   return &api;
 }
 
@@ -54,6 +73,162 @@ int comm_allreduce(Handle* h, void* buf, int64_t count, int dtype) {
   const int r = api->allreduce(buf, buf, (size_t)count, ty, op, h->nccl_comm, h->stream);
   if (r != 0) { h->err = std::string("ncclAllReduce: ") + (api->errstr ? api->errstr(r) : "error"); return EMBA_E_NCCL; }
   h->launches++;
+  return EMBA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// A12 exchange for the time-sharded path. Rank r holds, for every active pixel a, the sub-strip of the control
+// poses its own time slice touches (local window [lo_r(a), hi_r(a)]). Rank q owns the contiguous pixel range
+// [Np q / W, Np (q+1) / W). Because local strips are stored in pixel order, the sub-strips destined to q are ONE
+// contiguous chunk of the local strip buffer: the exchange is a plain all-to-all of contiguous chunks
+// (ncclSend/ncclRecv over NVLink), 1/W of the A12 volume per rank, no packing. The owner then merges the W
+// sub-strips of each of its pixels into the strip over the merged window, in rank order (deterministic).
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_pack_win(int64_t Np, const int32_t* __restrict__ lo, const int32_t* __restrict__ hi,
+                           int32_t* __restrict__ out) {
+  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= Np) return;
+  out[2 * a] = lo[a];
+  out[2 * a + 1] = hi[a];
+}
+
+// per source rank s: lengths of the sub-strips of my pixels; merged windows and lengths
+__global__ void k_own_len(int W, int64_t Np, int64_t a0, int64_t n_own, const int32_t* __restrict__ win_all,
+                          int64_t* __restrict__ own_len, int32_t* __restrict__ gwinlo, int32_t* __restrict__ gwinhi,
+                          int64_t* __restrict__ glen) {
+  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a > Np) return;
+  if (a == Np) { glen[Np] = 0; return; }
+  const bool mine = a >= a0 && a < a0 + n_own;
+  int glo = INT_MAX, ghi = -1;
+  if (mine) {
+    for (int s = 0; s < W; s++) {
+      const int lo = win_all[((size_t)s * Np + a) * 2], hi = win_all[((size_t)s * Np + a) * 2 + 1];
+      const int64_t len = hi >= lo ? (int64_t)(hi - lo + 1) : 0;
+      own_len[(size_t)s * (n_own + 1) + (a - a0)] = len;
+      if (len > 0) { glo = min(glo, lo); ghi = max(ghi, hi); }
+    }
+  }
+  gwinlo[a] = glo;
+  gwinhi[a] = ghi;
+  glen[a] = ghi >= glo ? (int64_t)(ghi - glo + 1) : 0;
+}
+
+__global__ void k_zero_tail(int W, int64_t n_own, int64_t* __restrict__ own_len) {
+  const int s = threadIdx.x;
+  if (s < W) own_len[(size_t)s * (n_own + 1) + n_own] = 0;
+}
+
+// one warp per owned pixel: strip over the merged window = sum over source ranks (fixed order) of their sub-strips
+__global__ void k_merge_strips(int W, int64_t Np, int64_t a0, int64_t n_own, const int32_t* __restrict__ win_all,
+                               const int64_t* __restrict__ own_off, const int64_t* __restrict__ recvbase,
+                               const double* __restrict__ recv, const int32_t* __restrict__ gwinlo,
+                               const int64_t* __restrict__ gstripoff, double* __restrict__ gstrip) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= n_own) return;
+  const int64_t a = a0 + i;
+  const int glo = gwinlo[a];
+  const int64_t goff = gstripoff[a];
+  const int64_t glen = gstripoff[a + 1] - goff;
+  for (int64_t e = lane; e < glen * 6; e += 32) {
+    const int pose = glo + (int)(e / 6);
+    double v = 0.0;
+    for (int s = 0; s < W; s++) {
+      const int lo = win_all[((size_t)s * Np + a) * 2], hi = win_all[((size_t)s * Np + a) * 2 + 1];
+      if (pose >= lo && pose <= hi)
+        v += recv[(recvbase[s] + own_off[(size_t)s * (n_own + 1) + i] + (pose - lo)) * 6 + (e % 6)];
+    }
+    gstrip[goff * 6 + e] = v;
+  }
+}
+
+}  // namespace emba
+#include <cub/cub.cuh>
+#include <climits>
+namespace emba {
+
+int comm_exchange_strips(Handle* h) {
+  NcclApi* api = nccl_api();
+  if (!api || !h->nccl_comm) { h->err = "multi-GPU shard without a communicator: call emba_comm_init"; return EMBA_E_NCCL; }
+  const int W = h->world, r = h->rank;
+  const int64_t Np = h->Np;
+  const int T = 256;
+  auto own0 = [&](int q) { return Np * q / W; };
+  const int64_t a0 = own0(r), n_own = own0(r + 1) - a0;
+  EMBA_TRY(dev_reserve(h, &h->d_win_all, &h->win_all_cap, (int64_t)W * Np * 2 + 2 * Np));
+  EMBA_TRY(dev_reserve(h, &h->d_own_len, &h->own_cap, (int64_t)2 * W * (n_own + 1) + 4 * W + 16));
+  if (!h->d_win2) {
+    EMBA_TRY(dev_alloc(h, &h->d_win2, 2 * (h->P + 1)));
+    EMBA_TRY(dev_alloc(h, &h->d_gwinlo, h->P + 1));
+    EMBA_TRY(dev_alloc(h, &h->d_gwinhi, h->P + 1));
+    EMBA_TRY(dev_alloc(h, &h->d_gstripoff, h->P + 2));
+  }
+  int64_t* own_len = h->d_own_len;
+  int64_t* own_off = own_len + (size_t)W * (n_own + 1);
+  int64_t* recvbase_dev = own_off + (size_t)W * (n_own + 1);
+  k_pack_win<<<ceil_div64(Np, T), T, 0, h->stream>>>(Np, h->d_winlo, h->d_winhi, h->d_win2);
+  EMBA_LAUNCH_CHECK();
+  // ncclInt32 = 2
+  int rc = api->allgather(h->d_win2, h->d_win_all, (size_t)Np * 2, 2, h->nccl_comm, h->stream);
+  if (rc != 0) { h->err = "ncclAllGather failed"; return EMBA_E_NCCL; }
+  h->launches++;
+  k_own_len<<<ceil_div64(Np + 1, T), T, 0, h->stream>>>(W, Np, a0, n_own, h->d_win_all, own_len, h->d_gwinlo,
+                                                        h->d_gwinhi, h->d_len);
+  EMBA_LAUNCH_CHECK();
+  k_zero_tail<<<1, 64, 0, h->stream>>>(W, n_own, own_len);
+  EMBA_LAUNCH_CHECK();
+  // scans: per source rank over my pixels; merged strip offsets over all pixels
+  auto scan64 = [&](const int64_t* in, int64_t* out, int64_t count) -> int {
+    size_t tb = 0;
+    EMBA_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, (int)count, h->stream));
+    if (tb > h->cub_tmp_bytes) {
+      if (h->d_cub_tmp) cudaFree(h->d_cub_tmp);
+      h->d_cub_tmp = nullptr; h->cub_tmp_bytes = 0;
+      EMBA_CUDA(cudaMalloc(&h->d_cub_tmp, tb));
+      h->cub_tmp_bytes = tb;
+    }
+    EMBA_CUDA(cub::DeviceScan::ExclusiveSum(h->d_cub_tmp, tb, in, out, (int)count, h->stream));
+    h->launches += 2;
+    return EMBA_OK;
+  };
+  for (int s = 0; s < W; s++) EMBA_TRY(scan64(own_len + (size_t)s * (n_own + 1), own_off + (size_t)s * (n_own + 1), n_own + 1));
+  EMBA_TRY(scan64(h->d_len, h->d_gstripoff, Np + 1));
+  // host needs: recv counts (W), my local strip offsets at the ownership boundaries (W+1), merged total (1)
+  std::vector<int64_t> recv_cnt(W), send_off(W + 1), recvbase(W + 1);
+  int64_t gtot = 0;
+  for (int s = 0; s < W; s++)
+    EMBA_CUDA(cudaMemcpyAsync(&recv_cnt[s], own_off + (size_t)s * (n_own + 1) + n_own, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+  for (int q = 0; q <= W; q++)
+    EMBA_CUDA(cudaMemcpyAsync(&send_off[q], h->d_stripoff + own0(q), sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+  EMBA_CUDA(cudaMemcpyAsync(&gtot, h->d_gstripoff + Np, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+  EMBA_CUDA(cudaStreamSynchronize(h->stream));
+  recvbase[0] = 0;
+  for (int s = 0; s < W; s++) recvbase[s + 1] = recvbase[s] + recv_cnt[s];
+  EMBA_TRY(dev_reserve(h, &h->d_recv, &h->recv_cap, recvbase[W] * 6 + recvbase[W] * 3));
+  EMBA_TRY(dev_reserve(h, &h->d_gstrip, &h->gstrip_cap, gtot * 6 + gtot * 3));
+  EMBA_CUDA(cudaMemcpyAsync(recvbase_dev, recvbase.data(), sizeof(int64_t) * (W + 1), cudaMemcpyHostToDevice, h->stream));
+  // all-to-all of contiguous chunks (ncclFloat64 = 8)
+  if (api->group_start() != 0) { h->err = "ncclGroupStart failed"; return EMBA_E_NCCL; }
+  for (int q = 0; q < W; q++) {
+    if (q == r) continue;
+    const int64_t scount = (send_off[q + 1] - send_off[q]) * 6;
+    const int64_t rcount = recv_cnt[q] * 6;
+    if (scount > 0) rc |= api->send(h->d_strip + send_off[q] * 6, (size_t)scount, 8, q, h->nccl_comm, h->stream);
+    if (rcount > 0) rc |= api->recv(h->d_recv + recvbase[q] * 6, (size_t)rcount, 8, q, h->nccl_comm, h->stream);
+  }
+  if (api->group_end() != 0 || rc != 0) { h->err = "ncclSend/ncclRecv failed"; return EMBA_E_NCCL; }
+  h->launches++;
+  if (recv_cnt[r] > 0)
+    EMBA_CUDA(cudaMemcpyAsync(h->d_recv + recvbase[r] * 6, h->d_strip + send_off[r] * 6, sizeof(double) * recv_cnt[r] * 6,
+                              cudaMemcpyDeviceToDevice, h->stream));
+  if (n_own > 0) {
+    k_merge_strips<<<ceil_div64(n_own * 32, T), T, 0, h->stream>>>(W, Np, a0, n_own, h->d_win_all, own_off, recvbase_dev,
+                                                                  h->d_recv, h->d_gwinlo, h->d_gstripoff, h->d_gstrip);
+    EMBA_LAUNCH_CHECK();
+  }
+  h->sv_winlo = h->d_gwinlo; h->sv_winhi = h->d_gwinhi; h->sv_stripoff = h->d_gstripoff; h->sv_strip = h->d_gstrip;
+  h->sv_strip_total = gtot;
   return EMBA_OK;
 }
 

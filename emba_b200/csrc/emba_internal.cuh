@@ -119,6 +119,27 @@ struct Handle {
   int64_t strip_total = 0;
   double* d_strip = nullptr;    // [strip_total*6] A12, per pixel per pose: 3 rows x 2 cols
   int64_t strip_cap = 0;
+  // solve view of A12: with one GPU it aliases the arrays above; with several GPUs every rank owns a contiguous
+  // range of active pixels and holds their complete strips (merged from all time slices), the other pixels have
+  // empty windows (lo > hi)
+  int32_t* sv_winlo = nullptr;
+  int32_t* sv_winhi = nullptr;
+  int64_t* sv_stripoff = nullptr;
+  double* sv_strip = nullptr;
+  int64_t sv_strip_total = 0;
+  int32_t* d_win2 = nullptr;       // [Np*2] packed local windows
+  int32_t* d_win_all = nullptr;    // [world][Np*2] windows of every rank
+  int64_t win_all_cap = 0;
+  int64_t* d_own_len = nullptr;    // [world][n_own+1] sub-strip lengths of my pixels per source rank
+  int64_t* d_own_off = nullptr;    // [world][n_own+1] exclusive scans of the above
+  int64_t own_cap = 0;
+  int32_t* d_gwinlo = nullptr;     // [Np] merged windows (owned pixels), empty elsewhere
+  int32_t* d_gwinhi = nullptr;
+  int64_t* d_gstripoff = nullptr;  // [Np+1]
+  double* d_gstrip = nullptr;
+  int64_t gstrip_cap = 0;
+  double* d_recv = nullptr;        // received sub-strips, one contiguous chunk per source rank
+  int64_t recv_cap = 0;
   double* d_A22 = nullptr;      // [Np*3] xx, xy, yy
   double* d_b2 = nullptr;       // [Np*2]
   double* d_acc_part = nullptr; // [n_items*91]

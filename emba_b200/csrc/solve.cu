@@ -142,7 +142,8 @@ k_schur_tiles(int64_t Np, int d, int fix, int nt, int Z, const int32_t* __restri
 // S = A11m - sum_z partial tiles (fixed order); rhs = b1 - (...). A11m = A11 + lambda*diag(A11) (model.cpp:728-730).
 __global__ void k_schur_finish(int d, int fix, int n, int nt, int npairs, int Z, const double* __restrict__ Spart,
                                const double* __restrict__ A11, const double* __restrict__ b1, double lambda,
-                               double* __restrict__ S, double* __restrict__ rhs) {
+                               double* __restrict__ S, double* __restrict__ rhs, double* __restrict__ T, int mode) {
+  // mode 0: S = A11m - sum, rhs = b1 - sum (single GPU); mode 1: T = sum only; mode 2: S = A11m - T, rhs = b1 - T
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t total = (int64_t)d * (d + 1);
   if (idx >= total) return;
@@ -156,7 +157,12 @@ __global__ void k_schur_finish(int d, int fix, int n, int nt, int npairs, int Z,
   pair += J - I;
   const int ri = ii % kST, rj = jj % kST;
   double s = 0.0;
-  for (int z = 0; z < Z; z++) s += Spart[((size_t)z * npairs + pair) * (kST * kST) + ri * kST + rj];
+  if (mode == 2) {
+    s = T[idx];
+  } else {
+    for (int z = 0; z < Z; z++) s += Spart[((size_t)z * npairs + pair) * (kST * kST) + ri * kST + rj];
+    if (mode == 1) { T[idx] = s; return; }
+  }
   const int d3 = 3 * n;
   if (j == d) {
     rhs[i] = b1[3 * fix + i] - s;
@@ -330,6 +336,11 @@ __global__ void k_solve_x2(int64_t Np, const int32_t* __restrict__ winlo, const 
   const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= Np) return;
   const int lo = winlo[a], hi = winhi[a];
+  if (hi < lo) {  // pixel owned by another rank (multi-GPU): its owner computes x2, combined by all-reduce
+    x2[2 * a] = 0.0;
+    x2[2 * a + 1] = 0.0;
+    return;
+  }
   const double* sp = strip + stripoff[a] * 6;
   double t0 = 0.0, t1 = 0.0;
   for (int q = lo; q <= hi; q++) {
@@ -394,7 +405,7 @@ k_cg_pix(int64_t Np, int d, int fix, const int32_t* __restrict__ winlo, const in
     const int lo = winlo[a], hi = winhi[a];
     const double* sp = strip + stripoff[a] * 6;
     const double pa = p2[2 * a], pb = p2[2 * a + 1];
-    const int rows = (hi - lo + 1) * 3;
+    const int rows = hi >= lo ? (hi - lo + 1) * 3 : 0;
     double t0 = 0.0, t1 = 0.0;
     for (int rr = threadIdx.x; rr < rows; rr += blockDim.x) {
       const int grow = 3 * (lo - fix) + rr;  // row in the reduced system
@@ -548,13 +559,25 @@ int solve_schur(Handle* h, double lambda, int fix) {
   Z = (int)std::min<int64_t>(Z, std::max<int64_t>(1, (Np + 255) / 256));
   EMBA_TRY(dev_reserve(h, &h->d_Spart, &h->Spart_cap, (int64_t)Z * npairs * kST * kST));
   dim3 grid(npairs, Z);
-  k_schur_tiles<<<grid, 256, 0, h->stream>>>(Np, d, fix, nt, Z, h->d_winlo, h->d_winhi, h->d_stripoff, h->d_strip,
+  k_schur_tiles<<<grid, 256, 0, h->stream>>>(Np, d, fix, nt, Z, h->sv_winlo, h->sv_winhi, h->sv_stripoff, h->sv_strip,
                                              h->d_C, h->d_b2, h->d_Spart);
   EMBA_LAUNCH_CHECK();
   const int64_t tot = (int64_t)d * (d + 1);
-  k_schur_finish<<<ceil_div64(tot, T), T, 0, h->stream>>>(d, fix, n, nt, npairs, Z, h->d_Spart, h->d_A11, h->d_b1,
-                                                         lambda, h->d_S, h->d_rhs);
-  EMBA_LAUNCH_CHECK();
+  if (h->world == 1) {
+    k_schur_finish<<<ceil_div64(tot, T), T, 0, h->stream>>>(d, fix, n, nt, npairs, Z, h->d_Spart, h->d_A11, h->d_b1,
+                                                           lambda, h->d_S, h->d_rhs, nullptr, 0);
+    EMBA_LAUNCH_CHECK();
+  } else {
+    // every rank holds the Schur contributions of the pixels it owns: combine them over NVLink, then apply
+    EMBA_TRY(dev_reserve(h, &h->d_cg, &h->cg_cap, tot));
+    k_schur_finish<<<ceil_div64(tot, T), T, 0, h->stream>>>(d, fix, n, nt, npairs, Z, h->d_Spart, h->d_A11, h->d_b1,
+                                                           lambda, h->d_S, h->d_rhs, h->d_cg, 1);
+    EMBA_LAUNCH_CHECK();
+    EMBA_TRY(comm_allreduce(h, h->d_cg, tot, 1));
+    k_schur_finish<<<ceil_div64(tot, T), T, 0, h->stream>>>(d, fix, n, nt, npairs, Z, h->d_Spart, h->d_A11, h->d_b1,
+                                                           lambda, h->d_S, h->d_rhs, h->d_cg, 2);
+    EMBA_LAUNCH_CHECK();
+  }
   EMBA_CUDA(cudaMemsetAsync(h->d_flags, 0, sizeof(int32_t) * 16, h->stream));
   EMBA_TRY(dev_reserve(h, &h->d_ldlt_w, &h->ldlt_w_cap, (int64_t)d * kNB));
   for (int k0 = 0; k0 < d; k0 += kNB) {
@@ -574,9 +597,10 @@ int solve_schur(Handle* h, double lambda, int fix) {
   k_expand_x1<<<ceil_div64(3 * n, T), T, 0, h->stream>>>(n, fix, h->d_rhs, h->d_x1);
   EMBA_LAUNCH_CHECK();
   if (Np > 0) {
-    k_solve_x2<<<ceil_div64(Np, 128), 128, 0, h->stream>>>(Np, h->d_winlo, h->d_winhi, h->d_stripoff, h->d_strip,
+    k_solve_x2<<<ceil_div64(Np, 128), 128, 0, h->stream>>>(Np, h->sv_winlo, h->sv_winhi, h->sv_stripoff, h->sv_strip,
                                                            h->d_C, h->d_b2, h->d_x1, h->d_x2);
     EMBA_LAUNCH_CHECK();
+    if (h->world > 1) EMBA_TRY(comm_allreduce(h, h->d_x2, 2 * Np, 1));  // owners contribute, the others hold zeros
   }
   int32_t fl = 0;
   EMBA_CUDA(cudaMemcpyAsync(&fl, h->d_flags, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -586,6 +610,10 @@ int solve_schur(Handle* h, double lambda, int fix) {
 }
 
 int solve_pcg(Handle* h, double lambda, int fix, int* iters_out, double* err_out) {
+  if (h->world > 1) {
+    h->err = "the PCG solve is single-GPU in this version; use the Schur solve with several GPUs";
+    return EMBA_E_ARG;
+  }
   const int n = h->n;
   const int d = 3 * (n - fix);
   const int64_t Np = h->Np;

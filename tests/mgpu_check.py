@@ -37,9 +37,17 @@ def main():
         Np = eng.form_normal_eq(5, 0, 1.0, 5.0)
         A11, A12, A22, b1, b2, act = eng.get_normal_eq(True)
         assert np.array_equal(act, ref["active"])
+        # A12 is pixel-sharded: every rank holds the complete columns of the pixels it owns and zeros elsewhere
+        sums = torch.from_numpy(np.concatenate([A12.sum(1), A12.sum(0), [np.sum(A12 * A12)]])).cuda()
+        dist.all_reduce(sums)
+        sums = sums.cpu().numpy()
+        d3 = A12.shape[0]
         for a, b in ((ref["A11"], A11), (ref["b1"], b1), (ref["A22"], A22), (ref["b2"], b2),
-                     (ref["A12_rowsum"], A12.sum(1)), (ref["A12_colsum"], A12.sum(0))):
+                     (ref["A12_rowsum"], sums[:d3]), (ref["A12_colsum"], sums[d3:-1]),
+                     (float(ref["A12_fro"]), np.sqrt(sums[-1]))):
             assert rel(a, b) < 1e-9, rel(a, b)
+        own = np.nonzero(np.abs(A12).sum(0))[0] // 2
+        assert own.size == 0 or (own.min() >= Np * rank // world and own.max() < Np * (rank + 1) // world)
         x1, x2, _, _ = eng.solve(1e-3, False, True)
         assert rel(ref["x1"], x1) < 1e-7 and rel(ref["x2"], x2) < 1e-7
         eng.set_state(0, t0, dt, sc.quat_init, sc.Gx_init, sc.Gy_init)
