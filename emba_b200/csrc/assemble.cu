@@ -112,16 +112,15 @@ k_asm_pose(const WorkItem* __restrict__ items, const MeasRec* __restrict__ rec, 
       double4 Hh = make_double4(0.0, 0.0, 0.0, 0.0);
       int32_t a = -1;  // model.cpp:396-412: outliers and inactive pixels are skipped
       if (pix >= 0) {
-        Hh = H3[pix];
+        Hh = ldg256(H3 + pix);
         a = (int32_t)__double_as_longlong(Hh.w);
       }
       skey[m] = a >= 0 ? (uint32_t)a : invalid_key;
       sval[m] = (uint32_t)m;
       if (a >= 0) {
-        const double2 r0 = reinterpret_cast<const double2*>(rec)[2 * m];
-        const double2 r1 = reinterpret_cast<const double2*>(rec)[2 * m + 1];
-        const double bx = r0.x, by = r0.y, bz = r1.x;
-        const unsigned long long rw = (unsigned long long)__double_as_longlong(r1.y);
+        const double4 r0 = ldg256(rec + m);
+        const double bx = r0.x, by = r0.y, bz = r0.z;
+        const unsigned long long rw = (unsigned long long)__double_as_longlong(r0.w);
         const uint32_t bc = (uint32_t)rw & 0x7FFFFFFFu, bp = (uint32_t)(rw >> 32);
         const double2 dpv = dp_in[m];
         double e = e_in[m];
@@ -131,8 +130,8 @@ k_asm_pose(const WorkItem* __restrict__ items, const MeasRec* __restrict__ rec, 
         const double h1 = g.y + dpv.x * Hh.y + dpv.y * Hh.z;
         double vc[3], vp[3], wc[3], wp[3];
         {
-          const double4 rt = RotTab[bc];
-          const double4 jt = JacTab[bc];
+          const double4 rt = ldg256(RotTab + bc);
+          const double4 jt = ldg256(JacTab + bc);
           double X, Y, Z, M[6];
           rotate_bearing(knot_c, rt.x, rt.y, bx, by, bz, X, Y, Z);
           project_jac(cam, X, Y, Z, M);
@@ -142,8 +141,8 @@ k_asm_pose(const WorkItem* __restrict__ items, const MeasRec* __restrict__ rec, 
           row_times_A(knot_c, jt.x, jt.y, jt.z, vc, wc);
         }
         {
-          const double4 rt = RotTab[bp];
-          const double4 jt = JacTab[bp];
+          const double4 rt = ldg256(RotTab + bp);
+          const double4 jt = ldg256(JacTab + bp);
           double X, Y, Z, M[6];
           rotate_bearing(knot_p, rt.x, rt.y, bx, by, bz, X, Y, Z);
           project_jac(cam, X, Y, Z, M);

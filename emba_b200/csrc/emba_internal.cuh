@@ -19,7 +19,7 @@ constexpr int kRecDoubles = 16;     // Jacobian-row record: Jc[6] Jp[6] e dp[2] 
 constexpr double kSophusEps = 1e-10;  // Sophus::Constants<double>::epsilon()
 
 // static per-measurement record, canonical order (sorted by (cp_c, cp_p), then time of the current event)
-struct __align__(16) MeasRec {
+struct __align__(32) MeasRec {
   double bx, by, bz;  // bearing vector of the sensor pixel (both events of a pair share it): saves a LUT gather
   uint32_t bc_pol;    // batch of the current event | polarity << 31
   uint32_t bp;        // batch of the previous event
@@ -355,6 +355,14 @@ __device__ __forceinline__ void row_times_A(const double* __restrict__ kt, doubl
   w[0] = al * v[0] + be * a0 + ga * b0;
   w[1] = al * v[1] + be * a1 + ga * b1;
   w[2] = al * v[2] + be * a2 + ga * b2;
+}
+
+// 256-bit read-only global load (sm_100: LDG.E.ENL2.256): one instruction per 32-byte table entry / record, half
+// the L1TEX wavefronts of two 128-bit gathers. The address must be 32-byte aligned.
+__device__ __forceinline__ double4 ldg256(const void* p) {
+  double4 r;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
 }
 
 struct PanoCam {

@@ -141,23 +141,22 @@ k_eval(const MeasRec* __restrict__ rec, int64_t Mc, const double* __restrict__ l
   double cost = 0.0;
   double cnt = 0.0;
   for (int64_t m = (int64_t)blockIdx.x * kEvalThreads + threadIdx.x; m < Mc; m += (int64_t)gridDim.x * kEvalThreads) {
-    const double2 r0 = reinterpret_cast<const double2*>(rec)[2 * m];
-    const double2 r1 = reinterpret_cast<const double2*>(rec)[2 * m + 1];
-    const double bx = r0.x, by = r0.y, bz = r1.x;
-    const unsigned long long w = (unsigned long long)__double_as_longlong(r1.y);
+    const double4 r0 = ldg256(rec + m);
+    const double bx = r0.x, by = r0.y, bz = r0.z;
+    const unsigned long long w = (unsigned long long)__double_as_longlong(r0.w);
     const uint32_t bcp = (uint32_t)w, bp = (uint32_t)(w >> 32);
     const uint32_t bc = bcp & 0x7FFFFFFFu;
     const double pol = (bcp >> 31) ? 1.0 : 0.0;
     double pcx, pcy, ppx, ppy;
     {
-      const double4 rt = RotTab[bc];
+      const double4 rt = ldg256(RotTab + bc);
       const int sk = (int)__double_as_longlong(rt.z);
       double X, Y, Z;
       rotate_bearing(Ktab + (size_t)sk * kKnotStride, rt.x, rt.y, bx, by, bz, X, Y, Z);
       project_pm(cam, X, Y, Z, pcx, pcy);
     }
     {
-      const double4 rt = RotTab[bp];
+      const double4 rt = ldg256(RotTab + bp);
       const int sk = (int)__double_as_longlong(rt.z);
       double X, Y, Z;
       rotate_bearing(Ktab + (size_t)sk * kKnotStride, rt.x, rt.y, bx, by, bz, X, Y, Z);
