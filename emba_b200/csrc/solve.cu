@@ -53,7 +53,11 @@ k_schur_tiles(int64_t Np, int d, int fix, int nt, int Z, const int32_t* __restri
   const int pJ0 = rowJ0 / 3 + fix, pJ1 = min(d - 1, rowJ0 + kST - 1) / 3 + fix;
   __shared__ double VI[kSK][kST];
   __shared__ double VJ[kSK][kST];
-  __shared__ int32_t list[256];
+  // per listed pixel: first row of its window in the reduced system, number of rows, strip base, C, C b2
+  __shared__ int32_t m_row0[256], m_rows[256];
+  __shared__ int64_t m_base[256];
+  __shared__ double m_c[256][3], m_t[256][2];
+  __shared__ int32_t wcount[8];
   __shared__ int32_t nlist;
   const int tid = threadIdx.x, ti = tid & 15, tj = tid >> 4;
   double acc[3][3];
@@ -61,64 +65,88 @@ k_schur_tiles(int64_t Np, int d, int fix, int nt, int Z, const int32_t* __restri
   for (int r = 0; r < 3; r++)
 #pragma unroll
     for (int c = 0; c < 3; c++) acc[r][c] = 0.0;
+  // staging roles: 8 pixels x 2 sides x 48 rows = 768 double2 items per step, 3 per thread
+  int s_pl[3], s_side[3], s_rr[3];
+#pragma unroll
+  for (int q = 0; q < 3; q++) {
+    const int e = tid + 256 * q;
+    s_pl[q] = e / (kST * 2);
+    s_side[q] = (e % (kST * 2)) / kST;
+    s_rr[q] = e % kST;
+  }
+  const double2* strip2 = reinterpret_cast<const double2*>(strip);
 
   for (int64_t base = a0; base < a1; base += 256) {
     // compact the pixels of this block of 256 whose window meets both tiles (ballot order -> deterministic)
-    if (tid == 0) nlist = 0;
     __syncthreads();
     const int64_t a = base + tid;
     bool ok = false;
+    int lo = 0, hi = -1;
     if (a < a1) {
-      const int lo = winlo[a], hi = winhi[a];
+      lo = winlo[a]; hi = winhi[a];
       const bool mI = (rowI0 < d) && hi >= pI0 && lo <= pI1;
       const bool mJ = ((rowJ0 < d) && hi >= pJ0 && lo <= pJ1) || Jhas_rhs;
       ok = mI && mJ && hi >= lo;
     }
     const unsigned bal = __ballot_sync(0xffffffffu, ok);
-    __shared__ int32_t wcount[8];
     if ((tid & 31) == 0) wcount[tid >> 5] = __popc(bal);
     __syncthreads();
     int off = 0;
     for (int w = 0; w < (tid >> 5); w++) off += wcount[w];
-    if (ok) list[off + __popc(bal & ((1u << (tid & 31)) - 1))] = (int32_t)(a - base);
+    if (ok) {
+      const int l = off + __popc(bal & ((1u << (tid & 31)) - 1));
+      m_row0[l] = 3 * (lo - fix);
+      m_rows[l] = 3 * (hi - lo + 1);
+      m_base[l] = stripoff[a] * 3;  // in double2 units: 3 rows per pose
+      const double c00 = C[3 * a], c01 = C[3 * a + 1], c11 = C[3 * a + 2];
+      m_c[l][0] = c00; m_c[l][1] = c01; m_c[l][2] = c11;
+      const double bx = b2[2 * a], by = b2[2 * a + 1];
+      m_t[l][0] = c00 * bx + c01 * by;  // C_a b2_a: the right-hand-side "row"
+      m_t[l][1] = c01 * bx + c11 * by;
+    }
     if (tid == 255) nlist = off + __popc(bal);
     __syncthreads();
     const int nl = nlist;
-    for (int l0 = 0; l0 < nl; l0 += kSK / 2) {
-      // stage 8 pixels: thread -> (pixel slot pl = tid / 32, 32 lanes cover 48 rows x {I, J} in 3 passes)
-      for (int e = tid; e < (kSK / 2) * kST * 2; e += 256) {
-        const int pl = e / (kST * 2);
-        const int rem = e % (kST * 2);
-        const int side = rem / kST;  // 0: I rows, 1: J rows
-        const int rr = rem % kST;
-        double u0 = 0.0, u1 = 0.0;
-        if (l0 + pl < nl) {
-          const int64_t ap = base + list[l0 + pl];
-          const int grow = (side ? rowJ0 : rowI0) + rr;
+    // software pipeline: the loads of step l0+8 are in flight while step l0 is multiplied
+    double2 pre[3];
+    auto fetch = [&](int l0) {
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        double2 u = make_double2(0.0, 0.0);
+        const int l = l0 + s_pl[q];
+        if (l < nl) {
+          const int grow = (s_side[q] ? rowJ0 : rowI0) + s_rr[q];
           if (grow < d) {
-            const int pose = grow / 3 + fix, comp = grow % 3;
-            const int lo = winlo[ap], hi = winhi[ap];
-            if (pose >= lo && pose <= hi) {
-              const double* sp = strip + (stripoff[ap] + (pose - lo)) * 6 + comp * 2;
-              u0 = sp[0];
-              u1 = sp[1];
-            }
-            if (side) {  // J side carries C_a: (u0, u1) <- (u0, u1) C_a
-              const double c00 = C[3 * ap], c01 = C[3 * ap + 1], c11 = C[3 * ap + 2];
-              const double t0 = u0 * c00 + u1 * c01, t1 = u0 * c01 + u1 * c11;
-              u0 = t0; u1 = t1;
-            }
-          } else if (grow == d && side) {  // right-hand-side row: C_a b2_a
-            const double c00 = C[3 * ap], c01 = C[3 * ap + 1], c11 = C[3 * ap + 2];
-            const double bx = b2[2 * ap], by = b2[2 * ap + 1];
-            u0 = c00 * bx + c01 * by;
-            u1 = c01 * bx + c11 * by;
+            const int rel = grow - m_row0[l];
+            if (rel >= 0 && rel < m_rows[l]) u = strip2[m_base[l] + rel];
           }
         }
-        if (side) { VJ[2 * pl][rr] = u0; VJ[2 * pl + 1][rr] = u1; }
-        else { VI[2 * pl][rr] = u0; VI[2 * pl + 1][rr] = u1; }
+        pre[q] = u;
+      }
+    };
+    if (nl > 0) fetch(0);
+    for (int l0 = 0; l0 < nl; l0 += kSK / 2) {
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        double2 u = pre[q];
+        const int l = l0 + s_pl[q];
+        if (s_side[q]) {
+          if (l < nl) {
+            const int grow = rowJ0 + s_rr[q];
+            if (grow < d) {  // J side carries C_a: (u0, u1) <- (u0, u1) C_a
+              const double t0 = u.x * m_c[l][0] + u.y * m_c[l][1], t1 = u.x * m_c[l][1] + u.y * m_c[l][2];
+              u.x = t0; u.y = t1;
+            } else if (grow == d) {
+              u.x = m_t[l][0]; u.y = m_t[l][1];
+            }
+          }
+          VJ[2 * s_pl[q]][s_rr[q]] = u.x; VJ[2 * s_pl[q] + 1][s_rr[q]] = u.y;
+        } else {
+          VI[2 * s_pl[q]][s_rr[q]] = u.x; VI[2 * s_pl[q] + 1][s_rr[q]] = u.y;
+        }
       }
       __syncthreads();
+      if (l0 + kSK / 2 < nl) fetch(l0 + kSK / 2);
 #pragma unroll
       for (int k = 0; k < kSK; k++) {
         double av[3], bv[3];
@@ -364,6 +392,7 @@ __global__ void k_expand_x1(int n, int fix, const double* __restrict__ rhs_x, do
 // ---------------------------------------------------------------------------------------------------
 // Jacobi-PCG on [[A11m, A12], [A12^T, A22m]] (model.cpp:794-840). Vectors are laid out [x1 (d) | x2 (2Np)].
 // ---------------------------------------------------------------------------------------------------
+constexpr int kCgChunks = 592;  // 4 CTAs per SM
 // y1 = A11m p1 (+ A12 p2 accumulated by k_cg_a12), one thread per row
 __global__ void k_cg_a11(int d, int fix, int n, const double* __restrict__ A11, double lambda,
                          const double* __restrict__ p, double* __restrict__ y) {
@@ -386,52 +415,58 @@ __global__ void k_cg_a11(int d, int fix, int n, const double* __restrict__ A11, 
   if (threadIdx.x == 0) y[i] = sh[0];
 }
 
-// per pixel: y2_a = U_a^T p1 + A22m_a p2_a ; and the pixel's contribution U_a p2_a to y1, written to a
-// per-pixel-chunk partial buffer part[chunk][d] that k_cg_y1 sums in a fixed order
-constexpr int kCgChunks = 64;
+// SpMV with the strips. One warp per pixel (pixels dealt round-robin to the warps of a CTA inside a contiguous
+// chunk): y2_a = U_a^T p1 + A22m_a p2_a by a warp reduction, and the pixel's contribution U_a p2_a to y1 is added
+// into a per-WARP accumulator in shared memory (lanes own distinct rows, pixels come in a fixed order), so the
+// summation order is fixed: warp accumulators -> CTA partial (fixed order) -> k_cg_y1 (fixed order over chunks).
 __global__ void __launch_bounds__(256)
-k_cg_pix(int64_t Np, int d, int fix, const int32_t* __restrict__ winlo, const int32_t* __restrict__ winhi,
+k_cg_pix(int64_t Np, int d, int fix, int nwarps, const int32_t* __restrict__ winlo, const int32_t* __restrict__ winhi,
          const int64_t* __restrict__ stripoff, const double* __restrict__ strip, const double* __restrict__ A22,
          double lambda, const double* __restrict__ p, double* __restrict__ y, double* __restrict__ part) {
-  extern __shared__ double y1s[];  // [d]
+  extern __shared__ double y1s[];  // [nwarps][d]
   const int chunk = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t a0 = Np * chunk / gridDim.x, a1 = Np * (chunk + 1) / gridDim.x;
-  for (int i = threadIdx.x; i < d; i += blockDim.x) y1s[i] = 0.0;
+  for (int i = threadIdx.x; i < nwarps * d; i += blockDim.x) y1s[i] = 0.0;
   __syncthreads();
   const double* p1 = p;
   const double* p2 = p + d;
-  // sequential over pixels inside the chunk, threads parallel over the strip rows -> fixed summation order
-  for (int64_t a = a0; a < a1; a++) {
-    const int lo = winlo[a], hi = winhi[a];
-    const double* sp = strip + stripoff[a] * 6;
-    const double pa = p2[2 * a], pb = p2[2 * a + 1];
-    const int rows = hi >= lo ? (hi - lo + 1) * 3 : 0;
-    double t0 = 0.0, t1 = 0.0;
-    for (int rr = threadIdx.x; rr < rows; rr += blockDim.x) {
-      const int grow = 3 * (lo - fix) + rr;  // row in the reduced system
-      if (grow < 0) continue;
-      const double u0 = sp[2 * rr], u1 = sp[2 * rr + 1];
-      y1s[grow] += u0 * pa + u1 * pb;
-      const double x = p1[grow];
-      t0 += u0 * x;
-      t1 += u1 * x;
+  if (warp < nwarps) {
+    double* acc = y1s + (size_t)warp * d;
+    for (int64_t a = a0 + warp; a < a1; a += nwarps) {
+      const int lo = winlo[a], hi = winhi[a];
+      const double* sp = strip + stripoff[a] * 6;
+      const double pa = p2[2 * a], pb = p2[2 * a + 1];
+      const int rows = hi >= lo ? (hi - lo + 1) * 3 : 0;
+      double t0 = 0.0, t1 = 0.0;
+      for (int rr = lane; rr < rows; rr += 32) {
+        const int grow = 3 * (lo - fix) + rr;  // row in the reduced system (negative: fixed first pose)
+        if (grow < 0) continue;
+        const double2 u = reinterpret_cast<const double2*>(sp)[rr];
+        acc[grow] += u.x * pa + u.y * pb;
+        const double x = p1[grow];
+        t0 += u.x * x;
+        t1 += u.y * x;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        t0 += __shfl_down_sync(0xffffffffu, t0, o);
+        t1 += __shfl_down_sync(0xffffffffu, t1, o);
+      }
+      if (lane == 0) {
+        const double xx = A22[3 * a], xy = A22[3 * a + 1], yy = A22[3 * a + 2];
+        y[d + 2 * a] = t0 + (xx + lambda * xx) * pa + xy * pb;
+        y[d + 2 * a + 1] = t1 + xy * pa + (yy + lambda * yy) * pb;
+      }
+      __syncwarp();
     }
-    // block reduce (t0, t1)
-    __shared__ double r0[256], r1[256];
-    r0[threadIdx.x] = t0; r1[threadIdx.x] = t1;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-      if (threadIdx.x < o) { r0[threadIdx.x] += r0[threadIdx.x + o]; r1[threadIdx.x] += r1[threadIdx.x + o]; }
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-      const double xx = A22[3 * a], xy = A22[3 * a + 1], yy = A22[3 * a + 2];
-      y[d + 2 * a] = r0[0] + (xx + lambda * xx) * pa + xy * pb;
-      y[d + 2 * a + 1] = r1[0] + xy * pa + (yy + lambda * yy) * pb;
-    }
-    __syncthreads();
   }
-  for (int i = threadIdx.x; i < d; i += blockDim.x) part[(size_t)chunk * d + i] = y1s[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    double s = 0.0;
+    for (int w = 0; w < nwarps; w++) s += y1s[(size_t)w * d + i];
+    part[(size_t)chunk * d + i] = s;
+  }
 }
 
 __global__ void k_cg_y1(int d, int chunks, const double* __restrict__ part, double* __restrict__ y) {
@@ -648,10 +683,11 @@ int solve_pcg(Handle* h, double lambda, int fix, int* iters_out, double* err_out
     k_cg_a11<<<d, 128, 0, h->stream>>>(d, fix, n, h->d_A11, lambda, v, y);
     h->launches++;
     if (Np > 0) {
-      const size_t shm = sizeof(double) * d;
-      if (shm > 40 * 1024) EMBA_CUDA(cudaFuncSetAttribute(k_cg_pix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-      k_cg_pix<<<kCgChunks, 256, shm, h->stream>>>(Np, d, fix, h->d_winlo, h->d_winhi, h->d_stripoff, h->d_strip,
-                                                   h->d_A22, lambda, v, y, ypart);
+      const int nwarps = std::max(1, std::min(8, (int)((48 * 1024) / (sizeof(double) * (size_t)d))));
+      const size_t shm = sizeof(double) * (size_t)d * nwarps;
+      if (shm > 48 * 1024) EMBA_CUDA(cudaFuncSetAttribute(k_cg_pix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+      k_cg_pix<<<kCgChunks, 256, shm, h->stream>>>(Np, d, fix, nwarps, h->sv_winlo, h->sv_winhi, h->sv_stripoff,
+                                                   h->sv_strip, h->d_A22, lambda, v, y, ypart);
       k_cg_y1<<<ceil_div64(d, 128), 128, 0, h->stream>>>(d, kCgChunks, ypart, y);
       h->launches += 2;
     }

@@ -1,0 +1,133 @@
+"""world_size-2 gloo test (CPU) of the time-sharded decomposition the multi-GPU path uses:
+
+  * measurements are partitioned by contiguous control-pose (time) slices; num_ev_map is all-reduced BEFORE the
+    active-pixel decision, the cost is all-reduced;
+  * A11/b1/A22/b2 partials are all-reduced;
+  * A12 is exchanged as per-pixel sub-strips: every rank sends, for the pixels another rank owns, only its own
+    (pose-window) sub-strip; the owner merges them -- no rank ever holds all of A12.
+
+Each rank computes its partial quantities with the numpy oracle restricted to its slice; the combined result must
+equal the unsharded oracle (and therefore the reference golden vectors). This exercises the same collectives the
+CUDA library issues through NCCL, on gloo.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def _worker(rank, world, port, out):
+    from conftest import GoldenScene, load_golden_ref, rel
+    from oracle import emba_oracle as O
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sc, g = GoldenScene("tiny"), load_golden_ref("tiny")
+    orc = O.Oracle(sc.sensor_w, sc.sensor_h, sc.bearing_lut(), sc.pano_w, sc.pano_h, sc.C_th)
+    orc.set_events(sc.x, sc.y, sc.t_ns, sc.pol)
+    t0, dt = O.spline_base_ns(sc.t_beg, sc.dt_knots)
+    n, thres, alpha = sc.n_poses, int(g["thres"]), float(g["alpha"])
+    # full evaluation, then restrict to this rank's slice: canonical order = sorted by (cp_c, cp_p); the slice is a
+    # contiguous range of that order (what rebuild_static() assigns to a rank)
+    orc.evaluate(sc.quat_init, t0, dt, sc.Gx_init, sc.Gy_init, True)
+    st = orc.state
+    # all pairs incl. outliers are sharded in the library; the oracle state only keeps inliers -- same partition rule
+    key = st["cp_c"] * n + st["cp_p"]
+    order = np.argsort(key, kind="stable")
+    M = order.size
+    mine = order[M * rank // world: M * (rank + 1) // world]
+    # (1) histogram + cost all-reduce
+    W, H = sc.pano_w, sc.pano_h
+    hist = torch.from_numpy(np.bincount(st["pix"][mine], minlength=W * H).astype(np.int32))
+    dist.all_reduce(hist)
+    cost = torch.tensor([0.5 * float(st["ep"][mine] @ st["ep"][mine]), float(mine.size)], dtype=torch.float64)
+    dist.all_reduce(cost)
+    assert np.array_equal(hist.numpy().reshape(H, W), g["num_ev_map"])
+    assert abs(cost[0].item() - float(g["cost_data"])) < 1e-11 * float(g["cost_data"]) and int(cost[1]) == g["ep"].size
+    # (2) partial normal equations on the slice with the GLOBAL active set
+    sub = {k: (v[mine] if isinstance(v, np.ndarray) and v.shape[:1] == (M,) else v) for k, v in st.items()}
+    sub["num"] = hist.numpy().reshape(H, W)
+    orc.state = sub
+    A11, A12, A22, b1, b2, act = orc.form_normal_eq(n, thres)
+    assert np.array_equal(act, g["active"])
+    Np = act.size
+    for arr in (A11, A22, b1, b2):
+        t = torch.from_numpy(arr)
+        dist.all_reduce(t)
+    if rank == 0:  # the regulariser is added once
+        A22r, b2r = orc.apply_l2_reg(A22 * 0, b2 * 0, act, alpha, sc.Gx_init, sc.Gy_init)
+    else:
+        A22r, b2r = A22 * 0, b2 * 0
+    ta, tb = torch.from_numpy(A22r), torch.from_numpy(b2r)
+    dist.all_reduce(ta)
+    dist.all_reduce(tb)
+    A22, b2 = A22 + ta.numpy(), b2 + tb.numpy()
+    assert rel(g["A11"], A11) < 1e-11 and rel(g["b1"], b1) < 1e-11
+    assert rel(g["A22"], A22) < 1e-11 and rel(g["b2"], b2) < 1e-11
+    # (3) A12: local pose windows per pixel, sub-strips to the pixel owners, merge
+    A12p = A12.reshape(3 * n, Np, 2)
+    touched = np.abs(A12p).reshape(n, 3, Np, 2).sum((1, 3)) > 0  # [pose, pixel]
+    lo = np.where(touched.any(0), touched.argmax(0), n)
+    hi = np.where(touched.any(0), n - 1 - touched[::-1].argmax(0), -1)
+    own = lambda q: (Np * q // world, Np * (q + 1) // world)
+    send = []
+    for q in range(world):
+        a0, a1 = own(q)
+        send.append([(int(lo[a]), A12p[3 * lo[a]: 3 * (hi[a] + 1), a, :].copy()) if hi[a] >= lo[a] else (n, None)
+                     for a in range(a0, a1)])
+    gathered = [None] * world
+    dist.all_gather_object(gathered, send)  # gloo has no all_to_all: every rank picks the chunks addressed to it
+    a0, a1 = own(rank)
+    owned = np.zeros((3 * n, a1 - a0, 2))
+    for src in range(world):  # merge in rank order (deterministic)
+        for i, (l, blk) in enumerate(gathered[src][rank]):
+            if blk is not None:
+                owned[3 * l: 3 * l + blk.shape[0], i, :] += blk
+    # pose windows of different time slices overlap only at slice boundaries
+    full = np.zeros((3 * n, Np, 2))
+    full[:, a0:a1, :] = owned
+    t = torch.from_numpy(full)
+    dist.all_reduce(t)  # only to compare against the golden sums
+    A12full = t.numpy().reshape(3 * n, 2 * Np)
+    assert rel(g["A12_rowsum"], A12full.sum(1)) < 1e-11 and rel(g["A12_colsum"], A12full.sum(0)) < 1e-11
+    assert abs(np.linalg.norm(A12full) - float(g["A12_fro"])) < 1e-11 * float(g["A12_fro"])
+    # (4) Schur complement from the owners' partial sums, replicated solve, x2 from the owners
+    lam = float(g["lam"])
+    A11m = A11 + lam * np.diag(np.diag(A11))
+    A22m = A22.copy()
+    A22m[:, 0, 0] += lam * A22[:, 0, 0]
+    A22m[:, 1, 1] += lam * A22[:, 1, 1]
+    Cinv = np.linalg.inv(A22m)
+    Wo = np.einsum("rpi,pij->rpj", owned, Cinv[a0:a1])
+    Sp = torch.from_numpy(np.einsum("rpj,spj->rs", Wo, owned))
+    rp = torch.from_numpy(np.einsum("rpj,pj->r", Wo, b2.reshape(Np, 2)[a0:a1]))
+    dist.all_reduce(Sp)
+    dist.all_reduce(rp)
+    S = (A11m - Sp.numpy())[3:, 3:]
+    x1 = np.linalg.solve(S, (b1 - rp.numpy())[3:])
+    x1f = np.concatenate([np.zeros(3), x1])
+    x2 = np.zeros((Np, 2))
+    x2[a0:a1] = np.einsum("pij,pj->pi", Cinv[a0:a1], b2.reshape(Np, 2)[a0:a1] - np.einsum("rpj,r->pj", owned, x1f))
+    t2 = torch.from_numpy(x2)
+    dist.all_reduce(t2)
+    assert rel(g["x1"], x1) < 1e-8 and rel(g["x2"], t2.numpy().reshape(-1)) < 1e-8
+    out[rank] = 1
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_time_sharded_decomposition_world2_gloo():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, 29611, out), nprocs=world, join=True)
+    assert sorted(out.keys()) == [0, 1]
