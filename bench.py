@@ -249,13 +249,14 @@ def main():
     clocks = ClockSampler(local_rank)
     clocks.start()
     l0 = eng.launch_count()
-    dev_ms, k_eval_ms, k_asm_ms, k_map_ms, ev_ms, form_ms = [], [], [], [], [], []
+    dev_ms, k_eval_ms, k_asm_ms, k_map_ms, ev_ms, form_ms, k_pix_ms, k_sort_ms = [], [], [], [], [], [], [], []
     wall = time.perf_counter()
     for _ in range(args.steps):
         cost, M, Np, tm_e, tm_f = one_pass()
         dev_ms.append(tm_e["evaluate"] + tm_f["form"])
         ev_ms.append(tm_e["evaluate"]); form_ms.append(tm_f["form"])
         k_eval_ms.append(tm_e["eval_kernel"]); k_asm_ms.append(tm_f["asm_pose_kernel"]); k_map_ms.append(tm_f["map_side"])
+        k_pix_ms.append(tm_f["pix_kernel"]); k_sort_ms.append(tm_f["sort"])
     sync_all()
     wall = (time.perf_counter() - wall) / args.steps * 1e3
     launches = eng.launch_count() - l0
@@ -320,14 +321,21 @@ def main():
         peak, peak_src = measured_peak()
         nnz12 = eng.a12_entries()
         M_all = M
-        # algorithmic bytes (DESIGN.md "Kernels"): per-kernel figures x units one launch processes
-        b_eval = 44.0 * eng.num_pairs() / world + 20.0 * P + 0.8 * N
-        b_asm = 180.0 * M_all / world + 48.0 * P + 1.6 * N
-        b_map = 132.0 * M_all / world + 8.0 * nnz12 + 40.0 * Np
+        # algorithmic bytes: per-kernel figure x the units one launch processes on one rank
+        b_eval = 60.0 * eng.num_pairs() / world + 20.0 * P + 0.64 * N
+        b_asm = 196.0 * M_all / world + 48.0 * P + 0.64 * N
+        b_pix = 132.0 * M_all / world + 8.0 * nnz12 + 40.0 * Np
         kern = {"k_eval": (float(np.mean(k_eval_ms)), b_eval), "k_asm_pose": (float(np.mean(k_asm_ms)), b_asm),
-                "map_side(sort+k_pix)": (float(np.mean(k_map_ms)), b_map)}
+                "k_pix": (float(np.mean(k_pix_ms)), b_pix)}
         dom = max(kern, key=lambda k: kern[k][0])
         ach = kern[dom][1] / (kern[dom][0] * 1e-3) / 1e9
+        traffic = None
+        try:  # DRAM bytes per launch of the same kernel from the committed ncu --set full capture (profiles/)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if world == 1 and workload in tj:
+                traffic = tj[workload].get(dom)
+        except Exception:
+            traffic = None
         pass_bytes = 28.0 * N + 44.0 * P + 40.0 * Np + 8.0 * nnz12 + 72.0 * n * n + 2.2 * N
         out = {
             "metric": "events/s for residual+Jacobian+H assembly", "value": value, "unit": "events/s",
@@ -346,8 +354,9 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
-                         "kernels_ms": {k: v[0] for k, v in kern.items()},
+                         "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernels_ms": dict({k: v[0] for k, v in kern.items()}, row_sort=float(np.mean(k_sort_ms)),
+                                            map_side_total=float(np.mean(k_map_ms))),
                          "kernels_alg_gbs": {k: v[1] / (v[0] * 1e-3) / 1e9 for k, v in kern.items() if v[0] > 0},
                          "pass_alg_bytes": pass_bytes, "pass_frac": pass_bytes / (ms_step * 1e-3) / 1e9 / peak},
             "breakdown_ms": {"evaluate": float(np.mean(ev_ms)), "form": float(np.mean(form_ms)), "wall_per_step": wall_ms,

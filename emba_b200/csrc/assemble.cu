@@ -547,6 +547,7 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   EMBA_TRYC(dev_reserve(h, &h->d_strip, &h->strip_cap, tot * 6 + tot * 3));  // +50 %: windows drift between iterations
   // stable radix sort of the rows by active pixel index (rows of outliers / inactive pixels carry key Np)
   uint32_t* vs = h->d_sval;
+  EMBA_CUDAC(cudaEventRecord(h->ev[8], h->stream));
   if (Mc > 0) {
     int bits = 1;
     while (bits < 32 && ((uint64_t)Np >> bits)) bits++;
@@ -568,6 +569,7 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   } else {
     EMBA_CUDAC(cudaMemsetAsync(h->d_segoff, 0, sizeof(int32_t) * (Np + 1), h->stream));
   }
+  EMBA_CUDAC(cudaEventRecord(h->ev[9], h->stream));
   if (Np > 0) {
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((Np + kPixWarps - 1) / kPixWarps, (int64_t)h->sm_count * 16));
     const int pix_smem = kPixWarps * kPixSmemPerWarp;
@@ -578,6 +580,7 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
     h->launches++;
     EMBA_CUDAC(cudaGetLastError());
   }
+  EMBA_CUDAC(cudaEventRecord(h->ev[10], h->stream));
   h->sv_winlo = h->d_winlo; h->sv_winhi = h->d_winhi; h->sv_stripoff = h->d_stripoff; h->sv_strip = h->d_strip;
   h->sv_strip_total = tot;
   if (h->world > 1 && Np > 0) {
@@ -594,6 +597,8 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   cudaEventElapsedTime(&ms, h->ev[4], h->ev[7]); h->t_ms[2] = ms;
   cudaEventElapsedTime(&ms, h->ev[5], h->ev[6]); h->t_ms[3] = ms;
   cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]); h->t_ms[4] = ms;
+  cudaEventElapsedTime(&ms, h->ev[9], h->ev[10]); h->t_ms[6] = ms;
+  cudaEventElapsedTime(&ms, h->ev[8], h->ev[9]); h->t_ms[7] = ms;
   cleanup();
 #undef EMBA_TRYC
 #undef EMBA_CUDAC

@@ -162,8 +162,8 @@ struct Handle {
   int solved_fix = 0;
   bool solved = false;
   // timing
-  cudaEvent_t ev[8];
-  double t_ms[6] = {0, 0, 0, 0, 0, 0};
+  cudaEvent_t ev[12];
+  double t_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 #define EMBA_CUDA(call)                                                                     \

@@ -438,10 +438,10 @@ int emba_get_evaluation(emba_handle_t hh, int32_t which, double* ep_out, int32_t
   return EMBA_OK;
 }
 
-int emba_last_timings_ms(emba_handle_t hh, double* out6) {
+int emba_last_timings_ms(emba_handle_t hh, double* out8) {
   Handle* h = (Handle*)hh;
-  if (!h || !out6) return EMBA_E_ARG;
-  for (int i = 0; i < 6; i++) out6[i] = h->t_ms[i];
+  if (!h || !out8) return EMBA_E_ARG;
+  for (int i = 0; i < 8; i++) out8[i] = h->t_ms[i];
   return EMBA_OK;
 }
 int emba_launch_count(emba_handle_t hh, int64_t* out) {

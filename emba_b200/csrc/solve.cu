@@ -8,7 +8,11 @@
 //   rhs = b1   - sum_a U_a C_a b2_a
 // is a block-sparse SYRK: tiles of S are accumulated in registers over the pixels whose window meets the tile.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cooperative_groups.h>
 #include "emba_internal.cuh"
+namespace cg = cooperative_groups;
 
 namespace emba {
 
@@ -34,8 +38,9 @@ __global__ void k_a22_inv(int64_t Np, const double* __restrict__ A22, double lam
 // ---------------------------------------------------------------------------------------------------
 constexpr int kST = 48;
 constexpr int kSK = 16;
+constexpr int kSchurThreads = 128;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kSchurThreads)
 k_schur_tiles(int64_t Np, int d, int fix, int nt, int Z, const int32_t* __restrict__ winlo,
               const int32_t* __restrict__ winhi, const int64_t* __restrict__ stripoff,
               const double* __restrict__ strip, const double* __restrict__ C, const double* __restrict__ b2,
@@ -54,29 +59,31 @@ k_schur_tiles(int64_t Np, int d, int fix, int nt, int Z, const int32_t* __restri
   __shared__ double VI[kSK][kST];
   __shared__ double VJ[kSK][kST];
   // per listed pixel: first row of its window in the reduced system, number of rows, strip base, C, C b2
-  __shared__ int32_t m_row0[256], m_rows[256];
-  __shared__ int64_t m_base[256];
-  __shared__ double m_c[256][3], m_t[256][2];
-  __shared__ int32_t wcount[8];
+  __shared__ int32_t m_row0[kSchurThreads], m_rows[kSchurThreads];
+  __shared__ int64_t m_base[kSchurThreads];
+  __shared__ double m_c[kSchurThreads][3], m_t[kSchurThreads][2];
+  __shared__ int32_t wcount[kSchurThreads / 32];
   __shared__ int32_t nlist;
-  const int tid = threadIdx.x, ti = tid & 15, tj = tid >> 4;
-  double acc[3][3];
+  // 8 x 16 threads, 6 x 3 outputs each: 9 shared-memory loads per 18 FMAs
+  const int tid = threadIdx.x, ti = tid & 7, tj = tid >> 3;
+  double acc[6][3];
 #pragma unroll
-  for (int r = 0; r < 3; r++)
+  for (int r = 0; r < 6; r++)
 #pragma unroll
     for (int c = 0; c < 3; c++) acc[r][c] = 0.0;
-  // staging roles: 8 pixels x 2 sides x 48 rows = 768 double2 items per step, 3 per thread
-  int s_pl[3], s_side[3], s_rr[3];
+  // staging roles: 8 pixels x 2 sides x 48 rows = 768 double2 items per step, 6 per thread
+  constexpr int kStage = (kSK / 2) * kST * 2 / kSchurThreads;
+  int s_pl[kStage], s_side[kStage], s_rr[kStage];
 #pragma unroll
-  for (int q = 0; q < 3; q++) {
-    const int e = tid + 256 * q;
+  for (int q = 0; q < kStage; q++) {
+    const int e = tid + kSchurThreads * q;
     s_pl[q] = e / (kST * 2);
     s_side[q] = (e % (kST * 2)) / kST;
     s_rr[q] = e % kST;
   }
   const double2* strip2 = reinterpret_cast<const double2*>(strip);
 
-  for (int64_t base = a0; base < a1; base += 256) {
+  for (int64_t base = a0; base < a1; base += kSchurThreads) {
     // compact the pixels of this block of 256 whose window meets both tiles (ballot order -> deterministic)
     __syncthreads();
     const int64_t a = base + tid;
@@ -104,14 +111,14 @@ k_schur_tiles(int64_t Np, int d, int fix, int nt, int Z, const int32_t* __restri
       m_t[l][0] = c00 * bx + c01 * by;  // C_a b2_a: the right-hand-side "row"
       m_t[l][1] = c01 * bx + c11 * by;
     }
-    if (tid == 255) nlist = off + __popc(bal);
+    if (tid == kSchurThreads - 1) nlist = off + __popc(bal);
     __syncthreads();
     const int nl = nlist;
     // software pipeline: the loads of step l0+8 are in flight while step l0 is multiplied
-    double2 pre[3];
+    double2 pre[kStage];
     auto fetch = [&](int l0) {
 #pragma unroll
-      for (int q = 0; q < 3; q++) {
+      for (int q = 0; q < kStage; q++) {
         double2 u = make_double2(0.0, 0.0);
         const int l = l0 + s_pl[q];
         if (l < nl) {
@@ -127,7 +134,7 @@ k_schur_tiles(int64_t Np, int d, int fix, int nt, int Z, const int32_t* __restri
     if (nl > 0) fetch(0);
     for (int l0 = 0; l0 < nl; l0 += kSK / 2) {
 #pragma unroll
-      for (int q = 0; q < 3; q++) {
+      for (int q = 0; q < kStage; q++) {
         double2 u = pre[q];
         const int l = l0 + s_pl[q];
         if (s_side[q]) {
@@ -149,11 +156,13 @@ k_schur_tiles(int64_t Np, int d, int fix, int nt, int Z, const int32_t* __restri
       if (l0 + kSK / 2 < nl) fetch(l0 + kSK / 2);
 #pragma unroll
       for (int k = 0; k < kSK; k++) {
-        double av[3], bv[3];
+        double av[6], bv[3];
 #pragma unroll
-        for (int r = 0; r < 3; r++) { av[r] = VI[k][3 * ti + r]; bv[r] = VJ[k][3 * tj + r]; }
+        for (int r = 0; r < 6; r++) av[r] = VI[k][6 * ti + r];
 #pragma unroll
-        for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) bv[c] = VJ[k][3 * tj + c];
+#pragma unroll
+        for (int r = 0; r < 6; r++)
 #pragma unroll
           for (int c = 0; c < 3; c++) acc[r][c] += av[r] * bv[c];
       }
@@ -162,9 +171,9 @@ k_schur_tiles(int64_t Np, int d, int fix, int nt, int Z, const int32_t* __restri
   }
   double* out = Spart + ((size_t)z * gridDim.x + blockIdx.x) * (kST * kST);
 #pragma unroll
-  for (int r = 0; r < 3; r++)
+  for (int r = 0; r < 6; r++)
 #pragma unroll
-    for (int c = 0; c < 3; c++) out[(3 * ti + r) * kST + 3 * tj + c] = acc[r][c];
+    for (int c = 0; c < 3; c++) out[(6 * ti + r) * kST + 3 * tj + c] = acc[r][c];
 }
 
 // S = A11m - sum_z partial tiles (fixed order); rhs = b1 - (...). A11m = A11 + lambda*diag(A11) (model.cpp:728-730).
@@ -210,10 +219,16 @@ __global__ void k_schur_finish(int d, int fix, int n, int nt, int npairs, int Z,
 // Then k_ldlt_subst (one CTA): blocked forward / diagonal / backward substitution.
 constexpr int kNB = 32;
 
-__global__ void __launch_bounds__(256)
-k_ldlt_panel(int d, int k0, int nb, double* __restrict__ S, double* __restrict__ W, int32_t* __restrict__ flags) {
-  __shared__ double Dk[kNB][kNB + 1];
+constexpr int kLdltSmemDoubles = 2 * kNB * (kNB + 1) + 64 * (kNB + 1);  // == 2 * 64 * (kNB + 1)
+
+__device__ __forceinline__ void ldlt_panel_body(int d, int k0, int nb, double* __restrict__ S, double* __restrict__ W,
+                                                int32_t* __restrict__ flags, int slab, int nslab_stride, int nslabs,
+                                                double* __restrict__ sm) {
+  double (*Dk)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(sm);
+  double (*Li)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(sm + kNB * (kNB + 1));
+  double (*As)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(sm + 2 * kNB * (kNB + 1));
   const int tid = threadIdx.x;
+  __syncthreads();
   for (int e = tid; e < nb * nb; e += 256) {
     const int i = e / nb, j = e % nb;
     Dk[i][j] = (j <= i) ? S[(size_t)(k0 + i) * d + k0 + j] : 0.0;
@@ -221,7 +236,7 @@ k_ldlt_panel(int d, int k0, int nb, double* __restrict__ S, double* __restrict__
   __syncthreads();
   for (int j = 0; j < nb; j++) {
     const double dj = Dk[j][j];
-    if (tid == 0 && blockIdx.x == 0 && (dj == 0.0 || !isfinite(dj))) atomicOr(flags, 8);
+    if (tid == 0 && slab == 0 && (dj == 0.0 || !isfinite(dj))) atomicOr(flags, 8);
     __syncthreads();
     // column j: l_ij = a_ij / d_j ; keep y_ij = a_ij in the upper triangle slot for the update below
     if (tid > j && tid < nb) {
@@ -237,42 +252,60 @@ k_ldlt_panel(int d, int k0, int nb, double* __restrict__ S, double* __restrict__
     }
     __syncthreads();
   }
-  if (blockIdx.x == 0) {
+  if (slab == 0) {
     for (int e = tid; e < nb * nb; e += 256) {
       const int i = e / nb, j = e % nb;
       if (j <= i) S[(size_t)(k0 + i) * d + k0 + j] = Dk[i][j];
     }
   }
-  // rows below the diagonal block: one thread per row
-  const int r = k0 + nb + blockIdx.x * 64 + tid;
-  if (tid < 64 && r < d) {
-    double y[kNB];
-    double* row = S + (size_t)r * d + k0;
-#pragma unroll 4
-    for (int j = 0; j < nb; j++) {
-      double a = row[j];
-      for (int m = 0; m < j; m++) a -= y[m] * Dk[j][m];
-      y[j] = a;
+  // rows below the diagonal block: y = a L^-T, i.e. y_j = sum_{m<=j} a_m Linv[j][m] with the explicit inverse of
+  // the unit lower-triangular block (32 x 32, computed in shared memory) -> fully parallel, coalesced row access
+  if (tid < nb) {  // column tid of L^-1 by forward substitution
+    const int j = tid;
+    for (int i = 0; i < nb; i++) Li[i][j] = (i == j) ? 1.0 : 0.0;
+    for (int i = j + 1; i < nb; i++) {
+      double x = 0.0;
+      for (int m = j; m < i; m++) x -= Dk[i][m] * Li[m][j];
+      Li[i][j] = x;
     }
-    double* w = W + (size_t)r * kNB;
-    for (int j = 0; j < nb; j++) {
-      w[j] = y[j];
-      row[j] = y[j] / Dk[j][j];
+  }
+  for (int sl = slab; sl < nslabs; sl += nslab_stride) {
+    const int r0 = k0 + nb + sl * 64;
+    __syncthreads();
+    for (int e = tid; e < 64 * nb; e += 256) {
+      const int rr = e / nb, j = e % nb;
+      As[rr][j] = (r0 + rr < d) ? S[(size_t)(r0 + rr) * d + k0 + j] : 0.0;
+    }
+    __syncthreads();
+    for (int e = tid; e < 64 * nb; e += 256) {
+      const int rr = e / nb, j = e % nb;
+      if (r0 + rr >= d) continue;
+      double y = 0.0;
+      for (int m = 0; m <= j; m++) y += As[rr][m] * Li[j][m];
+      W[(size_t)(r0 + rr) * kNB + j] = y;
+      S[(size_t)(r0 + rr) * d + k0 + j] = y / Dk[j][j];
     }
   }
 }
 
 __global__ void __launch_bounds__(256)
-k_ldlt_update(int d, int k0, int nb, double* __restrict__ S, const double* __restrict__ W) {
+k_ldlt_panel(int d, int k0, int nb, double* __restrict__ S, double* __restrict__ W, int32_t* __restrict__ flags) {
+  __shared__ double sm[kLdltSmemDoubles];
+  ldlt_panel_body(d, k0, nb, S, W, flags, blockIdx.x, gridDim.x, gridDim.x, sm);
+}
+
+__device__ __forceinline__ void ldlt_update_body(int d, int k0, int nb, double* __restrict__ S,
+                                                 const double* __restrict__ W, int pair_in, double* __restrict__ sm) {
   // lower-triangular tile pair (I >= J) of the trailing matrix starting at k1 = k0 + nb
   const int k1 = k0 + nb;
-  int pair = blockIdx.x, I = 0;
+  int pair = pair_in, I = 0;
   while (pair > I) { pair -= I + 1; I++; }
   const int J = pair;
   const int i0 = k1 + I * 64, j0 = k1 + J * 64;
-  __shared__ double Yt[64][kNB + 1];
-  __shared__ double Lt[64][kNB + 1];
+  double (*Yt)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(sm);
+  double (*Lt)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(sm + 64 * (kNB + 1));
   const int tid = threadIdx.x;
+  __syncthreads();
   for (int e = tid; e < 64 * kNB; e += 256) {
     const int rr = e / kNB, m = e % kNB;
     const int gi = i0 + rr, gj = j0 + rr;
@@ -303,6 +336,33 @@ k_ldlt_update(int d, int k0, int nb, double* __restrict__ S, const double* __res
       const int gi = i0 + ti * 4 + a, gj = j0 + tj * 4 + b;
       if (gi < d && gj <= gi) S[(size_t)gi * d + gj] -= acc[a][b];
     }
+}
+
+__global__ void __launch_bounds__(256)
+k_ldlt_update(int d, int k0, int nb, double* __restrict__ S, const double* __restrict__ W) {
+  __shared__ double sm[kLdltSmemDoubles];
+  ldlt_update_body(d, k0, nb, S, W, blockIdx.x, sm);
+}
+
+// The whole factorisation in ONE cooperative launch (grid-wide barriers between the panel and update phases):
+// for the small systems of this path (d = a few hundred) the per-panel launches are latency bound.
+__global__ void __launch_bounds__(256)
+k_ldlt_fused(int d, double* __restrict__ S, double* __restrict__ W, int32_t* __restrict__ flags) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double sm[kLdltSmemDoubles];
+  for (int k0 = 0; k0 < d; k0 += kNB) {
+    const int nb = min(kNB, d - k0);
+    const int rows_below = d - (k0 + nb);
+    const int nslabs = (rows_below + 63) / 64;
+    ldlt_panel_body(d, k0, nb, S, W, flags, blockIdx.x, gridDim.x, nslabs, sm);
+    grid.sync();
+    if (rows_below > 0) {
+      const int ntile = (rows_below + 63) / 64;
+      const int npair = ntile * (ntile + 1) / 2;
+      for (int pr = blockIdx.x; pr < npair; pr += gridDim.x) ldlt_update_body(d, k0, nb, S, W, pr, sm);
+    }
+    grid.sync();
+  }
 }
 
 // x <- S^-1 x with S = L D L^T from above (unit lower L below the diagonal, D on the diagonal)
@@ -583,6 +643,9 @@ static int dot(Handle* h, int64_t n, const double* a, const double* b, double* o
 }
 
 int solve_schur(Handle* h, double lambda, int fix) {
+  static const bool dbg = getenv("EMBA_DEBUG_TIMING") != nullptr;
+  cudaEvent_t de[6];
+  if (dbg) { for (auto& e : de) cudaEventCreate(&e); cudaEventRecord(de[0], h->stream); }
   const int n = h->n;
   const int d = 3 * (n - fix);
   const int64_t Np = h->Np;
@@ -590,14 +653,15 @@ int solve_schur(Handle* h, double lambda, int fix) {
   if (Np > 0) { k_a22_inv<<<ceil_div64(Np, T), T, 0, h->stream>>>(Np, h->d_A22, lambda, h->d_C); EMBA_LAUNCH_CHECK(); }
   const int nt = (d + 1 + kST - 1) / kST;
   const int npairs = nt * (nt + 1) / 2;
-  int Z = std::max(1, (h->sm_count * 4) / npairs);
-  Z = (int)std::min<int64_t>(Z, std::max<int64_t>(1, (Np + 255) / 256));
+  int Z = std::max(1, (h->sm_count * 8) / npairs);
+  Z = (int)std::min<int64_t>(Z, std::max<int64_t>(1, (Np + kSchurThreads - 1) / kSchurThreads));
   EMBA_TRY(dev_reserve(h, &h->d_Spart, &h->Spart_cap, (int64_t)Z * npairs * kST * kST));
   dim3 grid(npairs, Z);
-  k_schur_tiles<<<grid, 256, 0, h->stream>>>(Np, d, fix, nt, Z, h->sv_winlo, h->sv_winhi, h->sv_stripoff, h->sv_strip,
+  k_schur_tiles<<<grid, kSchurThreads, 0, h->stream>>>(Np, d, fix, nt, Z, h->sv_winlo, h->sv_winhi, h->sv_stripoff, h->sv_strip,
                                              h->d_C, h->d_b2, h->d_Spart);
   EMBA_LAUNCH_CHECK();
   const int64_t tot = (int64_t)d * (d + 1);
+  if (dbg) cudaEventRecord(de[1], h->stream);
   if (h->world == 1) {
     k_schur_finish<<<ceil_div64(tot, T), T, 0, h->stream>>>(d, fix, n, nt, npairs, Z, h->d_Spart, h->d_A11, h->d_b1,
                                                            lambda, h->d_S, h->d_rhs, nullptr, 0);
@@ -613,22 +677,40 @@ int solve_schur(Handle* h, double lambda, int fix) {
                                                            lambda, h->d_S, h->d_rhs, h->d_cg, 2);
     EMBA_LAUNCH_CHECK();
   }
+  if (dbg) cudaEventRecord(de[2], h->stream);
   EMBA_CUDA(cudaMemsetAsync(h->d_flags, 0, sizeof(int32_t) * 16, h->stream));
   EMBA_TRY(dev_reserve(h, &h->d_ldlt_w, &h->ldlt_w_cap, (int64_t)d * kNB));
-  for (int k0 = 0; k0 < d; k0 += kNB) {
-    const int nb = std::min(kNB, d - k0);
-    const int rows_below = d - (k0 + nb);
-    const int slabs = std::max(1, (rows_below + 63) / 64);
-    k_ldlt_panel<<<slabs, 256, 0, h->stream>>>(d, k0, nb, h->d_S, h->d_ldlt_w, h->d_flags);
+  if (d <= 1536) {
+    // small system: one cooperative launch, grid barriers instead of 2 launches per panel
+    int per_sm = 0;
+    EMBA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ldlt_fused, 256, 0));
+    const int ntile0 = (d + 63) / 64;
+    int grid_f = std::min(h->sm_count * std::max(1, per_sm), std::max(1, ntile0 * (ntile0 + 1) / 2));
+    int dd = d;
+    double* Sp = h->d_S;
+    double* Wp = h->d_ldlt_w;
+    int32_t* fp = h->d_flags;
+    void* args[] = {&dd, &Sp, &Wp, &fp};
+    EMBA_CUDA(cudaLaunchCooperativeKernel((void*)k_ldlt_fused, dim3(grid_f), dim3(256), args, 0, h->stream));
     h->launches++;
-    if (rows_below > 0) {
-      const int nt = (rows_below + 63) / 64;
-      k_ldlt_update<<<nt * (nt + 1) / 2, 256, 0, h->stream>>>(d, k0, nb, h->d_S, h->d_ldlt_w);
+  } else {
+    for (int k0 = 0; k0 < d; k0 += kNB) {
+      const int nb = std::min(kNB, d - k0);
+      const int rows_below = d - (k0 + nb);
+      const int slabs = std::max(1, (rows_below + 63) / 64);
+      k_ldlt_panel<<<slabs, 256, 0, h->stream>>>(d, k0, nb, h->d_S, h->d_ldlt_w, h->d_flags);
       h->launches++;
+      if (rows_below > 0) {
+        const int nt = (rows_below + 63) / 64;
+        k_ldlt_update<<<nt * (nt + 1) / 2, 256, 0, h->stream>>>(d, k0, nb, h->d_S, h->d_ldlt_w);
+        h->launches++;
+      }
     }
   }
+  if (dbg) cudaEventRecord(de[3], h->stream);
   k_ldlt_subst<<<1, 1024, 0, h->stream>>>(d, h->d_S, h->d_rhs);
   EMBA_LAUNCH_CHECK();
+  if (dbg) cudaEventRecord(de[4], h->stream);
   k_expand_x1<<<ceil_div64(3 * n, T), T, 0, h->stream>>>(n, fix, h->d_rhs, h->d_x1);
   EMBA_LAUNCH_CHECK();
   if (Np > 0) {
@@ -638,8 +720,16 @@ int solve_schur(Handle* h, double lambda, int fix) {
     if (h->world > 1) EMBA_TRY(comm_allreduce(h, h->d_x2, 2 * Np, 1));  // owners contribute, the others hold zeros
   }
   int32_t fl = 0;
+  if (dbg) cudaEventRecord(de[5], h->stream);
   EMBA_CUDA(cudaMemcpyAsync(&fl, h->d_flags, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   EMBA_CUDA(cudaStreamSynchronize(h->stream));
+  if (dbg) {
+    float a, b, c, e2, f;
+    cudaEventElapsedTime(&a, de[0], de[1]); cudaEventElapsedTime(&b, de[1], de[2]); cudaEventElapsedTime(&c, de[2], de[3]);
+    cudaEventElapsedTime(&e2, de[3], de[4]); cudaEventElapsedTime(&f, de[4], de[5]);
+    fprintf(stderr, "[emba solve] d=%d a22inv+tiles %.3f finish %.3f ldlt %.3f subst %.3f x2 %.3f ms\n", d, a, b, c, e2, f);
+    for (auto& e : de) cudaEventDestroy(e);
+  }
   if (fl & 8) { h->err = "zero or non-finite pivot in the LDL^T factorisation of the Schur complement"; return EMBA_E_NUMERIC; }
   return EMBA_OK;
 }

@@ -170,10 +170,10 @@ class Engine:
         return rows, fc.value
 
     def timings_ms(self):
-        out = np.zeros(6)
+        out = np.zeros(8)
         self._chk(self.L.emba_last_timings_ms(self.h, ptr(out)))
         return dict(evaluate=out[0], eval_kernel=out[1], form=out[2], asm_pose_kernel=out[3], map_side=out[4],
-                    solve=out[5])
+                    solve=out[5], pix_kernel=out[6], sort=out[7])
 
     def launch_count(self):
         v = C.c_int64(0)

@@ -164,10 +164,11 @@ EMBA_API int emba_solve_time_window(emba_handle_t h, const emba_lm_settings_t* s
                            int32_t* n_log, double* final_cost);
 
 /* ---- measurement hooks used by bench.py (CUDA events on the handle's stream) */
-/* elapsed device time of the kernels launched by the last emba_evaluate / emba_form_normal_eq / emba_solve, ms:
- * out[0]=evaluate total, out[1]=per-measurement residual kernel, out[2]=form total, out[3]=pose-block assembly
- * kernel, out[4]=map-block assembly kernel, out[5]=solve total */
-EMBA_API int emba_last_timings_ms(emba_handle_t h, double* out6);
+/* elapsed device time (CUDA events on the handle's stream) of the last emba_evaluate / emba_form_normal_eq /
+ * emba_solve, ms: out[0]=evaluate total, out[1]=per-measurement residual kernel (k_eval), out[2]=form total,
+ * out[3]=pose-block assembly kernel (k_asm_pose), out[4]=map side total (sort + segments + k_pix + exchange),
+ * out[5]=solve total, out[6]=map-block assembly kernel alone (k_pix), out[7]=row sort alone */
+EMBA_API int emba_last_timings_ms(emba_handle_t h, double* out8);
 /* number of kernel launches issued by this handle so far */
 EMBA_API int emba_launch_count(emba_handle_t h, int64_t* out);
 EMBA_API int emba_synchronize(emba_handle_t h);
