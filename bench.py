@@ -261,6 +261,7 @@ def main():
     wall = (time.perf_counter() - wall) / args.steps * 1e3
     launches = eng.launch_count() - l0
     clk = clocks.stop()
+    nnz12_local = eng.a12_entries()
     ms_dev = float(np.mean(dev_ms))
     t_red = torch.tensor([ms_dev, wall], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -319,7 +320,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        nnz12 = eng.a12_entries()
+        nnz12 = nnz12_local * world  # every rank owns 1/world of the pixels
         M_all = M
         # algorithmic bytes: per-kernel figure x the units one launch processes on one rank
         b_eval = 60.0 * eng.num_pairs() / world + 20.0 * P + 0.64 * N

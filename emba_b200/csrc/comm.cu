@@ -2,6 +2,8 @@
 // num_ev_map histogram, the cost scalars, A11/b1, A22/b2 and the A12 strips on the handle's stream. NCCL is
 // loaded lazily (dlopen) so that the library has no hard dependency on it for single-GPU use.
 #include <dlfcn.h>
+#include <cstdio>
+#include <cstdlib>
 #include <climits>
 #include <vector>
 
@@ -154,6 +156,9 @@ int comm_exchange_strips(Handle* h) {
   const int W = h->world, r = h->rank;
   const int64_t Np = h->Np;
   const int T = 256;
+  static const bool dbg = getenv("EMBA_DEBUG_TIMING") != nullptr;
+  cudaEvent_t de[5];
+  if (dbg) { for (auto& e : de) cudaEventCreate(&e); cudaEventRecord(de[0], h->stream); }
   auto own0 = [&](int q) { return Np * q / W; };
   const int64_t a0 = own0(r), n_own = own0(r + 1) - a0;
   EMBA_TRY(dev_reserve(h, &h->d_win_all, &h->win_all_cap, (int64_t)W * Np * 2 + 2 * Np));
@@ -194,6 +199,7 @@ int comm_exchange_strips(Handle* h) {
   };
   for (int s = 0; s < W; s++) EMBA_TRY(scan64(own_len + (size_t)s * (n_own + 1), own_off + (size_t)s * (n_own + 1), n_own + 1));
   EMBA_TRY(scan64(h->d_len, h->d_gstripoff, Np + 1));
+  if (dbg) cudaEventRecord(de[1], h->stream);
   // host needs: recv counts (W), my local strip offsets at the ownership boundaries (W+1), merged total (1)
   std::vector<int64_t> recv_cnt(W), send_off(W + 1), recvbase(W + 1);
   int64_t gtot = 0;
@@ -208,6 +214,7 @@ int comm_exchange_strips(Handle* h) {
   EMBA_TRY(dev_reserve(h, &h->d_recv, &h->recv_cap, recvbase[W] * 6 + recvbase[W] * 3));
   EMBA_TRY(dev_reserve(h, &h->d_gstrip, &h->gstrip_cap, gtot * 6 + gtot * 3));
   EMBA_CUDA(cudaMemcpyAsync(recvbase_dev, recvbase.data(), sizeof(int64_t) * (W + 1), cudaMemcpyHostToDevice, h->stream));
+  if (dbg) cudaEventRecord(de[2], h->stream);
   // all-to-all of contiguous chunks (ncclFloat64 = 8)
   if (api->group_start() != 0) { h->err = "ncclGroupStart failed"; return EMBA_E_NCCL; }
   for (int q = 0; q < W; q++) {
@@ -222,10 +229,21 @@ int comm_exchange_strips(Handle* h) {
   if (recv_cnt[r] > 0)
     EMBA_CUDA(cudaMemcpyAsync(h->d_recv + recvbase[r] * 6, h->d_strip + send_off[r] * 6, sizeof(double) * recv_cnt[r] * 6,
                               cudaMemcpyDeviceToDevice, h->stream));
+  if (dbg) cudaEventRecord(de[3], h->stream);
   if (n_own > 0) {
     k_merge_strips<<<ceil_div64(n_own * 32, T), T, 0, h->stream>>>(W, Np, a0, n_own, h->d_win_all, own_off, recvbase_dev,
                                                                   h->d_recv, h->d_gwinlo, h->d_gstripoff, h->d_gstrip);
     EMBA_LAUNCH_CHECK();
+  }
+  if (dbg) {
+    cudaEventRecord(de[4], h->stream);
+    cudaStreamSynchronize(h->stream);
+    float a, b, c, d2;
+    cudaEventElapsedTime(&a, de[0], de[1]); cudaEventElapsedTime(&b, de[1], de[2]); cudaEventElapsedTime(&c, de[2], de[3]);
+    cudaEventElapsedTime(&d2, de[3], de[4]);
+    if (r == 0) fprintf(stderr, "[emba exchange] windows+scans %.3f host-roundtrip %.3f send/recv %.3f merge %.3f ms (recv %.1f MB)\n",
+                        a, b, c, d2, recvbase[W] * 48.0 / 1e6);
+    for (auto& e : de) cudaEventDestroy(e);
   }
   h->sv_winlo = h->d_gwinlo; h->sv_winhi = h->d_gwinhi; h->sv_stripoff = h->d_gstripoff; h->sv_strip = h->d_gstrip;
   h->sv_strip_total = gtot;

@@ -3,6 +3,8 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include "emba_internal.cuh"
 
 namespace emba {
@@ -316,8 +318,17 @@ int evaluate_slot(Handle* h, int slot, int cost_type, double eta, double alpha) 
   EMBA_LAUNCH_CHECK();
   if (h->world > 1) {
     // the active-pixel decision is global: combine the histogram and the scalars
+    static const bool dbg = getenv("EMBA_DEBUG_TIMING") != nullptr;
+    cudaEvent_t d0, d1;
+    if (dbg) { cudaEventCreate(&d0); cudaEventCreate(&d1); cudaEventRecord(d0, h->stream); }
     EMBA_TRY(comm_allreduce(h, s.hist, h->P, 0));
     EMBA_TRY(comm_allreduce(h, h->d_scal, 2, 1));
+    if (dbg) {
+      cudaEventRecord(d1, h->stream); cudaStreamSynchronize(h->stream);
+      float ms; cudaEventElapsedTime(&ms, d0, d1);
+      if (h->rank == 0) fprintf(stderr, "[emba evaluate] hist+scalar all-reduce %.3f ms\n", ms);
+      cudaEventDestroy(d0); cudaEventDestroy(d1);
+    }
   }
   EMBA_CUDA(cudaEventRecord(h->ev[3], h->stream));
   double sc[3];

@@ -311,10 +311,10 @@ CONFIGS = {
                dt_knots=0.05, texture_std=1.25),
     # C3: shapes.launch-style, 2048x1024, t in [1,11], n=201, ~30M events
     "C3": dict(sensor_w=240, sensor_h=180, fx=200.0, pano_w=2048, pano_h=1024, C_th=0.2, t_beg=1.0, t_end=11.0,
-               dt_knots=0.05, texture_std=1.9),
+               dt_knots=0.05, texture_std=1.9, periodic=True),
     # C4: as C3 with ~100M events
     "C4": dict(sensor_w=240, sensor_h=180, fx=200.0, pano_w=2048, pano_h=1024, C_th=0.2, t_beg=1.0, t_end=11.0,
-               dt_knots=0.05, texture_std=6.3),
+               dt_knots=0.05, texture_std=6.3, periodic=True),
 }
 
 

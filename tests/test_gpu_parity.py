@@ -237,3 +237,71 @@ def test_empty_and_ragged_events(tiny):
         res.append(eng.evaluate(0, 0, 1.0, ALPHA))
     assert res[0] == res[1]
     eng.close()
+
+
+def test_lm_variants_vs_oracle(tiny):
+    """LM with the robust (Huber) IRLS cost and LM with the PCG solver, against the numpy oracle's LM loop."""
+    from oracle import emba_oracle as O
+
+    sc = tiny
+    t0, dt = _base(sc)
+    orc = _oracle(sc)
+    eng = _engine(sc)
+    for kw_o, kw_e in ((dict(irls_type=2, eta=0.3), dict(cost_type=2, eta=0.3)),
+                       (dict(use_cg=True), dict(use_cg=True))):
+        q_o, gx_o, gy_o, log_o = orc.solve_time_window(sc.quat_init, t0, dt, sc.Gx_init, sc.Gy_init, max_num_iter=6,
+                                                       alpha=ALPHA, thres=THRES, **kw_o)
+        eng.set_state(0, t0, dt, sc.quat_init, sc.Gx_init, sc.Gy_init)
+        log, fc = eng.solve_time_window(max_num_iter=6, alpha=ALPHA, thres=THRES, **kw_e)
+        assert log.shape[0] == log_o.shape[0]
+        assert np.array_equal(log[:, 4], log_o[:, 4])
+        assert np.max(np.abs(log[:, 3] - log_o[:, 3]) / log_o[:, 3]) < 1e-6
+        q, gx, gy = eng.get_state(0)
+        ang = 2 * np.arccos(np.abs(np.sum(q * q_o, -1)).clip(0, 1))
+        assert np.max(ang) < 1e-5 and rel(gx_o, gx) < 1e-4 and rel(gy_o, gy) < 1e-4
+    eng.close()
+
+
+def test_thresholds_and_window_reuse(tiny):
+    """Other active-pixel thresholds (incl. one that leaves no active pixel), no gauge fixing, and re-using one
+    handle for a second event window."""
+    sc = tiny
+    t0, dt = _base(sc)
+    orc = _oracle(sc)
+    eng = _engine(sc)
+    eng.set_state(0, t0, dt, sc.quat_init, sc.Gx_init, sc.Gy_init)
+    orc.evaluate(sc.quat_init, t0, dt, sc.Gx_init, sc.Gy_init, True)
+    for thres in (1, 2, 40):
+        eng.evaluate(0, 0, 1.0, ALPHA)
+        Np = eng.form_normal_eq(thres, 0, 1.0, 0.0)
+        B11, B12, B22, c1, c2, act = orc.form_normal_eq(sc.n_poses, thres)
+        A11, A12, A22, b1, b2, a = eng.get_normal_eq(True)
+        assert Np == act.size and np.array_equal(a, act)
+        assert rel(B11, A11) < 1e-9 and rel(B12, A12) < 1e-9 and rel(B22, A22) < 1e-9 and rel(c2, b2) < 1e-9
+    eng.evaluate(0, 0, 1.0, ALPHA)
+    assert eng.form_normal_eq(10**6, 0, 1.0, ALPHA) == 0  # no active pixel: only the pose block is formed
+    A11, _, _, b1, _, _ = eng.get_normal_eq(False)
+    assert np.all(A11 == 0) and np.all(b1 == 0)
+    # second window on the same handle: the first half of the events
+    half = (sc.x.size // 200) * 100
+    eng.set_events(sc.x[:half], sc.y[:half], sc.t_ns[:half], sc.pol[:half])
+    eng.set_state(0, t0, dt, sc.quat_init, sc.Gx_init, sc.Gy_init)
+    cd, _, M = eng.evaluate(0, 0, 1.0, ALPHA)
+    orc2 = _oracle(sc)
+    orc2.set_events(sc.x[:half], sc.y[:half], sc.t_ns[:half], sc.pol[:half])
+    ep2, _ = orc2.evaluate(sc.quat_init, t0, dt, sc.Gx_init, sc.Gy_init, False)
+    assert M == ep2.size and abs(cd - 0.5 * ep2 @ ep2) < 1e-10 * cd
+    eng.close()
+
+
+def test_bad_events_are_rejected(tiny):
+    from emba_b200.capi import EmbaError
+    from emba_b200.legm import Engine
+
+    sc = tiny
+    eng = Engine(sc.sensor_w, sc.sensor_h, sc.bearing_lut(), sc.C_th, sc.pano_w, sc.pano_h)
+    x = sc.x[:1000].copy()
+    x[17] = sc.sensor_w  # outside the sensor: the reference would index its EventMap out of bounds
+    with pytest.raises(EmbaError):
+        eng.set_events(x, sc.y[:1000], sc.t_ns[:1000], sc.pol[:1000])
+    eng.close()
