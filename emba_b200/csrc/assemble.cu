@@ -77,11 +77,11 @@ __device__ __forceinline__ void tri_tile(double (&a)[25], const double (*tile)[k
 
 template <int COST>
 __global__ void __launch_bounds__(kAsmThreads, 2)
-k_asm_pose(const WorkItem* __restrict__ items, const MeasRec* __restrict__ rec, const double* __restrict__ lut,
+k_asm_pose(const WorkItem* __restrict__ items, const MeasRec* __restrict__ rec,
            const double* __restrict__ Ktab, const double4* __restrict__ RotTab, const double4* __restrict__ JacTab,
            const double2* __restrict__ G2,
            const double4* __restrict__ H3, const double2* __restrict__ dp_in, const double* __restrict__ e_in,
-           const int32_t* __restrict__ pix_in, const int32_t* __restrict__ amap, PanoCam cam, double eta,
+           const int32_t* __restrict__ pix_in, PanoCam cam, double eta,
            uint32_t invalid_key, double* __restrict__ jrec, uint32_t* __restrict__ skey, uint32_t* __restrict__ sval,
            int32_t* __restrict__ winlo, int32_t* __restrict__ winhi, double* __restrict__ acc_part) {
   // rows 0..11: Jc, Jp; 12: e; 13,14: dp; 15: meta  (row-major [field][measurement], padded against conflicts)
@@ -507,9 +507,9 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   EMBA_CUDAC(cudaEventRecord(h->ev[5], h->stream));
   if (h->n_items > 0) {
 #define EMBA_ASM_LAUNCH(C)                                                                                         \
-  k_asm_pose<C><<<h->n_items, kAsmThreads, 0, h->stream>>>(h->d_items, h->d_rec, h->d_lut, s.Ktab, s.RotTab,      \
+  k_asm_pose<C><<<h->n_items, kAsmThreads, 0, h->stream>>>(h->d_items, h->d_rec, s.Ktab, s.RotTab,                \
                                                            s.JacTab, s.G2,                                        \
-                                                           s.H3, s.dp, s.e, s.pix, h->d_amap, cam, eta,            \
+                                                           s.H3, s.dp, s.e, s.pix, cam, eta,                       \
                                                            (uint32_t)Np, h->d_jrec, h->d_skey, h->d_sval,          \
                                                            h->d_winlo, h->d_winhi, h->d_acc_part)
     if (cost_type == EMBA_COST_QUADRATIC) EMBA_ASM_LAUNCH(EMBA_COST_QUADRATIC);

@@ -212,27 +212,6 @@ inline int ceil_div64(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 struct Vec3 { double x, y, z; };
 struct Mat3 { double m[9]; };  // row-major
 
-__device__ __forceinline__ Mat3 mat_mul(const Mat3& a, const Mat3& b) {
-  Mat3 c;
-#pragma unroll
-  for (int i = 0; i < 3; i++)
-#pragma unroll
-    for (int j = 0; j < 3; j++) c.m[3 * i + j] = a.m[3 * i] * b.m[j] + a.m[3 * i + 1] * b.m[3 + j] + a.m[3 * i + 2] * b.m[6 + j];
-  return c;
-}
-__device__ __forceinline__ Mat3 mat_T(const Mat3& a) {
-  Mat3 c;
-#pragma unroll
-  for (int i = 0; i < 3; i++)
-#pragma unroll
-    for (int j = 0; j < 3; j++) c.m[3 * i + j] = a.m[3 * j + i];
-  return c;
-}
-__device__ __forceinline__ Mat3 hat(const Vec3& v) {
-  Mat3 c = {{0, -v.z, v.y, v.z, 0, -v.x, -v.y, v.x, 0}};
-  return c;
-}
-
 // Hamilton product, xyzw (Sophus SO3::operator*)
 __device__ __forceinline__ double4 quat_mul(const double4& a, const double4& b) {
   double4 r;
@@ -286,47 +265,6 @@ __device__ __forceinline__ double4 so3_exp(const Vec3& o) {
   }
   double4 q = {imag * o.x, imag * o.y, imag * o.z, real};
   return q;
-}
-
-// Sophus::leftJacobianSO3 (reference thirdparty/basalt-headers/include/basalt/utils/sophus_utils.hpp:333-362)
-__device__ __forceinline__ Mat3 left_jacobian(const Vec3& p) {
-  const double n2 = p.x * p.x + p.y * p.y + p.z * p.z;
-  const Mat3 H = hat(p);
-  const Mat3 H2 = mat_mul(H, H);
-  double a, b;
-  if (n2 > kSophusEps) {
-    const double n = sqrt(n2);
-    a = (1 - cos(n)) / n2;
-    b = (n - sin(n)) / (n2 * n);
-  } else {
-    a = 0.5;
-    b = 1.0 / 6.0;
-  }
-  Mat3 J;
-#pragma unroll
-  for (int i = 0; i < 9; i++) J.m[i] = H.m[i] * a + H2.m[i] * b;
-  J.m[0] += 1; J.m[4] += 1; J.m[8] += 1;
-  return J;
-}
-
-// Sophus::leftJacobianInvSO3 (sophus_utils.hpp:373-414)
-__device__ __forceinline__ Mat3 left_jacobian_inv(const Vec3& p) {
-  const double n2 = p.x * p.x + p.y * p.y + p.z * p.z;
-  const Mat3 H = hat(p);
-  const Mat3 H2 = mat_mul(H, H);
-  double c;
-  if (n2 > kSophusEps) {
-    const double n = sqrt(n2);
-    if (n < 3.14159265358979323846 - 1e-5) c = 1 / n2 - (1 + cos(n)) / (2 * n * sin(n));
-    else c = 1.0 / (3.14159265358979323846 * 3.14159265358979323846);
-  } else {
-    c = 1.0 / 12.0;
-  }
-  Mat3 J;
-#pragma unroll
-  for (int i = 0; i < 9; i++) J.m[i] = -0.5 * H.m[i] + H2.m[i] * c;
-  J.m[0] += 1; J.m[4] += 1; J.m[8] += 1;
-  return J;
 }
 
 // Batch pose applied to a bearing vector. The linear SO(3) spline gives R_batch = Exp(u delta_w) R_s with

@@ -136,7 +136,7 @@ constexpr int kEvalThreads = 256;
 
 template <int COST>
 __global__ void __launch_bounds__(kEvalThreads)
-k_eval(const MeasRec* __restrict__ rec, int64_t Mc, const double* __restrict__ lut, const double* __restrict__ Ktab,
+k_eval(const MeasRec* __restrict__ rec, int64_t Mc, const double* __restrict__ Ktab,
        const double4* __restrict__ RotTab, const double2* __restrict__ G2, PanoCam cam, int W, int H, double C_th, double eta,
        double2* __restrict__ dp_out, double* __restrict__ e_out, int32_t* __restrict__ pix_out,
        int32_t* __restrict__ hist, double* __restrict__ part, int32_t* __restrict__ flags) {
@@ -297,7 +297,7 @@ int evaluate_slot(Handle* h, int slot, int cost_type, double eta, double alpha) 
   EMBA_CUDA(cudaEventRecord(h->ev[1], h->stream));
   if (h->Mc > 0) {
 #define EMBA_EVAL_LAUNCH(C)                                                                                       \
-  k_eval<C><<<grid, kEvalThreads, 0, h->stream>>>(h->d_rec, h->Mc, h->d_lut, s.Ktab, s.RotTab, s.G2, cam, h->Wp, h->Hp,     \
+  k_eval<C><<<grid, kEvalThreads, 0, h->stream>>>(h->d_rec, h->Mc, s.Ktab, s.RotTab, s.G2, cam, h->Wp, h->Hp,     \
                                                   h->C_th, eta, s.dp, s.e, s.pix, s.hist, h->d_part, h->d_flags)
     if (cost_type == EMBA_COST_QUADRATIC) EMBA_EVAL_LAUNCH(EMBA_COST_QUADRATIC);
     else if (cost_type == EMBA_COST_CAUCHY) EMBA_EVAL_LAUNCH(EMBA_COST_CAUCHY);

@@ -1,0 +1,89 @@
+"""GPU tests at BASELINE.json's sizes: configuration C1 (~0.93 M events, playroom.launch shape) against the CPU
+oracle element by element, and configuration C2 (~10 M events) through size-independent properties (bitwise
+determinism, count conservation, symmetry, two independent solvers agreeing, monotone LM)."""
+import numpy as np
+import pytest
+
+from conftest import rel
+
+pytestmark = pytest.mark.gpu
+ALPHA, THRES = 5.0, 5
+
+
+def _setup(name):
+    from emba_b200 import synth
+    from emba_b200.legm import Engine, spline_base_ns
+
+    sc = synth.make_config(name, device="cuda")
+    eng = Engine(sc.sensor_w, sc.sensor_h, sc.bearing_lut(), sc.C_th, sc.pano_w, sc.pano_h)
+    eng.set_events(sc.x, sc.y, sc.t_ns, sc.pol)
+    t0, dt = spline_base_ns(sc.t_beg, sc.dt_knots)
+    eng.set_state(0, t0, dt, sc.quat_init, sc.Gx_init, sc.Gy_init)
+    return sc, eng, t0, dt
+
+
+def test_c1_against_oracle():
+    from oracle import emba_oracle as O
+
+    sc, eng, t0, dt = _setup("C1")
+    assert 800_000 < sc.n_events < 1_100_000 and sc.n_poses == 47
+    orc = O.Oracle(sc.sensor_w, sc.sensor_h, sc.bearing_lut(), sc.pano_w, sc.pano_h, sc.C_th)
+    orc.set_events(sc.x, sc.y, sc.t_ns, sc.pol)
+    ep_o, num_o = orc.evaluate(sc.quat_init, t0, dt, sc.Gx_init, sc.Gy_init, True)
+    cd, cr, M = eng.evaluate(0, 0, 1.0, ALPHA)
+    ep, num = eng.get_evaluation(0, M)
+    assert M == ep_o.size and np.array_equal(num, num_o)
+    assert rel(ep_o, ep) < 1e-10 and abs(cd - 0.5 * ep_o @ ep_o) < 1e-11 * cd
+    Np = eng.form_normal_eq(THRES, 0, 1.0, ALPHA)
+    A11, A12, A22, b1, b2, act = eng.get_normal_eq(True)
+    B11, B12, B22, c1, c2, act_o = orc.form_normal_eq(sc.n_poses, THRES)
+    B22, c2 = orc.apply_l2_reg(B22, c2, act_o, ALPHA, sc.Gx_init, sc.Gy_init)
+    assert Np == act_o.size and np.array_equal(act, act_o)
+    for a, b in ((B11, A11), (B12, A12), (B22, A22), (c1, b1), (c2, b2)):
+        assert rel(a, b) < 1e-9
+    x1, x2, _, _ = eng.solve(1e-3, False, True)
+    G11, G12, g1 = orc.gauge_fix(B11, B12, c1)
+    y1, y2 = orc.solve_normal_eq(G11, G12, B22, g1, c2, 1e-3)
+    assert rel(y1, x1) < 1e-6 and rel(y2, x2) < 1e-6
+    eng.close()
+
+
+def test_c2_properties():
+    sc, eng, t0, dt = _setup("C2")
+    assert 9_000_000 < sc.n_events < 12_000_000 and sc.n_poses == 97
+    # bitwise determinism of the whole pass + solve
+    out = []
+    for _ in range(2):
+        eng.set_state(0, t0, dt, sc.quat_init, sc.Gx_init, sc.Gy_init)
+        cd, cr, M = eng.evaluate(0, 0, 1.0, ALPHA)
+        _, num = eng.get_evaluation(0, None, False, True)
+        Np = eng.form_normal_eq(THRES, 0, 1.0, ALPHA)
+        A11, _, A22, b1, b2, act = eng.get_normal_eq(False)
+        x1, x2, _, _ = eng.solve(1e-3, False, True)
+        out.append((cd, cr, M, num, Np, A11, A22, b1, b2, act, x1, x2))
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    cd, cr, M, num, Np, A11, A22, b1, b2, act, x1, x2 = out[0]
+    # conservation: every inlier measurement lands in exactly one panorama pixel; active set = thresholded histogram
+    assert int(num.sum()) == M and M <= eng.num_pairs() and num.min() >= 0
+    assert np.array_equal(act, np.nonzero(num.reshape(-1) >= THRES)[0])
+    # structure: A11 symmetric, banded by the largest pose gap of a pair; A22 blocks positive definite (alpha > 0)
+    assert np.max(np.abs(A11 - A11.T)) <= 1e-12 * np.abs(A11).max()
+    assert np.all(A22[:, 0, 0] >= ALPHA) and np.all(A22[:, 1, 1] >= ALPHA)
+    assert np.all(A22[:, 0, 0] * A22[:, 1, 1] - A22[:, 0, 1] ** 2 > 0)
+    assert np.all(np.diag(A11)[3:] > 0)
+    # two independent solvers (direct Schur vs Jacobi-PCG on the full system) agree on the pose update
+    y1, y2, it, err = eng.solve(1e-1, True, True)
+    z1, z2, _, _ = eng.solve(1e-1, False, True)
+    assert err < 1e-4 and rel(z1, y1) < 5e-2 and rel(z2, y2) < 5e-2
+    # LM: accepted steps decrease the cost monotonically, the gauge pose is untouched
+    eng.set_state(0, t0, dt, sc.quat_init, sc.Gx_init, sc.Gy_init)
+    log, fc = eng.solve_time_window(max_num_iter=7, alpha=ALPHA, thres=THRES)
+    acc = log[log[:, 4] == 1]
+    assert acc.shape[0] >= 2 and np.all(np.diff(acc[:, 3]) < 0) and fc < log[0, 2]
+    assert np.all(acc[:, 3] < acc[:, 2])
+    q, gx, gy = eng.get_state(0)
+    assert np.array_equal(q[0], sc.quat_init[0]) and np.all(np.abs(np.linalg.norm(q, axis=1) - 1) < 1e-12)
+    inactive = np.ones(gx.size, dtype=bool)
+    assert np.isfinite(gx).all() and np.isfinite(gy).all()
+    eng.close()
