@@ -305,3 +305,39 @@ def test_bad_events_are_rejected(tiny):
     with pytest.raises(EmbaError):
         eng.set_events(x, sc.y[:1000], sc.t_ns[:1000], sc.pol[:1000])
     eng.close()
+
+
+def test_long_pose_windows_vs_oracle():
+    """Dense control-point spacing (n = 201 over 1 s): pixel pose windows exceed the shared-memory strip capacity, so
+    the map-side kernel takes its global-memory path, and the LDL^T runs several panels. Against the oracle."""
+    from emba_b200 import synth
+    from emba_b200.legm import Engine, spline_base_ns
+    from oracle import emba_oracle as O
+
+    sc = synth.make_config("small", dt_knots=0.005)
+    assert sc.n_poses == 201
+    t0, dt = spline_base_ns(sc.t_beg, sc.dt_knots)
+    eng = Engine(sc.sensor_w, sc.sensor_h, sc.bearing_lut(), sc.C_th, sc.pano_w, sc.pano_h)
+    eng.set_events(sc.x, sc.y, sc.t_ns, sc.pol)
+    eng.set_state(0, t0, dt, sc.quat_init, sc.Gx_init, sc.Gy_init)
+    orc = O.Oracle(sc.sensor_w, sc.sensor_h, sc.bearing_lut(), sc.pano_w, sc.pano_h, sc.C_th)
+    orc.set_events(sc.x, sc.y, sc.t_ns, sc.pol)
+    ep_o, num_o = orc.evaluate(sc.quat_init, t0, dt, sc.Gx_init, sc.Gy_init, True)
+    cd, cr, M = eng.evaluate(0, 0, 1.0, ALPHA)
+    assert M == ep_o.size
+    Np = eng.form_normal_eq(THRES, 0, 1.0, ALPHA)
+    A11, A12, A22, b1, b2, act = eng.get_normal_eq(True)
+    B11, B12, B22, c1, c2, act_o = orc.form_normal_eq(sc.n_poses, THRES)
+    B22, c2 = orc.apply_l2_reg(B22, c2, act_o, ALPHA, sc.Gx_init, sc.Gy_init)
+    assert np.array_equal(act, act_o)
+    # some pixel must really exceed the 64-pose shared-memory strip
+    touched = (np.abs(B12).reshape(sc.n_poses, 3, Np, 2).sum((1, 3)) > 0)
+    span = touched.shape[0] - touched[::-1].argmax(0) - touched.argmax(0)
+    assert span.max() > 64
+    for a, b in ((B11, A11), (B12, A12), (B22, A22), (c1, b1), (c2, b2)):
+        assert rel(a, b) < 1e-9
+    x1, x2, _, _ = eng.solve(1e-3, False, True)
+    G11, G12, g1 = orc.gauge_fix(B11, B12, c1)
+    y1, y2 = orc.solve_normal_eq(G11, G12, B22, g1, c2, 1e-3)
+    assert rel(y1, x1) < 1e-6 and rel(y2, x2) < 1e-6
+    eng.close()

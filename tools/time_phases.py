@@ -5,7 +5,11 @@ import numpy as np
 from emba_b200 import synth
 from emba_b200.legm import Engine, spline_base_ns
 name = sys.argv[1] if len(sys.argv) > 1 else "C2"
-sc = synth.make_config(name, device="cuda")
+over = {}
+for kv in sys.argv[2:]:
+    k, v = kv.split("=")
+    over[k] = float(v) if "." in v or "e" in v else int(v)
+sc = synth.make_config(name, device="cuda", **over)
 eng = Engine(sc.sensor_w, sc.sensor_h, sc.bearing_lut(), sc.C_th, sc.pano_w, sc.pano_h)
 t = time.perf_counter(); eng.set_events(sc.x, sc.y, sc.t_ns, sc.pol); t_ev = time.perf_counter() - t
 t0, dt = spline_base_ns(sc.t_beg, sc.dt_knots)
