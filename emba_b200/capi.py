@@ -70,6 +70,8 @@ SIGNATURES = {
     "emba_accept_candidate": (C.c_int, [_H]),
     "emba_solve_time_window": (C.c_int, [_H, C.POINTER(LMSettings), C.POINTER(LMLog), C.c_int32,
                                          C.POINTER(C.c_int32), _dp]),
+    "emba_fit_control_poses": (C.c_int, [C.c_int32, C.c_int64, C.POINTER(C.c_int64), _dp, C.c_double, C.c_double,
+                                         C.c_double, _dp, C.c_int32, C.POINTER(C.c_int32)]),
     "emba_last_timings_ms": (C.c_int, [_H, _dp]),
     "emba_launch_count": (C.c_int, [_H, C.POINTER(C.c_int64)]),
     "emba_synchronize": (C.c_int, [_H]),

@@ -25,6 +25,22 @@ def spline_base_ns(t_beg: float, dt_knots: float):
     return int(np.int64(np.float64(1e9) * np.float64(t_beg))), int(np.int64(np.float64(1e9) * np.float64(dt_knots)))
 
 
+def fit_control_poses(t_ns, quat_xyzw, t_beg, t_end, dt_knots, device=0):
+    """LinearTrajectory::generateCtrlPosesLong (src/utils/trajectory.cpp:258-294) on the GPU: initial control poses
+    from a dense front-end trajectory (time-sorted t_ns, xyzw quaternions)."""
+    L = capi.load()
+    t = np.ascontiguousarray(t_ns, dtype=np.int64)
+    q = np.ascontiguousarray(quat_xyzw, dtype=np.float64)
+    cap = int(round((t_end - t_beg) / dt_knots)) + 8
+    out = np.empty((cap, 4))
+    n = C.c_int32(0)
+    rc = L.emba_fit_control_poses(device, t.size, ptr(t, C.c_int64), ptr(q), float(t_beg), float(t_end),
+                                  float(dt_knots), ptr(out), cap, C.byref(n))
+    if rc != 0:
+        raise EmbaError(rc, "emba_fit_control_poses")
+    return out[: n.value].copy()
+
+
 class Engine:
     def __init__(self, sensor_w, sensor_h, bearing_lut, C_th, pano_w, pano_h, device=0):
         self.L = capi.load()

@@ -163,6 +163,15 @@ EMBA_API int emba_accept_candidate(emba_handle_t h);
 EMBA_API int emba_solve_time_window(emba_handle_t h, const emba_lm_settings_t* s, emba_lm_log_t* log, int32_t log_cap,
                            int32_t* n_log, double* final_cost);
 
+/* ---- "next" row N2: control-pose initialisation from a dense front-end trajectory,
+ * LinearTrajectory::generateCtrlPosesLong (src/utils/trajectory.cpp:258-294; generateCtrlPoses :245-256,
+ * fitCtrlPoses :149-229) as EMBA::Run calls it (src/emba/emba.cpp:416, sub-interval = dt_knots). poses: time-sorted
+ * (t_ns, quaternion xyzw). Writes floor((t_end - t_beg)/dt_knots + 1e-6) + 1 control poses (capacity cap).
+ * EMBA_E_SUPPORT if a knot interval holds fewer than 2 front-end poses (the reference aborts there). No handle. */
+EMBA_API int emba_fit_control_poses(int32_t device, int64_t n_poses, const int64_t* t_ns, const double* quat_xyzw,
+                                    double t_beg, double t_end, double dt_knots, double* ctrl_quat_xyzw_out,
+                                    int32_t cap, int32_t* n_ctrl_out);
+
 /* ---- measurement hooks used by bench.py (CUDA events on the handle's stream) */
 /* elapsed device time (CUDA events on the handle's stream) of the last emba_evaluate / emba_form_normal_eq /
  * emba_solve, ms: out[0]=evaluate total, out[1]=per-measurement residual kernel (k_eval), out[2]=form total,

@@ -64,8 +64,25 @@ class RefLib:
                                                     C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double,
                                                     C.c_double, C.c_int, _dp, C.c_int, _dp]
             L.embaref_get_timers.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_long)]
+            L.embaref_generate_ctrl_poses_long.restype = C.c_int
+            L.embaref_generate_ctrl_poses_long.argtypes = [C.c_long, C.POINTER(C.c_int64), _dp, C.c_double, C.c_double,
+                                                           C.c_double, C.c_double, _dp, C.c_int]
             cls._lib = L
         return cls._lib
+
+
+def ref_generate_ctrl_poses_long(t_ns, quat_xyzw, t_beg, t_end, dt_knots, sub_interval=None):
+    """LinearTrajectory::generateCtrlPosesLong of the reference (trajectory.cpp:258-294)."""
+    L = RefLib.lib()
+    t = np.ascontiguousarray(t_ns, dtype=np.int64)
+    q = np.ascontiguousarray(quat_xyzw, dtype=np.float64)
+    cap = int(round((t_end - t_beg) / dt_knots)) + 8
+    out = np.empty((cap, 4))
+    n = L.embaref_generate_ctrl_poses_long(t.size, _p(t, C.c_int64), _p(q), float(t_beg), float(t_end),
+                                           float(dt_knots), float(dt_knots if sub_interval is None else sub_interval),
+                                           _p(out), cap)
+    assert n >= 0
+    return out[:n].copy()
 
 
 class RefTraj:

@@ -470,6 +470,32 @@ int embaref_solve_time_window(void* hv, void** traj_io, double* Gx_io, double* G
   return nlog;
 }
 
+// LinearTrajectory::generateCtrlPosesLong (src/utils/trajectory.cpp:258-294 -> generateCtrlPoses :245-256 ->
+// fitCtrlPoses :149-229): control-pose initialisation from a dense front-end trajectory, as EMBA::Run calls it
+// (src/emba/emba.cpp:416, sub-interval length = dt_knots). poses: time-sorted (t_ns, quat xyzw).
+// Returns the number of control poses written to out_quat (capacity cap poses), or -1.
+int embaref_generate_ctrl_poses_long(long n_poses, const int64_t* t_ns, const double* quat_xyzw, double t_beg,
+                                     double t_end, double dt_knots, double sub_interval, double* out_quat, int cap) {
+  PoseMap poses;
+  for (long i = 0; i < n_poses; i++) {
+    ros::Time t; t.fromNSec((uint64_t)t_ns[i]);
+    Eigen::Quaterniond q(quat_xyzw[4 * i + 3], quat_xyzw[4 * i], quat_xyzw[4 * i + 1], quat_xyzw[4 * i + 2]);
+    poses.insert(poses.end(), std::make_pair(t, Sophus::SO3d(q)));
+  }
+  TrajectorySettings cfg;
+  cfg.t_beg = ros::Time(t_beg);
+  cfg.t_end = ros::Time(t_end);
+  cfg.dt_knots = dt_knots;
+  LinearTrajectory traj(cfg);
+  std::vector<Sophus::SO3d> cps = traj.generateCtrlPosesLong(poses, ros::Time(t_beg), ros::Time(t_end), sub_interval);
+  if ((int)cps.size() > cap) return -1;
+  for (size_t i = 0; i < cps.size(); i++) {
+    const Eigen::Quaterniond q = cps[i].unit_quaternion();
+    out_quat[4 * i] = q.x(); out_quat[4 * i + 1] = q.y(); out_quat[4 * i + 2] = q.z(); out_quat[4 * i + 3] = q.w();
+  }
+  return (int)cps.size();
+}
+
 // timers of the last embaref_solve_time_window: seconds and call counts
 void embaref_get_timers(void* hv, double* t3, long* c3) {
   RefHandle* h = (RefHandle*)hv;

@@ -65,6 +65,25 @@ def make(name):
     print(name, "N", sc.n_events, "M", ep.size, "Np", act.size, "LM solves", log.shape[0], "final cost", fcost)
 
 
+def make_frontend():
+    """Front-end trajectory fixture for the control-pose initialisation: 1 kHz poses of the
+    synthetic ground-truth trajectory with 0.1 deg noise, and the control poses the reference fits to them."""
+    rng = np.random.default_rng(3)
+    t_beg, t_end, dt = 0.1, 2.4, 0.05
+    tp = np.arange(0.0995, 2.4015, 0.001) + rng.uniform(-2e-4, 2e-4, 2302)
+    tp.sort()
+    t_ns = np.round(tp * 1e9).astype(np.int64)
+    q = synth._rotvec_to_quat(synth.gt_rotvec(tp) + rng.standard_normal((tp.size, 3)) * np.deg2rad(0.1))
+    cps = RB.ref_generate_ctrl_poses_long(t_ns, q, t_beg, t_end, dt)
+    np.savez_compressed(os.path.join(HERE, "frontend_ref.npz"), t_ns=t_ns, quat=q, t_beg=t_beg, t_end=t_end,
+                        dt_knots=dt, ctrl_poses=cps)
+    print("frontend", t_ns.size, "poses ->", cps.shape[0], "control poses")
+
+
 if __name__ == "__main__":
+    if not sys.argv[1:] or "frontend" in sys.argv[1:]:
+        make_frontend()
+        if "frontend" in sys.argv[1:]:
+            sys.exit(0)
     for nm in (sys.argv[1:] or ["tiny", "small"]):
         make(nm)
