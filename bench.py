@@ -269,6 +269,25 @@ def main():
     ms_step, wall_ms = float(t_red[0]), float(t_red[1])
     value = N / (ms_step * 1e-3)
 
+    # ---- the fp64-atomic map-block path, reported beside the deterministic one (north star: "also reported")
+    atomic = None
+    try:
+        eng.set_map_path(1)
+        for _ in range(2):
+            one_pass()
+        sync_all()
+        ms_a, pix_a = [], []
+        for _ in range(max(3, args.steps // 5)):
+            _, _, _, tm_e, tm_f = one_pass()
+            ms_a.append(tm_e["evaluate"] + tm_f["form"]); pix_a.append(tm_f["pix_kernel"])
+        sync_all()
+        atomic = {"ms_per_step": float(np.mean(ms_a)), "map_kernel_ms": float(np.mean(pix_a)),
+                  "value": N / (float(np.mean(ms_a)) * 1e-3), "note": "same values up to summation order; not bit-reproducible"}
+    except Exception as ex:
+        atomic = {"error": str(ex)}
+    eng.set_map_path(0)
+    one_pass()
+
     # ---- end to end through the C ABI with host buffers: H2D state, pass, D2H (cost, A11, b1, A22, b2)
     A11_h = torch.empty(9 * n * n, dtype=torch.float64).pin_memory()
     b1_h = torch.empty(3 * n, dtype=torch.float64).pin_memory()
@@ -363,6 +382,7 @@ def main():
             "breakdown_ms": {"evaluate": float(np.mean(ev_ms)), "form": float(np.mean(form_ms)), "wall_per_step": wall_ms,
                              "scene_generation_s": t_gen},
             "lm": lm,
+            "map_path_atomic": atomic,
         }
         if world == 1 and not args.no_cpu_baseline:
             # bounded sample: ~10-30 s of single-thread CPU work

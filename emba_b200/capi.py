@@ -62,6 +62,7 @@ SIGNATURES = {
     "emba_evaluate": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_double, C.c_double, _dp, _dp, C.POINTER(C.c_int64)]),
     "emba_get_evaluation": (C.c_int, [_H, C.c_int32, _dp, C.POINTER(C.c_int32)]),
     "emba_form_normal_eq": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_double, C.c_double, C.POINTER(C.c_int64)]),
+    "emba_set_map_path": (C.c_int, [_H, C.c_int32]),
     "emba_apply_l2_reg": (C.c_int, [_H, C.c_double]),
     "emba_get_normal_eq": (C.c_int, [_H, _dp, _dp, _dp, _dp, C.POINTER(C.c_int64), _dp]),
     "emba_a12_entries": (C.c_int, [_H, C.POINTER(C.c_int64)]),

@@ -422,6 +422,39 @@ k_pix(int64_t Np, const int32_t* __restrict__ segoff, const uint32_t* __restrict
   }
 }
 
+// fp64-atomic map-block path (reported beside the deterministic one): one thread per Jacobian row in canonical
+// order, 24 + 5 atomic adds into the pixel's strip / A22 / b2. Strips, A22 and b2 must be zeroed first.
+__global__ void __launch_bounds__(256)
+k_map_atomic(int64_t Mc, const uint32_t* __restrict__ skey, uint32_t invalid_key, const double* __restrict__ jrec,
+             const int32_t* __restrict__ winlo, const int64_t* __restrict__ stripoff, double* __restrict__ strip,
+             double* __restrict__ A22, double* __restrict__ b2) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= Mc) return;
+  const uint32_t a = skey[m];
+  if (a == invalid_key) return;
+  const double4* r4 = reinterpret_cast<const double4*>(jrec + (size_t)m * kRecDoubles);
+  const double4 q0 = ldg256(r4), q1 = ldg256(r4 + 1), q2 = ldg256(r4 + 2), q3 = ldg256(r4 + 3);
+  const double J[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+  const double e = q3.x, d0 = q3.y, d1 = q3.z;
+  const uint32_t key = (uint32_t)(unsigned long long)__double_as_longlong(q3.w);
+  const int cpc = (int)(key & 0xFFFFu), cpp = (int)(key >> 16);
+  double* sp = strip + (stripoff[a] - winlo[a]) * 6;
+  const int pose[4] = {cpc, cpc + 1, cpp, cpp + 1};
+#pragma unroll
+  for (int s = 0; s < 4; s++)
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      double* c = sp + pose[s] * 6 + r * 2;
+      atomicAdd(c, J[3 * s + r] * d0);
+      atomicAdd(c + 1, J[3 * s + r] * d1);
+    }
+  atomicAdd(&A22[3 * (size_t)a], d0 * d0);
+  atomicAdd(&A22[3 * (size_t)a + 1], d0 * d1);
+  atomicAdd(&A22[3 * (size_t)a + 2], d1 * d1);
+  atomicAdd(&b2[2 * (size_t)a], d0 * e);
+  atomicAdd(&b2[2 * (size_t)a + 1], d1 * e);
+}
+
 __global__ void k_l2_reg(int64_t Np, const int32_t* __restrict__ apix, const double* __restrict__ Gx,
                          const double* __restrict__ Gy, double alpha, double* __restrict__ A22,
                          double* __restrict__ b2) {
@@ -548,7 +581,25 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   // stable radix sort of the rows by active pixel index (rows of outliers / inactive pixels carry key Np)
   uint32_t* vs = h->d_sval;
   EMBA_CUDAC(cudaEventRecord(h->ev[8], h->stream));
-  if (Mc > 0) {
+  const bool atomic_path = h->map_path == EMBA_MAP_ATOMIC;
+  if (atomic_path) {
+    EMBA_CUDAC(cudaEventRecord(h->ev[9], h->stream));
+    EMBA_CUDAC(cudaMemsetAsync(h->d_strip, 0, sizeof(double) * 6 * (size_t)tot, h->stream));
+    EMBA_CUDAC(cudaMemsetAsync(h->d_A22, 0, sizeof(double) * 3 * (size_t)Np, h->stream));
+    EMBA_CUDAC(cudaMemsetAsync(h->d_b2, 0, sizeof(double) * 2 * (size_t)Np, h->stream));
+    if (Mc > 0) {
+      k_map_atomic<<<ceil_div64(Mc, 256), 256, 0, h->stream>>>(Mc, h->d_skey, (uint32_t)Np, h->d_jrec, h->d_winlo,
+                                                               h->d_stripoff, h->d_strip, h->d_A22, h->d_b2);
+      h->launches++;
+      EMBA_CUDAC(cudaGetLastError());
+    }
+    if (Np > 0) {
+      StateSlot& sc = h->st[h->cur];
+      k_l2_reg<<<ceil_div64(Np, 256), 256, 0, h->stream>>>(Np, h->d_apix, sc.Gx, sc.Gy, h->rank == 0 ? alpha : 0.0,
+                                                          h->d_A22, h->d_b2);
+      h->launches++;
+    }
+  } else if (Mc > 0) {
     int bits = 1;
     while (bits < 32 && ((uint64_t)Np >> bits)) bits++;
     cub::DoubleBuffer<uint32_t> dk(h->d_skey, h->d_skey2), dv(h->d_sval, h->d_sval2);
@@ -569,8 +620,8 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   } else {
     EMBA_CUDAC(cudaMemsetAsync(h->d_segoff, 0, sizeof(int32_t) * (Np + 1), h->stream));
   }
-  EMBA_CUDAC(cudaEventRecord(h->ev[9], h->stream));
-  if (Np > 0) {
+  if (!atomic_path) EMBA_CUDAC(cudaEventRecord(h->ev[9], h->stream));
+  if (Np > 0 && !atomic_path) {
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((Np + kPixWarps - 1) / kPixWarps, (int64_t)h->sm_count * 16));
     const int pix_smem = kPixWarps * kPixSmemPerWarp;
     EMBA_CUDAC(cudaFuncSetAttribute(k_pix, cudaFuncAttributeMaxDynamicSharedMemorySize, pix_smem));
@@ -622,6 +673,14 @@ int emba_form_normal_eq(emba_handle_t hh, int32_t thres, int32_t cost_type, doub
   EMBA_CUDA(cudaSetDevice(h->device));
   EMBA_TRY(form_normal_eq(h, thres, cost_type, eta, alpha));
   if (Np_out) *Np_out = h->Np;
+  return EMBA_OK;
+}
+
+int emba_set_map_path(emba_handle_t hh, int32_t mode) {
+  Handle* h = (Handle*)hh;
+  if (!h || (mode != EMBA_MAP_SORTED && mode != EMBA_MAP_ATOMIC)) return EMBA_E_ARG;
+  h->map_path = mode;
+  h->formed = h->solved = false;
   return EMBA_OK;
 }
 

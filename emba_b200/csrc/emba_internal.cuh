@@ -147,6 +147,7 @@ struct Handle {
   double* d_A11 = nullptr;      // [3n*3n]
   double* d_b1 = nullptr;       // [3n]
   bool formed = false;
+  int map_path = 0;  // EMBA_MAP_SORTED / EMBA_MAP_ATOMIC
   // solve
   double* d_C = nullptr;        // [Np*3] inverse of damped A22
   double* d_S = nullptr;        // [d*d]

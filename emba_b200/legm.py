@@ -138,6 +138,10 @@ class Engine:
         self.Np = Np.value
         return self.Np
 
+    def set_map_path(self, mode):
+        """0 = deterministic sorted segmented reduction (default), 1 = fp64-atomic path."""
+        self._chk(self.L.emba_set_map_path(self.h, int(mode)))
+
     def apply_l2_reg(self, alpha):
         self._chk(self.L.emba_apply_l2_reg(self.h, float(alpha)))
 

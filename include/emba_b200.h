@@ -136,6 +136,12 @@ EMBA_API int emba_get_evaluation(emba_handle_t h, int32_t which, double* ep_out,
  * evaluation of the CURRENT state. */
 EMBA_API int emba_form_normal_eq(emba_handle_t h, int32_t thres_valid_pixel, int32_t cost_type, double eta, double alpha,
                         int64_t* num_active_pixels);
+/* Map-block reduction path of emba_form_normal_eq: 0 (default) = deterministic segmented reduction over
+ * pixel-sorted rows (stable radix sort + one warp per pixel, bit-reproducible); 1 = fp64-atomic path (every row
+ * adds its 24 A12 + 5 A22/b2 products with red.global.add.f64, no sort; same values up to summation order). */
+enum { EMBA_MAP_SORTED = 0, EMBA_MAP_ATOMIC = 1 };
+EMBA_API int emba_set_map_path(emba_handle_t h, int32_t mode);
+
 /* ---- LEGM::applyL2Reg (model.cpp:689-719) as a separate step, for callers that form with alpha = 0 (the
  * reference calls it right after formNormalEq, solver.cpp:130): A22 += alpha*I, b2 -= alpha*(Gx,Gy)[active]. */
 EMBA_API int emba_apply_l2_reg(emba_handle_t h, double alpha);

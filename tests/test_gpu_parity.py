@@ -341,3 +341,25 @@ def test_long_pose_windows_vs_oracle():
     y1, y2 = orc.solve_normal_eq(G11, G12, B22, g1, c2, 1e-3)
     assert rel(y1, x1) < 1e-6 and rel(y2, x2) < 1e-6
     eng.close()
+
+
+def test_atomic_map_path_matches_sorted_path(small, small_ref):
+    """The fp64-atomic map-block path gives the same normal equations up to summation order (not bit-reproducible),
+    and the same LM decisions."""
+    sc, ref = small, small_ref
+    eng = _engine(sc)
+    t0, dt = _base(sc)
+    eng.set_state(0, t0, dt, sc.quat_init, sc.Gx_init, sc.Gy_init)
+    eng.set_map_path(1)
+    eng.evaluate(0, 0, 1.0, ALPHA)
+    Np = eng.form_normal_eq(THRES, 0, 1.0, ALPHA)
+    A11, A12, A22, b1, b2, act = eng.get_normal_eq(True)
+    assert np.array_equal(act, ref["active"])
+    assert rel(ref["A22"], A22) < 1e-9 and rel(ref["b2"], b2) < 1e-9
+    assert rel(ref["A12_rowsum"], A12.sum(1)) < 1e-9 and rel(ref["A12_colsum"], A12.sum(0)) < 1e-9
+    x1, x2, _, _ = eng.solve(LAM, False, True)
+    assert rel(ref["x1"], x1) < 1e-7 and rel(ref["x2"], x2) < 1e-7
+    eng.set_state(0, t0, dt, sc.quat_init, sc.Gx_init, sc.Gy_init)
+    log, fc = eng.solve_time_window(alpha=ALPHA, thres=THRES)
+    assert np.array_equal(log[:, 4], ref["lm_log"][:, 4])
+    eng.close()
