@@ -564,11 +564,10 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
     h->launches++;
     EMBA_CUDAC(cudaGetLastError());
   }
-  if (h->world > 1) {
-    // partial (H, g) of the time slices are combined over NVLink
-    EMBA_TRYC(comm_allreduce(h, h->d_A11, (int64_t)9 * n * n, 1));
-    EMBA_TRYC(comm_allreduce(h, h->d_b1, (int64_t)3 * n, 1));
-  }
+  // multi-GPU: A11 / b1 stay partial here. The damped pose block A11 + lambda*diag(A11) is linear in A11, so every
+  // rank subtracts its Schur contributions from its OWN partial and one all-reduce in the solve combines both
+  // (saves a 72 n^2-byte all-reduce per assembly); emba_get_normal_eq combines them on demand.
+  h->a11_partial = h->world > 1;
   // ---- 3. map side: pose windows -> strip offsets
   EMBA_CUDAC(cudaMemsetAsync(d_len, 0, sizeof(int64_t) * (Np + 1), h->stream));
   if (Np) { k_strip_len<<<ceil_div64(Np, T), T, 0, h->stream>>>(h->d_winlo, h->d_winhi, Np, d_len); h->launches++; }
@@ -707,6 +706,11 @@ int emba_get_normal_eq(emba_handle_t hh, double* A11, double* b1, double* A22, d
   EMBA_CUDA(cudaSetDevice(h->device));
   const int n = h->n;
   const int64_t Np = h->Np;
+  if (h->a11_partial) {  // parity / adapter download with several GPUs: combine the partial pose blocks now
+    EMBA_TRY(comm_allreduce(h, h->d_A11, (int64_t)9 * n * n, 1));
+    EMBA_TRY(comm_allreduce(h, h->d_b1, (int64_t)3 * n, 1));
+    h->a11_partial = false;
+  }
   if (A11) EMBA_CUDA(cudaMemcpyAsync(A11, h->d_A11, sizeof(double) * 9 * n * n, cudaMemcpyDeviceToHost, h->stream));
   if (b1) EMBA_CUDA(cudaMemcpyAsync(b1, h->d_b1, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, h->stream));
   if (b2 && Np) EMBA_CUDA(cudaMemcpyAsync(b2, h->d_b2, sizeof(double) * 2 * Np, cudaMemcpyDeviceToHost, h->stream));

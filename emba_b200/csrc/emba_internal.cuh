@@ -148,6 +148,7 @@ struct Handle {
   double* d_b1 = nullptr;       // [3n]
   bool formed = false;
   int map_path = 0;  // EMBA_MAP_SORTED / EMBA_MAP_ATOMIC
+  bool a11_partial = false;  // multi-GPU: A11/b1 hold this rank's partial sums (combined inside the Schur all-reduce)
   // solve
   double* d_C = nullptr;        // [Np*3] inverse of damped A22
   double* d_S = nullptr;        // [d*d]

@@ -667,15 +667,26 @@ int solve_schur(Handle* h, double lambda, int fix) {
                                                            lambda, h->d_S, h->d_rhs, nullptr, 0);
     EMBA_LAUNCH_CHECK();
   } else {
-    // every rank holds the Schur contributions of the pixels it owns: combine them over NVLink, then apply
-    EMBA_TRY(dev_reserve(h, &h->d_cg, &h->cg_cap, tot));
-    k_schur_finish<<<ceil_div64(tot, T), T, 0, h->stream>>>(d, fix, n, nt, npairs, Z, h->d_Spart, h->d_A11, h->d_b1,
-                                                           lambda, h->d_S, h->d_rhs, h->d_cg, 1);
-    EMBA_LAUNCH_CHECK();
-    EMBA_TRY(comm_allreduce(h, h->d_cg, tot, 1));
-    k_schur_finish<<<ceil_div64(tot, T), T, 0, h->stream>>>(d, fix, n, nt, npairs, Z, h->d_Spart, h->d_A11, h->d_b1,
-                                                           lambda, h->d_S, h->d_rhs, h->d_cg, 2);
-    EMBA_LAUNCH_CHECK();
+    // every rank holds the Schur contributions of the pixels it owns (and, right after an assembly, only its own
+    // partial A11 / b1): form the local S and rhs, combine them over NVLink with ONE all-reduce.
+    // A11m = A11 + lambda*diag(A11) is linear in A11, so summing the per-rank damped partials is exact.
+    if (h->a11_partial) {
+      k_schur_finish<<<ceil_div64(tot, T), T, 0, h->stream>>>(d, fix, n, nt, npairs, Z, h->d_Spart, h->d_A11, h->d_b1,
+                                                             lambda, h->d_S, h->d_rhs, nullptr, 0);
+      EMBA_LAUNCH_CHECK();
+      EMBA_TRY(comm_allreduce(h, h->d_S, (int64_t)d * d, 1));
+      EMBA_TRY(comm_allreduce(h, h->d_rhs, d, 1));
+    } else {
+      // A11 / b1 already combined (after emba_get_normal_eq): all-reduce only the Schur sums
+      EMBA_TRY(dev_reserve(h, &h->d_cg, &h->cg_cap, tot));
+      k_schur_finish<<<ceil_div64(tot, T), T, 0, h->stream>>>(d, fix, n, nt, npairs, Z, h->d_Spart, h->d_A11, h->d_b1,
+                                                             lambda, h->d_S, h->d_rhs, h->d_cg, 1);
+      EMBA_LAUNCH_CHECK();
+      EMBA_TRY(comm_allreduce(h, h->d_cg, tot, 1));
+      k_schur_finish<<<ceil_div64(tot, T), T, 0, h->stream>>>(d, fix, n, nt, npairs, Z, h->d_Spart, h->d_A11, h->d_b1,
+                                                             lambda, h->d_S, h->d_rhs, h->d_cg, 2);
+      EMBA_LAUNCH_CHECK();
+    }
   }
   if (dbg) cudaEventRecord(de[2], h->stream);
   EMBA_CUDA(cudaMemsetAsync(h->d_flags, 0, sizeof(int32_t) * 16, h->stream));
