@@ -66,13 +66,18 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
+    def mark(self):
+        """start of the timed region: only samples taken after this point are reported"""
+        self.i0 = len(self.rows)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        rows = self.rows[getattr(self, "i0", 0):] or self.rows[-1:]
+        for r in rows:
             f = [c.strip() for c in r.split(",")]
             if len(f) < 9:
                 continue
@@ -243,11 +248,12 @@ def main():
         return cd + cr, M, Np, tm_e, tm_f
 
     # ---- device-resident pass: W warm-up + K timed steps
+    clocks = ClockSampler(local_rank)
+    clocks.start()  # started before the warm-up so that nvidia-smi is already streaming when the timed region begins
     for _ in range(args.warmup):
         one_pass()
     sync_all()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
+    clocks.mark()
     l0 = eng.launch_count()
     dev_ms, k_eval_ms, k_asm_ms, k_map_ms, ev_ms, form_ms, k_pix_ms, k_sort_ms = [], [], [], [], [], [], [], []
     wall = time.perf_counter()
