@@ -363,3 +363,22 @@ def test_atomic_map_path_matches_sorted_path(small, small_ref):
     log, fc = eng.solve_time_window(alpha=ALPHA, thres=THRES)
     assert np.array_equal(log[:, 4], ref["lm_log"][:, 4])
     eng.close()
+
+
+def test_lm_without_gauge_fixing_vs_oracle(tiny):
+    """A later sliding window (EMBA::first_time_window_ == false): no control pose is fixed, the full 3n system is
+    solved (solver.cpp:227-234)."""
+    sc = tiny
+    t0, dt = _base(sc)
+    orc = _oracle(sc)
+    eng = _engine(sc)
+    q_o, gx_o, gy_o, log_o = orc.solve_time_window(sc.quat_init, t0, dt, sc.Gx_init, sc.Gy_init, max_num_iter=5,
+                                                   alpha=ALPHA, thres=THRES, first_window=False)
+    eng.set_state(0, t0, dt, sc.quat_init, sc.Gx_init, sc.Gy_init)
+    log, fc = eng.solve_time_window(max_num_iter=5, alpha=ALPHA, thres=THRES, first_window=False)
+    assert log.shape[0] == log_o.shape[0] and np.array_equal(log[:, 4], log_o[:, 4])
+    q, gx, gy = eng.get_state(0)
+    assert not np.array_equal(q[0], sc.quat_init[0])  # the first pose moves too
+    ang = 2 * np.arccos(np.abs(np.sum(q * q_o, -1)).clip(0, 1))
+    assert np.max(ang) < 1e-5 and rel(gx_o, gx) < 1e-4
+    eng.close()
