@@ -288,14 +288,14 @@ __global__ void k_seg_bounds(const uint32_t* __restrict__ keys, int64_t M, int64
 }
 
 // Map side: one warp per active pixel, rows in fixed (sorted) order. The 128-byte rows are gathered with cp.async
-// (16 B per lane, 4 rows per instruction) into a 3-stage shared-memory ring, so the DRAM latency of the gather
+// (16 B per lane, 4 rows per instruction) into a 2-stage shared-memory ring (4 CTAs = 32 warps per SM), so the DRAM latency of the gather
 // overlaps the reduction of the previous tiles. Lanes 0..23 own one A12 component (slot, row, col), lanes 24..28
 // own A22 xx, xy, yy and b2 x, y. A12 components are accumulated per run of equal (cp_c, cp_p) -- rows are sorted
 // by row id, i.e. grouped by control-pose pair -- and flushed into the pixel's strip in shared memory.
 constexpr int kPixWarps = 8;
 constexpr int kStripCap = 64;  // poses per shared-memory strip
 constexpr int kPixTile = 16;   // rows per stage
-constexpr int kPixStages = 3;
+constexpr int kPixStages = 2;
 constexpr int kPixSmemPerWarp = (kPixStages * kPixTile * kRecDoubles + kStripCap * 6) * 8;  // bytes
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -351,8 +351,8 @@ k_pix(int64_t Np, const int32_t* __restrict__ segoff, const uint32_t* __restrict
       }
       cp_async_commit();
     };
-    issue(0);
-    issue(1);
+#pragma unroll
+    for (int t = 0; t < kPixStages - 1; t++) issue(t);
     double acc = 0.0;
     uint32_t runkey = 0xFFFFFFFFu;
     bool have = false;
@@ -366,8 +366,8 @@ k_pix(int64_t Np, const int32_t* __restrict__ segoff, const uint32_t* __restrict
       if (lane < 24) acc = 0.0;
     };
     for (int t = 0; t < ntiles; t++) {
-      issue(t + 2);
-      cp_async_wait<2>();
+      issue(t + kPixStages - 1);
+      cp_async_wait<kPixStages - 1>();
       __syncwarp();
       const int cnt = (int)min((int64_t)kPixTile, seg1 - (seg0 + (int64_t)t * kPixTile));
       const double* tl = s_tile + (size_t)(t % kPixStages) * kPixTile * kRecDoubles;
