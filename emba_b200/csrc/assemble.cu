@@ -336,11 +336,19 @@ k_pix(int64_t Np, const int32_t* __restrict__ segoff, const uint32_t* __restrict
     double* sp = (len <= kStripCap) ? s_strip : gs;
     for (int i = lane; i < len * 6; i += 32) sp[i] = 0.0;
     const int ntiles = (int)((seg1 - seg0 + kPixTile - 1) / kPixTile);
+    // row indices of the next tile to be issued are fetched one step ahead, so the index load and the row gather it
+    // feeds are not two DRAM latencies in series
+    auto load_idx = [&](int t) -> uint32_t {
+      const int64_t base = seg0 + (int64_t)t * kPixTile;
+      return (t < ntiles && base + lane < seg1 && lane < kPixTile) ? sval[base + lane] : 0u;
+    };
+    uint32_t idx_next = load_idx(0);
     auto issue = [&](int t) {
+      const uint32_t mine = idx_next;
+      idx_next = load_idx(t + 1);
       if (t < ntiles) {
         const int64_t base = seg0 + (int64_t)t * kPixTile;
         const int cnt = (int)min((int64_t)kPixTile, seg1 - base);
-        const uint32_t mine = (lane < cnt) ? sval[base + lane] : 0u;
         double* dst = s_tile + (size_t)(t % kPixStages) * kPixTile * kRecDoubles;
 #pragma unroll
         for (int k = 0; k < kPixTile / 4; k++) {
