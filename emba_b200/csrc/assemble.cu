@@ -306,6 +306,104 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+// one pixel: rows [seg0, seg1) of the sorted list. SMEM: the strip accumulates in shared memory (typed shared
+// accesses) and is copied out at the end; otherwise (pose window longer than kStripCap) directly in global memory.
+template <bool SMEM>
+__device__ __forceinline__ void pix_one(int64_t seg0, int64_t seg1, int qlo, int len, double* __restrict__ gs,
+                                        double* s_tile, double* s_strip, const uint32_t* __restrict__ sval,
+                                        const double* __restrict__ jrec, int lane, int s, int r, int c, int ia,
+                                        int ib, double& acc_out) {
+  double* sp = SMEM ? s_strip : gs;
+  for (int i = lane; i < len * 6; i += 32) sp[i] = 0.0;
+  const int lrow = lane >> 3, lchunk = lane & 7;  // cp.async role: 4 rows per instruction, 8 x 16 B per row
+  const int ntiles = (int)((seg1 - seg0 + kPixTile - 1) / kPixTile);
+  // row indices of the next tile to be issued are fetched one step ahead, so the index load and the row gather it
+  // feeds are not two DRAM latencies in series
+  auto load_idx = [&](int t) -> uint32_t {
+    const int64_t base = seg0 + (int64_t)t * kPixTile;
+    return (t < ntiles && base + lane < seg1 && lane < kPixTile) ? sval[base + lane] : 0u;
+  };
+  uint32_t idx_next = load_idx(0);
+  auto issue = [&](int t) {
+    const uint32_t mine = idx_next;
+    idx_next = load_idx(t + 1);
+    if (t < ntiles) {
+      const int64_t base = seg0 + (int64_t)t * kPixTile;
+      const int cnt = (int)min((int64_t)kPixTile, seg1 - base);
+      double* dst = s_tile + (size_t)(t % kPixStages) * kPixTile * kRecDoubles;
+#pragma unroll
+      for (int k = 0; k < kPixTile / 4; k++) {
+        const int row = 4 * k + lrow;
+        const uint32_t m = __shfl_sync(0xffffffffu, mine, row);
+        if (row < cnt) cp_async16(dst + row * kRecDoubles + 2 * lchunk, jrec + (size_t)m * kRecDoubles + 2 * lchunk);
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int t = 0; t < kPixStages - 1; t++) issue(t);
+  double acc = 0.0;
+  uint32_t runkey = 0xFFFFFFFFu;
+  bool have = false;
+  const int lane_off = ((s & 1) - qlo) * 6 + r * 2 + c;
+  auto flush = [&]() {
+    const int pose = (int)(s >= 2 ? (runkey >> 16) : (runkey & 0xFFFFu));
+    double* cell = sp + pose * 6 + lane_off;
+    if (lane < 12) *cell += acc;
+    __syncwarp();
+    if (lane >= 12 && lane < 24) *cell += acc;
+    __syncwarp();
+    if (lane < 24) acc = 0.0;
+  };
+  for (int t = 0; t < ntiles; t++) {
+    issue(t + kPixStages - 1);
+    cp_async_wait<kPixStages - 1>();
+    __syncwarp();
+    const int cnt = (int)min((int64_t)kPixTile, seg1 - (seg0 + (int64_t)t * kPixTile));
+    const double* tl = s_tile + (size_t)(t % kPixStages) * kPixTile * kRecDoubles;
+    const double* pa = tl + ia;
+    const double* pb = tl + ib;
+    const uint32_t* pk = reinterpret_cast<const uint32_t*>(tl + 15);
+    int i = 0;
+    for (; i + 4 <= cnt; i += 4) {
+      const uint32_t k0 = pk[(i + 0) * 2 * kRecDoubles], k1 = pk[(i + 1) * 2 * kRecDoubles];
+      const uint32_t k2 = pk[(i + 2) * 2 * kRecDoubles], k3 = pk[(i + 3) * 2 * kRecDoubles];
+      const double a0 = pa[(i + 0) * kRecDoubles], b0 = pb[(i + 0) * kRecDoubles];
+      const double a1 = pa[(i + 1) * kRecDoubles], b1 = pb[(i + 1) * kRecDoubles];
+      const double a2 = pa[(i + 2) * kRecDoubles], b2v = pb[(i + 2) * kRecDoubles];
+      const double a3 = pa[(i + 3) * kRecDoubles], b3 = pb[(i + 3) * kRecDoubles];
+      if (have && k0 == runkey && k1 == runkey && k2 == runkey && k3 == runkey) {
+        acc = fma(a0, b0, acc);
+        acc = fma(a1, b1, acc);
+        acc = fma(a2, b2v, acc);
+        acc = fma(a3, b3, acc);
+      } else {
+        if (k0 != runkey || !have) { if (have) flush(); runkey = k0; have = true; }
+        acc = fma(a0, b0, acc);
+        if (k1 != runkey) { flush(); runkey = k1; }
+        acc = fma(a1, b1, acc);
+        if (k2 != runkey) { flush(); runkey = k2; }
+        acc = fma(a2, b2v, acc);
+        if (k3 != runkey) { flush(); runkey = k3; }
+        acc = fma(a3, b3, acc);
+      }
+    }
+    for (; i < cnt; i++) {
+      const uint32_t k0 = pk[i * 2 * kRecDoubles];
+      if (k0 != runkey || !have) { if (have) flush(); runkey = k0; have = true; }
+      acc = fma(pa[i * kRecDoubles], pb[i * kRecDoubles], acc);
+    }
+    __syncwarp();
+  }
+  cp_async_wait<0>();
+  if (have) flush();
+  __syncwarp();
+  if (SMEM) {
+    for (int i = lane; i < len * 6; i += 32) gs[i] = sp[i];
+  }
+  acc_out = acc;
+}
+
 __global__ void __launch_bounds__(kPixWarps * 32)
 k_pix(int64_t Np, const int32_t* __restrict__ segoff, const uint32_t* __restrict__ sval,
       const double* __restrict__ jrec, const int32_t* __restrict__ winlo, const int32_t* __restrict__ winhi,
@@ -326,99 +424,15 @@ k_pix(int64_t Np, const int32_t* __restrict__ segoff, const uint32_t* __restrict
   else if (lane == 26) { ia = 14; ib = 14; }
   else if (lane == 27) { ia = 13; ib = 12; }
   else if (lane == 28) { ia = 14; ib = 12; }
-  const int lrow = lane >> 3, lchunk = lane & 7;  // cp.async role: 4 rows per instruction, 8 x 16 B per row
   for (int64_t a = (int64_t)blockIdx.x * kPixWarps + warp; a < Np; a += nw) {
     const int64_t seg0 = segoff[a];
     const int64_t seg1 = segoff[a + 1];
     const int qlo = winlo[a];
     const int len = winhi[a] >= qlo ? winhi[a] - qlo + 1 : 0;  // empty window: no local rows (multi-GPU)
     double* gs = strip + stripoff[a] * 6;
-    double* sp = (len <= kStripCap) ? s_strip : gs;
-    for (int i = lane; i < len * 6; i += 32) sp[i] = 0.0;
-    const int ntiles = (int)((seg1 - seg0 + kPixTile - 1) / kPixTile);
-    // row indices of the next tile to be issued are fetched one step ahead, so the index load and the row gather it
-    // feeds are not two DRAM latencies in series
-    auto load_idx = [&](int t) -> uint32_t {
-      const int64_t base = seg0 + (int64_t)t * kPixTile;
-      return (t < ntiles && base + lane < seg1 && lane < kPixTile) ? sval[base + lane] : 0u;
-    };
-    uint32_t idx_next = load_idx(0);
-    auto issue = [&](int t) {
-      const uint32_t mine = idx_next;
-      idx_next = load_idx(t + 1);
-      if (t < ntiles) {
-        const int64_t base = seg0 + (int64_t)t * kPixTile;
-        const int cnt = (int)min((int64_t)kPixTile, seg1 - base);
-        double* dst = s_tile + (size_t)(t % kPixStages) * kPixTile * kRecDoubles;
-#pragma unroll
-        for (int k = 0; k < kPixTile / 4; k++) {
-          const int row = 4 * k + lrow;
-          const uint32_t m = __shfl_sync(0xffffffffu, mine, row);
-          if (row < cnt) cp_async16(dst + row * kRecDoubles + 2 * lchunk, jrec + (size_t)m * kRecDoubles + 2 * lchunk);
-        }
-      }
-      cp_async_commit();
-    };
-#pragma unroll
-    for (int t = 0; t < kPixStages - 1; t++) issue(t);
     double acc = 0.0;
-    uint32_t runkey = 0xFFFFFFFFu;
-    bool have = false;
-    auto flush = [&]() {
-      const int cpc = (int)(runkey & 0xFFFFu), cpp = (int)(runkey >> 16);
-      const int pose = (s == 0) ? cpc : (s == 1) ? cpc + 1 : (s == 2) ? cpp : cpp + 1;
-      if (lane < 12) sp[(pose - qlo) * 6 + r * 2 + c] += acc;
-      __syncwarp();
-      if (lane >= 12 && lane < 24) sp[(pose - qlo) * 6 + r * 2 + c] += acc;
-      __syncwarp();
-      if (lane < 24) acc = 0.0;
-    };
-    for (int t = 0; t < ntiles; t++) {
-      issue(t + kPixStages - 1);
-      cp_async_wait<kPixStages - 1>();
-      __syncwarp();
-      const int cnt = (int)min((int64_t)kPixTile, seg1 - (seg0 + (int64_t)t * kPixTile));
-      const double* tl = s_tile + (size_t)(t % kPixStages) * kPixTile * kRecDoubles;
-      const double* pa = tl + ia;
-      const double* pb = tl + ib;
-      const uint32_t* pk = reinterpret_cast<const uint32_t*>(tl + 15);
-      int i = 0;
-      for (; i + 4 <= cnt; i += 4) {
-        const uint32_t k0 = pk[(i + 0) * 2 * kRecDoubles], k1 = pk[(i + 1) * 2 * kRecDoubles];
-        const uint32_t k2 = pk[(i + 2) * 2 * kRecDoubles], k3 = pk[(i + 3) * 2 * kRecDoubles];
-        const double a0 = pa[(i + 0) * kRecDoubles], b0 = pb[(i + 0) * kRecDoubles];
-        const double a1 = pa[(i + 1) * kRecDoubles], b1 = pb[(i + 1) * kRecDoubles];
-        const double a2 = pa[(i + 2) * kRecDoubles], b2v = pb[(i + 2) * kRecDoubles];
-        const double a3 = pa[(i + 3) * kRecDoubles], b3 = pb[(i + 3) * kRecDoubles];
-        if (have && k0 == runkey && k1 == runkey && k2 == runkey && k3 == runkey) {
-          acc = fma(a0, b0, acc);
-          acc = fma(a1, b1, acc);
-          acc = fma(a2, b2v, acc);
-          acc = fma(a3, b3, acc);
-        } else {
-          if (k0 != runkey || !have) { if (have) flush(); runkey = k0; have = true; }
-          acc = fma(a0, b0, acc);
-          if (k1 != runkey) { flush(); runkey = k1; }
-          acc = fma(a1, b1, acc);
-          if (k2 != runkey) { flush(); runkey = k2; }
-          acc = fma(a2, b2v, acc);
-          if (k3 != runkey) { flush(); runkey = k3; }
-          acc = fma(a3, b3, acc);
-        }
-      }
-      for (; i < cnt; i++) {
-        const uint32_t k0 = pk[i * 2 * kRecDoubles];
-        if (k0 != runkey || !have) { if (have) flush(); runkey = k0; have = true; }
-        acc = fma(pa[i * kRecDoubles], pb[i * kRecDoubles], acc);
-      }
-      __syncwarp();
-    }
-    cp_async_wait<0>();
-    if (have) flush();
-    __syncwarp();
-    if (sp != gs) {
-      for (int i = lane; i < len * 6; i += 32) gs[i] = sp[i];
-    }
+    if (len <= kStripCap) pix_one<true>(seg0, seg1, qlo, len, gs, s_tile, s_strip, sval, jrec, lane, s, r, c, ia, ib, acc);
+    else pix_one<false>(seg0, seg1, qlo, len, gs, s_tile, s_strip, sval, jrec, lane, s, r, c, ia, ib, acc);
     // applyL2Reg (model.cpp:689-719): A22 += alpha*I, b2 -= alpha * (Gx, Gy)[pixel]
     const int32_t pix = apix[a];
     if (lane == 24) A22[3 * a] = acc + alpha;
