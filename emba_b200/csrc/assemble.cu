@@ -10,6 +10,7 @@
 //      per active pixel then reduces its rows in that fixed order into A22 / b2 and the pixel's A12 strip
 //      (3x2 block per control pose in the pixel's pose window) -- a deterministic segmented reduction.
 #include <climits>
+#include <cuda.h>
 #include <cub/cub.cuh>
 
 #include <algorithm>
@@ -50,43 +51,46 @@ __global__ void k_active_fill(const int32_t* __restrict__ flag, const int32_t* _
 
 // ---------------------------------------------------------------------------------------------------
 constexpr int kAsmThreads = 256;
-constexpr int kTileStride = kAsmThreads + 1;
 
-// Rows I0..I1-1 of the upper triangle of v v^T (13 x 13), accumulated into a[0..]. The CTA is split into four
-// 64-thread roles that own rows {0,1}, {2,3}, {4,5,6}, {7..12}: 25 / 21 / 24 / 21 accumulators per thread.
-template <int I0, int I1>
-__device__ __forceinline__ void tri_add(double (&a)[25], const double* v) {
-  int k = 0;
-#pragma unroll
-  for (int i = I0; i < I1; i++)
-#pragma unroll
-    for (int j = i; j < 13; j++) a[k++] += v[i] * v[j];
+// D += A * B with the fp64 tensor-core shape m8n8k4 (A 8x4 row-major, B 4x8 column-major). Lane l holds
+// A[l/4][l%4], B[l%4][l/4] and D[l/4][2*(l%4) + {0,1}].
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
 }
 
-template <int I0, int I1>
-__device__ __forceinline__ void tri_tile(double (&a)[25], const double (*tile)[kTileStride], int idx) {
-#pragma unroll
-  for (int q = 0; q < 4; q++) {
-    const int c = idx + 64 * q;
-    double v[13];
-#pragma unroll
-    for (int k = I0; k < 13; k++) v[k] = tile[k][c];
-    tri_add<I0, I1>(a, v);
-  }
-}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One 256-row x 128-byte box of the Jacobian-row tensor, shared -> global through the TMA (bulk async group).
+__device__ __forceinline__ void tma_store_rows(const CUtensorMap* map, const void* smem, int row0) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(0),
+               "r"(row0), "r"(smem_u32(smem))
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Work item -> A11 / b1 partial + Jacobian rows.
+//   * every thread forms one row [Jc(6) Jp(6) e | dp(2) meta] and drops it into the shared tile as a 128-byte
+//     record; the 16-byte chunks of record r sit at chunk ^ (r % 8) -- the TMA's 128-byte swizzle, which also
+//     makes the row-wise writes and the fragment reads below bank-conflict free;
+//   * full tiles leave for global memory as ONE TMA tensor store (the TMA undoes the swizzle), overlapping the
+//     next tile's gathers; the tail tile of an item is copied by the threads;
+//   * the 13 x 13 products [Jc Jp e]^T [Jc Jp e] run on the fp64 tensor cores: per warp, 32 rows = 8 k-steps of
+//     m8n8k4 on the field blocks (0..7) x (0..7), (0..7) x (8..15), (8..15) x (8..15); one fragment serves as A
+//     and as B. Six accumulator doubles per thread instead of a 91-entry triangle spread over thread roles.
 template <int COST>
-__global__ void __launch_bounds__(kAsmThreads, 2)
-k_asm_pose(const WorkItem* __restrict__ items, const MeasRec* __restrict__ rec,
-           const double* __restrict__ Ktab, const double4* __restrict__ RotTab, const double4* __restrict__ JacTab,
-           const double2* __restrict__ G2,
-           const double4* __restrict__ H3, const double2* __restrict__ dp_in, const double* __restrict__ e_in,
-           const int32_t* __restrict__ pix_in, PanoCam cam, double eta,
-           uint32_t invalid_key, double* __restrict__ jrec, uint32_t* __restrict__ skey, uint32_t* __restrict__ sval,
-           int32_t* __restrict__ winlo, int32_t* __restrict__ winhi, double* __restrict__ acc_part) {
-  // rows 0..11: Jc, Jp; 12: e; 13,14: dp; 15: meta  (row-major [field][measurement], padded against conflicts)
-  __shared__ double tile[kRecDoubles][kTileStride];
-  __shared__ double red[8][25];
+__global__ void __launch_bounds__(kAsmThreads, 3)
+k_asm_pose(const __grid_constant__ CUtensorMap jmap, const WorkItem* __restrict__ items,
+           const MeasRec* __restrict__ rec, const double* __restrict__ Ktab, const double4* __restrict__ RotTab,
+           const double4* __restrict__ JacTab, const double2* __restrict__ G2, const double4* __restrict__ H3,
+           const double2* __restrict__ dp_in, const double* __restrict__ e_in, const int32_t* __restrict__ pix_in,
+           PanoCam cam, double eta, uint32_t invalid_key, double* __restrict__ jrec, uint32_t* __restrict__ skey,
+           uint32_t* __restrict__ sval, int32_t* __restrict__ winlo, int32_t* __restrict__ winhi,
+           double* __restrict__ acc_part) {
+  __shared__ __align__(1024) double tile[kAsmThreads * kRecDoubles];  // [row][16], chunk-swizzled
   __shared__ double knots[2 * kKnotStride];  // knot-interval data of cp_c and cp_p: uniform over the work item
   const WorkItem it = items[blockIdx.x];
   const int tid = threadIdx.x;
@@ -95,11 +99,14 @@ k_asm_pose(const WorkItem* __restrict__ items, const MeasRec* __restrict__ rec,
   __syncthreads();
   const double* knot_c = knots;
   const double* knot_p = knots + kKnotStride;
-  const int role = tid >> 6, idx = tid & 63;
-  double acc[25];
-#pragma unroll
-  for (int k = 0; k < 25; k++) acc[k] = 0.0;
+  const int lane = tid & 31, warp = tid >> 5;
+  double c00a = 0.0, c00b = 0.0, c01a = 0.0, c01b = 0.0, c11a = 0.0, c11b = 0.0;
+  // fragment addressing: k-step s covers rows 32*warp + 8*(s/2) + (s%2) + 2*(lane%4); field lane/4 (+8)
+  const int fq = lane >> 2, kk = lane & 3;
   const unsigned long long meta_lo = (unsigned long long)((uint32_t)it.cp_c | ((uint32_t)it.cp_p << 16));
+  double2* trow = reinterpret_cast<double2*>(tile + tid * kRecDoubles);
+  const int swz = tid & 7;
+  bool store_pending = false;
   for (int t0 = 0; t0 < it.count; t0 += kAsmThreads) {
     const int j = t0 + tid;
     double row[13];
@@ -169,41 +176,100 @@ k_asm_pose(const WorkItem* __restrict__ items, const MeasRec* __restrict__ rec,
         atomicMax(&winhi[a], it.cp_c + 1);
       }
     }
-#pragma unroll
-    for (int k = 0; k < 13; k++) tile[k][tid] = row[k];
-    tile[13][tid] = d0;
-    tile[14][tid] = d1;
-    tile[15][tid] = __longlong_as_double((long long)(meta_lo | ((unsigned long long)(uint32_t)m << 32)));
+    // the previous tile's TMA store must have drained the tile (and every warp finished reading it)
+    if (store_pending && tid == 0) tma_store_wait_read();
     __syncthreads();
-    // Jacobian rows -> global, coalesced: 16 consecutive threads write one 128-byte record
-    {
-      const int nrec = min(kAsmThreads, it.count - t0);
-      double* out = jrec + ((size_t)it.start + t0) * kRecDoubles;
-      const int f = tid & 15;
-      for (int r = tid >> 4; r < nrec; r += kAsmThreads / 16) out[(size_t)r * kRecDoubles + f] = tile[f][r];
+#pragma unroll
+    for (int c = 0; c < 6; c++) trow[c ^ swz] = make_double2(row[2 * c], row[2 * c + 1]);
+    trow[6 ^ swz] = make_double2(row[12], d0);
+    trow[7 ^ swz] =
+        make_double2(d1, __longlong_as_double((long long)(meta_lo | ((unsigned long long)(uint32_t)m << 32))));
+    fence_async_smem();
+    __syncthreads();
+    // Jacobian rows -> global
+    const int nrec = min(kAsmThreads, it.count - t0);
+    if (nrec == kAsmThreads) {
+      if (tid == 0) tma_store_rows(&jmap, tile, it.start + t0);
+      store_pending = true;
+    } else {
+      double2* out = reinterpret_cast<double2*>(jrec + ((size_t)it.start + t0) * kRecDoubles);
+      const double2* t2 = reinterpret_cast<const double2*>(tile);
+      for (int i = tid; i < nrec * 8; i += kAsmThreads) {
+        const int r = i >> 3, c = i & 7;
+        out[i] = t2[r * 8 + (c ^ (r & 7))];
+      }
     }
-    if (role == 0) tri_tile<0, 2>(acc, tile, idx);
-    else if (role == 1) tri_tile<2, 4>(acc, tile, idx);
-    else if (role == 2) tri_tile<4, 7>(acc, tile, idx);
-    else tri_tile<7, 13>(acc, tile, idx);
-    __syncthreads();
+    // rank-32 update of the three 8x8 blocks from this warp's own rows
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+      const int r = 32 * warp + 8 * (s >> 1) + (s & 1) + 2 * kk;
+      const int rs = r & 7;
+      const double f0 = tile[r * kRecDoubles + (((fq >> 1) ^ rs) << 1) + (fq & 1)];
+      const double f1 = tile[r * kRecDoubles + ((((fq >> 1) + 4) ^ rs) << 1) + (fq & 1)];
+      dmma884(c00a, c00b, f0, f0);
+      dmma884(c01a, c01b, f0, f1);
+      dmma884(c11a, c11b, f1, f1);
+    }
   }
-  // reduce the accumulators over the 64 threads of each role: warp shuffles, then 2 warps through shared memory
-  const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-  for (int k = 0; k < 25; k++) {
-    double x = acc[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-    if (lane == 0) red[warp][k] = x;
+  // reduce the per-warp blocks in a fixed order (the tile doubles as scratch once the last store has read it)
+  if (store_pending && tid == 0) tma_store_wait_read();
+  __syncthreads();
+  {
+    double* red = tile + warp * 192;
+    const int o = fq * 8 + 2 * kk;
+    red[o] = c00a; red[o + 1] = c00b;
+    red[64 + o] = c01a; red[64 + o + 1] = c01b;
+    red[128 + o] = c11a; red[128 + o + 1] = c11b;
   }
   __syncthreads();
   if (tid < kAccN) {
-    // tri13 order is row-major: rows {0,1} -> 0..24, {2,3} -> 25..45, {4,5,6} -> 46..69, {7..12} -> 70..90
-    const int r = tid < 25 ? 0 : tid < 46 ? 1 : tid < 70 ? 2 : 3;
-    const int k = tid - (r == 0 ? 0 : r == 1 ? 25 : r == 2 ? 46 : 70);
-    acc_part[(size_t)blockIdx.x * kAccN + tid] = red[2 * r][k] + red[2 * r + 1][k];
+    // tri13 order: row-major upper triangle of the 13 x 13 matrix
+    int i = 0, k = tid;
+    while (k >= 13 - i) { k -= 13 - i; i++; }
+    const int jj = i + k;
+    const int blk = i < 8 ? (jj < 8 ? 0 : 1) : 2;
+    const int o = blk * 64 + (i & 7) * 8 + (jj & 7);
+    double x = 0.0;
+#pragma unroll
+    for (int w = 0; w < kAsmThreads / 32; w++) x += tile[w * 192 + o];
+    acc_part[(size_t)blockIdx.x * kAccN + tid] = x;
   }
+}
+
+// TMA descriptor of the Jacobian-row buffer: [Mc][16] fp64, box 256 rows x 16, 128-byte swizzle. Rebuilt only
+// when the buffer moves or the window's measurement count changes. cuTensorMapEncodeTiled comes from the
+// driver through the runtime's entry-point query (no link-time libcuda dependency).
+static int jrec_tensor_map(Handle* h) {
+  if (h->jrec_tmap_ptr == h->d_jrec && h->jrec_tmap_rows == h->Mc) return EMBA_OK;
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn ||
+        qr != cudaDriverEntryPointSuccess) {
+      h->err = "cuTensorMapEncodeTiled is not available from this driver";
+      return EMBA_E_SUPPORT;
+    }
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)kRecDoubles, (cuuint64_t)h->Mc};
+  const cuuint64_t strides[1] = {(cuuint64_t)kRecDoubles * sizeof(double)};
+  const cuuint32_t box[2] = {(cuuint32_t)kRecDoubles, (cuuint32_t)kAsmThreads};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(reinterpret_cast<CUtensorMap*>(h->jrec_tmap), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2,
+                            h->d_jrec, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    h->err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")";
+    return EMBA_E_CUDA;
+  }
+  h->jrec_tmap_ptr = h->d_jrec;
+  h->jrec_tmap_rows = h->Mc;
+  return EMBA_OK;
 }
 
 // per-group sums of the item partials, fixed order
@@ -561,8 +627,10 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   const PanoCam cam = make_cam(h);
   EMBA_CUDAC(cudaEventRecord(h->ev[5], h->stream));
   if (h->n_items > 0) {
+    EMBA_TRYC(jrec_tensor_map(h));
+    const CUtensorMap jmap = *reinterpret_cast<const CUtensorMap*>(h->jrec_tmap);
 #define EMBA_ASM_LAUNCH(C)                                                                                         \
-  k_asm_pose<C><<<h->n_items, kAsmThreads, 0, h->stream>>>(h->d_items, h->d_rec, s.Ktab, s.RotTab,                \
+  k_asm_pose<C><<<h->n_items, kAsmThreads, 0, h->stream>>>(jmap, h->d_items, h->d_rec, s.Ktab, s.RotTab,          \
                                                            s.JacTab, s.G2,                                        \
                                                            s.H3, s.dp, s.e, s.pix, cam, eta,                       \
                                                            (uint32_t)Np, h->d_jrec, h->d_skey, h->d_sval,          \

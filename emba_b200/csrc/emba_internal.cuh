@@ -106,6 +106,10 @@ struct Handle {
   int64_t Ma = 0;               // measurements on active pixels
   double* d_jrec = nullptr;     // [Mc*16] Jacobian rows
   int64_t jrec_cap = 0;
+  // TMA descriptor of d_jrec as a [Mc][16] fp64 tensor, 256-row boxes, 128-byte swizzle (k_asm_pose stores)
+  alignas(64) unsigned char jrec_tmap[128] = {};
+  const void* jrec_tmap_ptr = nullptr;
+  int64_t jrec_tmap_rows = 0;
   int64_t sort_cap = 0;
   uint32_t* d_skey = nullptr;   // sort keys/values (double-buffered)
   uint32_t* d_sval = nullptr;
