@@ -107,6 +107,26 @@ k_asm_pose(const __grid_constant__ CUtensorMap jmap, const WorkItem* __restrict_
   double2* trow = reinterpret_cast<double2*>(tile + tid * kRecDoubles);
   const int swz = tid & 7;
   bool store_pending = false;
+  // streamed per-measurement inputs of the NEXT tile are requested before the tensor-core phase of the current
+  // one, and all of them at once: the dependent gathers (map Hessian / gradient by pixel, batch tables by batch)
+  // then sit one memory latency behind them instead of three
+  int32_t pix_n = -1;
+  double4 r0_n = make_double4(0.0, 0.0, 0.0, 0.0);
+  double2 dp_n = make_double2(0.0, 0.0);
+  double e_n = 0.0;
+  auto fetch = [&](int t0) {
+    const int j = t0 + tid;
+    if (j < it.count) {
+      const int64_t m = (int64_t)it.start + j;
+      pix_n = pix_in[m];
+      r0_n = ldg256(rec + m);
+      dp_n = dp_in[m];
+      e_n = e_in[m];
+    } else {
+      pix_n = -1;
+    }
+  };
+  fetch(0);
   for (int t0 = 0; t0 < it.count; t0 += kAsmThreads) {
     const int j = t0 + tid;
     double row[13];
@@ -115,23 +135,24 @@ k_asm_pose(const __grid_constant__ CUtensorMap jmap, const WorkItem* __restrict_
     double d0 = 0.0, d1 = 0.0;
     const int64_t m = (int64_t)it.start + j;
     if (j < it.count) {
-      const int32_t pix = pix_in[m];
+      const int32_t pix = pix_n;
       double4 Hh = make_double4(0.0, 0.0, 0.0, 0.0);
+      double2 g = make_double2(0.0, 0.0);
       int32_t a = -1;  // model.cpp:396-412: outliers and inactive pixels are skipped
       if (pix >= 0) {
         Hh = ldg256(H3 + pix);
+        g = G2[pix];
         a = (int32_t)__double_as_longlong(Hh.w);
       }
       skey[m] = a >= 0 ? (uint32_t)a : invalid_key;
       sval[m] = (uint32_t)m;
       if (a >= 0) {
-        const double4 r0 = ldg256(rec + m);
+        const double4 r0 = r0_n;
         const double bx = r0.x, by = r0.y, bz = r0.z;
         const unsigned long long rw = (unsigned long long)__double_as_longlong(r0.w);
         const uint32_t bc = (uint32_t)rw & 0x7FFFFFFFu, bp = (uint32_t)(rw >> 32);
-        const double2 dpv = dp_in[m];
-        double e = e_in[m];
-        const double2 g = G2[pix];
+        const double2 dpv = dp_n;
+        double e = e_n;
         // temp = Gpm + dp^T * G2pm (model.cpp:233-238)
         const double h0 = g.x + dpv.x * Hh.x + dpv.y * Hh.y;
         const double h1 = g.y + dpv.x * Hh.y + dpv.y * Hh.z;
@@ -186,6 +207,7 @@ k_asm_pose(const __grid_constant__ CUtensorMap jmap, const WorkItem* __restrict_
         make_double2(d1, __longlong_as_double((long long)(meta_lo | ((unsigned long long)(uint32_t)m << 32))));
     fence_async_smem();
     __syncthreads();
+    fetch(t0 + kAsmThreads);
     // Jacobian rows -> global
     const int nrec = min(kAsmThreads, it.count - t0);
     if (nrec == kAsmThreads) {
