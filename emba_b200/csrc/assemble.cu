@@ -6,9 +6,10 @@
 //      [Jc Jp e]^T [Jc Jp e] (A11 blocks, b1) are accumulated in registers from a shared-memory tile and
 //      reduced with warp shuffles; per-item partials are combined in a fixed order (deterministic).
 //      The row is also written out (128-byte record) for the map side.
-//   3. map side: rows are ordered by target pixel with a stable radix sort of (active index, row id); one warp
-//      per active pixel then reduces its rows in that fixed order into A22 / b2 and the pixel's A12 strip
-//      (3x2 block per control pose in the pixel's pose window) -- a deterministic segmented reduction.
+//   3. map side: rows are ordered by target pixel with a stable radix sort of (pixel, row id) -- it needs only the
+//      evaluation's pixel lookups, so it runs on a side stream beside step 2; one warp per active pixel then
+//      reduces its rows in that fixed order into A22 / b2 and the pixel's A12 strip (3x2 block per control pose
+//      in the pixel's pose window) -- a deterministic segmented reduction.
 #include <climits>
 #include <cuda.h>
 #include <cub/cub.cuh>
@@ -87,9 +88,8 @@ k_asm_pose(const __grid_constant__ CUtensorMap jmap, const WorkItem* __restrict_
            const MeasRec* __restrict__ rec, const double* __restrict__ Ktab, const double4* __restrict__ RotTab,
            const double4* __restrict__ JacTab, const double2* __restrict__ G2, const double4* __restrict__ H3,
            const double2* __restrict__ dp_in, const double* __restrict__ e_in, const int32_t* __restrict__ pix_in,
-           PanoCam cam, double eta, uint32_t invalid_key, double* __restrict__ jrec, uint32_t* __restrict__ skey,
-           uint32_t* __restrict__ sval, int32_t* __restrict__ winlo, int32_t* __restrict__ winhi,
-           double* __restrict__ acc_part) {
+           PanoCam cam, double eta, double* __restrict__ jrec, int32_t* __restrict__ winlo,
+           int32_t* __restrict__ winhi, double* __restrict__ acc_part) {
   __shared__ __align__(1024) double tile[kAsmThreads * kRecDoubles];  // [row][16], chunk-swizzled
   __shared__ double knots[2 * kKnotStride];  // knot-interval data of cp_c and cp_p: uniform over the work item
   const WorkItem it = items[blockIdx.x];
@@ -144,8 +144,6 @@ k_asm_pose(const __grid_constant__ CUtensorMap jmap, const WorkItem* __restrict_
         g = G2[pix];
         a = (int32_t)__double_as_longlong(Hh.w);
       }
-      skey[m] = a >= 0 ? (uint32_t)a : invalid_key;
-      sval[m] = (uint32_t)m;
       if (a >= 0) {
         const double4 r0 = r0_n;
         const double bx = r0.x, by = r0.y, bz = r0.z;
@@ -361,18 +359,37 @@ __global__ void k_strip_len(const int32_t* __restrict__ winlo, const int32_t* __
   len[a] = hi >= lo ? (int64_t)(hi - lo + 1) : 0;
 }
 
-// segment [segoff[a], segoff[a+1]) of the rows of active pixel a in the sorted key array; segoff[Np] = number of
-// valid rows (rows of outliers / inactive pixels carry key Np and sort to the end)
-__global__ void k_seg_bounds(const uint32_t* __restrict__ keys, int64_t M, int64_t Np, int32_t* __restrict__ segoff) {
+// sort input: key = panorama pixel of the row (P for outliers, which then sort to the end), value = row id
+__global__ void k_sort_keys(const int32_t* __restrict__ pix, int64_t M, uint32_t P, uint32_t* __restrict__ key,
+                            uint32_t* __restrict__ val) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int32_t p = pix[m];
+  key[m] = p >= 0 ? (uint32_t)p : P;
+  val[m] = (uint32_t)m;
+}
+
+// rows [segoff[a], segend[a]) of the sorted list belong to active pixel a (rows of inactive pixels lie between)
+__global__ void k_seg_bounds(const uint32_t* __restrict__ keys, int64_t M, int64_t Np,
+                             const int32_t* __restrict__ apix, int32_t* __restrict__ segoff,
+                             int32_t* __restrict__ segend) {
   const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (a > Np) return;
+  if (a >= Np) return;
+  const uint32_t p = (uint32_t)apix[a];
   int64_t lo = 0, hi = M;
   while (lo < hi) {
     const int64_t mid = (lo + hi) >> 1;
-    if (keys[mid] < (uint32_t)a) lo = mid + 1;
+    if (keys[mid] < p) lo = mid + 1;
     else hi = mid;
   }
   segoff[a] = (int32_t)lo;
+  hi = M;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (keys[mid] <= p) lo = mid + 1;
+    else hi = mid;
+  }
+  segend[a] = (int32_t)lo;
 }
 
 // Map side: one warp per active pixel, rows in fixed (sorted) order. The 128-byte rows are gathered with cp.async
@@ -493,7 +510,8 @@ __device__ __forceinline__ void pix_one(int64_t seg0, int64_t seg1, int qlo, int
 }
 
 __global__ void __launch_bounds__(kPixWarps * 32)
-k_pix(int64_t Np, const int32_t* __restrict__ segoff, const uint32_t* __restrict__ sval,
+k_pix(int64_t Np, const int32_t* __restrict__ segoff, const int32_t* __restrict__ segend,
+      const uint32_t* __restrict__ sval,
       const double* __restrict__ jrec, const int32_t* __restrict__ winlo, const int32_t* __restrict__ winhi,
       const int64_t* __restrict__ stripoff, double* __restrict__ strip, const int32_t* __restrict__ apix,
       const double* __restrict__ Gx, const double* __restrict__ Gy, double alpha, double* __restrict__ A22,
@@ -514,7 +532,7 @@ k_pix(int64_t Np, const int32_t* __restrict__ segoff, const uint32_t* __restrict
   else if (lane == 28) { ia = 14; ib = 12; }
   for (int64_t a = (int64_t)blockIdx.x * kPixWarps + warp; a < Np; a += nw) {
     const int64_t seg0 = segoff[a];
-    const int64_t seg1 = segoff[a + 1];
+    const int64_t seg1 = segend[a];
     const int qlo = winlo[a];
     const int len = winhi[a] >= qlo ? winhi[a] - qlo + 1 : 0;  // empty window: no local rows (multi-GPU)
     double* gs = strip + stripoff[a] * 6;
@@ -535,13 +553,15 @@ k_pix(int64_t Np, const int32_t* __restrict__ segoff, const uint32_t* __restrict
 // fp64-atomic map-block path (reported beside the deterministic one): one thread per Jacobian row in canonical
 // order, 24 + 5 atomic adds into the pixel's strip / A22 / b2. Strips, A22 and b2 must be zeroed first.
 __global__ void __launch_bounds__(256)
-k_map_atomic(int64_t Mc, const uint32_t* __restrict__ skey, uint32_t invalid_key, const double* __restrict__ jrec,
+k_map_atomic(int64_t Mc, const int32_t* __restrict__ pix_in, const int32_t* __restrict__ amap,
+             const double* __restrict__ jrec,
              const int32_t* __restrict__ winlo, const int64_t* __restrict__ stripoff, double* __restrict__ strip,
              double* __restrict__ A22, double* __restrict__ b2) {
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= Mc) return;
-  const uint32_t a = skey[m];
-  if (a == invalid_key) return;
+  const int32_t pix = pix_in[m];
+  const int32_t a = pix >= 0 ? amap[pix] : -1;
+  if (a < 0) return;
   const double4* r4 = reinterpret_cast<const double4*>(jrec + (size_t)m * kRecDoubles);
   const double4 q0 = ldg256(r4), q1 = ldg256(r4 + 1), q2 = ldg256(r4 + 2), q3 = ldg256(r4 + 3);
   const double J[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
@@ -627,6 +647,36 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   h->thres = thres;
   h->formed = false;
   EMBA_CUDA(cudaEventRecord(h->ev[4], h->stream));
+  // ---- 0. side stream: stable radix sort of the rows by panorama pixel. It depends on the evaluation only, so it
+  // overlaps the active-set scan and the pose-side kernel; the main stream joins it before the map-side kernel.
+  const bool atomic_path = h->map_path == EMBA_MAP_ATOMIC;
+  uint32_t* sorted_keys = h->d_skey;
+  uint32_t* vs = h->d_sval;
+  if (!atomic_path && h->Mc > 0) {
+    const int64_t Mc = h->Mc;
+    int bits = 1;
+    while (bits < 32 && ((uint64_t)P >> bits)) bits++;  // keys 0..P
+    cub::DoubleBuffer<uint32_t> dk(h->d_skey, h->d_skey2), dv(h->d_sval, h->d_sval2);
+    size_t tb = 0;
+    EMBA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int)Mc, 0, bits, h->stream2));
+    if (tb > h->sort_tmp_bytes) {
+      if (h->d_sort_tmp) cudaFree(h->d_sort_tmp);
+      h->d_sort_tmp = nullptr;
+      h->sort_tmp_bytes = 0;
+      EMBA_CUDA(cudaMalloc(&h->d_sort_tmp, tb));
+      h->sort_tmp_bytes = tb;
+    }
+    EMBA_CUDA(cudaEventRecord(h->ev_fork, h->stream));
+    EMBA_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+    EMBA_CUDA(cudaEventRecord(h->ev_sort0, h->stream2));
+    k_sort_keys<<<ceil_div64(Mc, T), T, 0, h->stream2>>>(s.pix, Mc, (uint32_t)P, h->d_skey, h->d_sval);
+    EMBA_CUDA(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp, tb, dk, dv, (int)Mc, 0, bits, h->stream2));
+    h->launches += 2 + 2 * ((bits + 7) / 8);
+    sorted_keys = dk.Current();
+    vs = dv.Current();
+    EMBA_CUDA(cudaEventRecord(h->ev_sort1, h->stream2));
+    EMBA_CUDA(cudaEventRecord(h->ev_join, h->stream2));
+  }
   // ---- 1. active set (model.cpp:324-379): mask + exclusive scan reproduces the ascending std::set order
   int32_t *d_flag = h->d_pflag, *d_aidx = h->d_paidx;
   int64_t* d_len = h->d_len;
@@ -636,12 +686,12 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   k_active_flags<<<ceil_div64(P, T), T, 0, h->stream>>>(s.hist, P, thres, d_flag);
   h->launches++;
   EMBA_TRYC(cub_exclusive_sum(h, d_flag, d_aidx, P));
-  int32_t tail[2];
+  // Np goes back to the host through pinned memory; the host waits for it only after the pose-side kernel (which
+  // does not need it) has been queued, so the round trip hides behind that kernel
+  int32_t* tail = reinterpret_cast<int32_t*>(h->h_pin);
   EMBA_CUDAC(cudaMemcpyAsync(&tail[0], d_aidx + (P - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   EMBA_CUDAC(cudaMemcpyAsync(&tail[1], d_flag + (P - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-  EMBA_CUDAC(cudaStreamSynchronize(h->stream));
-  const int64_t Np = (int64_t)tail[0] + tail[1];
-  h->Np = Np;
+  EMBA_CUDAC(cudaEventRecord(h->ev_host, h->stream));
   k_active_fill<<<ceil_div64(P, T), T, 0, h->stream>>>(d_flag, d_aidx, P, h->d_amap, h->d_apix, h->d_winlo, h->d_winhi, s.H3);
   h->launches++;
   // ---- 2. pose side + Jacobian rows
@@ -655,7 +705,7 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   k_asm_pose<C><<<h->n_items, kAsmThreads, 0, h->stream>>>(jmap, h->d_items, h->d_rec, s.Ktab, s.RotTab,          \
                                                            s.JacTab, s.G2,                                        \
                                                            s.H3, s.dp, s.e, s.pix, cam, eta,                       \
-                                                           (uint32_t)Np, h->d_jrec, h->d_skey, h->d_sval,          \
+                                                           h->d_jrec,                                              \
                                                            h->d_winlo, h->d_winhi, h->d_acc_part)
     if (cost_type == EMBA_COST_QUADRATIC) EMBA_ASM_LAUNCH(EMBA_COST_QUADRATIC);
     else if (cost_type == EMBA_COST_CAUCHY) EMBA_ASM_LAUNCH(EMBA_COST_CAUCHY);
@@ -665,41 +715,47 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
     EMBA_CUDAC(cudaGetLastError());
   }
   EMBA_CUDAC(cudaEventRecord(h->ev[6], h->stream));
-  EMBA_CUDAC(cudaMemsetAsync(h->d_A11, 0, sizeof(double) * 9 * n * n, h->stream));
-  EMBA_CUDAC(cudaMemsetAsync(h->d_b1, 0, sizeof(double) * 3 * n, h->stream));
+  EMBA_CUDAC(cudaEventSynchronize(h->ev_host));
+  const int64_t Np = (int64_t)tail[0] + tail[1];
+  h->Np = Np;
+  // ---- 3. map side: pose windows -> strip offsets. The strip total is read back while the A11 / b1 gather runs.
+  EMBA_CUDAC(cudaMemsetAsync(d_len, 0, sizeof(int64_t) * (Np + 1), h->stream));
+  if (Np) { k_strip_len<<<ceil_div64(Np, T), T, 0, h->stream>>>(h->d_winlo, h->d_winhi, Np, d_len); h->launches++; }
+  EMBA_TRYC(cub_exclusive_sum(h, d_len, h->d_stripoff, Np + 1));
+  EMBA_CUDAC(cudaMemcpyAsync(h->h_pin + 2, h->d_stripoff + Np, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+  EMBA_CUDAC(cudaEventRecord(h->ev_host, h->stream));
+  // the small A11 / b1 gather is latency-bound on a tiny grid: it goes to the side stream (behind the sort) and
+  // runs beside the map-side kernel; the main stream joins it at the end
+  EMBA_CUDAC(cudaEventRecord(h->ev_fork2, h->stream));
+  EMBA_CUDAC(cudaStreamWaitEvent(h->stream2, h->ev_fork2, 0));
+  EMBA_CUDAC(cudaMemsetAsync(h->d_A11, 0, sizeof(double) * 9 * n * n, h->stream2));
+  EMBA_CUDAC(cudaMemsetAsync(h->d_b1, 0, sizeof(double) * 3 * n, h->stream2));
   if (h->n_groups > 0) {
-    k_group_sum<<<h->n_groups, 96, 0, h->stream>>>(h->d_acc_part, h->d_group_item0, h->n_groups, h->d_gsum);
+    k_group_sum<<<h->n_groups, 96, 0, h->stream2>>>(h->d_acc_part, h->d_group_item0, h->n_groups, h->d_gsum);
     h->launches++;
     const size_t shm = sizeof(double) * (9 * (size_t)n + 3);
     if (shm > 48 * 1024) EMBA_CUDAC(cudaFuncSetAttribute(k_a11_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-    k_a11_gather<<<n, 64, shm, h->stream>>>(n, h->dmax, h->d_gid, h->d_gsum, h->d_A11, h->d_b1);
+    k_a11_gather<<<n, 64, shm, h->stream2>>>(n, h->dmax, h->d_gid, h->d_gsum, h->d_A11, h->d_b1);
     h->launches++;
     EMBA_CUDAC(cudaGetLastError());
   }
+  EMBA_CUDAC(cudaEventRecord(h->ev_join2, h->stream2));
   // multi-GPU: A11 / b1 stay partial here. The damped pose block A11 + lambda*diag(A11) is linear in A11, so every
   // rank subtracts its Schur contributions from its OWN partial and one all-reduce in the solve combines both
   // (saves a 72 n^2-byte all-reduce per assembly); emba_get_normal_eq combines them on demand.
   h->a11_partial = h->world > 1;
-  // ---- 3. map side: pose windows -> strip offsets
-  EMBA_CUDAC(cudaMemsetAsync(d_len, 0, sizeof(int64_t) * (Np + 1), h->stream));
-  if (Np) { k_strip_len<<<ceil_div64(Np, T), T, 0, h->stream>>>(h->d_winlo, h->d_winhi, Np, d_len); h->launches++; }
-  EMBA_TRYC(cub_exclusive_sum(h, d_len, h->d_stripoff, Np + 1));
-  int64_t tot = 0;
-  EMBA_CUDAC(cudaMemcpyAsync(&tot, h->d_stripoff + Np, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
-  EMBA_CUDAC(cudaStreamSynchronize(h->stream));
+  EMBA_CUDAC(cudaEventSynchronize(h->ev_host));
+  const int64_t tot = h->h_pin[2];
   h->strip_total = tot;
   EMBA_TRYC(dev_reserve(h, &h->d_strip, &h->strip_cap, tot * 6 + tot * 3));  // +50 %: windows drift between iterations
-  // stable radix sort of the rows by active pixel index (rows of outliers / inactive pixels carry key Np)
-  uint32_t* vs = h->d_sval;
   EMBA_CUDAC(cudaEventRecord(h->ev[8], h->stream));
-  const bool atomic_path = h->map_path == EMBA_MAP_ATOMIC;
   if (atomic_path) {
     EMBA_CUDAC(cudaEventRecord(h->ev[9], h->stream));
     EMBA_CUDAC(cudaMemsetAsync(h->d_strip, 0, sizeof(double) * 6 * (size_t)tot, h->stream));
     EMBA_CUDAC(cudaMemsetAsync(h->d_A22, 0, sizeof(double) * 3 * (size_t)Np, h->stream));
     EMBA_CUDAC(cudaMemsetAsync(h->d_b2, 0, sizeof(double) * 2 * (size_t)Np, h->stream));
     if (Mc > 0) {
-      k_map_atomic<<<ceil_div64(Mc, 256), 256, 0, h->stream>>>(Mc, h->d_skey, (uint32_t)Np, h->d_jrec, h->d_winlo,
+      k_map_atomic<<<ceil_div64(Mc, 256), 256, 0, h->stream>>>(Mc, s.pix, h->d_amap, h->d_jrec, h->d_winlo,
                                                                h->d_stripoff, h->d_strip, h->d_A22, h->d_b2);
       h->launches++;
       EMBA_CUDAC(cudaGetLastError());
@@ -711,38 +767,28 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
       h->launches++;
     }
   } else if (Mc > 0) {
-    int bits = 1;
-    while (bits < 32 && ((uint64_t)Np >> bits)) bits++;
-    cub::DoubleBuffer<uint32_t> dk(h->d_skey, h->d_skey2), dv(h->d_sval, h->d_sval2);
-    size_t tb = 0;
-    EMBA_CUDAC(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int)Mc, 0, bits, h->stream));
-    if (tb > h->cub_tmp_bytes) {
-      if (h->d_cub_tmp) cudaFree(h->d_cub_tmp);
-      h->d_cub_tmp = nullptr;
-      h->cub_tmp_bytes = 0;
-      EMBA_CUDAC(cudaMalloc(&h->d_cub_tmp, tb));
-      h->cub_tmp_bytes = tb;
+    EMBA_CUDAC(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    if (Np > 0) {
+      k_seg_bounds<<<ceil_div64(Np, T), T, 0, h->stream>>>(sorted_keys, Mc, Np, h->d_apix, h->d_segoff, h->d_segend);
+      h->launches++;
     }
-    EMBA_CUDAC(cub::DeviceRadixSort::SortPairs(h->d_cub_tmp, tb, dk, dv, (int)Mc, 0, bits, h->stream));
-    h->launches += 1 + 2 * ((bits + 7) / 8);
-    vs = dv.Current();
-    k_seg_bounds<<<ceil_div64(Np + 1, T), T, 0, h->stream>>>(dk.Current(), Mc, Np, h->d_segoff);
-    h->launches++;
   } else {
     EMBA_CUDAC(cudaMemsetAsync(h->d_segoff, 0, sizeof(int32_t) * (Np + 1), h->stream));
+    EMBA_CUDAC(cudaMemsetAsync(h->d_segend, 0, sizeof(int32_t) * (Np + 1), h->stream));
   }
   if (!atomic_path) EMBA_CUDAC(cudaEventRecord(h->ev[9], h->stream));
   if (Np > 0 && !atomic_path) {
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((Np + kPixWarps - 1) / kPixWarps, (int64_t)h->sm_count * 16));
     const int pix_smem = kPixWarps * kPixSmemPerWarp;
     EMBA_CUDAC(cudaFuncSetAttribute(k_pix, cudaFuncAttributeMaxDynamicSharedMemorySize, pix_smem));
-    k_pix<<<grid, kPixWarps * 32, pix_smem, h->stream>>>(Np, h->d_segoff, vs, h->d_jrec, h->d_winlo, h->d_winhi,
+    k_pix<<<grid, kPixWarps * 32, pix_smem, h->stream>>>(Np, h->d_segoff, h->d_segend, vs, h->d_jrec, h->d_winlo, h->d_winhi,
                                                   h->d_stripoff, h->d_strip, h->d_apix, s.Gx, s.Gy,
                                                   h->rank == 0 ? alpha : 0.0, h->d_A22, h->d_b2);
     h->launches++;
     EMBA_CUDAC(cudaGetLastError());
   }
   EMBA_CUDAC(cudaEventRecord(h->ev[10], h->stream));
+  EMBA_CUDAC(cudaStreamWaitEvent(h->stream, h->ev_join2, 0));
   h->sv_winlo = h->d_winlo; h->sv_winhi = h->d_winhi; h->sv_stripoff = h->d_stripoff; h->sv_strip = h->d_strip;
   h->sv_strip_total = tot;
   if (h->world > 1 && Np > 0) {
@@ -760,7 +806,8 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   cudaEventElapsedTime(&ms, h->ev[5], h->ev[6]); h->t_ms[3] = ms;
   cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]); h->t_ms[4] = ms;
   cudaEventElapsedTime(&ms, h->ev[9], h->ev[10]); h->t_ms[6] = ms;
-  cudaEventElapsedTime(&ms, h->ev[8], h->ev[9]); h->t_ms[7] = ms;
+  h->t_ms[7] = 0.0;
+  if (!atomic_path && Mc > 0) { cudaEventElapsedTime(&ms, h->ev_sort0, h->ev_sort1); h->t_ms[7] = ms; }
   cleanup();
 #undef EMBA_TRYC
 #undef EMBA_CUDAC

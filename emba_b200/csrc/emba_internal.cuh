@@ -54,6 +54,11 @@ struct Handle {
   std::string err;
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // side stream: the row sort runs beside the pose-side assembly
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sort0 = nullptr, ev_sort1 = nullptr;
+  cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
+  cudaEvent_t ev_host = nullptr;   // marks a small device->host read-back the host waits for while later launches queue
+  int64_t* h_pin = nullptr;        // pinned host scratch (8 x int64) for those read-backs
   int sm_count = 148;
   int64_t launches = 0;
   // config
@@ -102,7 +107,8 @@ struct Handle {
   int32_t* d_paidx = nullptr;   // [P] scratch: exclusive scan of the flags
   int64_t* d_len = nullptr;     // [P+1] scratch: strip lengths
   int32_t* d_apix = nullptr;    // [Np] pixel index of each active pixel
-  int32_t* d_segoff = nullptr;  // [Np+1] offsets of the per-pixel row segments in the sorted row list
+  int32_t* d_segoff = nullptr;  // [Np] first row of each active pixel's segment in the sorted row list
+  int32_t* d_segend = nullptr;  // [Np] one past its last row
   int64_t Ma = 0;               // measurements on active pixels
   double* d_jrec = nullptr;     // [Mc*16] Jacobian rows
   int64_t jrec_cap = 0;
@@ -117,6 +123,8 @@ struct Handle {
   uint32_t* d_sval2 = nullptr;
   void* d_cub_tmp = nullptr;
   size_t cub_tmp_bytes = 0;
+  void* d_sort_tmp = nullptr;   // radix-sort scratch (side stream: must not alias the scans' scratch)
+  size_t sort_tmp_bytes = 0;
   int32_t* d_winlo = nullptr;   // [Np] first control pose touching the pixel
   int32_t* d_winhi = nullptr;   // [Np] last control pose touching the pixel
   int64_t* d_stripoff = nullptr;  // [Np+1] offsets (in poses) of the per-pixel A12 strips

@@ -215,6 +215,15 @@ int emba_create(const emba_config_t* cfg, emba_handle_t* out) {
   cudaGetDeviceProperties(&prop, h->device);
   h->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return EMBA_E_CUDA; }
+  if (cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess) { delete h; return EMBA_E_CUDA; }
+  cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_fork2, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_host, cudaEventDisableTiming);
+  if (cudaMallocHost((void**)&h->h_pin, 8 * sizeof(int64_t)) != cudaSuccess) { delete h; return EMBA_E_CUDA; }
+  cudaEventCreate(&h->ev_sort0);
+  cudaEventCreate(&h->ev_sort1);
   for (auto& e : h->ev) cudaEventCreate(&e);
   h->Ws = cfg->sensor_w; h->Hs = cfg->sensor_h; h->Wp = cfg->pano_w; h->Hp = cfg->pano_h;
   h->P = (int64_t)h->Wp * h->Hp;
@@ -242,6 +251,7 @@ int emba_create(const emba_config_t* cfg, emba_handle_t* out) {
        cudaMalloc((void**)&h->d_len, sizeof(int64_t) * P1) == cudaSuccess &&
        cudaMalloc((void**)&h->d_apix, sizeof(int32_t) * P1) == cudaSuccess &&
        cudaMalloc((void**)&h->d_segoff, sizeof(int32_t) * P1) == cudaSuccess &&
+       cudaMalloc((void**)&h->d_segend, sizeof(int32_t) * P1) == cudaSuccess &&
        cudaMalloc((void**)&h->d_winlo, sizeof(int32_t) * P1) == cudaSuccess &&
        cudaMalloc((void**)&h->d_winhi, sizeof(int32_t) * P1) == cudaSuccess &&
        cudaMalloc((void**)&h->d_stripoff, sizeof(int64_t) * P1) == cudaSuccess &&
@@ -258,17 +268,21 @@ int emba_destroy(emba_handle_t hh) {
   Handle* h = (Handle*)hh;
   if (!h) return EMBA_OK;
   cudaSetDevice(h->device);
+  if (h->stream2) cudaStreamSynchronize(h->stream2);
   if (h->stream) cudaStreamSynchronize(h->stream);
   comm_destroy(h);
   free_state(h->st[0]); free_state(h->st[1]);
   void* ptrs[] = {h->d_lut, h->d_tmid, h->d_spix_ev, h->d_pol, h->d_prev, h->d_refrank, h->d_bs, h->d_bu, h->d_rec, h->d_refpos,
                   h->d_items, h->d_gid, h->d_group_item0, h->d_part, h->d_scal, h->d_flags, h->d_amap, h->d_pflag, h->d_paidx, h->d_len, h->d_apix,
-                  h->d_segoff, h->d_jrec, h->d_skey, h->d_sval, h->d_skey2, h->d_sval2, h->d_cub_tmp, h->d_winlo,
+                  h->d_segoff, h->d_segend, h->d_jrec, h->d_skey, h->d_sval, h->d_skey2, h->d_sval2, h->d_cub_tmp, h->d_sort_tmp, h->d_winlo,
                   h->d_winhi, h->d_stripoff, h->d_strip, h->d_A22, h->d_b2, h->d_acc_part, h->d_gsum, h->d_A11,
                   h->d_b1, h->d_C, h->d_S, h->d_rhs, h->d_x1, h->d_x2, h->d_Spart, h->d_cg, h->d_ldlt_w, h->d_win2, h->d_win_all, h->d_own_len,
                   h->d_own_off, h->d_gwinlo, h->d_gwinhi, h->d_gstripoff, h->d_gstrip, h->d_recv};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : {h->ev_fork, h->ev_join, h->ev_fork2, h->ev_join2, h->ev_sort0, h->ev_sort1, h->ev_host}) if (e) cudaEventDestroy(e);
+  if (h->h_pin) cudaFreeHost(h->h_pin);
+  if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return EMBA_OK;
