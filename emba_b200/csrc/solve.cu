@@ -33,14 +33,34 @@ __global__ void k_a22_inv(int64_t Np, const double* __restrict__ A22, double lam
 
 // ---------------------------------------------------------------------------------------------------
 // Schur tiles. Extended index space [0, d]: rows 0..d-1 are pose unknowns (row = 3*(pose - fix) + r), row d is
-// the right-hand-side "row" (value C_a b2_a per pixel). Tile = 48 rows (16 poses). One CTA accumulates one
-// (I <= J) tile pair over one chunk of pixels; 16x16 threads, 3x3 outputs each, K step = 8 pixels x 2 columns.
+// the right-hand-side "row" (value b2_a per pixel on the J side). Tile = 48 rows (16 poses). One CTA accumulates
+// one (I <= J) tile pair over one chunk of pixels: sum_a W_I,a C_a W_J,a^T with W the pixel's strip rows (x2).
+//   * pixels whose pose window misses either tile are compacted away per block of 128 (ballot order);
+//   * the strip rows of 8 listed pixels per step go global -> shared with 16-byte cp.async (zero-filled outside
+//     the pixel's window), double-buffered, so no registers or store instructions are spent on staging;
+//   * the 48 x 48 x 16 products run on the fp64 tensor cores (m8n8k4): each of the 4 warps owns a 3 x 3 group of
+//     8x8 blocks; the 2x2 factor C_a is applied to the I-side fragment in registers (one shuffle with the lane
+//     holding the pixel's other column + 2 FMAs), so neither side needs a transformed copy in memory.
 // ---------------------------------------------------------------------------------------------------
 constexpr int kST = 48;
-constexpr int kSK = 16;
+constexpr int kSPix = 8;   // pixels per step (K = 16)
 constexpr int kSchurThreads = 128;
 
-__global__ void __launch_bounds__(kSchurThreads)
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+// 16-byte async copy; src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16_zfill(void* smem, const void* gmem, int src_bytes) {
+  const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_s() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_s() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(kSchurThreads, 4)
 k_schur_tiles(int64_t Np, int d, int fix, int nt, int Z, const int32_t* __restrict__ winlo,
               const int32_t* __restrict__ winhi, const int64_t* __restrict__ stripoff,
               const double* __restrict__ strip, const double* __restrict__ C, const double* __restrict__ b2,
@@ -56,35 +76,29 @@ k_schur_tiles(int64_t Np, int d, int fix, int nt, int Z, const int32_t* __restri
   // pose ranges covered by the tiles (poses are >= fix)
   const int pI0 = rowI0 / 3 + fix, pI1 = min(d - 1, rowI0 + kST - 1) / 3 + fix;
   const int pJ0 = rowJ0 / 3 + fix, pJ1 = min(d - 1, rowJ0 + kST - 1) / 3 + fix;
-  __shared__ double VI[kSK][kST];
-  __shared__ double VJ[kSK][kST];
-  // per listed pixel: first row of its window in the reduced system, number of rows, strip base, C, C b2
+  // [stage][side][pixel][row] as (column 0, column 1) pairs: k = 2*pixel + column
+  __shared__ __align__(16) double2 V[2][2][kSPix][kST];
+  // per listed pixel: first row of its window in the reduced system, number of rows, strip base, C, b2
   __shared__ int32_t m_row0[kSchurThreads], m_rows[kSchurThreads];
   __shared__ int64_t m_base[kSchurThreads];
-  __shared__ double m_c[kSchurThreads][3], m_t[kSchurThreads][2];
+  __shared__ double m_c[kSchurThreads][3];
+  __shared__ double2 m_b[kSchurThreads];
   __shared__ int32_t wcount[kSchurThreads / 32];
   __shared__ int32_t nlist;
-  // 8 x 16 threads, 6 x 3 outputs each: 9 shared-memory loads per 18 FMAs
-  const int tid = threadIdx.x, ti = tid & 7, tj = tid >> 3;
-  double acc[6][3];
+  const int tid = threadIdx.x;
+  const int fg = (tid & 31) >> 2, fk = tid & 3;                // fragment row / k index of this lane
+  const int rb0 = 3 * (tid >> 6), cb0 = 3 * ((tid >> 5) & 1);  // first 8-row / 8-column block of this warp
+  double acc[3][3][2];
 #pragma unroll
-  for (int r = 0; r < 6; r++)
+  for (int r = 0; r < 3; r++)
 #pragma unroll
-    for (int c = 0; c < 3; c++) acc[r][c] = 0.0;
-  // staging roles: 8 pixels x 2 sides x 48 rows = 768 double2 items per step, 6 per thread
-  constexpr int kStage = (kSK / 2) * kST * 2 / kSchurThreads;
-  int s_pl[kStage], s_side[kStage], s_rr[kStage];
-#pragma unroll
-  for (int q = 0; q < kStage; q++) {
-    const int e = tid + kSchurThreads * q;
-    s_pl[q] = e / (kST * 2);
-    s_side[q] = (e % (kST * 2)) / kST;
-    s_rr[q] = e % kST;
-  }
+    for (int c = 0; c < 3; c++) acc[r][c][0] = acc[r][c][1] = 0.0;
+  // staging roles: 8 pixels x 2 sides x 48 rows = 768 items of 16 bytes per step, 6 per thread
+  constexpr int kStage = kSPix * kST * 2 / kSchurThreads;
   const double2* strip2 = reinterpret_cast<const double2*>(strip);
 
   for (int64_t base = a0; base < a1; base += kSchurThreads) {
-    // compact the pixels of this block of 256 whose window meets both tiles (ballot order -> deterministic)
+    // compact the pixels of this block whose window meets both tiles (ballot order -> deterministic)
     __syncthreads();
     const int64_t a = base + tid;
     bool ok = false;
@@ -97,6 +111,8 @@ k_schur_tiles(int64_t Np, int d, int fix, int nt, int Z, const int32_t* __restri
     }
     const unsigned bal = __ballot_sync(0xffffffffu, ok);
     if ((tid & 31) == 0) wcount[tid >> 5] = __popc(bal);
+    // entries past the list must multiply the zero-filled rows by finite numbers
+    m_c[tid][0] = 0.0; m_c[tid][1] = 0.0; m_c[tid][2] = 0.0;
     __syncthreads();
     int off = 0;
     for (int w = 0; w < (tid >> 5); w++) off += wcount[w];
@@ -105,75 +121,74 @@ k_schur_tiles(int64_t Np, int d, int fix, int nt, int Z, const int32_t* __restri
       m_row0[l] = 3 * (lo - fix);
       m_rows[l] = 3 * (hi - lo + 1);
       m_base[l] = stripoff[a] * 3;  // in double2 units: 3 rows per pose
-      const double c00 = C[3 * a], c01 = C[3 * a + 1], c11 = C[3 * a + 2];
-      m_c[l][0] = c00; m_c[l][1] = c01; m_c[l][2] = c11;
-      const double bx = b2[2 * a], by = b2[2 * a + 1];
-      m_t[l][0] = c00 * bx + c01 * by;  // C_a b2_a: the right-hand-side "row"
-      m_t[l][1] = c01 * bx + c11 * by;
+      m_c[l][0] = C[3 * a]; m_c[l][1] = C[3 * a + 1]; m_c[l][2] = C[3 * a + 2];
+      m_b[l] = make_double2(b2[2 * a], b2[2 * a + 1]);
     }
     if (tid == kSchurThreads - 1) nlist = off + __popc(bal);
     __syncthreads();
     const int nl = nlist;
-    // software pipeline: the loads of step l0+8 are in flight while step l0 is multiplied
-    double2 pre[kStage];
-    auto fetch = [&](int l0) {
+    auto issue = [&](int l0, int st) {
+      if (l0 < nl) {
 #pragma unroll
-      for (int q = 0; q < kStage; q++) {
-        double2 u = make_double2(0.0, 0.0);
-        const int l = l0 + s_pl[q];
-        if (l < nl) {
-          const int grow = (s_side[q] ? rowJ0 : rowI0) + s_rr[q];
-          if (grow < d) {
-            const int rel = grow - m_row0[l];
-            if (rel >= 0 && rel < m_rows[l]) u = strip2[m_base[l] + rel];
+        for (int q = 0; q < kStage; q++) {
+          const int e = tid + kSchurThreads * q;
+          const int pl = e / (kST * 2), side = (e % (kST * 2)) / kST, rr = e % kST;
+          const int l = l0 + pl;
+          const int grow = (side ? rowJ0 : rowI0) + rr;
+          if (side && grow == d) {  // the right-hand-side "row" of the J tile carries b2_a (plain store)
+            V[st][1][pl][rr] = l < nl ? m_b[l] : make_double2(0.0, 0.0);
+            continue;
           }
-        }
-        pre[q] = u;
-      }
-    };
-    if (nl > 0) fetch(0);
-    for (int l0 = 0; l0 < nl; l0 += kSK / 2) {
-#pragma unroll
-      for (int q = 0; q < kStage; q++) {
-        double2 u = pre[q];
-        const int l = l0 + s_pl[q];
-        if (s_side[q]) {
+          const double2* src = strip2;
+          int bytes = 0;
           if (l < nl) {
-            const int grow = rowJ0 + s_rr[q];
-            if (grow < d) {  // J side carries C_a: (u0, u1) <- (u0, u1) C_a
-              const double t0 = u.x * m_c[l][0] + u.y * m_c[l][1], t1 = u.x * m_c[l][1] + u.y * m_c[l][2];
-              u.x = t0; u.y = t1;
-            } else if (grow == d) {
-              u.x = m_t[l][0]; u.y = m_t[l][1];
-            }
+            const int rel = grow - m_row0[l];
+            if (grow < d && rel >= 0 && rel < m_rows[l]) { src = strip2 + m_base[l] + rel; bytes = 16; }
           }
-          VJ[2 * s_pl[q]][s_rr[q]] = u.x; VJ[2 * s_pl[q] + 1][s_rr[q]] = u.y;
-        } else {
-          VI[2 * s_pl[q]][s_rr[q]] = u.x; VI[2 * s_pl[q] + 1][s_rr[q]] = u.y;
+          cp_async16_zfill(&V[st][side][pl][rr], src, bytes);
         }
       }
+      cp_async_commit_s();
+    };
+    issue(0, 0);
+    int st = 0;
+    for (int l0 = 0; l0 < nl; l0 += kSPix, st ^= 1) {
+      issue(l0 + kSPix, st ^ 1);
+      cp_async_wait_s<1>();
       __syncthreads();
-      if (l0 + kSK / 2 < nl) fetch(l0 + kSK / 2);
 #pragma unroll
-      for (int k = 0; k < kSK; k++) {
-        double av[6], bv[3];
+      for (int k0 = 0; k0 < 2 * kSPix; k0 += 4) {
+        const int pl = (k0 >> 1) + (fk >> 1);
+        const double* vi = reinterpret_cast<const double*>(&V[st][0][pl][0]) + (fk & 1);
+        const double* vj = reinterpret_cast<const double*>(&V[st][1][pl][0]) + (fk & 1);
+        const double cs = m_c[l0 + pl][2 * (fk & 1)], cx = m_c[l0 + pl][1];
+        double av[3], bv[3];
 #pragma unroll
-        for (int r = 0; r < 6; r++) av[r] = VI[k][6 * ti + r];
+        for (int r = 0; r < 3; r++) {
+          const double raw = vi[2 * (8 * (rb0 + r) + fg)];
+          const double other = __shfl_xor_sync(0xffffffffu, raw, 1);
+          av[r] = raw * cs + other * cx;  // (W_I C_a)[row][column fk & 1]
+        }
 #pragma unroll
-        for (int c = 0; c < 3; c++) bv[c] = VJ[k][3 * tj + c];
+        for (int c = 0; c < 3; c++) bv[c] = vj[2 * (8 * (cb0 + c) + fg)];
 #pragma unroll
-        for (int r = 0; r < 6; r++)
+        for (int r = 0; r < 3; r++)
 #pragma unroll
-          for (int c = 0; c < 3; c++) acc[r][c] += av[r] * bv[c];
+          for (int c = 0; c < 3; c++) dmma884(acc[r][c][0], acc[r][c][1], av[r], bv[c]);
       }
       __syncthreads();
     }
+    cp_async_wait_s<0>();
   }
   double* out = Spart + ((size_t)z * gridDim.x + blockIdx.x) * (kST * kST);
 #pragma unroll
-  for (int r = 0; r < 6; r++)
+  for (int r = 0; r < 3; r++)
 #pragma unroll
-    for (int c = 0; c < 3; c++) out[(6 * ti + r) * kST + 3 * tj + c] = acc[r][c];
+    for (int c = 0; c < 3; c++) {
+      double* o = out + (8 * (rb0 + r) + fg) * kST + 8 * (cb0 + c) + 2 * fk;
+      o[0] = acc[r][c][0];
+      o[1] = acc[r][c][1];
+    }
 }
 
 // S = A11m - sum_z partial tiles (fixed order); rhs = b1 - (...). A11m = A11 + lambda*diag(A11) (model.cpp:728-730).
