@@ -244,57 +244,87 @@ __device__ __forceinline__ void ldlt_panel_body(int d, int k0, int nb, double* _
   double (*As)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(sm + 2 * kNB * (kNB + 1));
   const int tid = threadIdx.x;
   __syncthreads();
-  for (int e = tid; e < nb * nb; e += 256) {
-    const int i = e / nb, j = e % nb;
-    Dk[i][j] = (j <= i) ? S[(size_t)(k0 + i) * d + k0 + j] : 0.0;
+  // diagonal block (padded with the identity past nb) and, beside it, the first slab of rows below the block:
+  // the slab does not depend on the factorisation, so its load latency hides behind the serial part
+  for (int e = tid; e < kNB * kNB; e += 256) {
+    const int i = e >> 5, j = e & 31;
+    Dk[i][j] = (i < nb && j < nb) ? (j <= i ? S[(size_t)(k0 + i) * d + k0 + j] : 0.0) : (i == j ? 1.0 : 0.0);
+  }
+  if (slab < nslabs) {
+    const int r0 = k0 + nb + slab * 64;
+    for (int e = tid; e < 64 * kNB; e += 256) {
+      const int rr = e >> 5, j = e & 31;
+      As[rr][j] = (r0 + rr < d && j < nb) ? S[(size_t)(r0 + rr) * d + k0 + j] : 0.0;
+    }
   }
   __syncthreads();
-  for (int j = 0; j < nb; j++) {
-    const double dj = Dk[j][j];
-    if (tid == 0 && slab == 0 && (dj == 0.0 || !isfinite(dj))) atomicOr(flags, 8);
-    __syncthreads();
-    // column j: l_ij = a_ij / d_j ; keep y_ij = a_ij in the upper triangle slot for the update below
-    if (tid > j && tid < nb) {
-      const double a = Dk[tid][j];
-      Dk[j][tid] = a;        // y_ij (upper slot)
-      Dk[tid][j] = a / dj;   // l_ij
+  // The 32x32 block is factored by ONE warp with its rows in registers (lane i owns row i; loops fully unrolled,
+  // static register indices): no block barriers on this serial critical path. Column j travels through a
+  // 32-entry shared array read back as broadcasts. Entries above the diagonal accumulate unused junk.
+  if (tid < 32) {
+    const int lane = tid;
+    double* ycol = &Li[0][0];
+    double a[kNB];
+#pragma unroll
+    for (int m = 0; m < kNB; m++) a[m] = Dk[lane][m];
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < kNB; j++) {
+      __syncwarp();
+      ycol[lane] = a[j];  // y_ij = a_ij (lanes i >= j)
+      __syncwarp();
+      const double dj = ycol[j];
+      bad = bad || (j < nb && (dj == 0.0 || !isfinite(dj)));
+      const double lij = a[j] / dj;  // l_ij
+#pragma unroll
+      for (int m = j + 1; m < kNB; m++) a[m] -= lij * ycol[m];  // a_im -= l_ij * y_mj (used for j < m <= i)
+      if (lane > j) a[j] = lij;
     }
-    __syncthreads();
-    // trailing update inside the block: a_im -= l_ij * y_mj for j < m <= i
-    for (int e = tid; e < nb * nb; e += 256) {
-      const int i = e / nb, m = e % nb;
-      if (m > j && i >= m) Dk[i][m] -= Dk[i][j] * Dk[j][m];
+    if (lane == 0 && slab == 0 && bad) atomicOr(flags, 8);
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < kNB; m++)
+      if (m <= lane) Dk[lane][m] = a[m];
+    __syncwarp();
+    // explicit inverse of the unit lower-triangular block: lane j builds column j by forward substitution,
+    // x_i = [i == j] - sum_{m < i} l_im x_m (entries above the diagonal stay exactly zero); l_im is a broadcast
+    double x[kNB];
+#pragma unroll
+    for (int i = 0; i < kNB; i++) {
+      double s0 = (i == lane) ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+      for (int m = 0; m + 1 < i; m += 2) {
+        s0 -= Dk[i][m] * x[m];
+        s1 -= Dk[i][m + 1] * x[m + 1];
+      }
+      if (i & 1) s0 -= Dk[i][i - 1] * x[i - 1];
+      x[i] = s0 + s1;
     }
-    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kNB; i++) Li[i][lane] = x[i];
   }
+  __syncthreads();
   if (slab == 0) {
-    for (int e = tid; e < nb * nb; e += 256) {
-      const int i = e / nb, j = e % nb;
-      if (j <= i) S[(size_t)(k0 + i) * d + k0 + j] = Dk[i][j];
+    for (int e = tid; e < kNB * kNB; e += 256) {
+      const int i = e >> 5, j = e & 31;
+      if (i < nb && j <= i) S[(size_t)(k0 + i) * d + k0 + j] = Dk[i][j];
     }
   }
   // rows below the diagonal block: y = a L^-T, i.e. y_j = sum_{m<=j} a_m Linv[j][m] with the explicit inverse of
-  // the unit lower-triangular block (32 x 32, computed in shared memory) -> fully parallel, coalesced row access
-  if (tid < nb) {  // column tid of L^-1 by forward substitution
-    const int j = tid;
-    for (int i = 0; i < nb; i++) Li[i][j] = (i == j) ? 1.0 : 0.0;
-    for (int i = j + 1; i < nb; i++) {
-      double x = 0.0;
-      for (int m = j; m < i; m++) x -= Dk[i][m] * Li[m][j];
-      Li[i][j] = x;
-    }
-  }
+  // the unit lower-triangular block -> fully parallel, coalesced row access
   for (int sl = slab; sl < nslabs; sl += nslab_stride) {
     const int r0 = k0 + nb + sl * 64;
-    __syncthreads();
-    for (int e = tid; e < 64 * nb; e += 256) {
-      const int rr = e / nb, j = e % nb;
-      As[rr][j] = (r0 + rr < d) ? S[(size_t)(r0 + rr) * d + k0 + j] : 0.0;
+    if (sl != slab) {
+      __syncthreads();
+      for (int e = tid; e < 64 * kNB; e += 256) {
+        const int rr = e >> 5, j = e & 31;
+        As[rr][j] = (r0 + rr < d && j < nb) ? S[(size_t)(r0 + rr) * d + k0 + j] : 0.0;
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    for (int e = tid; e < 64 * nb; e += 256) {
-      const int rr = e / nb, j = e % nb;
-      if (r0 + rr >= d) continue;
+    for (int e = tid; e < 64 * kNB; e += 256) {
+      const int rr = e >> 5, j = e & 31;
+      if (r0 + rr >= d || j >= nb) continue;
       double y = 0.0;
       for (int m = 0; m <= j; m++) y += As[rr][m] * Li[j][m];
       W[(size_t)(r0 + rr) * kNB + j] = y;
@@ -362,22 +392,31 @@ k_ldlt_update(int d, int k0, int nb, double* __restrict__ S, const double* __res
 // The whole factorisation in ONE cooperative launch (grid-wide barriers between the panel and update phases):
 // for the small systems of this path (d = a few hundred) the per-panel launches are latency bound.
 __global__ void __launch_bounds__(256)
-k_ldlt_fused(int d, double* __restrict__ S, double* __restrict__ W, int32_t* __restrict__ flags) {
+k_ldlt_fused(int d, double* __restrict__ S, double* __restrict__ W, int32_t* __restrict__ flags,
+             long long* __restrict__ dbg) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double sm[kLdltSmemDoubles];
+  long long t_panel = 0, t_sync1 = 0, t_upd = 0, t_sync2 = 0;  // EMBA_DEBUG_TIMING: clocks of CTA 0 per phase
   for (int k0 = 0; k0 < d; k0 += kNB) {
     const int nb = min(kNB, d - k0);
     const int rows_below = d - (k0 + nb);
     const int nslabs = (rows_below + 63) / 64;
+    const long long c0 = clock64();
     ldlt_panel_body(d, k0, nb, S, W, flags, blockIdx.x, gridDim.x, nslabs, sm);
+    const long long c1 = clock64();
     grid.sync();
+    const long long c2 = clock64();
     if (rows_below > 0) {
       const int ntile = (rows_below + 63) / 64;
       const int npair = ntile * (ntile + 1) / 2;
       for (int pr = blockIdx.x; pr < npair; pr += gridDim.x) ldlt_update_body(d, k0, nb, S, W, pr, sm);
     }
+    const long long c3 = clock64();
     grid.sync();
+    const long long c4 = clock64();
+    t_panel += c1 - c0; t_sync1 += c2 - c1; t_upd += c3 - c2; t_sync2 += c4 - c3;
   }
+  if (dbg && blockIdx.x == 0 && threadIdx.x == 0) { dbg[0] = t_panel; dbg[1] = t_sync1; dbg[2] = t_upd; dbg[3] = t_sync2; }
 }
 
 // x <- S^-1 x with S = L D L^T from above (unit lower L below the diagonal, D on the diagonal)
@@ -716,9 +755,18 @@ int solve_schur(Handle* h, double lambda, int fix) {
     double* Sp = h->d_S;
     double* Wp = h->d_ldlt_w;
     int32_t* fp = h->d_flags;
-    void* args[] = {&dd, &Sp, &Wp, &fp};
+    static long long* d_dbg = nullptr;
+    if (dbg && !d_dbg) cudaMalloc((void**)&d_dbg, 8 * sizeof(long long));
+    long long* dp = dbg ? d_dbg : nullptr;
+    void* args[] = {&dd, &Sp, &Wp, &fp, &dp};
     EMBA_CUDA(cudaLaunchCooperativeKernel((void*)k_ldlt_fused, dim3(grid_f), dim3(256), args, 0, h->stream));
     h->launches++;
+    if (dbg) {
+      long long hc[4];
+      cudaStreamSynchronize(h->stream);
+      cudaMemcpy(hc, d_dbg, sizeof(hc), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[emba ldlt] grid %d clocks(CTA 0): panel %lld sync %lld update %lld sync %lld\n", grid_f, hc[0], hc[1], hc[2], hc[3]);
+    }
   } else {
     for (int k0 = 0; k0 < d; k0 += kNB) {
       const int nb = std::min(kNB, d - k0);
