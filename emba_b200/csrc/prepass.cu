@@ -396,7 +396,7 @@ int rebuild_static(Handle* h) {
   EMBA_TRY(dev_alloc(h, &h->d_A11, (int64_t)9 * n * n));
   EMBA_TRY(dev_alloc(h, &h->d_b1, (int64_t)3 * n));
   EMBA_TRY(dev_alloc(h, &h->d_x1, (int64_t)3 * n));
-  EMBA_TRY(dev_alloc(h, &h->d_S, (int64_t)9 * n * n));
+  EMBA_TRY(dev_alloc(h, &h->d_S, (int64_t)(3 * n + 1) * (3 * n + 1)));  // bordered with the rhs row
   EMBA_TRY(dev_alloc(h, &h->d_rhs, (int64_t)3 * n));
   if (B == 0 || h->Mc_total == 0) {
     for (int s = 0; s < 2; s++) {

@@ -215,13 +215,20 @@ __global__ void k_schur_finish(int d, int fix, int n, int nt, int npairs, int Z,
     for (int z = 0; z < Z; z++) s += Spart[((size_t)z * npairs + pair) * (kST * kST) + ri * kST + rj];
     if (mode == 1) { T[idx] = s; return; }
   }
+  // S is stored bordered, (d+1) x (d+1): row d holds the right-hand side, so the factorisation below carries the
+  // forward substitution along (the last row of L becomes D^-1 L^-1 rhs)
   const int d3 = 3 * n;
+  const size_t ld = (size_t)d + 1;
   if (j == d) {
-    rhs[i] = b1[3 * fix + i] - s;
+    const double v = b1[3 * fix + i] - s;
+    rhs[i] = v;
+    S[(size_t)d * ld + i] = v;
+    S[(size_t)i * ld + d] = 0.0;
+    if (i == 0) S[(size_t)d * ld + d] = 1.0;  // placeholder pivot, never used
   } else {
     double a = A11[(size_t)(3 * fix + i) * d3 + 3 * fix + j];
     if (i == j) a += lambda * a;
-    S[(size_t)i * d + j] = a - s;
+    S[(size_t)i * ld + j] = a - s;
   }
 }
 
@@ -238,7 +245,7 @@ constexpr int kLdltSmemDoubles = 2 * kNB * (kNB + 1) + 64 * (kNB + 1);  // == 2 
 
 __device__ __forceinline__ void ldlt_panel_body(int d, int k0, int nb, double* __restrict__ S, double* __restrict__ W,
                                                 int32_t* __restrict__ flags, int slab, int nslab_stride, int nslabs,
-                                                double* __restrict__ sm) {
+                                                double* __restrict__ sm, int ncheck) {
   double (*Dk)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(sm);
   double (*Li)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(sm + kNB * (kNB + 1));
   double (*As)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(sm + 2 * kNB * (kNB + 1));
@@ -274,7 +281,7 @@ __device__ __forceinline__ void ldlt_panel_body(int d, int k0, int nb, double* _
       ycol[lane] = a[j];  // y_ij = a_ij (lanes i >= j)
       __syncwarp();
       const double dj = ycol[j];
-      bad = bad || (j < nb && (dj == 0.0 || !isfinite(dj)));
+      bad = bad || (k0 + j < ncheck && (dj == 0.0 || !isfinite(dj)));
       const double lij = a[j] / dj;  // l_ij
 #pragma unroll
       for (int m = j + 1; m < kNB; m++) a[m] -= lij * ycol[m];  // a_im -= l_ij * y_mj (used for j < m <= i)
@@ -334,9 +341,10 @@ __device__ __forceinline__ void ldlt_panel_body(int d, int k0, int nb, double* _
 }
 
 __global__ void __launch_bounds__(256)
-k_ldlt_panel(int d, int k0, int nb, double* __restrict__ S, double* __restrict__ W, int32_t* __restrict__ flags) {
+k_ldlt_panel(int d, int k0, int nb, double* __restrict__ S, double* __restrict__ W, int32_t* __restrict__ flags,
+             int ncheck) {
   __shared__ double sm[kLdltSmemDoubles];
-  ldlt_panel_body(d, k0, nb, S, W, flags, blockIdx.x, gridDim.x, gridDim.x, sm);
+  ldlt_panel_body(d, k0, nb, S, W, flags, blockIdx.x, gridDim.x, gridDim.x, sm, ncheck);
 }
 
 __device__ __forceinline__ void ldlt_update_body(int d, int k0, int nb, double* __restrict__ S,
@@ -392,17 +400,18 @@ k_ldlt_update(int d, int k0, int nb, double* __restrict__ S, const double* __res
 // The whole factorisation in ONE cooperative launch (grid-wide barriers between the panel and update phases):
 // for the small systems of this path (d = a few hundred) the per-panel launches are latency bound.
 __global__ void __launch_bounds__(256)
-k_ldlt_fused(int d, double* __restrict__ S, double* __restrict__ W, int32_t* __restrict__ flags,
+k_ldlt_fused(int d, int ncols, double* __restrict__ S, double* __restrict__ W, int32_t* __restrict__ flags,
              long long* __restrict__ dbg) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double sm[kLdltSmemDoubles];
   long long t_panel = 0, t_sync1 = 0, t_upd = 0, t_sync2 = 0;  // EMBA_DEBUG_TIMING: clocks of CTA 0 per phase
-  for (int k0 = 0; k0 < d; k0 += kNB) {
+  // d = order of the bordered matrix, ncols = number of real pivots (the border row never becomes a panel of its own)
+  for (int k0 = 0; k0 < ncols; k0 += kNB) {
     const int nb = min(kNB, d - k0);
     const int rows_below = d - (k0 + nb);
     const int nslabs = (rows_below + 63) / 64;
     const long long c0 = clock64();
-    ldlt_panel_body(d, k0, nb, S, W, flags, blockIdx.x, gridDim.x, nslabs, sm);
+    ldlt_panel_body(d, k0, nb, S, W, flags, blockIdx.x, gridDim.x, nslabs, sm, ncols);
     const long long c1 = clock64();
     grid.sync();
     const long long c2 = clock64();
@@ -419,43 +428,27 @@ k_ldlt_fused(int d, double* __restrict__ S, double* __restrict__ W, int32_t* __r
   if (dbg && blockIdx.x == 0 && threadIdx.x == 0) { dbg[0] = t_panel; dbg[1] = t_sync1; dbg[2] = t_upd; dbg[3] = t_sync2; }
 }
 
-// x <- S^-1 x with S = L D L^T from above (unit lower L below the diagonal, D on the diagonal)
-__global__ void __launch_bounds__(1024) k_ldlt_subst(int d, const double* __restrict__ S, double* __restrict__ x) {
+// x <- S^-1 rhs given the bordered factorisation: row d of L already holds z = D^-1 L^-1 rhs, so only the backward
+// substitution L^T x = z is left (unit lower L below the diagonal, leading dimension ld = d + 1)
+__global__ void __launch_bounds__(1024) k_ldlt_subst(int d, int ld, const double* __restrict__ Sm, double* __restrict__ x) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   __shared__ double xb[kNB];
-  // forward: L y = b, blocks of 32 rows
-  for (int k0 = 0; k0 < d; k0 += kNB) {
-    const int nb = min(kNB, d - k0);
-    // dot products with the already solved part: warp w handles row k0 + w
-    if (warp < nb) {
-      const double* row = S + (size_t)(k0 + warp) * d;
-      double s = 0.0;
-      for (int j = lane; j < k0; j += 32) s += row[j] * x[j];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-      if (lane == 0) xb[warp] = x[k0 + warp] - s;
-    }
-    __syncthreads();
-    if (warp == 0) {
-      double v = lane < nb ? xb[lane] : 0.0;
-      for (int j = 0; j < nb; j++) {
-        const double vj = __shfl_sync(0xffffffffu, v, j);
-        if (lane > j && lane < nb) v -= S[(size_t)(k0 + lane) * d + k0 + j] * vj;
-      }
-      if (lane < nb) x[k0 + lane] = v;
-    }
-    __syncthreads();
-  }
-  for (int i = tid; i < d; i += blockDim.x) x[i] /= S[(size_t)i * d + i];
+  for (int i = tid; i < d; i += blockDim.x) x[i] = Sm[(size_t)d * ld + i];
   __syncthreads();
   // backward: L^T z = y, blocks from the end
   for (int k0 = ((d - 1) / kNB) * kNB; k0 >= 0; k0 -= kNB) {
     const int nb = min(kNB, d - k0);
     if (warp == 0) {
+      // column `lane` of the block's L rows, all loads in flight at once (the serial loop below then runs from
+      // registers instead of paying one L2 round trip per step)
+      double lcol[kNB];
+#pragma unroll
+      for (int j = 0; j < kNB; j++) lcol[j] = (j < nb && lane < j) ? Sm[(size_t)(k0 + j) * ld + k0 + lane] : 0.0;
       double v = lane < nb ? x[k0 + lane] : 0.0;
-      for (int j = nb - 1; j >= 0; j--) {
+#pragma unroll
+      for (int j = kNB - 1; j >= 0; j--) {
         const double vj = __shfl_sync(0xffffffffu, v, j);
-        if (lane < j) v -= S[(size_t)(k0 + j) * d + k0 + lane] * vj;
+        v -= lcol[j] * vj;
       }
       if (lane < nb) { x[k0 + lane] = v; xb[lane] = v; }
     }
@@ -463,7 +456,7 @@ __global__ void __launch_bounds__(1024) k_ldlt_subst(int d, const double* __rest
     // x_i -= sum_{k in block} L_ki x_k for i < k0 (row k of L is contiguous in i)
     for (int i = tid; i < k0; i += blockDim.x) {
       double s = 0.0;
-      for (int kk = 0; kk < nb; kk++) s += S[(size_t)(k0 + kk) * d + i] * xb[kk];
+      for (int kk = 0; kk < nb; kk++) s += Sm[(size_t)(k0 + kk) * ld + i] * xb[kk];
       x[i] -= s;
     }
     __syncthreads();
@@ -728,8 +721,7 @@ int solve_schur(Handle* h, double lambda, int fix) {
       k_schur_finish<<<ceil_div64(tot, T), T, 0, h->stream>>>(d, fix, n, nt, npairs, Z, h->d_Spart, h->d_A11, h->d_b1,
                                                              lambda, h->d_S, h->d_rhs, nullptr, 0);
       EMBA_LAUNCH_CHECK();
-      EMBA_TRY(comm_allreduce(h, h->d_S, (int64_t)d * d, 1));
-      EMBA_TRY(comm_allreduce(h, h->d_rhs, d, 1));
+      EMBA_TRY(comm_allreduce(h, h->d_S, (int64_t)(d + 1) * (d + 1), 1));  // bordered: the rhs row rides along
     } else {
       // A11 / b1 already combined (after emba_get_normal_eq): all-reduce only the Schur sums
       EMBA_TRY(dev_reserve(h, &h->d_cg, &h->cg_cap, tot));
@@ -744,21 +736,22 @@ int solve_schur(Handle* h, double lambda, int fix) {
   }
   if (dbg) cudaEventRecord(de[2], h->stream);
   EMBA_CUDA(cudaMemsetAsync(h->d_flags, 0, sizeof(int32_t) * 16, h->stream));
-  EMBA_TRY(dev_reserve(h, &h->d_ldlt_w, &h->ldlt_w_cap, (int64_t)d * kNB));
-  if (d <= 1536) {
+  const int db = d + 1;  // order of the bordered matrix
+  EMBA_TRY(dev_reserve(h, &h->d_ldlt_w, &h->ldlt_w_cap, (int64_t)db * kNB));
+  if (db <= 1536) {
     // small system: one cooperative launch, grid barriers instead of 2 launches per panel
     int per_sm = 0;
     EMBA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ldlt_fused, 256, 0));
-    const int ntile0 = (d + 63) / 64;
+    const int ntile0 = (db + 63) / 64;
     int grid_f = std::min(h->sm_count * std::max(1, per_sm), std::max(1, ntile0 * (ntile0 + 1) / 2));
-    int dd = d;
+    int dd = db, ncols = d;
     double* Sp = h->d_S;
     double* Wp = h->d_ldlt_w;
     int32_t* fp = h->d_flags;
     static long long* d_dbg = nullptr;
     if (dbg && !d_dbg) cudaMalloc((void**)&d_dbg, 8 * sizeof(long long));
     long long* dp = dbg ? d_dbg : nullptr;
-    void* args[] = {&dd, &Sp, &Wp, &fp, &dp};
+    void* args[] = {&dd, &ncols, &Sp, &Wp, &fp, &dp};
     EMBA_CUDA(cudaLaunchCooperativeKernel((void*)k_ldlt_fused, dim3(grid_f), dim3(256), args, 0, h->stream));
     h->launches++;
     if (dbg) {
@@ -769,20 +762,20 @@ int solve_schur(Handle* h, double lambda, int fix) {
     }
   } else {
     for (int k0 = 0; k0 < d; k0 += kNB) {
-      const int nb = std::min(kNB, d - k0);
-      const int rows_below = d - (k0 + nb);
+      const int nb = std::min(kNB, db - k0);
+      const int rows_below = db - (k0 + nb);
       const int slabs = std::max(1, (rows_below + 63) / 64);
-      k_ldlt_panel<<<slabs, 256, 0, h->stream>>>(d, k0, nb, h->d_S, h->d_ldlt_w, h->d_flags);
+      k_ldlt_panel<<<slabs, 256, 0, h->stream>>>(db, k0, nb, h->d_S, h->d_ldlt_w, h->d_flags, d);
       h->launches++;
       if (rows_below > 0) {
         const int nt = (rows_below + 63) / 64;
-        k_ldlt_update<<<nt * (nt + 1) / 2, 256, 0, h->stream>>>(d, k0, nb, h->d_S, h->d_ldlt_w);
+        k_ldlt_update<<<nt * (nt + 1) / 2, 256, 0, h->stream>>>(db, k0, nb, h->d_S, h->d_ldlt_w);
         h->launches++;
       }
     }
   }
   if (dbg) cudaEventRecord(de[3], h->stream);
-  k_ldlt_subst<<<1, 1024, 0, h->stream>>>(d, h->d_S, h->d_rhs);
+  k_ldlt_subst<<<1, 1024, 0, h->stream>>>(d, db, h->d_S, h->d_rhs);
   EMBA_LAUNCH_CHECK();
   if (dbg) cudaEventRecord(de[4], h->stream);
   k_expand_x1<<<ceil_div64(3 * n, T), T, 0, h->stream>>>(n, fix, h->d_rhs, h->d_x1);
