@@ -468,21 +468,36 @@ __global__ void k_solve_x2(int64_t Np, const int32_t* __restrict__ winlo, const 
                            const int64_t* __restrict__ stripoff, const double* __restrict__ strip,
                            const double* __restrict__ C, const double* __restrict__ b2,
                            const double* __restrict__ x1full, double* __restrict__ x2) {
-  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= Np) return;
-  const int lo = winlo[a], hi = winhi[a];
+  // 8 lanes per pixel walk its strip as (column 0, column 1) pairs: pair e multiplies x1[3*lo + e]; coalesced
+  const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t a = gt >> 3;
+  const int sub = (int)(gt & 7);
+  double t0 = 0.0, t1 = 0.0;
+  int lo = 0, hi = -1;
+  if (a < Np) {
+    lo = winlo[a]; hi = winhi[a];
+    if (hi >= lo) {
+      const double2* sp = reinterpret_cast<const double2*>(strip) + stripoff[a] * 3;
+      const double* xv = x1full + 3 * lo;
+      const int ne = 3 * (hi - lo + 1);
+      for (int e = sub; e < ne; e += 8) {
+        const double2 u = sp[e];
+        const double xe = xv[e];
+        t0 += u.x * xe;
+        t1 += u.y * xe;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+    t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+  }
+  if (a >= Np || sub != 0) return;
   if (hi < lo) {  // pixel owned by another rank (multi-GPU): its owner computes x2, combined by all-reduce
     x2[2 * a] = 0.0;
     x2[2 * a + 1] = 0.0;
     return;
-  }
-  const double* sp = strip + stripoff[a] * 6;
-  double t0 = 0.0, t1 = 0.0;
-  for (int q = lo; q <= hi; q++) {
-    const double* u = sp + (size_t)(q - lo) * 6;
-    const double xa = x1full[3 * q], xb = x1full[3 * q + 1], xc = x1full[3 * q + 2];
-    t0 += u[0] * xa + u[2] * xb + u[4] * xc;
-    t1 += u[1] * xa + u[3] * xb + u[5] * xc;
   }
   const double r0 = b2[2 * a] - t0, r1 = b2[2 * a + 1] - t1;
   const double c00 = C[3 * a], c01 = C[3 * a + 1], c11 = C[3 * a + 2];
@@ -781,7 +796,7 @@ int solve_schur(Handle* h, double lambda, int fix) {
   k_expand_x1<<<ceil_div64(3 * n, T), T, 0, h->stream>>>(n, fix, h->d_rhs, h->d_x1);
   EMBA_LAUNCH_CHECK();
   if (Np > 0) {
-    k_solve_x2<<<ceil_div64(Np, 128), 128, 0, h->stream>>>(Np, h->sv_winlo, h->sv_winhi, h->sv_stripoff, h->sv_strip,
+    k_solve_x2<<<ceil_div64(Np * 8, 256), 256, 0, h->stream>>>(Np, h->sv_winlo, h->sv_winhi, h->sv_stripoff, h->sv_strip,
                                                            h->d_C, h->d_b2, h->d_x1, h->d_x2);
     EMBA_LAUNCH_CHECK();
     if (h->world > 1) EMBA_TRY(comm_allreduce(h, h->d_x2, 2 * Np, 1));  // owners contribute, the others hold zeros
