@@ -65,11 +65,14 @@ k_schur_tiles(int64_t Np, int d, int fix, int nt, int Z, const int32_t* __restri
               const int32_t* __restrict__ winhi, const int64_t* __restrict__ stripoff,
               const double* __restrict__ strip, const double* __restrict__ C, const double* __restrict__ b2,
               double* __restrict__ Spart) {
-  // decode (I, J) from the linear pair index
-  int pair = blockIdx.x, I = 0;
-  while (pair >= nt - I) { pair -= nt - I; I++; }
-  const int J = I + pair;
-  const int z = blockIdx.y;
+  // CTAs are ordered heaviest first: blockIdx.y walks the tile pairs diagonal by diagonal (pairs on and near the
+  // diagonal meet the most pose windows), blockIdx.x the pixel chunks; the light far-off-diagonal pairs fill the tail
+  int I = blockIdx.y, dgl = 0;
+  while (I >= nt - dgl) { I -= nt - dgl; dgl++; }
+  const int J = I + dgl;
+  int pair_lin = dgl;  // index of (I, J) in the I-major numbering k_schur_finish uses
+  for (int k = 0; k < I; k++) pair_lin += nt - k;
+  const int z = blockIdx.x;
   const int64_t a0 = Np * z / Z, a1 = Np * (z + 1) / Z;
   const int rowI0 = I * kST, rowJ0 = J * kST;
   const bool Jhas_rhs = (d >= rowJ0 && d < rowJ0 + kST);
@@ -180,7 +183,7 @@ k_schur_tiles(int64_t Np, int d, int fix, int nt, int Z, const int32_t* __restri
     }
     cp_async_wait_s<0>();
   }
-  double* out = Spart + ((size_t)z * gridDim.x + blockIdx.x) * (kST * kST);
+  double* out = Spart + ((size_t)z * gridDim.y + pair_lin) * (kST * kST);
 #pragma unroll
   for (int r = 0; r < 3; r++)
 #pragma unroll
@@ -715,10 +718,11 @@ int solve_schur(Handle* h, double lambda, int fix) {
   if (Np > 0) { k_a22_inv<<<ceil_div64(Np, T), T, 0, h->stream>>>(Np, h->d_A22, lambda, h->d_C); EMBA_LAUNCH_CHECK(); }
   const int nt = (d + 1 + kST - 1) / kST;
   const int npairs = nt * (nt + 1) / 2;
-  int Z = std::max(1, (h->sm_count * 8) / npairs);
+  static const int zmult = getenv("EMBA_SCHUR_ZMULT") ? atoi(getenv("EMBA_SCHUR_ZMULT")) : 16;
+  int Z = std::max(1, (h->sm_count * zmult) / npairs);
   Z = (int)std::min<int64_t>(Z, std::max<int64_t>(1, (Np + kSchurThreads - 1) / kSchurThreads));
   EMBA_TRY(dev_reserve(h, &h->d_Spart, &h->Spart_cap, (int64_t)Z * npairs * kST * kST));
-  dim3 grid(npairs, Z);
+  dim3 grid(Z, npairs);
   k_schur_tiles<<<grid, kSchurThreads, 0, h->stream>>>(Np, d, fix, nt, Z, h->sv_winlo, h->sv_winhi, h->sv_stripoff, h->sv_strip,
                                              h->d_C, h->d_b2, h->d_Spart);
   EMBA_LAUNCH_CHECK();
