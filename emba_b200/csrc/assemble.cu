@@ -359,14 +359,10 @@ __global__ void k_strip_len(const int32_t* __restrict__ winlo, const int32_t* __
   len[a] = hi >= lo ? (int64_t)(hi - lo + 1) : 0;
 }
 
-// sort input: key = panorama pixel of the row (P for outliers, which then sort to the end), value = row id
-__global__ void k_sort_keys(const int32_t* __restrict__ pix, int64_t M, uint32_t P, uint32_t* __restrict__ key,
-                            uint32_t* __restrict__ val) {
+// row ids 0..M-1: the constant value input of the row sort
+__global__ void k_iota(int64_t M, uint32_t* __restrict__ val) {
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= M) return;
-  const int32_t p = pix[m];
-  key[m] = p >= 0 ? (uint32_t)p : P;
-  val[m] = (uint32_t)m;
+  if (m < M) val[m] = (uint32_t)m;
 }
 
 // rows [segoff[a], segend[a]) of the sorted list belong to active pixel a (rows of inactive pixels lie between)
@@ -654,11 +650,14 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   uint32_t* vs = h->d_sval;
   if (!atomic_path && h->Mc > 0) {
     const int64_t Mc = h->Mc;
+    // keys = the evaluation's pixel lookups as they are: 0..P-1, or -1 for outliers, whose low `bits` bits are all
+    // ones (>= P because 2^bits > P) so they sort behind every pixel; values = the constant row ids
     int bits = 1;
-    while (bits < 32 && ((uint64_t)P >> bits)) bits++;  // keys 0..P
-    cub::DoubleBuffer<uint32_t> dk(h->d_skey, h->d_skey2), dv(h->d_sval, h->d_sval2);
+    while (bits < 32 && ((uint64_t)P >> bits)) bits++;
+    const uint32_t* keys_in = reinterpret_cast<const uint32_t*>(s.pix);
     size_t tb = 0;
-    EMBA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int)Mc, 0, bits, h->stream2));
+    EMBA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys_in, h->d_skey, h->d_sval2, h->d_sval, (int)Mc, 0, bits,
+                                              h->stream2));
     if (tb > h->sort_tmp_bytes) {
       if (h->d_sort_tmp) cudaFree(h->d_sort_tmp);
       h->d_sort_tmp = nullptr;
@@ -669,11 +668,16 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
     EMBA_CUDA(cudaEventRecord(h->ev_fork, h->stream));
     EMBA_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
     EMBA_CUDA(cudaEventRecord(h->ev_sort0, h->stream2));
-    k_sort_keys<<<ceil_div64(Mc, T), T, 0, h->stream2>>>(s.pix, Mc, (uint32_t)P, h->d_skey, h->d_sval);
-    EMBA_CUDA(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp, tb, dk, dv, (int)Mc, 0, bits, h->stream2));
-    h->launches += 2 + 2 * ((bits + 7) / 8);
-    sorted_keys = dk.Current();
-    vs = dv.Current();
+    if (h->iota_len != Mc) {
+      k_iota<<<ceil_div64(Mc, T), T, 0, h->stream2>>>(Mc, h->d_sval2);
+      h->iota_len = Mc;
+      h->launches++;
+    }
+    EMBA_CUDA(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp, tb, keys_in, h->d_skey, h->d_sval2, h->d_sval, (int)Mc, 0,
+                                              bits, h->stream2));
+    h->launches += 1 + 2 * ((bits + 7) / 8);
+    sorted_keys = h->d_skey;
+    vs = h->d_sval;
     EMBA_CUDA(cudaEventRecord(h->ev_sort1, h->stream2));
     EMBA_CUDA(cudaEventRecord(h->ev_join, h->stream2));
   }

@@ -493,6 +493,7 @@ int rebuild_static(Handle* h) {
     item0.push_back((int32_t)h->h_items.size());
     h->n_items = (int)h->h_items.size();
     h->n_groups = ng;
+    h->iota_len = 0;
     std::vector<int32_t> gid((size_t)n * (h->dmax + 1), -1);
     for (const WorkItem& w : h->h_items) gid[(size_t)w.cp_c * (h->dmax + 1) + (w.cp_c - w.cp_p)] = w.group;
     do {
@@ -501,7 +502,7 @@ int rebuild_static(Handle* h) {
           (rc = dev_alloc(h, &h->d_refpos, h->Mc)) ||
           (rc = dev_alloc(h, &h->d_acc_part, (int64_t)h->n_items * kAccN)) ||
           (rc = dev_alloc(h, &h->d_skey, h->Mc)) || (rc = dev_alloc(h, &h->d_sval, h->Mc)) ||
-          (rc = dev_alloc(h, &h->d_skey2, h->Mc)) || (rc = dev_alloc(h, &h->d_sval2, h->Mc)) ||
+          (rc = dev_alloc(h, &h->d_sval2, h->Mc)) ||
           (rc = dev_reserve(h, &h->d_jrec, &h->jrec_cap, h->Mc * kRecDoubles)) ||
           (rc = dev_alloc(h, &h->d_gsum, (int64_t)h->n_groups * kAccN)))
         break;
