@@ -150,6 +150,17 @@ __global__ void k_merge_strips(int W, int64_t Np, int64_t a0, int64_t n_own, con
 #include <climits>
 namespace emba {
 
+// the few numbers the host needs for the exchange: receive counts per source rank, my strip offsets at the
+// ownership boundaries, merged strip total
+__global__ void k_gather_meta(int W, int64_t Np, int64_t n_own, const int64_t* __restrict__ own_off,
+                              const int64_t* __restrict__ stripoff, const int64_t* __restrict__ gstripoff,
+                              int64_t* __restrict__ meta) {
+  const int t = threadIdx.x;
+  for (int s = t; s < W; s += blockDim.x) meta[s] = own_off[(size_t)s * (n_own + 1) + n_own];
+  for (int q = t; q <= W; q += blockDim.x) meta[W + q] = stripoff[Np * q / W];
+  if (t == 0) meta[2 * W + 1] = gstripoff[Np];
+}
+
 int comm_exchange_strips(Handle* h) {
   NcclApi* api = nccl_api();
   if (!api || !h->nccl_comm) { h->err = "multi-GPU shard without a communicator: call emba_comm_init"; return EMBA_E_NCCL; }
@@ -162,7 +173,7 @@ int comm_exchange_strips(Handle* h) {
   auto own0 = [&](int q) { return Np * q / W; };
   const int64_t a0 = own0(r), n_own = own0(r + 1) - a0;
   EMBA_TRY(dev_reserve(h, &h->d_win_all, &h->win_all_cap, (int64_t)W * Np * 2 + 2 * Np));
-  EMBA_TRY(dev_reserve(h, &h->d_own_len, &h->own_cap, (int64_t)2 * W * (n_own + 1) + 4 * W + 16));
+  EMBA_TRY(dev_reserve(h, &h->d_own_len, &h->own_cap, (int64_t)2 * W * (n_own + 1) + 8 * W + 32));
   if (!h->d_win2) {
     EMBA_TRY(dev_alloc(h, &h->d_win2, 2 * (h->P + 1)));
     EMBA_TRY(dev_alloc(h, &h->d_gwinlo, h->P + 1));
@@ -201,14 +212,19 @@ int comm_exchange_strips(Handle* h) {
   EMBA_TRY(scan64(h->d_len, h->d_gstripoff, Np + 1));
   if (dbg) cudaEventRecord(de[1], h->stream);
   // host needs: recv counts (W), my local strip offsets at the ownership boundaries (W+1), merged total (1)
+  // gathered on the device and read back with ONE copy into pinned memory
   std::vector<int64_t> recv_cnt(W), send_off(W + 1), recvbase(W + 1);
   int64_t gtot = 0;
-  for (int s = 0; s < W; s++)
-    EMBA_CUDA(cudaMemcpyAsync(&recv_cnt[s], own_off + (size_t)s * (n_own + 1) + n_own, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
-  for (int q = 0; q <= W; q++)
-    EMBA_CUDA(cudaMemcpyAsync(&send_off[q], h->d_stripoff + own0(q), sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
-  EMBA_CUDA(cudaMemcpyAsync(&gtot, h->d_gstripoff + Np, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+  if (2 * W + 2 > 1000) { h->err = "world size too large"; return EMBA_E_SUPPORT; }
+  int64_t* meta_dev = recvbase_dev + (W + 1);
+  k_gather_meta<<<1, 64, 0, h->stream>>>(W, Np, n_own, own_off, h->d_stripoff, h->d_gstripoff, meta_dev);
+  EMBA_LAUNCH_CHECK();
+  int64_t* meta = h->h_pin + 16;
+  EMBA_CUDA(cudaMemcpyAsync(meta, meta_dev, sizeof(int64_t) * (2 * W + 2), cudaMemcpyDeviceToHost, h->stream));
   EMBA_CUDA(cudaStreamSynchronize(h->stream));
+  for (int s = 0; s < W; s++) recv_cnt[s] = meta[s];
+  for (int q = 0; q <= W; q++) send_off[q] = meta[W + q];
+  gtot = meta[2 * W + 1];
   recvbase[0] = 0;
   for (int s = 0; s < W; s++) recvbase[s + 1] = recvbase[s] + recv_cnt[s];
   EMBA_TRY(dev_reserve(h, &h->d_recv, &h->recv_cap, recvbase[W] * 6 + recvbase[W] * 3));

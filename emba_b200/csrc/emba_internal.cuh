@@ -58,7 +58,7 @@ struct Handle {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sort0 = nullptr, ev_sort1 = nullptr;
   cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
   cudaEvent_t ev_host = nullptr;   // marks a small device->host read-back the host waits for while later launches queue
-  int64_t* h_pin = nullptr;        // pinned host scratch (8 x int64) for those read-backs
+  int64_t* h_pin = nullptr;        // pinned host scratch (1024 x int64) for those read-backs
   int sm_count = 148;
   int64_t launches = 0;
   // config

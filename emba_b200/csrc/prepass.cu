@@ -221,7 +221,7 @@ int emba_create(const emba_config_t* cfg, emba_handle_t* out) {
   cudaEventCreateWithFlags(&h->ev_fork2, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->ev_host, cudaEventDisableTiming);
-  if (cudaMallocHost((void**)&h->h_pin, 8 * sizeof(int64_t)) != cudaSuccess) { delete h; return EMBA_E_CUDA; }
+  if (cudaMallocHost((void**)&h->h_pin, 1024 * sizeof(int64_t)) != cudaSuccess) { delete h; return EMBA_E_CUDA; }
   cudaEventCreate(&h->ev_sort0);
   cudaEventCreate(&h->ev_sort1);
   for (auto& e : h->ev) cudaEventCreate(&e);
