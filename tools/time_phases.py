@@ -29,5 +29,6 @@ for rep in range(3):
           f"solve dev {ts['solve']:.3f} wall {w_s*1e3:.3f} | candidate wall {w_c*1e3:.3f} | eval cand wall {w_e2*1e3:.3f}")
 w = time.perf_counter(); log, fc = eng.solve_time_window(max_num_iter=9, alpha=5.0, thres=5); w = time.perf_counter() - w
 print(f"LM: {log.shape[0]} solves, {int(log[:,4].sum())} accepted, {w*1e3/log.shape[0]:.3f} ms/iteration, cost {log[0,2]:.1f} -> {fc:.1f}")
+eng.evaluate(0, 0, 1.0, 5.0); eng.form_normal_eq(5, 0, 1.0, 5.0)
 w = time.perf_counter(); x = eng.solve(1e-3, True, True, want=False); w = time.perf_counter() - w
 print(f"PCG: iters {x[2]} err {x[3]:.3e} wall {w*1e3:.2f} ms")
