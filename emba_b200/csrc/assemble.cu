@@ -413,7 +413,7 @@ template <bool SMEM>
 __device__ __forceinline__ void pix_one(int64_t seg0, int64_t seg1, int qlo, int len, double* __restrict__ gs,
                                         double* s_tile, double* s_strip, const uint32_t* __restrict__ sval,
                                         const double* __restrict__ jrec, int lane, int s, int r, int c, int ia,
-                                        int ib, double& acc_out) {
+                                        int ib, int group, double& acc_out, unsigned long long& mask_out) {
   double* sp = SMEM ? s_strip : gs;
   for (int i = lane; i < len * 6; i += 32) sp[i] = 0.0;
   const int lrow = lane >> 3, lchunk = lane & 7;  // cp.async role: 4 rows per instruction, 8 x 16 B per row
@@ -502,6 +502,7 @@ __device__ __forceinline__ void pix_one(int64_t seg0, int64_t seg1, int qlo, int
   if (SMEM) {
     for (int i = lane; i < len * 6; i += 32) gs[i] = sp[i];
   }
+  mask_out = strip_mask_warp(sp, len, qlo, group, lane);  // occupancy of the finished strip (emba_internal.cuh)
   acc_out = acc;
 }
 
@@ -511,7 +512,7 @@ k_pix(int64_t Np, const int32_t* __restrict__ segoff, const int32_t* __restrict_
       const double* __restrict__ jrec, const int32_t* __restrict__ winlo, const int32_t* __restrict__ winhi,
       const int64_t* __restrict__ stripoff, double* __restrict__ strip, const int32_t* __restrict__ apix,
       const double* __restrict__ Gx, const double* __restrict__ Gy, double alpha, double* __restrict__ A22,
-      double* __restrict__ b2) {
+      double* __restrict__ b2, int group, unsigned long long* __restrict__ gmask) {
   extern __shared__ __align__(16) unsigned char pix_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* s_tile = reinterpret_cast<double*>(pix_smem + (size_t)warp * kPixSmemPerWarp);  // [stage][row][16]
@@ -533,8 +534,10 @@ k_pix(int64_t Np, const int32_t* __restrict__ segoff, const int32_t* __restrict_
     const int len = winhi[a] >= qlo ? winhi[a] - qlo + 1 : 0;  // empty window: no local rows (multi-GPU)
     double* gs = strip + stripoff[a] * 6;
     double acc = 0.0;
-    if (len <= kStripCap) pix_one<true>(seg0, seg1, qlo, len, gs, s_tile, s_strip, sval, jrec, lane, s, r, c, ia, ib, acc);
-    else pix_one<false>(seg0, seg1, qlo, len, gs, s_tile, s_strip, sval, jrec, lane, s, r, c, ia, ib, acc);
+    unsigned long long mask = 0ull;
+    if (len <= kStripCap) pix_one<true>(seg0, seg1, qlo, len, gs, s_tile, s_strip, sval, jrec, lane, s, r, c, ia, ib, group, acc, mask);
+    else pix_one<false>(seg0, seg1, qlo, len, gs, s_tile, s_strip, sval, jrec, lane, s, r, c, ia, ib, group, acc, mask);
+    if (lane == 0) gmask[a] = mask;
     // applyL2Reg (model.cpp:689-719): A22 += alpha*I, b2 -= alpha * (Gx, Gy)[pixel]
     const int32_t pix = apix[a];
     if (lane == 24) A22[3 * a] = acc + alpha;
@@ -544,6 +547,19 @@ k_pix(int64_t Np, const int32_t* __restrict__ segoff, const int32_t* __restrict_
     if (lane == 28) b2[2 * a + 1] = acc - alpha * Gy[pix];
     __syncwarp();
   }
+}
+
+// occupancy masks of finished strips, one warp per pixel (used after the fp64-atomic path, which has no k_pix)
+__global__ void k_strip_mask(int64_t Np, const int32_t* __restrict__ winlo, const int32_t* __restrict__ winhi,
+                             const int64_t* __restrict__ stripoff, const double* __restrict__ strip, int group,
+                             unsigned long long* __restrict__ gmask) {
+  const int64_t a = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (a >= Np) return;
+  const int lo = winlo[a], hi = winhi[a];
+  const int len = hi >= lo ? hi - lo + 1 : 0;
+  const unsigned long long m = strip_mask_warp(strip + stripoff[a] * 6, len, lo, group, lane);
+  if (lane == 0) gmask[a] = m;
 }
 
 // fp64-atomic map-block path (reported beside the deterministic one): one thread per Jacobian row in canonical
@@ -642,6 +658,7 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   const int n = h->n;
   h->thres = thres;
   h->formed = false;
+  h->pose_group = 16 * ((n + 1023) / 1024);  // at most 64 groups
   EMBA_CUDA(cudaEventRecord(h->ev[4], h->stream));
   // ---- 0. side stream: stable radix sort of the rows by panorama pixel. It depends on the evaluation only, so it
   // overlaps the active-set scan and the pose-side kernel; the main stream joins it before the map-side kernel.
@@ -765,6 +782,9 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
       EMBA_CUDAC(cudaGetLastError());
     }
     if (Np > 0) {
+      k_strip_mask<<<ceil_div64(Np * 32, 256), 256, 0, h->stream>>>(Np, h->d_winlo, h->d_winhi, h->d_stripoff, h->d_strip,
+                                                                   h->pose_group, h->d_gmask);
+      h->launches++;
       StateSlot& sc = h->st[h->cur];
       k_l2_reg<<<ceil_div64(Np, 256), 256, 0, h->stream>>>(Np, h->d_apix, sc.Gx, sc.Gy, h->rank == 0 ? alpha : 0.0,
                                                           h->d_A22, h->d_b2);
@@ -787,13 +807,14 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
     EMBA_CUDAC(cudaFuncSetAttribute(k_pix, cudaFuncAttributeMaxDynamicSharedMemorySize, pix_smem));
     k_pix<<<grid, kPixWarps * 32, pix_smem, h->stream>>>(Np, h->d_segoff, h->d_segend, vs, h->d_jrec, h->d_winlo, h->d_winhi,
                                                   h->d_stripoff, h->d_strip, h->d_apix, s.Gx, s.Gy,
-                                                  h->rank == 0 ? alpha : 0.0, h->d_A22, h->d_b2);
+                                                  h->rank == 0 ? alpha : 0.0, h->d_A22, h->d_b2, h->pose_group, h->d_gmask);
     h->launches++;
     EMBA_CUDAC(cudaGetLastError());
   }
   EMBA_CUDAC(cudaEventRecord(h->ev[10], h->stream));
   EMBA_CUDAC(cudaStreamWaitEvent(h->stream, h->ev_join2, 0));
   h->sv_winlo = h->d_winlo; h->sv_winhi = h->d_winhi; h->sv_stripoff = h->d_stripoff; h->sv_strip = h->d_strip;
+  h->sv_gmask = h->d_gmask;
   h->sv_strip_total = tot;
   if (h->world > 1 && Np > 0) {
     // A22 / b2 are small: all-reduce. A12: every rank's strips cover (almost) disjoint pose ranges, so they are not

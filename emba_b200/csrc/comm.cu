@@ -125,7 +125,8 @@ __global__ void k_zero_tail(int W, int64_t n_own, int64_t* __restrict__ own_len)
 __global__ void k_merge_strips(int W, int64_t Np, int64_t a0, int64_t n_own, const int32_t* __restrict__ win_all,
                                const int64_t* __restrict__ own_off, const int64_t* __restrict__ recvbase,
                                const double* __restrict__ recv, const int32_t* __restrict__ gwinlo,
-                               const int64_t* __restrict__ gstripoff, double* __restrict__ gstrip) {
+                               const int64_t* __restrict__ gstripoff, double* __restrict__ gstrip, int group,
+                               unsigned long long* __restrict__ gmask) {
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (i >= n_own) return;
@@ -143,6 +144,9 @@ __global__ void k_merge_strips(int W, int64_t Np, int64_t a0, int64_t n_own, con
     }
     gstrip[goff * 6 + e] = v;
   }
+  __syncwarp();
+  const unsigned long long m = strip_mask_warp(gstrip + goff * 6, (int)glen, glo, group, lane);
+  if (lane == 0) gmask[a] = m;
 }
 
 }  // namespace emba
@@ -248,7 +252,8 @@ int comm_exchange_strips(Handle* h) {
   if (dbg) cudaEventRecord(de[3], h->stream);
   if (n_own > 0) {
     k_merge_strips<<<ceil_div64(n_own * 32, T), T, 0, h->stream>>>(W, Np, a0, n_own, h->d_win_all, own_off, recvbase_dev,
-                                                                  h->d_recv, h->d_gwinlo, h->d_gstripoff, h->d_gstrip);
+                                                                  h->d_recv, h->d_gwinlo, h->d_gstripoff, h->d_gstrip,
+                                                                  h->pose_group, h->d_gmask2);
     EMBA_LAUNCH_CHECK();
   }
   if (dbg) {
@@ -262,6 +267,7 @@ int comm_exchange_strips(Handle* h) {
     for (auto& e : de) cudaEventDestroy(e);
   }
   h->sv_winlo = h->d_gwinlo; h->sv_winhi = h->d_gwinhi; h->sv_stripoff = h->d_gstripoff; h->sv_strip = h->d_gstrip;
+  h->sv_gmask = h->d_gmask2;
   h->sv_strip_total = gtot;
   return EMBA_OK;
 }

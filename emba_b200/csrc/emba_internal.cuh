@@ -135,6 +135,13 @@ struct Handle {
   // solve view of A12: with one GPU it aliases the arrays above; with several GPUs every rank owns a contiguous
   // range of active pixels and holds their complete strips (merged from all time slices), the other pixels have
   // empty windows (lo > hi)
+  // coarse occupancy of each pixel's strip: bit k set when some entry of pose group k (pose_group poses per
+  // group, at most 64 groups) is non-zero. Revisiting trajectories leave long windows mostly empty; the Schur
+  // kernel skips (pixel, tile pair) products whose tiles hold no entries.
+  unsigned long long* d_gmask = nullptr;   // [P+1] local / single-GPU
+  unsigned long long* d_gmask2 = nullptr;  // [P+1] merged strips (multi-GPU owner view)
+  unsigned long long* sv_gmask = nullptr;
+  int pose_group = 16;
   int32_t* sv_winlo = nullptr;
   int32_t* sv_winhi = nullptr;
   int64_t* sv_stripoff = nullptr;
@@ -347,6 +354,16 @@ __device__ __forceinline__ void project_jac(const PanoCam& c, double X, double Y
   M[3] = -c.fy * Z * i1;
   M[4] = 0.0;
   M[5] = c.fy * X * i1;
+}
+
+// occupancy mask of one strip (len poses from pose lo, 6 doubles per pose) computed by a warp; every lane returns it
+__device__ __forceinline__ unsigned long long strip_mask_warp(const double* sp, int len, int lo, int group, int lane) {
+  unsigned long long m = 0ull;
+  for (int i = lane; i < len * 6; i += 32)
+    if (sp[i] != 0.0) m |= 1ull << min(63, (lo + i / 6) / group);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
+  return m;
 }
 
 // index into the packed upper triangle of a symmetric 13x13 (i <= j)

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(kSchurThreads, 4)
 k_schur_tiles(int64_t Np, int d, int fix, int nt, int Z, const int32_t* __restrict__ winlo,
               const int32_t* __restrict__ winhi, const int64_t* __restrict__ stripoff,
               const double* __restrict__ strip, const double* __restrict__ C, const double* __restrict__ b2,
-              double* __restrict__ Spart) {
+              const unsigned long long* __restrict__ gmask, int group, double* __restrict__ Spart) {
   // CTAs are ordered heaviest first: blockIdx.y walks the tile pairs diagonal by diagonal (pairs on and near the
   // diagonal meet the most pose windows), blockIdx.x the pixel chunks; the light far-off-diagonal pairs fill the tail
   int I = blockIdx.y, dgl = 0;
@@ -79,6 +79,13 @@ k_schur_tiles(int64_t Np, int d, int fix, int nt, int Z, const int32_t* __restri
   // pose ranges covered by the tiles (poses are >= fix)
   const int pI0 = rowI0 / 3 + fix, pI1 = min(d - 1, rowI0 + kST - 1) / 3 + fix;
   const int pJ0 = rowJ0 / 3 + fix, pJ1 = min(d - 1, rowJ0 + kST - 1) / 3 + fix;
+  // pose groups the tiles overlap (occupancy masks of the strips): a pixel with no entry in one of the tiles adds
+  // nothing to this pair even when its window spans it
+  auto bits = [&](int p0, int p1) -> unsigned long long {
+    const int g0 = min(63, p0 / group), g1 = min(63, p1 / group);
+    return (g1 >= 63 ? ~0ull : ((1ull << (g1 + 1)) - 1ull)) & ~((1ull << g0) - 1ull);
+  };
+  const unsigned long long bitsI = bits(pI0, pI1), bitsJ = bits(pJ0, pJ1);
   // [stage][side][pixel][row] as (column 0, column 1) pairs: k = 2*pixel + column
   __shared__ __align__(16) double2 V[2][2][kSPix][kST];
   // per listed pixel: first row of its window in the reduced system, number of rows, strip base, C, b2
@@ -108,8 +115,9 @@ k_schur_tiles(int64_t Np, int d, int fix, int nt, int Z, const int32_t* __restri
     int lo = 0, hi = -1;
     if (a < a1) {
       lo = winlo[a]; hi = winhi[a];
-      const bool mI = (rowI0 < d) && hi >= pI0 && lo <= pI1;
-      const bool mJ = ((rowJ0 < d) && hi >= pJ0 && lo <= pJ1) || Jhas_rhs;
+      const unsigned long long occ = gmask[a];
+      const bool mI = (rowI0 < d) && hi >= pI0 && lo <= pI1 && (occ & bitsI);
+      const bool mJ = ((rowJ0 < d) && hi >= pJ0 && lo <= pJ1 && (occ & bitsJ)) || Jhas_rhs;
       ok = mI && mJ && hi >= lo;
     }
     const unsigned bal = __ballot_sync(0xffffffffu, ok);
@@ -724,7 +732,7 @@ int solve_schur(Handle* h, double lambda, int fix) {
   EMBA_TRY(dev_reserve(h, &h->d_Spart, &h->Spart_cap, (int64_t)Z * npairs * kST * kST));
   dim3 grid(Z, npairs);
   k_schur_tiles<<<grid, kSchurThreads, 0, h->stream>>>(Np, d, fix, nt, Z, h->sv_winlo, h->sv_winhi, h->sv_stripoff, h->sv_strip,
-                                             h->d_C, h->d_b2, h->d_Spart);
+                                             h->d_C, h->d_b2, h->sv_gmask, h->pose_group, h->d_Spart);
   EMBA_LAUNCH_CHECK();
   const int64_t tot = (int64_t)d * (d + 1);
   if (dbg) cudaEventRecord(de[1], h->stream);
