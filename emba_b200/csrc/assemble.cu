@@ -413,7 +413,7 @@ template <bool SMEM>
 __device__ __forceinline__ void pix_one(int64_t seg0, int64_t seg1, int qlo, int len, double* __restrict__ gs,
                                         double* s_tile, double* s_strip, const uint32_t* __restrict__ sval,
                                         const double* __restrict__ jrec, int lane, int s, int r, int c, int ia,
-                                        int ib, int group, double& acc_out, unsigned long long& mask_out) {
+                                        int ib, int group, double& acc_out, unsigned long long& mask0, unsigned long long& mask1) {
   double* sp = SMEM ? s_strip : gs;
   for (int i = lane; i < len * 6; i += 32) sp[i] = 0.0;
   const int lrow = lane >> 3, lchunk = lane & 7;  // cp.async role: 4 rows per instruction, 8 x 16 B per row
@@ -502,7 +502,7 @@ __device__ __forceinline__ void pix_one(int64_t seg0, int64_t seg1, int qlo, int
   if (SMEM) {
     for (int i = lane; i < len * 6; i += 32) gs[i] = sp[i];
   }
-  mask_out = strip_mask_warp(sp, len, qlo, group, lane);  // occupancy of the finished strip (emba_internal.cuh)
+  strip_mask_warp(sp, len, qlo, group, lane, mask0, mask1);  // occupancy of the finished strip (emba_internal.cuh)
   acc_out = acc;
 }
 
@@ -534,10 +534,10 @@ k_pix(int64_t Np, const int32_t* __restrict__ segoff, const int32_t* __restrict_
     const int len = winhi[a] >= qlo ? winhi[a] - qlo + 1 : 0;  // empty window: no local rows (multi-GPU)
     double* gs = strip + stripoff[a] * 6;
     double acc = 0.0;
-    unsigned long long mask = 0ull;
-    if (len <= kStripCap) pix_one<true>(seg0, seg1, qlo, len, gs, s_tile, s_strip, sval, jrec, lane, s, r, c, ia, ib, group, acc, mask);
-    else pix_one<false>(seg0, seg1, qlo, len, gs, s_tile, s_strip, sval, jrec, lane, s, r, c, ia, ib, group, acc, mask);
-    if (lane == 0) gmask[a] = mask;
+    unsigned long long mask0 = 0ull, mask1 = 0ull;
+    if (len <= kStripCap) pix_one<true>(seg0, seg1, qlo, len, gs, s_tile, s_strip, sval, jrec, lane, s, r, c, ia, ib, group, acc, mask0, mask1);
+    else pix_one<false>(seg0, seg1, qlo, len, gs, s_tile, s_strip, sval, jrec, lane, s, r, c, ia, ib, group, acc, mask0, mask1);
+    if (lane == 0) { gmask[2 * a] = mask0; gmask[2 * a + 1] = mask1; }
     // applyL2Reg (model.cpp:689-719): A22 += alpha*I, b2 -= alpha * (Gx, Gy)[pixel]
     const int32_t pix = apix[a];
     if (lane == 24) A22[3 * a] = acc + alpha;
@@ -558,8 +558,9 @@ __global__ void k_strip_mask(int64_t Np, const int32_t* __restrict__ winlo, cons
   if (a >= Np) return;
   const int lo = winlo[a], hi = winhi[a];
   const int len = hi >= lo ? hi - lo + 1 : 0;
-  const unsigned long long m = strip_mask_warp(strip + stripoff[a] * 6, len, lo, group, lane);
-  if (lane == 0) gmask[a] = m;
+  unsigned long long m0, m1;
+  strip_mask_warp(strip + stripoff[a] * 6, len, lo, group, lane, m0, m1);
+  if (lane == 0) { gmask[2 * a] = m0; gmask[2 * a + 1] = m1; }
 }
 
 // fp64-atomic map-block path (reported beside the deterministic one): one thread per Jacobian row in canonical

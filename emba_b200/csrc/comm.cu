@@ -145,8 +145,9 @@ __global__ void k_merge_strips(int W, int64_t Np, int64_t a0, int64_t n_own, con
     gstrip[goff * 6 + e] = v;
   }
   __syncwarp();
-  const unsigned long long m = strip_mask_warp(gstrip + goff * 6, (int)glen, glo, group, lane);
-  if (lane == 0) gmask[a] = m;
+  unsigned long long m0, m1;
+  strip_mask_warp(gstrip + goff * 6, (int)glen, glo, group, lane, m0, m1);
+  if (lane == 0) { gmask[2 * a] = m0; gmask[2 * a + 1] = m1; }
 }
 
 }  // namespace emba

@@ -138,8 +138,8 @@ struct Handle {
   // coarse occupancy of each pixel's strip: bit k set when some entry of pose group k (pose_group poses per
   // group, at most 64 groups) is non-zero. Revisiting trajectories leave long windows mostly empty; the Schur
   // kernel skips (pixel, tile pair) products whose tiles hold no entries.
-  unsigned long long* d_gmask = nullptr;   // [P+1] local / single-GPU
-  unsigned long long* d_gmask2 = nullptr;  // [P+1] merged strips (multi-GPU owner view)
+  unsigned long long* d_gmask = nullptr;   // [2(P+1)] local / single-GPU: (fix = 0, fix = 1) per pixel
+  unsigned long long* d_gmask2 = nullptr;  // [2(P+1)] merged strips (multi-GPU owner view)
   unsigned long long* sv_gmask = nullptr;
   int pose_group = 16;
   int32_t* sv_winlo = nullptr;
@@ -356,14 +356,23 @@ __device__ __forceinline__ void project_jac(const PanoCam& c, double X, double Y
   M[5] = c.fy * X * i1;
 }
 
-// occupancy mask of one strip (len poses from pose lo, 6 doubles per pose) computed by a warp; every lane returns it
-__device__ __forceinline__ unsigned long long strip_mask_warp(const double* sp, int len, int lo, int group, int lane) {
-  unsigned long long m = 0ull;
+// occupancy masks of one strip (len poses from pose lo, 6 doubles per pose) computed by a warp; every lane returns
+// them. Two masks, one per gauge choice of the solve (fix = 0 / 1 drops the first pose, which shifts the 16-pose
+// Schur tiles by one pose): bit k of m[fix] <-> poses [group*k + fix, group*(k+1) + fix)
+__device__ __forceinline__ void strip_mask_warp(const double* sp, int len, int lo, int group, int lane,
+                                                unsigned long long& m0, unsigned long long& m1) {
+  m0 = 0ull; m1 = 0ull;
   for (int i = lane; i < len * 6; i += 32)
-    if (sp[i] != 0.0) m |= 1ull << min(63, (lo + i / 6) / group);
+    if (sp[i] != 0.0) {
+      const int pose = lo + i / 6;
+      m0 |= 1ull << min(63, pose / group);
+      if (pose >= 1) m1 |= 1ull << min(63, (pose - 1) / group);
+    }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
-  return m;
+  for (int o = 16; o > 0; o >>= 1) {
+    m0 |= __shfl_xor_sync(0xffffffffu, m0, o);
+    m1 |= __shfl_xor_sync(0xffffffffu, m1, o);
+  }
 }
 
 // index into the packed upper triangle of a symmetric 13x13 (i <= j)

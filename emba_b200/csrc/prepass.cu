@@ -252,8 +252,8 @@ int emba_create(const emba_config_t* cfg, emba_handle_t* out) {
        cudaMalloc((void**)&h->d_apix, sizeof(int32_t) * P1) == cudaSuccess &&
        cudaMalloc((void**)&h->d_segoff, sizeof(int32_t) * P1) == cudaSuccess &&
        cudaMalloc((void**)&h->d_segend, sizeof(int32_t) * P1) == cudaSuccess &&
-       cudaMalloc((void**)&h->d_gmask, sizeof(unsigned long long) * P1) == cudaSuccess &&
-       cudaMalloc((void**)&h->d_gmask2, sizeof(unsigned long long) * P1) == cudaSuccess &&
+       cudaMalloc((void**)&h->d_gmask, sizeof(unsigned long long) * 2 * P1) == cudaSuccess &&
+       cudaMalloc((void**)&h->d_gmask2, sizeof(unsigned long long) * 2 * P1) == cudaSuccess &&
        cudaMalloc((void**)&h->d_winlo, sizeof(int32_t) * P1) == cudaSuccess &&
        cudaMalloc((void**)&h->d_winhi, sizeof(int32_t) * P1) == cudaSuccess &&
        cudaMalloc((void**)&h->d_stripoff, sizeof(int64_t) * P1) == cudaSuccess &&

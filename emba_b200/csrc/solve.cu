@@ -81,8 +81,10 @@ k_schur_tiles(int64_t Np, int d, int fix, int nt, int Z, const int32_t* __restri
   const int pJ0 = rowJ0 / 3 + fix, pJ1 = min(d - 1, rowJ0 + kST - 1) / 3 + fix;
   // pose groups the tiles overlap (occupancy masks of the strips): a pixel with no entry in one of the tiles adds
   // nothing to this pair even when its window spans it
+  // (masks are stored per gauge choice, so that bit k <-> poses [group*k + fix, group*(k+1) + fix): with group == 16
+  // a tile is exactly one bit)
   auto bits = [&](int p0, int p1) -> unsigned long long {
-    const int g0 = min(63, p0 / group), g1 = min(63, p1 / group);
+    const int g0 = min(63, (p0 - fix) / group), g1 = min(63, (p1 - fix) / group);
     return (g1 >= 63 ? ~0ull : ((1ull << (g1 + 1)) - 1ull)) & ~((1ull << g0) - 1ull);
   };
   const unsigned long long bitsI = bits(pI0, pI1), bitsJ = bits(pJ0, pJ1);
@@ -115,7 +117,7 @@ k_schur_tiles(int64_t Np, int d, int fix, int nt, int Z, const int32_t* __restri
     int lo = 0, hi = -1;
     if (a < a1) {
       lo = winlo[a]; hi = winhi[a];
-      const unsigned long long occ = gmask[a];
+      const unsigned long long occ = gmask[2 * a + (fix ? 1 : 0)];
       const bool mI = (rowI0 < d) && hi >= pI0 && lo <= pI1 && (occ & bitsI);
       const bool mJ = ((rowJ0 < d) && hi >= pJ0 && lo <= pJ1 && (occ & bitsJ)) || Jhas_rhs;
       ok = mI && mJ && hi >= lo;
