@@ -397,7 +397,6 @@ constexpr int kPixWarps = 8;
 constexpr int kStripCap = 64;  // poses per shared-memory strip
 constexpr int kPixTile = 16;   // rows per stage
 constexpr int kPixStages = 2;
-constexpr int kPixSmemPerWarp = (kPixStages * kPixTile * kRecDoubles + kStripCap * 6) * 8;  // bytes
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -502,7 +501,14 @@ __device__ __forceinline__ void pix_one(int64_t seg0, int64_t seg1, int qlo, int
   if (SMEM) {
     for (int i = lane; i < len * 6; i += 32) gs[i] = sp[i];
   }
-  strip_mask_warp(sp, len, qlo, group, lane, mask0, mask1);  // occupancy of the finished strip (emba_internal.cuh)
+  if (SMEM) {
+    strip_mask_warp(sp, len, qlo, group, lane, mask0, mask1);  // occupancy of the finished strip (emba_internal.cuh)
+  } else {
+    // a long strip lives in global memory: re-reading it here would cost its whole size again inside the assembly
+    // pass. The solve fills these masks in before its first Schur product (k_strip_mask, min_len = kStripCap + 1).
+    mask0 = ~0ull;
+    mask1 = ~0ull;
+  }
   acc_out = acc;
 }
 
@@ -512,10 +518,11 @@ k_pix(int64_t Np, const int32_t* __restrict__ segoff, const int32_t* __restrict_
       const double* __restrict__ jrec, const int32_t* __restrict__ winlo, const int32_t* __restrict__ winhi,
       const int64_t* __restrict__ stripoff, double* __restrict__ strip, const int32_t* __restrict__ apix,
       const double* __restrict__ Gx, const double* __restrict__ Gy, double alpha, double* __restrict__ A22,
-      double* __restrict__ b2, int group, unsigned long long* __restrict__ gmask) {
+      double* __restrict__ b2, int group, unsigned long long* __restrict__ gmask, int strip_cap) {
   extern __shared__ __align__(16) unsigned char pix_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* s_tile = reinterpret_cast<double*>(pix_smem + (size_t)warp * kPixSmemPerWarp);  // [stage][row][16]
+  const size_t smem_per_warp = (size_t)(kPixStages * kPixTile * kRecDoubles + strip_cap * 6) * 8;
+  double* s_tile = reinterpret_cast<double*>(pix_smem + (size_t)warp * smem_per_warp);  // [stage][row][16]
   double* s_strip = s_tile + kPixStages * kPixTile * kRecDoubles;
   const int64_t nw = (int64_t)gridDim.x * kPixWarps;
   const int s = lane / 6, r = (lane % 6) >> 1, c = lane & 1;
@@ -535,7 +542,7 @@ k_pix(int64_t Np, const int32_t* __restrict__ segoff, const int32_t* __restrict_
     double* gs = strip + stripoff[a] * 6;
     double acc = 0.0;
     unsigned long long mask0 = 0ull, mask1 = 0ull;
-    if (len <= kStripCap) pix_one<true>(seg0, seg1, qlo, len, gs, s_tile, s_strip, sval, jrec, lane, s, r, c, ia, ib, group, acc, mask0, mask1);
+    if (len <= strip_cap) pix_one<true>(seg0, seg1, qlo, len, gs, s_tile, s_strip, sval, jrec, lane, s, r, c, ia, ib, group, acc, mask0, mask1);
     else pix_one<false>(seg0, seg1, qlo, len, gs, s_tile, s_strip, sval, jrec, lane, s, r, c, ia, ib, group, acc, mask0, mask1);
     if (lane == 0) { gmask[2 * a] = mask0; gmask[2 * a + 1] = mask1; }
     // applyL2Reg (model.cpp:689-719): A22 += alpha*I, b2 -= alpha * (Gx, Gy)[pixel]
@@ -549,18 +556,30 @@ k_pix(int64_t Np, const int32_t* __restrict__ segoff, const int32_t* __restrict_
   }
 }
 
-// occupancy masks of finished strips, one warp per pixel (used after the fp64-atomic path, which has no k_pix)
+// occupancy masks of finished strips with at least min_len poses, one warp per pixel (the solve calls it for the
+// strips k_pix kept in global memory, or for all of them after the fp64-atomic path, which has no k_pix)
 __global__ void k_strip_mask(int64_t Np, const int32_t* __restrict__ winlo, const int32_t* __restrict__ winhi,
                              const int64_t* __restrict__ stripoff, const double* __restrict__ strip, int group,
-                             unsigned long long* __restrict__ gmask) {
+                             unsigned long long* __restrict__ gmask, int min_len) {
   const int64_t a = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (a >= Np) return;
   const int lo = winlo[a], hi = winhi[a];
   const int len = hi >= lo ? hi - lo + 1 : 0;
+  if (len < min_len) return;
   unsigned long long m0, m1;
   strip_mask_warp(strip + stripoff[a] * 6, len, lo, group, lane, m0, m1);
   if (lane == 0) { gmask[2 * a] = m0; gmask[2 * a + 1] = m1; }
+}
+
+int fill_strip_masks(Handle* h) {
+  if (h->mask_min_len < 0 || h->Np <= 0) return EMBA_OK;
+  k_strip_mask<<<ceil_div64(h->Np * 32, 256), 256, 0, h->stream>>>(h->Np, h->sv_winlo, h->sv_winhi, h->sv_stripoff,
+                                                                  h->sv_strip, h->pose_group, h->sv_gmask,
+                                                                  h->mask_min_len);
+  EMBA_LAUNCH_CHECK();
+  h->mask_min_len = -1;
+  return EMBA_OK;
 }
 
 // fp64-atomic map-block path (reported beside the deterministic one): one thread per Jacobian row in canonical
@@ -783,9 +802,6 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
       EMBA_CUDAC(cudaGetLastError());
     }
     if (Np > 0) {
-      k_strip_mask<<<ceil_div64(Np * 32, 256), 256, 0, h->stream>>>(Np, h->d_winlo, h->d_winhi, h->d_stripoff, h->d_strip,
-                                                                   h->pose_group, h->d_gmask);
-      h->launches++;
       StateSlot& sc = h->st[h->cur];
       k_l2_reg<<<ceil_div64(Np, 256), 256, 0, h->stream>>>(Np, h->d_apix, sc.Gx, sc.Gy, h->rank == 0 ? alpha : 0.0,
                                                           h->d_A22, h->d_b2);
@@ -802,13 +818,21 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
     EMBA_CUDAC(cudaMemsetAsync(h->d_segend, 0, sizeof(int32_t) * (Np + 1), h->stream));
   }
   if (!atomic_path) EMBA_CUDAC(cudaEventRecord(h->ev[9], h->stream));
+  int strip_cap_used = kStripCap;
   if (Np > 0 && !atomic_path) {
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((Np + kPixWarps - 1) / kPixWarps, (int64_t)h->sm_count * 16));
-    const int pix_smem = kPixWarps * kPixSmemPerWarp;
+    // shared-memory strip capacity per warp: 64 poses (4 CTAs/SM). Longer windows accumulate in global memory;
+    // larger capacities were measured slower (C3, mean window 76 poses: 3.3 ms at 64, 3.7 / 4.4 / 3.9 ms at
+    // 96 / 128 / 160) because of the occupancy they cost. EMBA_PIX_CAP overrides for experiments.
+    static const int cap_env = getenv("EMBA_PIX_CAP") ? atoi(getenv("EMBA_PIX_CAP")) : 0;
+    const int strip_cap = cap_env > 0 ? cap_env : kStripCap;
+    strip_cap_used = strip_cap;
+    const int pix_smem = kPixWarps * (kPixStages * kPixTile * kRecDoubles + strip_cap * 6) * 8;
     EMBA_CUDAC(cudaFuncSetAttribute(k_pix, cudaFuncAttributeMaxDynamicSharedMemorySize, pix_smem));
+    const int ctas_per_sm = std::max(1, std::min(4, (227 * 1024) / (pix_smem + 1024)));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((Np + kPixWarps - 1) / kPixWarps, (int64_t)h->sm_count * 4 * ctas_per_sm));
     k_pix<<<grid, kPixWarps * 32, pix_smem, h->stream>>>(Np, h->d_segoff, h->d_segend, vs, h->d_jrec, h->d_winlo, h->d_winhi,
                                                   h->d_stripoff, h->d_strip, h->d_apix, s.Gx, s.Gy,
-                                                  h->rank == 0 ? alpha : 0.0, h->d_A22, h->d_b2, h->pose_group, h->d_gmask);
+                                                  h->rank == 0 ? alpha : 0.0, h->d_A22, h->d_b2, h->pose_group, h->d_gmask, strip_cap);
     h->launches++;
     EMBA_CUDAC(cudaGetLastError());
   }
@@ -816,6 +840,7 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   EMBA_CUDAC(cudaStreamWaitEvent(h->stream, h->ev_join2, 0));
   h->sv_winlo = h->d_winlo; h->sv_winhi = h->d_winhi; h->sv_stripoff = h->d_stripoff; h->sv_strip = h->d_strip;
   h->sv_gmask = h->d_gmask;
+  h->mask_min_len = atomic_path ? 0 : strip_cap_used + 1;  // strips whose masks the solve still has to fill in (-1: none)
   h->sv_strip_total = tot;
   if (h->world > 1 && Np > 0) {
     // A22 / b2 are small: all-reduce. A12: every rank's strips cover (almost) disjoint pose ranges, so they are not

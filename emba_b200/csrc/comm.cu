@@ -134,6 +134,7 @@ __global__ void k_merge_strips(int W, int64_t Np, int64_t a0, int64_t n_own, con
   const int glo = gwinlo[a];
   const int64_t goff = gstripoff[a];
   const int64_t glen = gstripoff[a + 1] - goff;
+  unsigned long long m0 = 0ull, m1 = 0ull;
   for (int64_t e = lane; e < glen * 6; e += 32) {
     const int pose = glo + (int)(e / 6);
     double v = 0.0;
@@ -143,10 +144,16 @@ __global__ void k_merge_strips(int W, int64_t Np, int64_t a0, int64_t n_own, con
         v += recv[(recvbase[s] + own_off[(size_t)s * (n_own + 1) + i] + (pose - lo)) * 6 + (e % 6)];
     }
     gstrip[goff * 6 + e] = v;
+    if (v != 0.0) {  // occupancy masks of the merged strip, straight from the merged values
+      m0 |= 1ull << min(63, pose / group);
+      if (pose >= 1) m1 |= 1ull << min(63, (pose - 1) / group);
+    }
   }
-  __syncwarp();
-  unsigned long long m0, m1;
-  strip_mask_warp(gstrip + goff * 6, (int)glen, glo, group, lane, m0, m1);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m0 |= __shfl_xor_sync(0xffffffffu, m0, o);
+    m1 |= __shfl_xor_sync(0xffffffffu, m1, o);
+  }
   if (lane == 0) { gmask[2 * a] = m0; gmask[2 * a + 1] = m1; }
 }
 
@@ -269,6 +276,7 @@ int comm_exchange_strips(Handle* h) {
   }
   h->sv_winlo = h->d_gwinlo; h->sv_winhi = h->d_gwinhi; h->sv_stripoff = h->d_gstripoff; h->sv_strip = h->d_gstrip;
   h->sv_gmask = h->d_gmask2;
+  h->mask_min_len = -1;  // the merge wrote every owned pixel's masks
   h->sv_strip_total = gtot;
   return EMBA_OK;
 }

@@ -142,6 +142,7 @@ struct Handle {
   unsigned long long* d_gmask2 = nullptr;  // [2(P+1)] merged strips (multi-GPU owner view)
   unsigned long long* sv_gmask = nullptr;
   int pose_group = 16;
+  int mask_min_len = -1;  // >= 0: masks of strips at least this long are still to be computed (by the solve)
   int32_t* sv_winlo = nullptr;
   int32_t* sv_winhi = nullptr;
   int64_t* sv_stripoff = nullptr;

@@ -17,6 +17,7 @@ namespace cg = cooperative_groups;
 namespace emba {
 
 int comm_allreduce(Handle* h, void* buf, int64_t count, int dtype);
+int fill_strip_masks(Handle* h);
 
 // C_a = inverse of the damped 2x2 block (model.cpp:743-759)
 __global__ void k_a22_inv(int64_t Np, const double* __restrict__ A22, double lambda, double* __restrict__ C) {
@@ -732,6 +733,7 @@ int solve_schur(Handle* h, double lambda, int fix) {
   int Z = std::max(1, (h->sm_count * zmult) / npairs);
   Z = (int)std::min<int64_t>(Z, std::max<int64_t>(1, (Np + kSchurThreads - 1) / kSchurThreads));
   EMBA_TRY(dev_reserve(h, &h->d_Spart, &h->Spart_cap, (int64_t)Z * npairs * kST * kST));
+  EMBA_TRY(fill_strip_masks(h));  // occupancy masks of the strips k_pix left in global memory (once per assembly)
   dim3 grid(Z, npairs);
   k_schur_tiles<<<grid, kSchurThreads, 0, h->stream>>>(Np, d, fix, nt, Z, h->sv_winlo, h->sv_winhi, h->sv_stripoff, h->sv_strip,
                                              h->d_C, h->d_b2, h->sv_gmask, h->pose_group, h->d_Spart);
