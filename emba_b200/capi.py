@@ -73,6 +73,11 @@ SIGNATURES = {
                                          C.POINTER(C.c_int32), _dp]),
     "emba_fit_control_poses": (C.c_int, [C.c_int32, C.c_int64, C.POINTER(C.c_int64), _dp, C.c_double, C.c_double,
                                          C.c_double, _dp, C.c_int32, C.POINTER(C.c_int32)]),
+    "emba_poisson_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "emba_poisson_destroy": (C.c_int, [C.c_void_p]),
+    "emba_poisson_reconstruct": (C.c_int, [C.c_void_p, _dp, _dp, _dp]),
+    "emba_poisson_last_ms": (C.c_int, [C.c_void_p, _dp, C.POINTER(C.c_int64)]),
+    "emba_reconstruct_map": (C.c_int, [_H, C.c_int32, _dp]),
     "emba_last_timings_ms": (C.c_int, [_H, _dp]),
     "emba_launch_count": (C.c_int, [_H, C.POINTER(C.c_int64)]),
     "emba_synchronize": (C.c_int, [_H]),

@@ -184,6 +184,7 @@ struct Handle {
   int64_t cg_cap = 0;
   int solved_fix = 0;
   bool solved = false;
+  void* poisson = nullptr;  // lazily created PoissonPlan of emba_reconstruct_map (poisson.cu)
   // timing
   cudaEvent_t ev[12];
   double t_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};

@@ -191,6 +191,8 @@ static int64_t batch_mid_time(int64_t t_bgn, int64_t t_end) {
 
 int rebuild_static(Handle* h);
 void comm_destroy(Handle* h);
+struct PoissonPlan;
+void poisson_plan_destroy(PoissonPlan* p);
 
 }  // namespace emba
 
@@ -273,6 +275,7 @@ int emba_destroy(emba_handle_t hh) {
   if (h->stream2) cudaStreamSynchronize(h->stream2);
   if (h->stream) cudaStreamSynchronize(h->stream);
   comm_destroy(h);
+  if (h->poisson) { poisson_plan_destroy((PoissonPlan*)h->poisson); h->poisson = nullptr; }
   free_state(h->st[0]); free_state(h->st[1]);
   void* ptrs[] = {h->d_lut, h->d_tmid, h->d_spix_ev, h->d_pol, h->d_prev, h->d_refrank, h->d_bs, h->d_bu, h->d_rec, h->d_refpos,
                   h->d_items, h->d_gid, h->d_group_item0, h->d_part, h->d_scal, h->d_flags, h->d_amap, h->d_pflag, h->d_paidx, h->d_len, h->d_apix,

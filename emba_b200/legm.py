@@ -41,6 +41,58 @@ def fit_control_poses(t_ns, quat_xyzw, t_beg, t_end, dt_knots, device=0):
     return out[: n.value].copy()
 
 
+class PoissonPlan:
+    """poisson_reconstruction::reconstructFromGradient (src/image_rec/poisson_reconstruction.cpp:9-50) on the GPU for
+    one panorama size; `reconstruct(Gx, Gy)` returns the intensity map (pano_h x pano_w)."""
+
+    def __init__(self, pano_w, pano_h, device=0):
+        self.L = capi.load()
+        self.pano_w, self.pano_h = int(pano_w), int(pano_h)
+        self.h = C.c_void_p()
+        rc = self.L.emba_poisson_create(int(device), self.pano_w, self.pano_h, C.byref(self.h))
+        if rc != 0:
+            raise EmbaError(rc, "emba_poisson_create")
+
+    def reconstruct(self, Gx, Gy):
+        gx = np.ascontiguousarray(Gx, dtype=np.float64)
+        gy = np.ascontiguousarray(Gy, dtype=np.float64)
+        assert gx.shape == (self.pano_h, self.pano_w) and gy.shape == gx.shape
+        out = np.empty_like(gx)
+        rc = self.L.emba_poisson_reconstruct(self.h, ptr(gx), ptr(gy), ptr(out))
+        if rc != 0:
+            raise EmbaError(rc, "emba_poisson_reconstruct")
+        return out
+
+    def last_ms(self):
+        ms = C.c_double(0.0)
+        n = C.c_int64(0)
+        self.L.emba_poisson_last_ms(self.h, C.byref(ms), C.byref(n))
+        return ms.value, n.value
+
+    def close(self):
+        if self.h:
+            self.L.emba_poisson_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def reconstructFromGradient(gradients, device=0):
+    """Reference-shaped entry point: `gradients` is the H x W x 2 array cv::merge({Gx, Gy}) produces
+    (src/emba/solver.cpp:412-417); returns the H x W intensity map."""
+    g = np.asarray(gradients, dtype=np.float64)
+    assert g.ndim == 3 and g.shape[2] == 2
+    plan = PoissonPlan(g.shape[1], g.shape[0], device)
+    try:
+        return plan.reconstruct(g[:, :, 0], g[:, :, 1])
+    finally:
+        plan.close()
+
+
 class Engine:
     def __init__(self, sensor_w, sensor_h, bearing_lut, C_th, pano_w, pano_h, device=0):
         self.L = capi.load()
@@ -115,6 +167,12 @@ class Engine:
         gy = np.empty((self.pano_h, self.pano_w))
         self._chk(self.L.emba_get_state(self.h, which, ptr(q), ptr(gx), ptr(gy)))
         return q, gx, gy
+
+    def reconstruct_map(self, which=capi.STATE_CURRENT):
+        """Poisson intensity map of the device-resident gradient maps (solver.cpp:412-417)."""
+        img = np.empty((self.pano_h, self.pano_w))
+        self._chk(self.L.emba_reconstruct_map(self.h, which, ptr(img)))
+        return img
 
     # -- evaluate ----------------------------------------------------------------------------------
     def evaluate(self, which=capi.STATE_CURRENT, cost_type=0, eta=1.0, alpha=0.0):

@@ -178,6 +178,22 @@ EMBA_API int emba_fit_control_poses(int32_t device, int64_t n_poses, const int64
                                     double t_beg, double t_end, double dt_knots, double* ctrl_quat_xyzw_out,
                                     int32_t cap, int32_t* n_ctrl_out);
 
+/* ---- "next" row N3: intensity map from the gradient map,
+ * poisson_reconstruction::reconstructFromGradient (src/image_rec/poisson_reconstruction.cpp:9-50; pde::poisolve with
+ * zero Dirichlet boundary, src/image_rec/laplace.cpp:587-797), which the solver applies to cv::merge({Gx, Gy})
+ * (src/emba/solver.cpp:412-417, :466-471). A plan owns the sine-transform matrices of one panorama size (the
+ * counterpart of the FFTW plans the reference makes per call). Width and height must be even (EMBA_E_SUPPORT).
+ * Gx, Gy, img_out: pano_h x pano_w row-major fp64 host buffers. */
+typedef struct emba_poisson_s* emba_poisson_t;
+EMBA_API int emba_poisson_create(int32_t device, int32_t pano_w, int32_t pano_h, emba_poisson_t* out);
+EMBA_API int emba_poisson_destroy(emba_poisson_t p);
+EMBA_API int emba_poisson_reconstruct(emba_poisson_t p, const double* Gx, const double* Gy, double* img_out);
+/* device time of the last reconstruction (ms) and kernels launched by the plan so far; either may be NULL */
+EMBA_API int emba_poisson_last_ms(emba_poisson_t p, double* ms_out, int64_t* launches_out);
+/* the same reconstruction of the optimiser's own device-resident map (which: 0 = CURRENT, 1 = CANDIDATE): only the
+ * image crosses PCIe */
+EMBA_API int emba_reconstruct_map(emba_handle_t h, int32_t which, double* img_out);
+
 /* ---- measurement hooks used by bench.py (CUDA events on the handle's stream) */
 /* elapsed device time (CUDA events on the handle's stream) of the last emba_evaluate / emba_form_normal_eq /
  * emba_solve, ms: out[0]=evaluate total, out[1]=per-measurement residual kernel (k_eval), out[2]=form total,

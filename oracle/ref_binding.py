@@ -67,8 +67,22 @@ class RefLib:
             L.embaref_generate_ctrl_poses_long.restype = C.c_int
             L.embaref_generate_ctrl_poses_long.argtypes = [C.c_long, C.POINTER(C.c_int64), _dp, C.c_double, C.c_double,
                                                            C.c_double, C.c_double, _dp, C.c_int]
+            L.embaref_poisson_reconstruct.restype = C.c_int
+            L.embaref_poisson_reconstruct.argtypes = [_dp, _dp, C.c_int, C.c_int, _dp]
             cls._lib = L
         return cls._lib
+
+
+def ref_poisson_reconstruct(Gx, Gy):
+    """poisson_reconstruction::reconstructFromGradient of the reference (poisson_reconstruction.cpp:9-50)."""
+    L = RefLib.lib()
+    gx = np.ascontiguousarray(Gx, dtype=np.float64)
+    gy = np.ascontiguousarray(Gy, dtype=np.float64)
+    H, W = gx.shape
+    out = np.empty((H, W))
+    rc = L.embaref_poisson_reconstruct(_p(gx), _p(gy), H, W, _p(out))
+    assert rc == 0
+    return out
 
 
 def ref_generate_ctrl_poses_long(t_ns, quat_xyzw, t_beg, t_end, dt_knots, sub_interval=None):

@@ -496,6 +496,21 @@ int embaref_generate_ctrl_poses_long(long n_poses, const int64_t* t_ns, const do
   return (int)cps.size();
 }
 
+// poisson_reconstruction::reconstructFromGradient (src/image_rec/poisson_reconstruction.cpp:9-50) on the two-channel
+// gradient map the solver builds with cv::merge({Gx, Gy}) (src/emba/solver.cpp:412-417). Gx, Gy, out: H x W row-major.
+int embaref_poisson_reconstruct(const double* Gx, const double* Gy, int H, int W, double* out) {
+  cv::Mat g(H, W, CV_64FC2);
+  for (int i = 0; i < H; i++)
+    for (int j = 0; j < W; j++) {
+      g.at<cv::Vec2d>(i, j)[0] = Gx[(size_t)i * W + j];
+      g.at<cv::Vec2d>(i, j)[1] = Gy[(size_t)i * W + j];
+    }
+  const cv::Mat m = poisson_reconstruction::reconstructFromGradient(g);
+  if (m.rows != H || m.cols != W) return -1;
+  std::memcpy(out, m.data, sizeof(double) * (size_t)H * W);
+  return 0;
+}
+
 // timers of the last embaref_solve_time_window: seconds and call counts
 void embaref_get_timers(void* hv, double* t3, long* c3) {
   RefHandle* h = (RefHandle*)hv;

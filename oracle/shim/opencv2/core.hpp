@@ -62,6 +62,7 @@ template <typename T, int n> struct Vec {
   const T& operator[](int i) const { return val[i]; }
 };
 typedef Vec<int, 3> Vec3i;
+typedef Vec<double, 2> Vec2d;
 
 enum MarkerTypes { MARKER_CROSS = 0, MARKER_TILTED_CROSS = 1, MARKER_STAR = 2, MARKER_DIAMOND = 3,
                    MARKER_SQUARE = 4, MARKER_TRIANGLE_UP = 5, MARKER_TRIANGLE_DOWN = 6 };
@@ -93,6 +94,7 @@ public:
 
   Mat() {}
   Mat(int r, int c, int type) { create(r, c, type); }
+  Mat(Size s, int type) { create(s.height, s.width, type); }
 
   void create(int r, int c, int type) {
     if (data && r == rows && c == cols && type == type_) return;

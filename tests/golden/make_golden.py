@@ -80,7 +80,29 @@ def make_frontend():
     print("frontend", t_ns.size, "poses ->", cps.shape[0], "control poses")
 
 
+def make_poisson():
+    """Poisson reconstruction fixture: a smooth seeded gradient map plus noise, 96 x 192,
+    and the intensity map the compiled reference (poisson_reconstruction.cpp + laplace.cpp) reconstructs from it."""
+    rng = np.random.default_rng(11)
+    H, W = 96, 192
+    yy, xx = np.mgrid[0:H, 0:W]
+    img = np.sin(xx / 17.0) * np.cos(yy / 11.0) + 0.3 * np.sin((xx + 2 * yy) / 29.0)
+    Gx = np.zeros((H, W)); Gy = np.zeros((H, W))
+    Gx[:, :-1] = img[:, 1:] - img[:, :-1]
+    Gy[:-1, :] = img[1:, :] - img[:-1, :]
+    Gx += 0.05 * rng.standard_normal((H, W))
+    Gy += 0.05 * rng.standard_normal((H, W))
+    M = RB.ref_poisson_reconstruct(Gx, Gy)
+    np.savez_compressed(os.path.join(HERE, "poisson_ref.npz"), Gx=Gx, Gy=Gy, img=M)
+    print("poisson", H, W, "max |img|", np.abs(M).max())
+
+
 if __name__ == "__main__":
+    if "poisson" in sys.argv[1:]:
+        make_poisson()
+        sys.exit(0)
+    if not sys.argv[1:]:
+        make_poisson()
     if not sys.argv[1:] or "frontend" in sys.argv[1:]:
         make_frontend()
         if "frontend" in sys.argv[1:]:
