@@ -345,6 +345,21 @@ def main():
     except Exception as ex:  # keep the headline even if the short LM run fails
         lm = {"error": str(ex)}
 
+    # ---- "next" row N3: Poisson reconstruction of the intensity map from the device-resident gradient maps
+    poisson = None
+    if rank == 0:
+        try:
+            eng.reconstruct_map(0)  # plan creation (sine matrices) + warm-up
+            tp = []
+            for _ in range(5):
+                t0p = time.perf_counter(); eng.reconstruct_map(0); tp.append((time.perf_counter() - t0p) * 1e3)
+            flop = 4.0 * (sc.pano_h * sc.pano_w * (sc.pano_w + sc.pano_h))  # 2 x (S_H X S_W), 2 flop per MAC
+            poisson = {"panorama": [sc.pano_w, sc.pano_h], "wall_ms_incl_d2h": float(np.median(tp)),
+                       "fp64_gflop": flop / 1e9,
+                       "note": "DST-I as fp64 tensor-core GEMMs (csrc/poisson.cu); wall time includes the D2H copy of the image"}
+        except Exception as ex:
+            poisson = {"error": str(ex)}
+
     if rank == 0:
         peak, peak_src = measured_peak()
         nnz12 = nnz12_local * world  # every rank owns 1/world of the pixels
@@ -391,6 +406,7 @@ def main():
                              "scene_generation_s": t_gen},
             "lm": lm,
             "map_path_atomic": atomic,
+            "poisson_reconstruction": poisson,
         }
         if world == 1 and not args.no_cpu_baseline:
             # bounded sample: ~10-30 s of single-thread CPU work

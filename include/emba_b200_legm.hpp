@@ -284,3 +284,33 @@ private:
 };
 
 }  // namespace EMBA
+
+// Drop-in for poisson_reconstruction::reconstructFromGradient (src/image_rec/poisson_reconstruction.cpp:9-50;
+// declared in include/image_rec/poisson_reconstruction.h:8), same argument and return types: the CV_64FC2 gradient
+// map cv::merge({Gx, Gy}) in, the CV_64F intensity map out. The plan (sine-transform matrices of this panorama size)
+// is kept between calls, as solver.cpp calls it once per recorded iteration (:417, :471).
+namespace poisson_reconstruction_b200 {
+inline cv::Mat reconstructFromGradient(const cv::Mat& gradients, int device = 0) {
+  static emba_poisson_t plan = nullptr;
+  static int plan_w = 0, plan_h = 0;
+  const int H = gradients.rows, W = gradients.cols;
+  if (!plan || plan_w != W || plan_h != H) {
+    if (plan) emba_poisson_destroy(plan);
+    plan = nullptr;
+    if (emba_poisson_create(device, W, H, &plan) != EMBA_OK) throw std::runtime_error("emba_poisson_create failed");
+    plan_w = W;
+    plan_h = H;
+  }
+  std::vector<double> gx((size_t)H * W), gy((size_t)H * W);
+  for (int i = 0; i < H; i++)
+    for (int j = 0; j < W; j++) {
+      const cv::Vec2d& g = gradients.at<cv::Vec2d>(i, j);
+      gx[(size_t)i * W + j] = g[0];
+      gy[(size_t)i * W + j] = g[1];
+    }
+  cv::Mat img(H, W, CV_64F);
+  if (emba_poisson_reconstruct(plan, gx.data(), gy.data(), img.ptr<double>(0)) != EMBA_OK)
+    throw std::runtime_error("emba_poisson_reconstruct failed");
+  return img;
+}
+}  // namespace poisson_reconstruction_b200

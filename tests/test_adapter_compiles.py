@@ -28,6 +28,8 @@ int use_it(const sensor_msgs::CameraInfo& ci) {
   m.updateMap(Gx, Gy, x2, 1.0, act, inact);
   emba_lm_settings_t s{};
   m.solveTimeWindowOnDevice(traj, Gx, Gy, ev, s);
+  cv::Mat grad(512, 1024, CV_64FC2);
+  cv::Mat img = poisson_reconstruction_b200::reconstructFromGradient(grad);
   return r.first + (int)m.evaluateRegError(Gx, Gy).size() + (int)m.evaluateRobustDataCost(ep, "huber", 0.1);
 }
 '''
