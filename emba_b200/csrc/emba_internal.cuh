@@ -340,6 +340,15 @@ __device__ __forceinline__ void project_pm(const PanoCam& c, double X, double Y,
   py = c.cy + theta * c.fy;
 }
 
+// the same for a UNIT bearing (records hold normalised bearings, rotations keep the norm to rounding): no norm, no
+// division; the clamp only guards asin against |y| = 1 + 1 ulp at the poles
+__device__ __forceinline__ void project_pm_unit(const PanoCam& c, double X, double Y, double Z, double& px, double& py) {
+  const double phi = atan2(X, Z);
+  const double theta = asin(fmin(1.0, fmax(-1.0, Y)));
+  px = c.cx + phi * c.fx;
+  py = c.cy + theta * c.fy;
+}
+
 // M = dpm_drb * drb_ddrot (2x3): projection Jacobian (equirectangular_camera.h:31-43) times -[rb]x
 // (src/utils/event_pano_warper.cpp:62-65). With rb = (X, Y, Z), s = X^2 + Z^2 the product of the reference's
 // two matrices simplifies exactly to

@@ -155,14 +155,14 @@ k_eval(const MeasRec* __restrict__ rec, int64_t Mc, const double* __restrict__ K
       const int sk = (int)__double_as_longlong(rt.z);
       double X, Y, Z;
       rotate_bearing(Ktab + (size_t)sk * kKnotStride, rt.x, rt.y, bx, by, bz, X, Y, Z);
-      project_pm(cam, X, Y, Z, pcx, pcy);
+      project_pm_unit(cam, X, Y, Z, pcx, pcy);
     }
     {
       const double4 rt = ldg256(RotTab + bp);
       const int sk = (int)__double_as_longlong(rt.z);
       double X, Y, Z;
       rotate_bearing(Ktab + (size_t)sk * kKnotStride, rt.x, rt.y, bx, by, bz, X, Y, Z);
-      project_pm(cam, X, Y, Z, ppx, ppy);
+      project_pm_unit(cam, X, Y, Z, ppx, ppy);
     }
     const double dx = pcx - ppx, dy = pcy - ppy;
     // dp.norm() > 10 (model.cpp:199-200), evaluated without FMA contraction like the CPU build

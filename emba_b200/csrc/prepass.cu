@@ -116,7 +116,12 @@ __global__ void k_build_recs(const uint32_t* __restrict__ sev, int64_t m_lo, int
   const uint32_t ev = sev[m_lo + j];
   MeasRec r;
   const size_t sp = spix[ev];
-  r.bx = lut[3 * sp]; r.by = lut[3 * sp + 1]; r.bz = lut[3 * sp + 2];
+  // unit bearing: rotations keep the norm, and both the projection (atan2 of a ratio, asin of y / norm) and its
+  // Jacobian are homogeneous of degree 0 in the bearing, so the per-measurement norm and division
+  // (equirectangular_camera.h:22-24) are done once here instead of twice per evaluation
+  const double lx = lut[3 * sp], ly = lut[3 * sp + 1], lz = lut[3 * sp + 2];
+  const double inv = 1.0 / sqrt(lx * lx + ly * ly + lz * lz);
+  r.bx = lx * inv; r.by = ly * inv; r.bz = lz * inv;
   r.bc_pol = (ev / kBatch) | ((uint32_t)(pol[ev] ? 1u : 0u) << 31);
   r.bp = (uint32_t)prev[ev] / kBatch;
   rec[j] = r;
