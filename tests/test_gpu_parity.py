@@ -343,6 +343,43 @@ def test_long_pose_windows_vs_oracle():
     eng.close()
 
 
+def test_many_control_poses_solve_satisfies_the_normal_equations():
+    """n = 1112 control poses (> 1024: the strip occupancy masks fall back to 32-pose groups; d = 3333 > 1536: the
+    LDL^T runs as per-panel launches instead of the fused cooperative kernel). The Schur solution must satisfy the
+    damped normal equations assembled from the library's own blocks -- a check that needs no O(n^2 Np) oracle solve."""
+    from emba_b200 import synth
+    from emba_b200.legm import Engine, spline_base_ns
+
+    sc = synth.make_config("small", dt_knots=0.0009, C_th=0.04)
+    n = sc.n_poses
+    assert n == 1112 and sc.n_events > 500_000
+    t0, dt = spline_base_ns(sc.t_beg, sc.dt_knots)
+    eng = Engine(sc.sensor_w, sc.sensor_h, sc.bearing_lut(), sc.C_th, sc.pano_w, sc.pano_h)
+    eng.set_events(sc.x, sc.y, sc.t_ns, sc.pol)
+    eng.set_state(0, t0, dt, sc.quat_init, sc.Gx_init, sc.Gy_init)
+    eng.evaluate(0, 0, 1.0, ALPHA)
+    Np = eng.form_normal_eq(THRES, 0, 1.0, ALPHA)
+    A11, A12, A22, b1, b2, act = eng.get_normal_eq(True)
+    lam = 1e-3
+    x1, x2, _, _ = eng.solve(lam, False, True)
+    assert x1.shape == (3 * (n - 1),) and x2.shape == (2 * Np,)
+    # damped system with the first pose fixed (solver.cpp:156-165, model.cpp:728-759)
+    A11g, A12g, b1g = A11[3:, 3:], A12[3:, :], b1[3:]
+    A11m = A11g + lam * np.diag(np.diag(A11g))
+    A22 = np.asarray(A22).reshape(Np, 2, 2)
+    A22m = A22.copy()
+    A22m[:, 0, 0] *= 1.0 + lam
+    A22m[:, 1, 1] *= 1.0 + lam
+    r1 = A11m @ x1 + A12g @ x2 - b1g
+    r2 = A12g.T @ x1 + np.einsum("pij,pj->pi", A22m, x2.reshape(Np, 2)).reshape(-1) - b2
+    assert np.linalg.norm(r1) < 1e-8 * np.linalg.norm(b1g)
+    assert np.linalg.norm(r2) < 1e-8 * np.linalg.norm(b2)
+    # and the PCG path agrees with it
+    y1, y2, iters, err = eng.solve(lam, True, True)
+    assert rel(x1, y1) < 5e-2 and rel(x2, y2) < 5e-2
+    eng.close()
+
+
 def test_atomic_map_path_matches_sorted_path(small, small_ref):
     """The fp64-atomic map-block path gives the same normal equations up to summation order (not bit-reproducible),
     and the same LM decisions."""
