@@ -846,9 +846,7 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
     // A22 / b2 are small: all-reduce. A12: every rank's strips cover (almost) disjoint pose ranges, so they are not
     // summed everywhere; each rank becomes the owner of a contiguous range of pixels and receives only the
     // sub-strips of those pixels (1/world of the volume), see comm.cu
-    EMBA_TRYC(comm_allreduce(h, h->d_A22, 3 * Np, 1));
-    EMBA_TRYC(comm_allreduce(h, h->d_b2, 2 * Np, 1));
-    EMBA_TRYC(comm_exchange_strips(h));
+    EMBA_TRYC(comm_exchange_strips(h));  // (the A22 / b2 all-reduces are grouped with its window all-gather)
   }
   EMBA_CUDAC(cudaEventRecord(h->ev[7], h->stream));
   EMBA_CUDAC(cudaStreamSynchronize(h->stream));

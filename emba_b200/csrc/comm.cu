@@ -78,6 +78,19 @@ int comm_allreduce(Handle* h, void* buf, int64_t count, int dtype) {
   return EMBA_OK;
 }
 
+// the evaluation's two reductions (int32 histogram over the panorama, fp64 cost and count) as ONE NCCL group
+int comm_allreduce_eval(Handle* h, int32_t* hist, int64_t P, double* scal2) {
+  if (h->world <= 1) return EMBA_OK;
+  NcclApi* api = nccl_api();
+  if (!api || !h->nccl_comm) { h->err = "multi-GPU shard without a communicator: call emba_comm_init"; return EMBA_E_NCCL; }
+  if (api->group_start() != 0) { h->err = "ncclGroupStart failed"; return EMBA_E_NCCL; }
+  int rc = api->allreduce(hist, hist, (size_t)P, 2, 0, h->nccl_comm, h->stream);
+  rc |= api->allreduce(scal2, scal2, 2, 8, 0, h->nccl_comm, h->stream);
+  if (api->group_end() != 0 || rc != 0) { h->err = "ncclAllReduce (histogram, cost) failed"; return EMBA_E_NCCL; }
+  h->launches++;
+  return EMBA_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // A12 exchange for the time-sharded path. Rank r holds, for every active pixel a, the sub-strip of the control
 // poses its own time slice touches (local window [lo_r(a), hi_r(a)]). Rank q owns the contiguous pixel range
@@ -197,9 +210,13 @@ int comm_exchange_strips(Handle* h) {
   int64_t* recvbase_dev = own_off + (size_t)W * (n_own + 1);
   k_pack_win<<<ceil_div64(Np, T), T, 0, h->stream>>>(Np, h->d_winlo, h->d_winhi, h->d_win2);
   EMBA_LAUNCH_CHECK();
-  // ncclInt32 = 2
-  int rc = api->allgather(h->d_win2, h->d_win_all, (size_t)Np * 2, 2, h->nccl_comm, h->stream);
-  if (rc != 0) { h->err = "ncclAllGather failed"; return EMBA_E_NCCL; }
+  // one NCCL group (= one launch): the small A22 / b2 all-reduces ride with the window all-gather
+  // (ncclInt32 = 2, ncclFloat64 = 8, ncclSum = 0)
+  if (api->group_start() != 0) { h->err = "ncclGroupStart failed"; return EMBA_E_NCCL; }
+  int rc = api->allreduce(h->d_A22, h->d_A22, (size_t)(3 * Np), 8, 0, h->nccl_comm, h->stream);
+  rc |= api->allreduce(h->d_b2, h->d_b2, (size_t)(2 * Np), 8, 0, h->nccl_comm, h->stream);
+  rc |= api->allgather(h->d_win2, h->d_win_all, (size_t)Np * 2, 2, h->nccl_comm, h->stream);
+  if (api->group_end() != 0 || rc != 0) { h->err = "ncclAllReduce/ncclAllGather (A22, b2, windows) failed"; return EMBA_E_NCCL; }
   h->launches++;
   k_own_len<<<ceil_div64(Np + 1, T), T, 0, h->stream>>>(W, Np, a0, n_own, h->d_win_all, own_len, h->d_gwinlo,
                                                         h->d_gwinhi, h->d_len);

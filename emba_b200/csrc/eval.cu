@@ -11,6 +11,7 @@ namespace emba {
 
 int rebuild_static(Handle* h);
 int comm_allreduce(Handle* h, void* buf, int64_t count, int dtype);  // dtype: 0 = int32, 1 = fp64
+int comm_allreduce_eval(Handle* h, int32_t* hist, int64_t P, double* scal2);
 
 // ---------------------------------------------------------------------------------------------------
 // Second-order gradient maps (model.cpp:87-97): 0.125 * 3x3 Sobel (cv::Sobel defaults: scale 1,
@@ -321,8 +322,7 @@ int evaluate_slot(Handle* h, int slot, int cost_type, double eta, double alpha) 
     static const bool dbg = getenv("EMBA_DEBUG_TIMING") != nullptr;
     cudaEvent_t d0, d1;
     if (dbg) { cudaEventCreate(&d0); cudaEventCreate(&d1); cudaEventRecord(d0, h->stream); }
-    EMBA_TRY(comm_allreduce(h, s.hist, h->P, 0));
-    EMBA_TRY(comm_allreduce(h, h->d_scal, 2, 1));
+    EMBA_TRY(comm_allreduce_eval(h, s.hist, h->P, h->d_scal));
     if (dbg) {
       cudaEventRecord(d1, h->stream); cudaStreamSynchronize(h->stream);
       float ms; cudaEventElapsedTime(&ms, d0, d1);
