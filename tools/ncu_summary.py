@@ -1,5 +1,5 @@
 """Summarise the ncu artefacts of one bench command into profiles/ (text summary + per-kernel DRAM traffic json).
-usage: python tools/ncu_summary.py <launch_list.csv> <full_report.ncu-rep> <bench_default.json> <round tag, e.g. r01>
+usage: python tools/ncu_summary.py <launch_list.csv> <full_report.ncu-rep> <bench_default.json> <round tag, e.g. r01> [more .ncu-rep ...]
 
   launch list : ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file <launch_list.csv> python bench.py ...
   full report : ncu --set full --clock-control none --import-source on -k regex:... -o <report> python bench.py ...
@@ -36,8 +36,12 @@ total = sum(v[1] for k, v in agg.items() if "k_sim" not in k and "k_gather" not 
 lst = sorted(agg.items(), key=lambda kv: -kv[1][1])
 
 # ---- full report: one row per captured launch
-raw = subprocess.run(["ncu", "-i", report, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rr = list(csv.reader(io.StringIO(raw)))
+def read_report(path):
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    return list(csv.reader(io.StringIO(raw)))
+
+
+rr = read_report(report)
 hdr = rr[0]
 col = {h: i for i, h in enumerate(hdr)}
 want = [("time_us", "gpu__time_duration.sum"), ("dram_rd_GB", "dram__bytes_read.sum"), ("dram_wr_GB", "dram__bytes_write.sum"),
@@ -47,9 +51,13 @@ want = [("time_us", "gpu__time_duration.sum"), ("dram_rd_GB", "dram__bytes_read.
         ("l1tex%", "l1tex__throughput.avg.pct_of_peak_sustained_active"),
         ("lts%", "lts__throughput.avg.pct_of_peak_sustained_elapsed"),
         ("dram%", "dram__throughput.avg.pct_of_peak_sustained_elapsed")]
-units = rr[1]
 seen = OrderedDict()
-for r in rr[2:]:
+all_rows = [(rr[1], col, r) for r in rr[2:]]
+for extra in sys.argv[5:]:  # further reports of the same command (e.g. the solve kernels captured separately)
+    er = read_report(extra)
+    ecol = {h: i for i, h in enumerate(er[0])}
+    all_rows += [(er[1], ecol, r) for r in er[2:]]
+for units, col, r in all_rows:
     k = short(r[col["Kernel Name"]])
     if k in seen:
         continue
@@ -82,7 +90,8 @@ with open(os.path.join(out_dir, f"{tag}_ncu_summary.txt"), "w") as f:
     f.write("Commands (each ncu pass only after the same command exited 0 without ncu, same gpurun call):\n"
             "  python bench.py --steps 3 --warmup 2 --no-cpu-baseline --lm-iters 3\n"
             f"  ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv   -> {tag}_launches_bench_{wl}.csv\n"
-            "  ncu --set full --clock-control none --import-source on -k regex:\"k_eval|k_asm_pose|k_pix|k_schur_tiles|k_ldlt_fused\"\n"
+            "  ncu --set full --clock-control none --import-source on -k regex:\"k_eval|k_asm_pose|k_pix\" -s 12 -c 3\n"
+            "  ncu --set full --clock-control none --import-source on -k regex:\"k_schur_tiles|k_ldlt_fused|k_gemm_f64\" -c 6\n"
             f"Default bench of the same build (python bench.py): {tag}_bench_default_{wl}.json\n")
     rf = bench["roofline"]
     f.write(f"  value {bench['value']:.4g} events/s ({bench['ms_per_step']:.3f} ms per pass), e2e {bench['e2e']['value']:.4g} events/s, "
