@@ -134,7 +134,10 @@ __global__ void k_zero_tail(int W, int64_t n_own, int64_t* __restrict__ own_len)
   if (s < W) own_len[(size_t)s * (n_own + 1) + n_own] = 0;
 }
 
-// one warp per owned pixel: strip over the merged window = sum over source ranks (fixed order) of their sub-strips
+// one warp per owned pixel: strip over the merged window = sum over source ranks (fixed order) of their sub-strips.
+// The per-source windows and receive offsets are loaded once per pixel (not per element), elements move as
+// double2; MAXW > 0 keeps them in registers for worlds up to MAXW ranks, MAXW == 0 is the generic loop.
+template <int MAXW>
 __global__ void k_merge_strips(int W, int64_t Np, int64_t a0, int64_t n_own, const int32_t* __restrict__ win_all,
                                const int64_t* __restrict__ own_off, const int64_t* __restrict__ recvbase,
                                const double* __restrict__ recv, const int32_t* __restrict__ gwinlo,
@@ -147,17 +150,45 @@ __global__ void k_merge_strips(int W, int64_t Np, int64_t a0, int64_t n_own, con
   const int glo = gwinlo[a];
   const int64_t goff = gstripoff[a];
   const int64_t glen = gstripoff[a + 1] - goff;
-  unsigned long long m0 = 0ull, m1 = 0ull;
-  for (int64_t e = lane; e < glen * 6; e += 32) {
-    const int pose = glo + (int)(e / 6);
-    double v = 0.0;
-    for (int s = 0; s < W; s++) {
-      const int lo = win_all[((size_t)s * Np + a) * 2], hi = win_all[((size_t)s * Np + a) * 2 + 1];
-      if (pose >= lo && pose <= hi)
-        v += recv[(recvbase[s] + own_off[(size_t)s * (n_own + 1) + i] + (pose - lo)) * 6 + (e % 6)];
+  constexpr int NW = MAXW > 0 ? MAXW : 1;
+  int lo[NW], hi[NW];
+  int64_t base[NW];  // double2 index of the source's sub-strip in the receive buffer
+  if (MAXW > 0) {
+#pragma unroll
+    for (int s = 0; s < NW; s++) {
+      lo[s] = INT_MAX; hi[s] = -1; base[s] = 0;
+      if (s < W) {
+        lo[s] = win_all[((size_t)s * Np + a) * 2];
+        hi[s] = win_all[((size_t)s * Np + a) * 2 + 1];
+        base[s] = own_off[(size_t)s * (n_own + 1) + i] * 3;  // flattened scan: receive-chunk base included
+      }
     }
-    gstrip[goff * 6 + e] = v;
-    if (v != 0.0) {  // occupancy masks of the merged strip, straight from the merged values
+  }
+  const double2* recv2 = reinterpret_cast<const double2*>(recv);
+  double2* out2 = reinterpret_cast<double2*>(gstrip) + goff * 3;
+  unsigned long long m0 = 0ull, m1 = 0ull;
+  for (int64_t e = lane; e < glen * 3; e += 32) {
+    const int pose = glo + (int)(e / 3);
+    const int comp = (int)(e % 3);
+    double2 v = make_double2(0.0, 0.0);
+    if (MAXW > 0) {
+#pragma unroll
+      for (int s = 0; s < NW; s++)
+        if (pose >= lo[s] && pose <= hi[s]) {
+          const double2 u = recv2[base[s] + (int64_t)(pose - lo[s]) * 3 + comp];
+          v.x += u.x; v.y += u.y;
+        }
+    } else {
+      for (int s = 0; s < W; s++) {
+        const int l = win_all[((size_t)s * Np + a) * 2], h2 = win_all[((size_t)s * Np + a) * 2 + 1];
+        if (pose >= l && pose <= h2) {
+          const double2 u = recv2[(own_off[(size_t)s * (n_own + 1) + i] + (pose - l)) * 3 + comp];
+          v.x += u.x; v.y += u.y;
+        }
+      }
+    }
+    out2[e] = v;
+    if (v.x != 0.0 || v.y != 0.0) {  // occupancy masks of the merged strip, straight from the merged values
       m0 |= 1ull << min(63, pose / group);
       if (pose >= 1) m1 |= 1ull << min(63, (pose - 1) / group);
     }
@@ -181,7 +212,8 @@ __global__ void k_gather_meta(int W, int64_t Np, int64_t n_own, const int64_t* _
                               const int64_t* __restrict__ stripoff, const int64_t* __restrict__ gstripoff,
                               int64_t* __restrict__ meta) {
   const int t = threadIdx.x;
-  for (int s = t; s < W; s += blockDim.x) meta[s] = own_off[(size_t)s * (n_own + 1) + n_own];
+  for (int s = t; s < W; s += blockDim.x)
+    meta[s] = own_off[(size_t)s * (n_own + 1) + n_own] - own_off[(size_t)s * (n_own + 1)];  // poses received from s
   for (int q = t; q <= W; q += blockDim.x) meta[W + q] = stripoff[Np * q / W];
   if (t == 0) meta[2 * W + 1] = gstripoff[Np];
 }
@@ -237,7 +269,9 @@ int comm_exchange_strips(Handle* h) {
     h->launches += 2;
     return EMBA_OK;
   };
-  for (int s = 0; s < W; s++) EMBA_TRY(scan64(own_len + (size_t)s * (n_own + 1), own_off + (size_t)s * (n_own + 1), n_own + 1));
+  // ONE scan over the flattened [source][pixel] lengths (each source's tail entry is 0): own_off[s][i] is then the
+  // offset of pixel i's sub-strip from source s in the receive buffer, chunk base included
+  EMBA_TRY(scan64(own_len, own_off, (int64_t)W * (n_own + 1)));
   EMBA_TRY(scan64(h->d_len, h->d_gstripoff, Np + 1));
   if (dbg) cudaEventRecord(de[1], h->stream);
   // host needs: recv counts (W), my local strip offsets at the ownership boundaries (W+1), merged total (1)
@@ -258,7 +292,6 @@ int comm_exchange_strips(Handle* h) {
   for (int s = 0; s < W; s++) recvbase[s + 1] = recvbase[s] + recv_cnt[s];
   EMBA_TRY(dev_reserve(h, &h->d_recv, &h->recv_cap, recvbase[W] * 6 + recvbase[W] * 3));
   EMBA_TRY(dev_reserve(h, &h->d_gstrip, &h->gstrip_cap, gtot * 6 + gtot * 3));
-  EMBA_CUDA(cudaMemcpyAsync(recvbase_dev, recvbase.data(), sizeof(int64_t) * (W + 1), cudaMemcpyHostToDevice, h->stream));
   if (dbg) cudaEventRecord(de[2], h->stream);
   // all-to-all of contiguous chunks (ncclFloat64 = 8)
   if (api->group_start() != 0) { h->err = "ncclGroupStart failed"; return EMBA_E_NCCL; }
@@ -276,9 +309,14 @@ int comm_exchange_strips(Handle* h) {
                               cudaMemcpyDeviceToDevice, h->stream));
   if (dbg) cudaEventRecord(de[3], h->stream);
   if (n_own > 0) {
-    k_merge_strips<<<ceil_div64(n_own * 32, T), T, 0, h->stream>>>(W, Np, a0, n_own, h->d_win_all, own_off, recvbase_dev,
-                                                                  h->d_recv, h->d_gwinlo, h->d_gstripoff, h->d_gstrip,
-                                                                  h->pose_group, h->d_gmask2);
+    if (W <= 8)
+      k_merge_strips<8><<<ceil_div64(n_own * 32, T), T, 0, h->stream>>>(W, Np, a0, n_own, h->d_win_all, own_off, recvbase_dev,
+                                                                       h->d_recv, h->d_gwinlo, h->d_gstripoff, h->d_gstrip,
+                                                                       h->pose_group, h->d_gmask2);
+    else
+      k_merge_strips<0><<<ceil_div64(n_own * 32, T), T, 0, h->stream>>>(W, Np, a0, n_own, h->d_win_all, own_off, recvbase_dev,
+                                                                       h->d_recv, h->d_gwinlo, h->d_gstripoff, h->d_gstrip,
+                                                                       h->pose_group, h->d_gmask2);
     EMBA_LAUNCH_CHECK();
   }
   if (dbg) {
