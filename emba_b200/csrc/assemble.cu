@@ -721,9 +721,8 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   // ---- 1. active set (model.cpp:324-379): mask + exclusive scan reproduces the ascending std::set order
   int32_t *d_flag = h->d_pflag, *d_aidx = h->d_paidx;
   int64_t* d_len = h->d_len;
-  auto cleanup = [&]() {};
-#define EMBA_TRYC(x) do { int _r = (x); if (_r != EMBA_OK) { cleanup(); return _r; } } while (0)
-#define EMBA_CUDAC(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { h->err = std::string(#x) + ": " + cudaGetErrorString(_e); cleanup(); return EMBA_E_CUDA; } } while (0)
+#define EMBA_TRYC(x) do { int _r = (x); if (_r != EMBA_OK) return _r; } while (0)
+#define EMBA_CUDAC(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { h->err = std::string(#x) + ": " + cudaGetErrorString(_e); return EMBA_E_CUDA; } } while (0)
   k_active_flags<<<ceil_div64(P, T), T, 0, h->stream>>>(s.hist, P, thres, d_flag);
   h->launches++;
   EMBA_TRYC(cub_exclusive_sum(h, d_flag, d_aidx, P));
@@ -857,7 +856,6 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   cudaEventElapsedTime(&ms, h->ev[9], h->ev[10]); h->t_ms[6] = ms;
   h->t_ms[7] = 0.0;
   if (!atomic_path && Mc > 0) { cudaEventElapsedTime(&ms, h->ev_sort0, h->ev_sort1); h->t_ms[7] = ms; }
-  cleanup();
 #undef EMBA_TRYC
 #undef EMBA_CUDAC
   h->formed = true;

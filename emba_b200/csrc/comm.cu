@@ -139,7 +139,7 @@ __global__ void k_zero_tail(int W, int64_t n_own, int64_t* __restrict__ own_len)
 // double2; MAXW > 0 keeps them in registers for worlds up to MAXW ranks, MAXW == 0 is the generic loop.
 template <int MAXW>
 __global__ void k_merge_strips(int W, int64_t Np, int64_t a0, int64_t n_own, const int32_t* __restrict__ win_all,
-                               const int64_t* __restrict__ own_off, const int64_t* __restrict__ recvbase,
+                               const int64_t* __restrict__ own_off,
                                const double* __restrict__ recv, const int32_t* __restrict__ gwinlo,
                                const int64_t* __restrict__ gstripoff, double* __restrict__ gstrip, int group,
                                unsigned long long* __restrict__ gmask) {
@@ -310,11 +310,11 @@ int comm_exchange_strips(Handle* h) {
   if (dbg) cudaEventRecord(de[3], h->stream);
   if (n_own > 0) {
     if (W <= 8)
-      k_merge_strips<8><<<ceil_div64(n_own * 32, T), T, 0, h->stream>>>(W, Np, a0, n_own, h->d_win_all, own_off, recvbase_dev,
+      k_merge_strips<8><<<ceil_div64(n_own * 32, T), T, 0, h->stream>>>(W, Np, a0, n_own, h->d_win_all, own_off,
                                                                        h->d_recv, h->d_gwinlo, h->d_gstripoff, h->d_gstrip,
                                                                        h->pose_group, h->d_gmask2);
     else
-      k_merge_strips<0><<<ceil_div64(n_own * 32, T), T, 0, h->stream>>>(W, Np, a0, n_own, h->d_win_all, own_off, recvbase_dev,
+      k_merge_strips<0><<<ceil_div64(n_own * 32, T), T, 0, h->stream>>>(W, Np, a0, n_own, h->d_win_all, own_off,
                                                                        h->d_recv, h->d_gwinlo, h->d_gstripoff, h->d_gstrip,
                                                                        h->pose_group, h->d_gmask2);
     EMBA_LAUNCH_CHECK();

@@ -119,7 +119,6 @@ struct Handle {
   int64_t sort_cap = 0;
   uint32_t* d_skey = nullptr;   // sort keys/values (double-buffered)
   uint32_t* d_sval = nullptr;
-  uint32_t* d_skey2 = nullptr;   // (unused scratch)
   uint32_t* d_sval2 = nullptr;   // row ids 0..Mc-1, the sort's constant value input
   int64_t iota_len = 0;          // number of valid entries in d_sval2 (0 after the buffers are rebuilt)
   void* d_cub_tmp = nullptr;

@@ -197,8 +197,9 @@ EMBA_API int emba_reconstruct_map(emba_handle_t h, int32_t which, double* img_ou
 /* ---- measurement hooks used by bench.py (CUDA events on the handle's stream) */
 /* elapsed device time (CUDA events on the handle's stream) of the last emba_evaluate / emba_form_normal_eq /
  * emba_solve, ms: out[0]=evaluate total, out[1]=per-measurement residual kernel (k_eval), out[2]=form total,
- * out[3]=pose-block assembly kernel (k_asm_pose), out[4]=map side total (sort + segments + k_pix + exchange),
- * out[5]=solve total, out[6]=map-block assembly kernel alone (k_pix), out[7]=row sort alone */
+ * out[3]=pose-block assembly kernel (k_asm_pose), out[4]=everything after it (segments + k_pix + multi-GPU exchange),
+ * out[5]=solve total, out[6]=map-block assembly kernel alone (k_pix), out[7]=row sort on its side stream (it runs
+ * beside k_asm_pose, so its elapsed time includes the contention and is not additive) */
 EMBA_API int emba_last_timings_ms(emba_handle_t h, double* out8);
 /* number of kernel launches issued by this handle so far */
 EMBA_API int emba_launch_count(emba_handle_t h, int64_t* out);
