@@ -558,7 +558,8 @@ __global__ void k_cg_a11(int d, int fix, int n, const double* __restrict__ A11, 
 __global__ void __launch_bounds__(256)
 k_cg_pix(int64_t Np, int d, int fix, int nwarps, const int32_t* __restrict__ winlo, const int32_t* __restrict__ winhi,
          const int64_t* __restrict__ stripoff, const double* __restrict__ strip, const double* __restrict__ A22,
-         double lambda, const double* __restrict__ p, double* __restrict__ y, double* __restrict__ part) {
+         double lambda, const double* __restrict__ p, double* __restrict__ y, double* __restrict__ part,
+         int64_t own0, int64_t own1) {
   extern __shared__ double y1s[];  // [nwarps][d]
   const int chunk = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -590,7 +591,10 @@ k_cg_pix(int64_t Np, int d, int fix, int nwarps, const int32_t* __restrict__ win
         t1 += __shfl_down_sync(0xffffffffu, t1, o);
       }
       if (lane == 0) {
-        const double xx = A22[3 * a], xy = A22[3 * a + 1], yy = A22[3 * a + 2];
+        // several GPUs: A22 is replicated, so only the pixel's owner adds the A22m term (the strips of the other
+        // pixels are empty here and t0 = t1 = 0); the partial vectors are summed by one all-reduce
+        double xx = 0.0, xy = 0.0, yy = 0.0;
+        if (a >= own0 && a < own1) { xx = A22[3 * a]; xy = A22[3 * a + 1]; yy = A22[3 * a + 2]; }
         y[d + 2 * a] = t0 + (xx + lambda * xx) * pa + xy * pb;
         y[d + 2 * a + 1] = t1 + xy * pa + (yy + lambda * yy) * pb;
       }
@@ -833,13 +837,21 @@ int solve_schur(Handle* h, double lambda, int fix) {
 }
 
 int solve_pcg(Handle* h, double lambda, int fix, int* iters_out, double* err_out) {
-  if (h->world > 1) {
-    h->err = "the PCG solve is single-GPU in this version; use the Schur solve with several GPUs";
-    return EMBA_E_ARG;
-  }
   const int n = h->n;
   const int d = 3 * (n - fix);
   const int64_t Np = h->Np;
+  // Several GPUs: every vector is replicated; the matrix is not. A12 lives with the pixel owners (solve view), A11 /
+  // b1 are combined here once if they are still per-rank partials, A22 / b2 are already global. A product y = A v
+  // is then a sum of per-rank partial vectors -- rank 0 adds the A11m block, owners add their A22m blocks and their
+  // strips' contributions -- combined by ONE all-reduce of (d + 2 Np) doubles per iteration. All ranks see the
+  // same y, so the scalars (dot products) need no communication and every rank takes the same decisions.
+  const int W = h->world;
+  if (W > 1 && h->a11_partial) {
+    EMBA_TRY(comm_allreduce(h, h->d_A11, (int64_t)9 * n * n, 1));
+    EMBA_TRY(comm_allreduce(h, h->d_b1, (int64_t)3 * n, 1));
+    h->a11_partial = false;
+  }
+  const int64_t own0 = W > 1 ? Np * h->rank / W : 0, own1 = W > 1 ? Np * (h->rank + 1) / W : Np;
   const int64_t tot = d + 2 * Np;
   const int T = 256;
   const int G = ceil_div64(tot, T);
@@ -868,18 +880,23 @@ int solve_pcg(Handle* h, double lambda, int fix, int* iters_out, double* err_out
     return EMBA_OK;
   };
   auto matvec = [&](const double* v, double* y) -> int {
-    k_cg_a11<<<d, 128, 0, h->stream>>>(d, fix, n, h->d_A11, lambda, v, y);
-    h->launches++;
+    if (h->rank == 0) {
+      k_cg_a11<<<d, 128, 0, h->stream>>>(d, fix, n, h->d_A11, lambda, v, y);
+      h->launches++;
+    } else {
+      EMBA_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * d, h->stream));
+    }
     if (Np > 0) {
       const int nwarps = std::max(1, std::min(8, (int)((48 * 1024) / (sizeof(double) * (size_t)d))));
       const size_t shm = sizeof(double) * (size_t)d * nwarps;
       if (shm > 48 * 1024) EMBA_CUDA(cudaFuncSetAttribute(k_cg_pix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
       k_cg_pix<<<kCgChunks, 256, shm, h->stream>>>(Np, d, fix, nwarps, h->sv_winlo, h->sv_winhi, h->sv_stripoff,
-                                                   h->sv_strip, h->d_A22, lambda, v, y, ypart);
+                                                   h->sv_strip, h->d_A22, lambda, v, y, ypart, own0, own1);
       k_cg_y1<<<ceil_div64(d, 128), 128, 0, h->stream>>>(d, kCgChunks, ypart, y);
       h->launches += 2;
     }
     EMBA_CUDA(cudaGetLastError());
+    if (W > 1) EMBA_TRY(comm_allreduce(h, y, tot, 1));
     return EMBA_OK;
   };
   double rhs2 = 0, rn2 = 0;

@@ -50,6 +50,11 @@ def main():
         assert own.size == 0 or (own.min() >= Np * rank // world and own.max() < Np * (rank + 1) // world)
         x1, x2, _, _ = eng.solve(1e-3, False, True)
         assert rel(ref["x1"], x1) < 1e-7 and rel(ref["x2"], x2) < 1e-7
+        # PCG with the pixel-sharded A12 (one all-reduce of the product vector per iteration): same iteration count
+        # and solution as the reference's Eigen::ConjugateGradient on one process
+        y1, y2, it, err = eng.solve(1e-3, True, True)
+        assert it == int(ref["cg_iters"]), (it, int(ref["cg_iters"]))
+        assert rel(ref["x1_cg"], y1) < 1e-6 and rel(ref["x2_cg"], y2) < 1e-6
         eng.set_state(0, t0, dt, sc.quat_init, sc.Gx_init, sc.Gy_init)
         log, fcost = eng.solve_time_window(alpha=5.0, thres=5)
         rlog = ref["lm_log"]
