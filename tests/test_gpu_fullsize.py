@@ -87,3 +87,36 @@ def test_c2_properties():
     inactive = np.ones(gx.size, dtype=bool)
     assert np.isfinite(gx).all() and np.isfinite(gy).all()
     eng.close()
+
+
+@pytest.mark.parametrize("pano_w,pano_h,dt_knots", [(512, 256, 0.1), (4096, 2048, 0.01)])
+def test_c5_sweep_corners(pano_w, pano_h, dt_knots):
+    """BASELINE.json's C5 sweep, its two corners: the coarsest panorama with the widest control-point spacing (most
+    rows per map pixel -> scatter contention on the map side) and the finest panorama with dense control points
+    (largest per-pixel buffers, long LDL^T). Size-independent properties; Schur and PCG must agree."""
+    from emba_b200 import synth
+    from emba_b200.legm import Engine, spline_base_ns
+
+    sc = synth.make_config("C2", pano_w=pano_w, pano_h=pano_h, dt_knots=dt_knots, t_end=1.1, device="cuda")
+    assert sc.n_poses == int(round(1.0 / dt_knots)) + 1 and sc.n_events > 500_000
+    eng = Engine(sc.sensor_w, sc.sensor_h, sc.bearing_lut(), sc.C_th, sc.pano_w, sc.pano_h)
+    eng.set_events(sc.x, sc.y, sc.t_ns, sc.pol)
+    t0, dt = spline_base_ns(sc.t_beg, sc.dt_knots)
+    eng.set_state(0, t0, dt, sc.quat_init, sc.Gx_init, sc.Gy_init)
+    cd, cr, M = eng.evaluate(0, 0, 1.0, ALPHA)
+    _, num = eng.get_evaluation(0, None, False, True)
+    assert int(num.sum()) == M and 0 < M <= eng.num_pairs()
+    Np = eng.form_normal_eq(THRES, 0, 1.0, ALPHA)
+    A11, _, A22, b1, b2, act = eng.get_normal_eq(False)
+    assert np.array_equal(act, np.nonzero(num.reshape(-1) >= THRES)[0]) and Np == act.size
+    assert np.max(np.abs(A11 - A11.T)) <= 1e-12 * np.abs(A11).max() and np.all(np.diag(A11)[3:] > 0)
+    assert np.all(A22[:, 0, 0] * A22[:, 1, 1] - A22[:, 0, 1] ** 2 > 0)
+    y1, y2, it, err = eng.solve(1e-1, True, True)
+    z1, z2, _, _ = eng.solve(1e-1, False, True)
+    assert err < 1e-4 and rel(z1, y1) < 5e-2 and rel(z2, y2) < 5e-2
+    log, fc = eng.solve_time_window(max_num_iter=5, alpha=ALPHA, thres=THRES)
+    acc = log[log[:, 4] == 1]
+    assert acc.shape[0] >= 1 and np.all(np.diff(acc[:, 3]) < 0) and fc < log[0, 2]
+    img = eng.reconstruct_map(0)
+    assert img.shape == (pano_h, pano_w) and np.isfinite(img).all()
+    eng.close()
