@@ -31,8 +31,8 @@ __global__ void k_active_flags(const int32_t* __restrict__ hist, int64_t P, int 
 }
 
 __global__ void k_active_fill(const int32_t* __restrict__ flag, const int32_t* __restrict__ aidx, int64_t P,
-                              int32_t* __restrict__ amap, int32_t* __restrict__ apix, int32_t* __restrict__ winlo,
-                              int32_t* __restrict__ winhi, double4* __restrict__ H3) {
+                              int32_t* __restrict__ amap, int32_t* __restrict__ apix, int2* __restrict__ win,
+                              double4* __restrict__ H3) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
   // the active index also rides in the spare lane of the Hessian entry, so the assembly kernel gets it with the
@@ -43,8 +43,7 @@ __global__ void k_active_fill(const int32_t* __restrict__ flag, const int32_t* _
     const int32_t a = aidx[p];
     amap[p] = a;
     apix[a] = (int32_t)p;
-    winlo[a] = INT_MAX;
-    winhi[a] = -1;
+    win[a] = make_int2(INT_MAX, -1);
   } else {
     amap[p] = -1;
   }
@@ -88,8 +87,8 @@ k_asm_pose(const __grid_constant__ CUtensorMap jmap, const WorkItem* __restrict_
            const MeasRec* __restrict__ rec, const double* __restrict__ Ktab, const double4* __restrict__ RotTab,
            const double4* __restrict__ JacTab, const double2* __restrict__ G2, const double4* __restrict__ H3,
            const double2* __restrict__ dp_in, const double* __restrict__ e_in, const int32_t* __restrict__ pix_in,
-           PanoCam cam, double eta, double* __restrict__ jrec, int32_t* __restrict__ winlo,
-           int32_t* __restrict__ winhi, double* __restrict__ acc_part) {
+           PanoCam cam, double eta, double* __restrict__ jrec, int2* __restrict__ win,
+           double* __restrict__ acc_part) {
   __shared__ __align__(1024) double tile[kAsmThreads * kRecDoubles];  // [row][16], chunk-swizzled
   __shared__ double knots[2 * kKnotStride];  // knot-interval data of cp_c and cp_p: uniform over the work item
   const WorkItem it = items[blockIdx.x];
@@ -191,8 +190,11 @@ k_asm_pose(const __grid_constant__ CUtensorMap jmap, const WorkItem* __restrict_
         row[12] = sw * e;
         d0 = sw * dpv.x;
         d1 = sw * dpv.y;
-        atomicMin(&winlo[a], it.cp_p);
-        atomicMax(&winhi[a], it.cp_c + 1);
+        // pose window of the pixel: one 8-byte look first, the integer atomics only when the window really grows.
+        // Windows only grow, so a stale look costs at most a redundant atomic, never a missed one.
+        const int2 w = win[a];
+        if (it.cp_p < w.x) atomicMin(&win[a].x, it.cp_p);
+        if (it.cp_c + 1 > w.y) atomicMax(&win[a].y, it.cp_c + 1);
       }
     }
     // the previous tile's TMA store must have drained the tile (and every warp finished reading it)
@@ -351,11 +353,14 @@ __global__ void k_a11_gather(int n, int dmax, const int32_t* __restrict__ gid, c
 
 // ---------------------------------------------------------------------------------------------------
 // pose windows -> strip lengths
-__global__ void k_strip_len(const int32_t* __restrict__ winlo, const int32_t* __restrict__ winhi, int64_t Np,
+__global__ void k_strip_len(const int2* __restrict__ win, int32_t* __restrict__ winlo, int32_t* __restrict__ winhi, int64_t Np,
                             int64_t* __restrict__ len) {
   const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= Np) return;
-  const int32_t lo = winlo[a], hi = winhi[a];
+  const int2 w = win[a];
+  const int32_t lo = w.x, hi = w.y;
+  winlo[a] = lo;
+  winhi[a] = hi;
   len[a] = hi >= lo ? (int64_t)(hi - lo + 1) : 0;
 }
 
@@ -732,7 +737,7 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   EMBA_CUDAC(cudaMemcpyAsync(&tail[0], d_aidx + (P - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   EMBA_CUDAC(cudaMemcpyAsync(&tail[1], d_flag + (P - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   EMBA_CUDAC(cudaEventRecord(h->ev_host, h->stream));
-  k_active_fill<<<ceil_div64(P, T), T, 0, h->stream>>>(d_flag, d_aidx, P, h->d_amap, h->d_apix, h->d_winlo, h->d_winhi, s.H3);
+  k_active_fill<<<ceil_div64(P, T), T, 0, h->stream>>>(d_flag, d_aidx, P, h->d_amap, h->d_apix, h->d_win64, s.H3);
   h->launches++;
   // ---- 2. pose side + Jacobian rows
   const int64_t Mc = h->Mc;
@@ -746,7 +751,7 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
                                                            s.JacTab, s.G2,                                        \
                                                            s.H3, s.dp, s.e, s.pix, cam, eta,                       \
                                                            h->d_jrec,                                              \
-                                                           h->d_winlo, h->d_winhi, h->d_acc_part)
+                                                           h->d_win64, h->d_acc_part)
     if (cost_type == EMBA_COST_QUADRATIC) EMBA_ASM_LAUNCH(EMBA_COST_QUADRATIC);
     else if (cost_type == EMBA_COST_CAUCHY) EMBA_ASM_LAUNCH(EMBA_COST_CAUCHY);
     else EMBA_ASM_LAUNCH(EMBA_COST_HUBER);
@@ -760,7 +765,7 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   h->Np = Np;
   // ---- 3. map side: pose windows -> strip offsets. The strip total is read back while the A11 / b1 gather runs.
   EMBA_CUDAC(cudaMemsetAsync(d_len, 0, sizeof(int64_t) * (Np + 1), h->stream));
-  if (Np) { k_strip_len<<<ceil_div64(Np, T), T, 0, h->stream>>>(h->d_winlo, h->d_winhi, Np, d_len); h->launches++; }
+  if (Np) { k_strip_len<<<ceil_div64(Np, T), T, 0, h->stream>>>(h->d_win64, h->d_winlo, h->d_winhi, Np, d_len); h->launches++; }
   EMBA_TRYC(cub_exclusive_sum(h, d_len, h->d_stripoff, Np + 1));
   EMBA_CUDAC(cudaMemcpyAsync(h->h_pin + 2, h->d_stripoff + Np, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
   EMBA_CUDAC(cudaEventRecord(h->ev_host, h->stream));

@@ -125,6 +125,7 @@ struct Handle {
   size_t cub_tmp_bytes = 0;
   void* d_sort_tmp = nullptr;   // radix-sort scratch (side stream: must not alias the scans' scratch)
   size_t sort_tmp_bytes = 0;
+  int2* d_win64 = nullptr;      // [Np] (first, last) control pose touching the pixel while k_asm_pose accumulates them
   int32_t* d_winlo = nullptr;   // [Np] first control pose touching the pixel
   int32_t* d_winhi = nullptr;   // [Np] last control pose touching the pixel
   int64_t* d_stripoff = nullptr;  // [Np+1] offsets (in poses) of the per-pixel A12 strips

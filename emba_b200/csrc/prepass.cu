@@ -261,6 +261,7 @@ int emba_create(const emba_config_t* cfg, emba_handle_t* out) {
        cudaMalloc((void**)&h->d_segend, sizeof(int32_t) * P1) == cudaSuccess &&
        cudaMalloc((void**)&h->d_gmask, sizeof(unsigned long long) * 2 * P1) == cudaSuccess &&
        cudaMalloc((void**)&h->d_gmask2, sizeof(unsigned long long) * 2 * P1) == cudaSuccess &&
+       cudaMalloc((void**)&h->d_win64, sizeof(int2) * P1) == cudaSuccess &&
        cudaMalloc((void**)&h->d_winlo, sizeof(int32_t) * P1) == cudaSuccess &&
        cudaMalloc((void**)&h->d_winhi, sizeof(int32_t) * P1) == cudaSuccess &&
        cudaMalloc((void**)&h->d_stripoff, sizeof(int64_t) * P1) == cudaSuccess &&
@@ -284,7 +285,7 @@ int emba_destroy(emba_handle_t hh) {
   free_state(h->st[0]); free_state(h->st[1]);
   void* ptrs[] = {h->d_lut, h->d_tmid, h->d_spix_ev, h->d_pol, h->d_prev, h->d_refrank, h->d_bs, h->d_bu, h->d_rec, h->d_refpos,
                   h->d_items, h->d_gid, h->d_group_item0, h->d_part, h->d_scal, h->d_flags, h->d_amap, h->d_pflag, h->d_paidx, h->d_len, h->d_apix,
-                  h->d_segoff, h->d_segend, h->d_gmask, h->d_gmask2, h->d_jrec, h->d_skey, h->d_sval, h->d_sval2, h->d_cub_tmp, h->d_sort_tmp, h->d_winlo,
+                  h->d_segoff, h->d_segend, h->d_gmask, h->d_gmask2, h->d_jrec, h->d_skey, h->d_sval, h->d_sval2, h->d_cub_tmp, h->d_sort_tmp, h->d_win64, h->d_winlo,
                   h->d_winhi, h->d_stripoff, h->d_strip, h->d_A22, h->d_b2, h->d_acc_part, h->d_gsum, h->d_A11,
                   h->d_b1, h->d_C, h->d_S, h->d_rhs, h->d_x1, h->d_x2, h->d_Spart, h->d_cg, h->d_ldlt_w, h->d_win2, h->d_win_all, h->d_own_len,
                   h->d_own_off, h->d_gwinlo, h->d_gwinhi, h->d_gstripoff, h->d_gstrip, h->d_recv};
