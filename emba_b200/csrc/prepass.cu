@@ -474,9 +474,10 @@ int rebuild_static(Handle* h) {
       const int64_t s0 = gstart[g], s1 = (g + 1 < G) ? gstart[g + 1] : Mt;
       const int cc = (int)(gkey[g] / (uint32_t)n), cp = (int)(gkey[g] % (uint32_t)n);
       h->dmax = std::max(h->dmax, cc - cp);
-      for (int64_t s = s0; s < s1; s += kItemMax) {
+      static const int64_t item_max = getenv("EMBA_ITEM_MAX") ? atoll(getenv("EMBA_ITEM_MAX")) : kItemMax;
+      for (int64_t s = s0; s < s1; s += item_max) {
         WorkItem w;
-        w.cp_c = cc; w.cp_p = cp; w.start = (int32_t)s; w.count = (int32_t)std::min<int64_t>(kItemMax, s1 - s); w.group = g;
+        w.cp_c = cc; w.cp_p = cp; w.start = (int32_t)s; w.count = (int32_t)std::min<int64_t>(item_max, s1 - s); w.group = g;
         all.push_back(w);
       }
     }
