@@ -4,7 +4,9 @@
     active-pixel decision, the cost is all-reduced;
   * A11/b1/A22/b2 partials are all-reduced;
   * A12 is exchanged as per-pixel sub-strips: every rank sends, for the pixels another rank owns, only its own
-    (pose-window) sub-strip; the owner merges them -- no rank ever holds all of A12.
+    (pose-window) sub-strip; the owner merges them -- no rank ever holds all of A12;
+  * Schur: owners' partial sums all-reduced, replicated factorisation, x2 from the owners;
+  * PCG: replicated vectors, partial matrix-vector products combined by one all-reduce per iteration.
 
 Each rank computes its partial quantities with the numpy oracle restricted to its slice; the combined result must
 equal the unsharded oracle (and therefore the reference golden vectors). This exercises the same collectives the
@@ -120,6 +122,48 @@ def _worker(rank, world, port, out):
     t2 = torch.from_numpy(x2)
     dist.all_reduce(t2)
     assert rel(g["x1"], x1) < 1e-8 and rel(g["x2"], t2.numpy().reshape(-1)) < 1e-8
+    # (5) Jacobi-PCG with the pixel-sharded matrix (solve_pcg with several GPUs): vectors replicated, rank 0 adds
+    # the A11m block, pixel owners add their A22m blocks and strip products, ONE all-reduce per product; the scalars
+    # need no communication. Same iteration count and solution as Eigen's ConjugateGradient in the reference.
+    d = 3 * (n - 1)
+    own_g = owned[3:]                     # gauge: first pose fixed
+    A11g = A11m[3:, 3:]
+    bvec = np.concatenate([b1[3:], b2])
+    dinv = 1.0 / np.concatenate([np.diag(A11g), np.stack([A22m[:, 0, 0], A22m[:, 1, 1]], 1).reshape(-1)])
+
+    def matvec(v):
+        v1, v2 = v[:d], v[d:].reshape(Np, 2)
+        y = np.zeros(d + 2 * Np)
+        if rank == 0:
+            y[:d] += A11g @ v1
+        y[:d] += np.einsum("rpj,pj->r", own_g, v2[a0:a1])
+        y2 = np.zeros((Np, 2))
+        y2[a0:a1] = np.einsum("pij,pj->pi", A22m[a0:a1], v2[a0:a1]) + np.einsum("rpj,r->pj", own_g, v1)
+        y[d:] = y2.reshape(-1)
+        t = torch.from_numpy(y)
+        dist.all_reduce(t)
+        return t.numpy()
+
+    x = np.zeros(d + 2 * Np)
+    r = bvec.copy()
+    rhs2 = float(bvec @ bvec)
+    thr = max(1e-12 * rhs2, np.finfo(np.float64).tiny)  # tolerance 1e-6 squared (model.cpp:828-831)
+    p_ = dinv * r
+    abs_new = float(r @ p_)
+    it = 0
+    while it < 100:
+        tmp = matvec(p_)
+        alpha_ = abs_new / float(p_ @ tmp)
+        x += alpha_ * p_
+        r -= alpha_ * tmp
+        if float(r @ r) < thr:
+            break
+        z = dinv * r
+        abs_old, abs_new = abs_new, float(r @ z)
+        p_ = z + (abs_new / abs_old) * p_
+        it += 1
+    assert it == int(g["cg_iters"]), (it, int(g["cg_iters"]))
+    assert rel(g["x1_cg"], x[:d]) < 1e-6 and rel(g["x2_cg"], x[d:]) < 1e-6
     out[rank] = 1
     dist.barrier()
     dist.destroy_process_group()
