@@ -120,3 +120,35 @@ def test_c5_sweep_corners(pano_w, pano_h, dt_knots):
     img = eng.reconstruct_map(0)
     assert img.shape == (pano_h, pano_w) and np.isfinite(img).all()
     eng.close()
+
+
+def test_c3_properties():
+    """Configuration C3 (~35 M events, 2048x1024 panorama, n = 201): mean pose window 76 > 64 poses, so most strips take
+    k_pix's global-memory path and the solve fills their occupancy masks lazily. Size-independent properties."""
+    sc, eng, t0, dt = _setup("C3")
+    assert 25_000_000 < sc.n_events < 45_000_000 and sc.n_poses == 201
+    out = []
+    for _ in range(2):
+        eng.set_state(0, t0, dt, sc.quat_init, sc.Gx_init, sc.Gy_init)
+        cd, cr, M = eng.evaluate(0, 0, 1.0, ALPHA)
+        Np = eng.form_normal_eq(THRES, 0, 1.0, ALPHA)
+        A11, _, A22, b1, b2, act = eng.get_normal_eq(False)
+        x1, x2, _, _ = eng.solve(1e-3, False, True)
+        out.append((cd, cr, M, Np, A11, A22, b1, b2, act, x1, x2))
+    for a, b in zip(out[0], out[1]):  # bitwise determinism
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    cd, cr, M, Np, A11, A22, b1, b2, act, x1, x2 = out[0]
+    _, num = eng.get_evaluation(0, None, False, True)
+    assert int(num.sum()) == M and np.array_equal(act, np.nonzero(num.reshape(-1) >= THRES)[0])
+    assert eng.a12_entries() / (6.0 * Np) > 64  # the long-window path really is exercised
+    assert np.max(np.abs(A11 - A11.T)) <= 1e-12 * np.abs(A11).max()
+    assert np.isfinite(x1).all() and np.isfinite(x2).all()
+    # the direct solution satisfies the pose block of the damped normal equations after eliminating the map:
+    # compare with the PCG solution of the full system (independent code path, no Schur tiles, no masks)
+    y1, y2, it, err = eng.solve(1e-1, True, True)
+    z1, z2, _, _ = eng.solve(1e-1, False, True)
+    assert err < 1e-4 and rel(z1, y1) < 5e-2 and rel(z2, y2) < 5e-2
+    log, fc = eng.solve_time_window(max_num_iter=3, alpha=ALPHA, thres=THRES)
+    acc = log[log[:, 4] == 1]
+    assert acc.shape[0] >= 1 and np.all(np.diff(acc[:, 3]) < 0) and fc < log[0, 2]
+    eng.close()
