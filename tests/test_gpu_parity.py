@@ -382,6 +382,35 @@ def test_many_control_poses_solve_satisfies_the_normal_equations():
     eng.close()
 
 
+def test_small_angle_branches_vs_oracle(tiny):
+    """Identical and nearly identical consecutive control poses (a camera at rest): the knot interval's rotation
+    increment is 0 or ~1e-7 rad, so the small-angle branches of exp / log / Jl / Jl^-1 (sophus_utils.hpp:333-414,
+    so3.hpp:247,583: thresholds 1e-10 and 1e-20 on the squared angle) are taken on the device as in the oracle."""
+    from oracle import emba_oracle as O
+
+    sc = tiny
+    q = sc.quat_init.copy()
+    q[3] = q[2]                                        # exactly equal: delta = 0
+    q[5] = O.quat_normalize(O.quat_mul(O.so3_exp(np.array([[3e-8, -5e-8, 8e-8]])), q[4:5]))[0]  # |delta| ~ 1e-7
+    q[7] = O.quat_normalize(O.quat_mul(O.so3_exp(np.array([[2e-6, 1e-6, -3e-6]])), q[6:7]))[0]  # just above 1e-10
+    eng = _engine(sc)
+    t0, dt = _base(sc)
+    eng.set_state(0, t0, dt, q, sc.Gx_init, sc.Gy_init)
+    orc = _oracle(sc)
+    ep_o, num_o = orc.evaluate(q, t0, dt, sc.Gx_init, sc.Gy_init, True)
+    cd, cr, M = eng.evaluate(0, 0, 1.0, ALPHA)
+    ep, num = eng.get_evaluation(0, M)
+    assert M == ep_o.size and np.array_equal(num, num_o) and rel(ep_o, ep) < 1e-10
+    Np = eng.form_normal_eq(THRES, 0, 1.0, ALPHA)
+    A11, A12, A22, b1, b2, act = eng.get_normal_eq(True)
+    B11, B12, B22, c1, c2, act_o = orc.form_normal_eq(sc.n_poses, THRES)
+    B22, c2 = orc.apply_l2_reg(B22, c2, act_o, ALPHA, sc.Gx_init, sc.Gy_init)
+    assert np.array_equal(act, act_o)
+    for a, b in ((B11, A11), (B12, A12), (B22, A22), (c1, b1), (c2, b2)):
+        assert rel(a, b) < 1e-9
+    eng.close()
+
+
 def test_atomic_map_path_matches_sorted_path(small, small_ref):
     """The fp64-atomic map-block path gives the same normal equations up to summation order (not bit-reproducible),
     and the same LM decisions."""
