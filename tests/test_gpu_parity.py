@@ -411,6 +411,40 @@ def test_small_angle_branches_vs_oracle(tiny):
     eng.close()
 
 
+def test_error_codes_range_and_numeric(tiny):
+    """EMBA_E_RANGE where the reference would read the map out of bounds (a warped event rounds to column W: camera
+    looking at the panorama seam, model.cpp:209-213), EMBA_E_NUMERIC for a singular Schur complement (a control pose
+    no measurement touches; Eigen's LDLT would return garbage there)."""
+    from emba_b200.capi import EmbaError
+    from oracle import emba_oracle as O
+
+    sc = tiny
+    t0, dt = _base(sc)
+    eng = _engine(sc)
+    # yaw by pi: the optical axis points at the seam phi = +-pi, half of the sensor lands within 0.5 px of column W
+    half_turn = np.array([[0.0, 1.0, 0.0, 0.0]])  # xyzw: rotation by pi about y
+    q_seam = O.quat_normalize(O.quat_mul(np.repeat(half_turn, sc.n_poses, 0), sc.quat_init))
+    eng.set_state(0, t0, dt, q_seam, sc.Gx_init, sc.Gy_init)
+    with pytest.raises(EmbaError) as ei:
+        eng.evaluate(0, 0, 1.0, ALPHA)
+    assert ei.value.code == -4
+    # one more control pose than the events reach: its rows of A11 are zero
+    q_ext = np.concatenate([sc.quat_init, sc.quat_init[-1:], sc.quat_init[-1:]], 0)
+    eng.set_state(0, t0, dt, q_ext, sc.Gx_init, sc.Gy_init)
+    eng.evaluate(0, 0, 1.0, ALPHA)
+    eng.form_normal_eq(THRES, 0, 1.0, ALPHA)
+    A11, _, _, _, _, _ = eng.get_normal_eq(False)
+    assert np.all(A11[-3:, :] == 0.0)
+    with pytest.raises(EmbaError) as ei:
+        eng.solve(LAM, False, True)
+    assert ei.value.code == -6
+    # the handle stays usable
+    eng.set_state(0, t0, dt, sc.quat_init, sc.Gx_init, sc.Gy_init)
+    cd, cr, M = eng.evaluate(0, 0, 1.0, ALPHA)
+    assert M > 0
+    eng.close()
+
+
 def test_atomic_map_path_matches_sorted_path(small, small_ref):
     """The fp64-atomic map-block path gives the same normal equations up to summation order (not bit-reproducible),
     and the same LM decisions."""
