@@ -40,7 +40,12 @@ class LMSettings(C.Structure):
 
 class LMLog(C.Structure):
     _fields_ = [("iter", C.c_int32), ("lambda_", C.c_double), ("cost_min", C.c_double), ("cost_new", C.c_double),
-                ("accepted", C.c_int32), ("num_active_pixels", C.c_int64), ("num_measurements", C.c_int64)]
+                ("accepted", C.c_int32), ("num_active_pixels", C.c_int64), ("num_measurements", C.c_int64),
+                ("cg_iters", C.c_int32), ("cg_error", C.c_double), ("ms_form", C.c_double), ("ms_solve", C.c_double),
+                ("ms_evaluate", C.c_double)]
+
+
+LM_CALLBACK = C.CFUNCTYPE(C.c_int, C.POINTER(LMLog), C.c_void_p)
 
 
 _dp = C.POINTER(C.c_double)
@@ -71,7 +76,22 @@ SIGNATURES = {
     "emba_accept_candidate": (C.c_int, [_H]),
     "emba_solve_time_window": (C.c_int, [_H, C.POINTER(LMSettings), C.POINTER(LMLog), C.c_int32,
                                          C.POINTER(C.c_int32), _dp]),
-    "emba_fit_control_poses": (C.c_int, [C.c_int32, C.c_int64, C.POINTER(C.c_int64), _dp, C.c_double, C.c_double,
+    "emba_solve_time_window_cb": (C.c_int, [_H, C.POINTER(LMSettings), C.POINTER(LMLog), C.c_int32,
+                                            C.POINTER(C.c_int32), _dp, LM_CALLBACK, C.c_void_p]),
+    "emba_set_strict_range": (C.c_int, [_H, C.c_int32]),
+    "emba_get_jacobian_rows": (C.c_int, [_H, _dp, C.c_int64, C.POINTER(C.c_int64)]),
+    "emba_last_setup_ms": (C.c_int, [_H, _dp]),
+    "emba_events_create": (C.c_int, [C.c_int32, C.c_int64, C.POINTER(C.c_uint16), C.POINTER(C.c_uint16),
+                                     C.POINTER(C.c_int64), C.POINTER(C.c_uint8), C.POINTER(C.c_void_p)]),
+    "emba_events_destroy": (C.c_int, [C.c_void_p]),
+    "emba_events_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "emba_events_sort_by_time": (C.c_int, [C.c_void_p]),
+    "emba_events_subsample": (C.c_int, [C.c_void_p, C.c_int32]),
+    "emba_events_window": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "emba_events_download": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_uint16), C.POINTER(C.c_uint16),
+                                       C.POINTER(C.c_int64), C.POINTER(C.c_uint8)]),
+    "emba_set_events_dev": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_int64]),
+    "emba_fit_control_poses": (C.c_int, [C.c_int32, C.c_int64, C.POINTER(C.c_int64), _dp, C.c_int64, C.c_int64,
                                          C.c_double, _dp, C.c_int32, C.POINTER(C.c_int32)]),
     "emba_poisson_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "emba_poisson_destroy": (C.c_int, [C.c_void_p]),

@@ -6,13 +6,16 @@
 //      [Jc Jp e]^T [Jc Jp e] (A11 blocks, b1) are accumulated in registers from a shared-memory tile and
 //      reduced with warp shuffles; per-item partials are combined in a fixed order (deterministic).
 //      The row is also written out (128-byte record) for the map side.
-//   3. map side: rows are ordered by target pixel with a stable radix sort of (pixel, row id) -- it needs only the
-//      evaluation's pixel lookups, so it runs on a side stream beside step 2; one warp per active pixel then
-//      reduces its rows in that fixed order into A22 / b2 and the pixel's A12 strip (3x2 block per control pose
-//      in the pixel's pose window) -- a deterministic segmented reduction.
+//   3. map side: rows are grouped by target pixel WITHOUT a global sort. The evaluation's histogram is exactly the
+//      segment-length table (scan -> segment offsets), and the value its counting atomic returned is a unique slot
+//      of the row inside its pixel's segment: k_place drops every row id into place (one 4-byte scattered store per
+//      row), k_seg_sort then orders each segment by row id (bitonic network in registers, one warp per pixel; CTA-wide
+//      shared-memory network for the rare segments above 1024 rows), which makes the summation order canonical
+//      (= stable sort by pixel) again. Both need only the evaluation, so they run on a side stream beside step 2;
+//      one warp per active pixel then reduces its rows in that fixed order into A22 / b2 and the pixel's A12 strip
+//      (3x2 block per control pose in the pixel's pose window) -- a deterministic segmented reduction.
 #include <climits>
 #include <cuda.h>
-#include <cub/cub.cuh>
 
 #include <algorithm>
 #include "emba_internal.cuh"
@@ -24,28 +27,179 @@ int comm_allreduce(Handle* h, void* buf, int64_t count, int dtype);
 int comm_exchange_strips(Handle* h);
 
 // ---------------------------------------------------------------------------------------------------
-__global__ void k_active_flags(const int32_t* __restrict__ hist, int64_t P, int thres, int32_t* __restrict__ flag) {
+// flag = pixel active (global count >= thres, model.cpp:333); segcnt = this rank's rows on it if active, else 0
+__global__ void k_active_flags(const int32_t* __restrict__ hist, const int32_t* __restrict__ hist_loc, int64_t P,
+                               int thres, int32_t* __restrict__ flag, int32_t* __restrict__ segcnt) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
-  flag[p] = hist[p] >= thres ? 1 : 0;  // model.cpp:333
+  const int f = hist[p] >= thres ? 1 : 0;
+  flag[p] = f;
+  segcnt[p] = f ? hist_loc[p] : 0;
 }
 
-__global__ void k_active_fill(const int32_t* __restrict__ flag, const int32_t* __restrict__ aidx, int64_t P,
+// aidx / rowbase: exclusive scans of flag / segcnt. rowbase is rewritten in place to "first row of the pixel's
+// segment, or -1 if the pixel is inactive" (what k_place looks up per row).
+__global__ void k_active_fill(const int32_t* __restrict__ flag, const int32_t* __restrict__ aidx,
+                              const int32_t* __restrict__ hist_loc, int32_t* __restrict__ rowbase, int64_t P,
                               int32_t* __restrict__ amap, int32_t* __restrict__ apix, int2* __restrict__ win,
-                              double4* __restrict__ H3) {
+                              double4* __restrict__ H3, int32_t* __restrict__ segoff, int32_t* __restrict__ segend,
+                              int64_t* __restrict__ totals) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
   // the active index also rides in the spare lane of the Hessian entry, so the assembly kernel gets it with the
   // gather it does anyway
-  const int32_t av = flag[p] ? aidx[p] : -1;
-  reinterpret_cast<double*>(H3 + p)[3] = __longlong_as_double((long long)av);
-  if (flag[p]) {
-    const int32_t a = aidx[p];
+  const int f = flag[p];
+  const int32_t a = aidx[p];
+  const int32_t base = rowbase[p];
+  reinterpret_cast<double*>(H3 + p)[3] = __longlong_as_double((long long)(f ? a : -1));
+  if (p == P - 1) { totals[0] = (int64_t)a + f; totals[1] = (int64_t)base + (f ? hist_loc[p] : 0); }
+  if (f) {
     amap[p] = a;
     apix[a] = (int32_t)p;
     win[a] = make_int2(INT_MAX, -1);
+    segoff[a] = base;
+    segend[a] = base + hist_loc[p];
   } else {
     amap[p] = -1;
+    rowbase[p] = -1;
+  }
+}
+
+// every inlier row on an active pixel goes to its slot of the pixel's segment
+__global__ void __launch_bounds__(256)
+k_place(int64_t Mc, const int32_t* __restrict__ pix, const int32_t* __restrict__ slot,
+        const int32_t* __restrict__ rowbase, uint32_t* __restrict__ sval) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= Mc) return;
+  const int32_t p = pix[m];
+  if (p < 0) return;
+  const int32_t base = rowbase[p];
+  if (base >= 0) sval[(int64_t)base + slot[m]] = (uint32_t)m;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Segment sort: ascending row ids inside every pixel's segment. "Normalised" bitonic network (every
+// compare-exchange puts the minimum at the lower index: first step of a merge of size k pairs i with i ^ (k-1), the
+// following steps i with i ^ j), so a segment padded with +inf behind its last element sorts correctly.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kSegWarps = 4;
+constexpr int kSegRegCap = 1024;   // longest segment a single warp sorts in registers (32 per lane)
+
+// element i = lane * K + r  (blocked: a lane's K keys are consecutive)
+template <int K>
+__device__ __forceinline__ void warp_bitonic(uint32_t (&a)[K], int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32 * K; k <<= 1) {
+    // flip step: i <-> i ^ (k - 1)
+    if (k <= K) {
+#pragma unroll
+      for (int r = 0; r < K; r++) {
+        const int q = r ^ (k - 1);
+        if (q > r) { const uint32_t lo = min(a[r], a[q]), hi = max(a[r], a[q]); a[r] = lo; a[q] = hi; }
+      }
+    } else {
+      const int lm = k / K - 1;  // lane ^= lm, r -> K - 1 - r
+      const bool lower = (lane & ((lm + 1) >> 1)) == 0;  // the top flipped lane bit decides who is the lower index
+      uint32_t t[K];
+#pragma unroll
+      for (int r = 0; r < K; r++) t[r] = __shfl_xor_sync(0xffffffffu, a[K - 1 - r], lm);
+#pragma unroll
+      for (int r = 0; r < K; r++) a[r] = lower ? min(a[r], t[r]) : max(a[r], t[r]);
+    }
+#pragma unroll
+    for (int j = k >> 2; j >= 1; j >>= 1) {
+      if (j < K) {
+#pragma unroll
+        for (int r = 0; r < K; r++) {
+          const int q = r ^ j;
+          if (q > r) { const uint32_t lo = min(a[r], a[q]), hi = max(a[r], a[q]); a[r] = lo; a[q] = hi; }
+        }
+      } else {
+        const int lm = j / K;
+        const bool lower = (lane & lm) == 0;
+#pragma unroll
+        for (int r = 0; r < K; r++) {
+          const uint32_t o = __shfl_xor_sync(0xffffffffu, a[r], lm);
+          a[r] = lower ? min(a[r], o) : max(a[r], o);
+        }
+      }
+    }
+  }
+}
+
+template <int K>
+__device__ __forceinline__ void seg_sort_regs(uint32_t* __restrict__ seg, int L, int lane) {
+  uint32_t a[K];
+#pragma unroll
+  for (int r = 0; r < K; r++) {
+    const int i = lane * K + r;
+    a[r] = i < L ? seg[i] : 0xFFFFFFFFu;
+  }
+  warp_bitonic<K>(a, lane);
+#pragma unroll
+  for (int r = 0; r < K; r++) {
+    const int i = lane * K + r;
+    if (i < L) seg[i] = a[r];
+  }
+}
+
+__global__ void __launch_bounds__(kSegWarps * 32)
+k_seg_sort(int64_t Np, const int32_t* __restrict__ segoff, const int32_t* __restrict__ segend,
+           uint32_t* __restrict__ sval, int32_t* __restrict__ longlist) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nw = (int64_t)gridDim.x * kSegWarps;
+  for (int64_t a = (int64_t)blockIdx.x * kSegWarps + (threadIdx.x >> 5); a < Np; a += nw) {
+    const int s0 = segoff[a];
+    const int L = segend[a] - s0;
+    uint32_t* seg = sval + s0;
+    if (L <= 1) continue;
+    if (L <= 32) seg_sort_regs<1>(seg, L, lane);
+    else if (L <= 64) seg_sort_regs<2>(seg, L, lane);
+    else if (L <= 128) seg_sort_regs<4>(seg, L, lane);
+    else if (L <= 256) seg_sort_regs<8>(seg, L, lane);
+    else if (L <= 512) seg_sort_regs<16>(seg, L, lane);
+    else if (L <= kSegRegCap) seg_sort_regs<32>(seg, L, lane);
+    else if (lane == 0) longlist[1 + atomicAdd(&longlist[0], 1)] = (int32_t)a;  // k_seg_sort_long takes it
+  }
+}
+
+// segments above kSegRegCap rows: one CTA each, network in shared memory (up to cap_smem ids) or, beyond that, in
+// place in global memory
+__global__ void __launch_bounds__(512)
+k_seg_sort_long(const int32_t* __restrict__ longlist, const int32_t* __restrict__ segoff,
+                const int32_t* __restrict__ segend, uint32_t* __restrict__ sval, int cap_smem) {
+  extern __shared__ uint32_t sbuf[];
+  const int nlong = longlist[0];
+  for (int li = blockIdx.x; li < nlong; li += gridDim.x) {
+    const int a = longlist[1 + li];
+    const int s0 = segoff[a];
+    const int L = segend[a] - s0;
+    uint32_t* seg = sval + s0;
+    const bool in_smem = L <= cap_smem;
+    uint32_t* d = in_smem ? sbuf : seg;
+    __syncthreads();
+    if (in_smem) {
+      for (int i = threadIdx.x; i < L; i += blockDim.x) sbuf[i] = seg[i];
+    }
+    __syncthreads();
+    int n2 = 1;
+    while (n2 < L) n2 <<= 1;
+    for (int k = 2; k <= n2; k <<= 1) {
+      for (int j = k >> 1; j >= 1; j >>= 1) {
+        const int mask = (j == (k >> 1)) ? (k - 1) : j;  // flip step first, then plain steps
+        for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+          const int q = i ^ mask;
+          if (q > i && q < L) {
+            const uint32_t x = d[i], y = d[q];
+            if (y < x) { d[i] = y; d[q] = x; }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    if (in_smem) {
+      for (int i = threadIdx.x; i < L; i += blockDim.x) seg[i] = sbuf[i];
+    }
   }
 }
 
@@ -364,35 +518,6 @@ __global__ void k_strip_len(const int2* __restrict__ win, int32_t* __restrict__ 
   len[a] = hi >= lo ? (int64_t)(hi - lo + 1) : 0;
 }
 
-// row ids 0..M-1: the constant value input of the row sort
-__global__ void k_iota(int64_t M, uint32_t* __restrict__ val) {
-  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m < M) val[m] = (uint32_t)m;
-}
-
-// rows [segoff[a], segend[a]) of the sorted list belong to active pixel a (rows of inactive pixels lie between)
-__global__ void k_seg_bounds(const uint32_t* __restrict__ keys, int64_t M, int64_t Np,
-                             const int32_t* __restrict__ apix, int32_t* __restrict__ segoff,
-                             int32_t* __restrict__ segend) {
-  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= Np) return;
-  const uint32_t p = (uint32_t)apix[a];
-  int64_t lo = 0, hi = M;
-  while (lo < hi) {
-    const int64_t mid = (lo + hi) >> 1;
-    if (keys[mid] < p) lo = mid + 1;
-    else hi = mid;
-  }
-  segoff[a] = (int32_t)lo;
-  hi = M;
-  while (lo < hi) {
-    const int64_t mid = (lo + hi) >> 1;
-    if (keys[mid] <= p) lo = mid + 1;
-    else hi = mid;
-  }
-  segend[a] = (int32_t)lo;
-}
-
 // Map side: one warp per active pixel, rows in fixed (sorted) order. The 128-byte rows are gathered with cp.async
 // (16 B per lane, 4 rows per instruction) into a 2-stage shared-memory ring (4 CTAs = 32 warps per SM), so the DRAM latency of the gather
 // overlaps the reduction of the previous tiles. Lanes 0..23 own one A12 component (slot, row, col), lanes 24..28
@@ -661,21 +786,6 @@ __global__ void k_i32_to_i64(const int32_t* __restrict__ in, int64_t n, int64_t*
   if (i < n) out[i] = in[i];
 }
 
-template <typename T>
-static int cub_exclusive_sum(Handle* h, const T* in, T* out, int64_t count) {
-  size_t tb = 0;
-  EMBA_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, (int)count, h->stream));
-  if (tb > h->cub_tmp_bytes) {
-    if (h->d_cub_tmp) cudaFree(h->d_cub_tmp);
-    h->d_cub_tmp = nullptr;
-    EMBA_CUDA(cudaMalloc(&h->d_cub_tmp, tb));
-    h->cub_tmp_bytes = tb;
-  }
-  EMBA_CUDA(cub::DeviceScan::ExclusiveSum(h->d_cub_tmp, tb, in, out, (int)count, h->stream));
-  h->launches += 2;
-  return EMBA_OK;
-}
-
 int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha) {
   StateSlot& s = h->st[h->cur];
   const int64_t P = h->P;
@@ -685,60 +795,43 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   h->formed = false;
   h->pose_group = 16 * ((n + 1023) / 1024);  // at most 64 groups
   EMBA_CUDA(cudaEventRecord(h->ev[4], h->stream));
-  // ---- 0. side stream: stable radix sort of the rows by panorama pixel. It depends on the evaluation only, so it
-  // overlaps the active-set scan and the pose-side kernel; the main stream joins it before the map-side kernel.
   const bool atomic_path = h->map_path == EMBA_MAP_ATOMIC;
-  uint32_t* sorted_keys = h->d_skey;
   uint32_t* vs = h->d_sval;
-  if (!atomic_path && h->Mc > 0) {
-    const int64_t Mc = h->Mc;
-    // keys = the evaluation's pixel lookups as they are: 0..P-1, or -1 for outliers, whose low `bits` bits are all
-    // ones (>= P because 2^bits > P) so they sort behind every pixel; values = the constant row ids
-    int bits = 1;
-    while (bits < 32 && ((uint64_t)P >> bits)) bits++;
-    const uint32_t* keys_in = reinterpret_cast<const uint32_t*>(s.pix);
-    size_t tb = 0;
-    EMBA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys_in, h->d_skey, h->d_sval2, h->d_sval, (int)Mc, 0, bits,
-                                              h->stream2));
-    if (tb > h->sort_tmp_bytes) {
-      if (h->d_sort_tmp) cudaFree(h->d_sort_tmp);
-      h->d_sort_tmp = nullptr;
-      h->sort_tmp_bytes = 0;
-      EMBA_CUDA(cudaMalloc(&h->d_sort_tmp, tb));
-      h->sort_tmp_bytes = tb;
-    }
-    EMBA_CUDA(cudaEventRecord(h->ev_fork, h->stream));
-    EMBA_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
-    EMBA_CUDA(cudaEventRecord(h->ev_sort0, h->stream2));
-    if (h->iota_len != Mc) {
-      k_iota<<<ceil_div64(Mc, T), T, 0, h->stream2>>>(Mc, h->d_sval2);
-      h->iota_len = Mc;
-      h->launches++;
-    }
-    EMBA_CUDA(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp, tb, keys_in, h->d_skey, h->d_sval2, h->d_sval, (int)Mc, 0,
-                                              bits, h->stream2));
-    h->launches += 1 + 2 * ((bits + 7) / 8);
-    sorted_keys = h->d_skey;
-    vs = h->d_sval;
-    EMBA_CUDA(cudaEventRecord(h->ev_sort1, h->stream2));
-    EMBA_CUDA(cudaEventRecord(h->ev_join, h->stream2));
-  }
-  // ---- 1. active set (model.cpp:324-379): mask + exclusive scan reproduces the ascending std::set order
+  h->jrec_valid = false;
+  // ---- 1. active set (model.cpp:324-379): mask + exclusive scan reproduces the ascending std::set order. The same
+  // pass sizes the row segment of every active pixel from the evaluation's (rank-local) histogram.
   int32_t *d_flag = h->d_pflag, *d_aidx = h->d_paidx;
+  int32_t* d_rowbase = h->d_segcnt;
   int64_t* d_len = h->d_len;
+  void* scan_tmp2 = reinterpret_cast<char*>(h->d_scan_tmp) + scan_scratch_bytes(P + 2);
 #define EMBA_TRYC(x) do { int _r = (x); if (_r != EMBA_OK) return _r; } while (0)
 #define EMBA_CUDAC(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { h->err = std::string(#x) + ": " + cudaGetErrorString(_e); return EMBA_E_CUDA; } } while (0)
-  k_active_flags<<<ceil_div64(P, T), T, 0, h->stream>>>(s.hist, P, thres, d_flag);
+  k_active_flags<<<ceil_div64(P, T), T, 0, h->stream>>>(s.hist, s.hist_loc, P, thres, d_flag, d_rowbase);
   h->launches++;
-  EMBA_TRYC(cub_exclusive_sum(h, d_flag, d_aidx, P));
+  EMBA_TRYC(scan_exclusive<int32_t>(h, h->stream, d_flag, d_aidx, P, h->d_scan_tmp));
+  EMBA_TRYC(scan_exclusive<int32_t>(h, h->stream, d_rowbase, d_rowbase, P, scan_tmp2));
   // Np goes back to the host through pinned memory; the host waits for it only after the pose-side kernel (which
   // does not need it) has been queued, so the round trip hides behind that kernel
-  int32_t* tail = reinterpret_cast<int32_t*>(h->h_pin);
-  EMBA_CUDAC(cudaMemcpyAsync(&tail[0], d_aidx + (P - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-  EMBA_CUDAC(cudaMemcpyAsync(&tail[1], d_flag + (P - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-  EMBA_CUDAC(cudaEventRecord(h->ev_host, h->stream));
-  k_active_fill<<<ceil_div64(P, T), T, 0, h->stream>>>(d_flag, d_aidx, P, h->d_amap, h->d_apix, h->d_win64, s.H3);
+  int64_t* d_totals = reinterpret_cast<int64_t*>(h->d_scal + 32);
+  k_active_fill<<<ceil_div64(P, T), T, 0, h->stream>>>(d_flag, d_aidx, s.hist_loc, d_rowbase, P, h->d_amap, h->d_apix,
+                                                      h->d_win64, s.H3, h->d_segoff, h->d_segend, d_totals);
   h->launches++;
+  EMBA_CUDAC(cudaMemcpyAsync(h->h_pin, d_totals, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+  EMBA_CUDAC(cudaEventRecord(h->ev_host, h->stream));
+  // ---- 1b. side stream: rows -> pixel segments (k_place) and the per-segment ordering (k_seg_sort). They need only
+  // the evaluation and the segment offsets, so they run beside the pose-side kernel; the main stream joins them
+  // before the map-side kernel. The grid of k_seg_sort is sized for the worst case (every pixel active), warps past
+  // the real count find empty segments.
+  if (!atomic_path && h->Mc > 0) {
+    const int64_t Mc = h->Mc;
+    EMBA_CUDAC(cudaEventRecord(h->ev_fork, h->stream));
+    EMBA_CUDAC(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+    EMBA_CUDAC(cudaEventRecord(h->ev_sort0, h->stream2));
+    EMBA_CUDAC(cudaMemsetAsync(h->d_longlist, 0, sizeof(int32_t), h->stream2));
+    k_place<<<ceil_div64(Mc, T), T, 0, h->stream2>>>(Mc, s.pix, s.slot, d_rowbase, h->d_sval);
+    h->launches++;
+    EMBA_CUDAC(cudaGetLastError());
+  }
   // ---- 2. pose side + Jacobian rows
   const int64_t Mc = h->Mc;
   const PanoCam cam = make_cam(h);
@@ -761,12 +854,27 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   }
   EMBA_CUDAC(cudaEventRecord(h->ev[6], h->stream));
   EMBA_CUDAC(cudaEventSynchronize(h->ev_host));
-  const int64_t Np = (int64_t)tail[0] + tail[1];
+  const int64_t Np = h->h_pin[0];
   h->Np = Np;
+  h->Ma = h->h_pin[1];
+  if (!atomic_path && Mc > 0) {
+    if (Np > 0) {
+      const int sgrid = (int)std::max<int64_t>(1, std::min<int64_t>((Np + kSegWarps - 1) / kSegWarps, (int64_t)h->sm_count * 32));
+      k_seg_sort<<<sgrid, kSegWarps * 32, 0, h->stream2>>>(Np, h->d_segoff, h->d_segend, h->d_sval, h->d_longlist);
+      h->launches++;
+      const int long_smem = 160 * 1024;
+      EMBA_CUDAC(cudaFuncSetAttribute(k_seg_sort_long, cudaFuncAttributeMaxDynamicSharedMemorySize, long_smem));
+      k_seg_sort_long<<<h->sm_count, 512, long_smem, h->stream2>>>(h->d_longlist, h->d_segoff, h->d_segend, h->d_sval, long_smem / 4);
+      h->launches++;
+      EMBA_CUDAC(cudaGetLastError());
+    }
+    EMBA_CUDAC(cudaEventRecord(h->ev_sort1, h->stream2));
+    EMBA_CUDAC(cudaEventRecord(h->ev_join, h->stream2));
+  }
   // ---- 3. map side: pose windows -> strip offsets. The strip total is read back while the A11 / b1 gather runs.
   EMBA_CUDAC(cudaMemsetAsync(d_len, 0, sizeof(int64_t) * (Np + 1), h->stream));
   if (Np) { k_strip_len<<<ceil_div64(Np, T), T, 0, h->stream>>>(h->d_win64, h->d_winlo, h->d_winhi, Np, d_len); h->launches++; }
-  EMBA_TRYC(cub_exclusive_sum(h, d_len, h->d_stripoff, Np + 1));
+  EMBA_TRYC(scan_exclusive<int64_t>(h, h->stream, d_len, h->d_stripoff, Np + 1, h->d_scan_tmp));
   EMBA_CUDAC(cudaMemcpyAsync(h->h_pin + 2, h->d_stripoff + Np, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
   EMBA_CUDAC(cudaEventRecord(h->ev_host, h->stream));
   // the small A11 / b1 gather is latency-bound on a tiny grid: it goes to the side stream (behind the sort) and
@@ -813,13 +921,6 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
     }
   } else if (Mc > 0) {
     EMBA_CUDAC(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
-    if (Np > 0) {
-      k_seg_bounds<<<ceil_div64(Np, T), T, 0, h->stream>>>(sorted_keys, Mc, Np, h->d_apix, h->d_segoff, h->d_segend);
-      h->launches++;
-    }
-  } else {
-    EMBA_CUDAC(cudaMemsetAsync(h->d_segoff, 0, sizeof(int32_t) * (Np + 1), h->stream));
-    EMBA_CUDAC(cudaMemsetAsync(h->d_segend, 0, sizeof(int32_t) * (Np + 1), h->stream));
   }
   if (!atomic_path) EMBA_CUDAC(cudaEventRecord(h->ev[9], h->stream));
   int strip_cap_used = kStripCap;
@@ -864,6 +965,7 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
 #undef EMBA_TRYC
 #undef EMBA_CUDAC
   h->formed = true;
+  h->jrec_valid = true;
   h->solved = false;
   return EMBA_OK;
 }

@@ -78,14 +78,17 @@ int comm_allreduce(Handle* h, void* buf, int64_t count, int dtype) {
   return EMBA_OK;
 }
 
-// the evaluation's two reductions (int32 histogram over the panorama, fp64 cost and count) as ONE NCCL group
-int comm_allreduce_eval(Handle* h, int32_t* hist, int64_t P, double* scal2) {
+// the evaluation's reductions as ONE NCCL group: int32 histogram over the panorama (rank-local counts in, global
+// counts out -- the local ones size the rank's row segments afterwards), fp64 cost and count, and the range flag
+// (max), so that every rank takes the same decision on it
+int comm_allreduce_eval(Handle* h, const int32_t* hist_loc, int32_t* hist, int64_t P, double* scal2, int32_t* flags) {
   if (h->world <= 1) return EMBA_OK;
   NcclApi* api = nccl_api();
   if (!api || !h->nccl_comm) { h->err = "multi-GPU shard without a communicator: call emba_comm_init"; return EMBA_E_NCCL; }
   if (api->group_start() != 0) { h->err = "ncclGroupStart failed"; return EMBA_E_NCCL; }
-  int rc = api->allreduce(hist, hist, (size_t)P, 2, 0, h->nccl_comm, h->stream);
+  int rc = api->allreduce(hist_loc, hist, (size_t)P, 2, 0, h->nccl_comm, h->stream);
   rc |= api->allreduce(scal2, scal2, 2, 8, 0, h->nccl_comm, h->stream);
+  rc |= api->allreduce(flags, flags, 1, 2, 2, h->nccl_comm, h->stream);
   if (api->group_end() != 0 || rc != 0) { h->err = "ncclAllReduce (histogram, cost) failed"; return EMBA_E_NCCL; }
   h->launches++;
   return EMBA_OK;
@@ -201,10 +204,6 @@ __global__ void k_merge_strips(int W, int64_t Np, int64_t a0, int64_t n_own, con
   if (lane == 0) { gmask[2 * a] = m0; gmask[2 * a + 1] = m1; }
 }
 
-}  // namespace emba
-#include <cub/cub.cuh>
-#include <climits>
-namespace emba {
 
 // the few numbers the host needs for the exchange: receive counts per source rank, my strip offsets at the
 // ownership boundaries, merged strip total
@@ -257,17 +256,7 @@ int comm_exchange_strips(Handle* h) {
   EMBA_LAUNCH_CHECK();
   // scans: per source rank over my pixels; merged strip offsets over all pixels
   auto scan64 = [&](const int64_t* in, int64_t* out, int64_t count) -> int {
-    size_t tb = 0;
-    EMBA_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, (int)count, h->stream));
-    if (tb > h->cub_tmp_bytes) {
-      if (h->d_cub_tmp) cudaFree(h->d_cub_tmp);
-      h->d_cub_tmp = nullptr; h->cub_tmp_bytes = 0;
-      EMBA_CUDA(cudaMalloc(&h->d_cub_tmp, tb));
-      h->cub_tmp_bytes = tb;
-    }
-    EMBA_CUDA(cub::DeviceScan::ExclusiveSum(h->d_cub_tmp, tb, in, out, (int)count, h->stream));
-    h->launches += 2;
-    return EMBA_OK;
+    return scan_exclusive<int64_t>(h, h->stream, in, out, count, h->d_scan_tmp);
   };
   // ONE scan over the flattened [source][pixel] lengths (each source's tail entry is 0): own_off[s][i] is then the
   // offset of pixel i's sub-strip from source s in the receive buffer, chunk base included

@@ -31,6 +31,46 @@ struct WorkItem {
   int32_t group;       // group id
 };
 
+// One grow-only device allocation carved into 256-byte aligned pieces: the per-window structures are laid out in
+// arenas, so a window of the size of the previous one allocates nothing (and the first one calls cudaMalloc once
+// per arena, not once per array).
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0;
+  void reset() { off = 0; }
+  static size_t pad(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+  template <typename T>
+  T* take(int64_t count) {
+    const size_t bytes = pad(sizeof(T) * (size_t)(count > 0 ? count : 1));
+    if (off + bytes > cap) return nullptr;
+    T* p = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    return p;
+  }
+};
+
+// host -> device copies of caller memory: direct when the source is page-locked, otherwise staged through two pinned
+// 8 MB buffers (memcpy of chunk k+1 overlaps the DMA of chunk k)
+struct Uploader {
+  void* stage[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  int turn = 0;
+};
+constexpr size_t kStageBytes = (size_t)8 << 20;
+
+// device-resident event sequence (include/emba_b200.h: emba_events_t)
+struct EventStore {
+  int device = 0;
+  int64_t N = 0, cap = 0;
+  uint16_t *x = nullptr, *y = nullptr;
+  int64_t* t = nullptr;
+  uint8_t* pol = nullptr;
+  cudaStream_t stream = nullptr;
+  Uploader up;
+  int64_t* h_pin = nullptr;
+  std::string err;
+};
+
 // device-resident optimisation state + outputs of its last evaluation
 struct StateSlot {
   double* quat = nullptr;    // [n*4] xyzw
@@ -44,7 +84,10 @@ struct StateSlot {
   double2* dp = nullptr;     // [Mc] displacement pm_c - pm_p
   double* e = nullptr;       // [Mc] residual
   int32_t* pix = nullptr;    // [Mc] pano pixel index of the current event, -1 = outlier
-  int32_t* hist = nullptr;   // [P] num_ev_map
+  int32_t* slot = nullptr;   // [Mc] arrival rank of the measurement among the (local) rows of its pixel: the value the
+                             //      histogram atomic returns; unique per pixel, arbitrary order
+  int32_t* hist = nullptr;   // [P] num_ev_map (global: all-reduced over the ranks)
+  int32_t* hist_loc = nullptr;  // [P] this rank's own counts (== hist with one GPU)
   double cost_data = 0, cost_reg = 0;
   int64_t M = 0;
   bool evaluated = false;
@@ -61,6 +104,10 @@ struct Handle {
   int64_t* h_pin = nullptr;        // pinned host scratch (1024 x int64) for those read-backs
   int sm_count = 148;
   int64_t launches = 0;
+  Arena ar_ev, ar_meas, ar_tmp;    // per-window event-level / measurement-level structures, scratch
+  Uploader up;
+  int strict_range = 0;            // emba_set_strict_range
+  double t_setup_ms[2] = {0, 0};   // device time of the last emba_set_events / static rebuild
   // config
   int Ws = 0, Hs = 0, Wp = 0, Hp = 0;
   int64_t P = 0;
@@ -68,7 +115,6 @@ struct Handle {
   double* d_lut = nullptr;  // [Ws*Hs*3]
   // events
   int64_t N = 0, Nuse = 0, B = 0;
-  std::vector<int64_t> h_tmid;
   int64_t* d_tmid = nullptr;     // [B]
   uint32_t* d_spix_ev = nullptr; // [Nuse] sensor pixel per event
   uint8_t* d_pol = nullptr;      // [Nuse]
@@ -116,15 +162,11 @@ struct Handle {
   alignas(64) unsigned char jrec_tmap[128] = {};
   const void* jrec_tmap_ptr = nullptr;
   int64_t jrec_tmap_rows = 0;
-  int64_t sort_cap = 0;
-  uint32_t* d_skey = nullptr;   // sort keys/values (double-buffered)
-  uint32_t* d_sval = nullptr;
-  uint32_t* d_sval2 = nullptr;   // row ids 0..Mc-1, the sort's constant value input
-  int64_t iota_len = 0;          // number of valid entries in d_sval2 (0 after the buffers are rebuilt)
-  void* d_cub_tmp = nullptr;
-  size_t cub_tmp_bytes = 0;
-  void* d_sort_tmp = nullptr;   // radix-sort scratch (side stream: must not alias the scans' scratch)
-  size_t sort_tmp_bytes = 0;
+  uint32_t* d_sval = nullptr;   // [Mc] row ids grouped by active pixel, ascending inside a pixel
+  int32_t* d_segcnt = nullptr;  // [P+1] scratch: local rows of each pixel if it is active, else 0
+  int32_t* d_longlist = nullptr;  // [P+1] active pixels whose segment is too long for the warp sort; [0] = count
+  void* d_scan_tmp = nullptr;   // block sums of the scans over the panorama
+  bool jrec_valid = false;      // d_jrec holds the rows of the last assembly (it doubles as scratch of downloads)
   int2* d_win64 = nullptr;      // [Np] (first, last) control pose touching the pixel while k_asm_pose accumulates them
   int32_t* d_winlo = nullptr;   // [Np] first control pose touching the pixel
   int32_t* d_winhi = nullptr;   // [Np] last control pose touching the pixel
@@ -167,6 +209,7 @@ struct Handle {
   double* d_gsum = nullptr;     // [n_groups*91]
   double* d_A11 = nullptr;      // [3n*3n]
   double* d_b1 = nullptr;       // [3n]
+  int64_t A11_cap = 0, b1_cap = 0, x1_cap = 0, S_cap = 0, rhs_cap = 0;
   bool formed = false;
   int map_path = 0;  // EMBA_MAP_SORTED / EMBA_MAP_ATOMIC
   bool a11_partial = false;  // multi-GPU: A11/b1 hold this rank's partial sums (combined inside the Schur all-reduce)
@@ -212,11 +255,41 @@ struct Handle {
     EMBA_CUDA(cudaGetLastError()); \
   } while (0)
 
+// (re)allocation: the new buffer is obtained first, so a failure leaves the old one (and the handle) intact
 template <typename T>
 inline int dev_alloc(Handle* h, T** p, int64_t count) {
-  if (*p) { cudaFree(*p); *p = nullptr; }
   if (count <= 0) count = 1;
-  EMBA_CUDA(cudaMalloc((void**)p, sizeof(T) * (size_t)count));
+  T* q = nullptr;
+  cudaError_t e = cudaMalloc((void**)&q, sizeof(T) * (size_t)count);
+  if (e != cudaSuccess && *p) {  // not enough room for both: give the old one back and retry once
+    cudaGetLastError();
+    cudaFree(*p);
+    *p = nullptr;
+    e = cudaMalloc((void**)&q, sizeof(T) * (size_t)count);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    h->err = std::string("cudaMalloc of ") + std::to_string(sizeof(T) * (size_t)count) + " bytes: " + cudaGetErrorString(e);
+    return EMBA_E_CUDA;
+  }
+  if (*p) cudaFree(*p);
+  *p = q;
+  return EMBA_OK;
+}
+inline int arena_reserve(Handle* h, Arena& a, size_t bytes) {
+  a.off = 0;
+  if (a.base && a.cap >= bytes) return EMBA_OK;
+  const size_t want = bytes + bytes / 16 + 4096;
+  char* q = nullptr;
+  if (a.base) { cudaFree(a.base); a.base = nullptr; a.cap = 0; }
+  cudaError_t e = cudaMalloc((void**)&q, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    h->err = std::string("cudaMalloc of ") + std::to_string(want) + " bytes (arena): " + cudaGetErrorString(e);
+    return EMBA_E_CUDA;
+  }
+  a.base = q;
+  a.cap = want;
   return EMBA_OK;
 }
 template <typename T>
@@ -229,6 +302,18 @@ inline int dev_reserve(Handle* h, T** p, int64_t* cap, int64_t count) {
 }
 
 inline int ceil_div64(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// prims.cu: device-wide exclusive scan and stable radix sort (hand-written; the library uses no CUB)
+size_t scan_scratch_bytes(int64_t count);
+template <typename T>
+int scan_exclusive(Handle* h, cudaStream_t st, const T* in, T* out, int64_t count, void* scratch);
+bool is_pinned(const void* p);
+cudaError_t upload_bytes(Uploader& up, cudaStream_t st, void* dst, const void* src, size_t bytes);
+cudaError_t download_bytes(Uploader& up, cudaStream_t st, void* dst, const void* src, size_t bytes);
+void uploader_free(Uploader& up);
+size_t radix_scratch_bytes(int64_t count);
+int radix_sort_pairs(Handle* h, cudaStream_t st, uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, int64_t count,
+                     int nbits, void* scratch, bool iota, bool keep_keys, int* which);
 
 // ------------------------------------------------------------------------------------------------
 // device math

@@ -1,7 +1,5 @@
 // LEGM::evaluateDataError on the device (reference src/emba/model.cpp:72-258): second-order maps, per-batch
 // spline poses, and the per-measurement residual kernel.
-#include <cub/cub.cuh>
-
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -11,7 +9,7 @@ namespace emba {
 
 int rebuild_static(Handle* h);
 int comm_allreduce(Handle* h, void* buf, int64_t count, int dtype);  // dtype: 0 = int32, 1 = fp64
-int comm_allreduce_eval(Handle* h, int32_t* hist, int64_t P, double* scal2);
+int comm_allreduce_eval(Handle* h, const int32_t* hist_loc, int32_t* hist, int64_t P, double* scal2, int32_t* flags);
 
 // ---------------------------------------------------------------------------------------------------
 // Second-order gradient maps (model.cpp:87-97): 0.125 * 3x3 Sobel (cv::Sobel defaults: scale 1,
@@ -140,7 +138,8 @@ __global__ void __launch_bounds__(kEvalThreads)
 k_eval(const MeasRec* __restrict__ rec, int64_t Mc, const double* __restrict__ Ktab,
        const double4* __restrict__ RotTab, const double2* __restrict__ G2, PanoCam cam, int W, int H, double C_th, double eta,
        double2* __restrict__ dp_out, double* __restrict__ e_out, int32_t* __restrict__ pix_out,
-       int32_t* __restrict__ hist, double* __restrict__ part, int32_t* __restrict__ flags) {
+       int32_t* __restrict__ slot_out, int32_t* __restrict__ hist, double* __restrict__ part,
+       int32_t* __restrict__ flags) {
   double cost = 0.0;
   double cnt = 0.0;
   for (int64_t m = (int64_t)blockIdx.x * kEvalThreads + threadIdx.x; m < Mc; m += (int64_t)gridDim.x * kEvalThreads) {
@@ -168,19 +167,24 @@ k_eval(const MeasRec* __restrict__ rec, int64_t Mc, const double* __restrict__ K
     const double dx = pcx - ppx, dy = pcy - ppy;
     // dp.norm() > 10 (model.cpp:199-200), evaluated without FMA contraction like the CPU build
     const double nrm = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-    int32_t pix = -1;
+    int32_t pix = -1, slot = -1;
     double e = 0.0;
     if (!(nrm > 10.0)) {
       const int px = (int)round(pcx), py = (int)round(pcy);  // std::round, model.cpp:209-210
-      if (px < 0 || px >= W || py < 0 || py >= H) {
-        atomicOr(flags, 4);  // the reference reads out of bounds here
+      // cv::Mat::at(py, px) of a continuous row-major matrix is element py*W + px: column W (a pixel within half a
+      // pixel of the phi = +-pi seam) is element (py + 1, 0), which is what the reference's release build reads
+      // and counts (model.cpp:213-227). Only an index past the last element is out of bounds there: such a pair is
+      // dropped as an outlier (and reported, see emba_set_strict_range).
+      const long long lin = (long long)py * W + px;
+      if (px < 0 || px > W || py < 0 || lin >= (long long)W * H) {
+        atomicOr(flags, 4);
       } else {
-        pix = py * W + px;
+        pix = (int32_t)lin;
         const double2 g = G2[pix];
         const double C_pred = g.x * dx + g.y * dy;        // model.cpp:217
         const double C_meas = 2.0 * (pol - 0.5) * C_th;   // model.cpp:219
         e = C_meas - C_pred;
-        atomicAdd(&hist[pix], 1);                         // model.cpp:227
+        slot = atomicAdd(&hist[pix], 1);                  // model.cpp:227; the old count is this row's slot in the pixel
         cost += rho_of<COST>(e, eta);
         cnt += 1.0;
       }
@@ -188,6 +192,7 @@ k_eval(const MeasRec* __restrict__ rec, int64_t Mc, const double* __restrict__ K
     dp_out[m] = make_double2(dx, dy);
     e_out[m] = e;
     pix_out[m] = pix;
+    slot_out[m] = slot;
   }
   // block reduction, fixed tree
   __shared__ double s_cost[kEvalThreads / 32], s_cnt[kEvalThreads / 32];
@@ -256,10 +261,37 @@ __global__ void k_scatter_ref(const uint32_t* __restrict__ refpos, const int32_t
   }
 }
 __global__ void k_compact_ref(const double* __restrict__ tmp_e, const int32_t* __restrict__ flag,
-                              const int32_t* __restrict__ pos, int64_t Mt, double* __restrict__ out) {
+                              const int32_t* __restrict__ pos, int64_t Mt, double* __restrict__ out,
+                              int64_t* __restrict__ total) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= Mt) return;
   if (flag[r]) out[pos[r]] = tmp_e[r];
+  if (r == Mt - 1) *total = (int64_t)pos[r] + flag[r];
+}
+// the same for the 128-byte Jacobian rows (emba_get_jacobian_rows): 8 threads per row, 16 bytes each; the meta
+// slot (last double) is cleared
+__global__ void k_scatter_rows(const uint32_t* __restrict__ refpos, const int32_t* __restrict__ pix,
+                               const double* __restrict__ jrec, int64_t Mc, double* __restrict__ tmp,
+                               int32_t* __restrict__ tmp_flag) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t m = i >> 3;
+  const int c = (int)(i & 7);
+  if (m >= Mc || pix[m] < 0) return;
+  const uint32_t r = refpos[m];
+  double2 v = reinterpret_cast<const double2*>(jrec)[m * 8 + c];
+  if (c == 7) v.y = 0.0;
+  reinterpret_cast<double2*>(tmp)[(int64_t)r * 8 + c] = v;
+  if (c == 0) tmp_flag[r] = 1;
+}
+__global__ void k_compact_rows(const double* __restrict__ tmp, const int32_t* __restrict__ flag,
+                               const int32_t* __restrict__ pos, int64_t Mt, double* __restrict__ out,
+                               int64_t* __restrict__ total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r = i >> 3;
+  const int c = (int)(i & 7);
+  if (r >= Mt) return;
+  if (flag[r]) reinterpret_cast<double2*>(out)[(int64_t)pos[r] * 8 + c] = reinterpret_cast<const double2*>(tmp)[r * 8 + c];
+  if (r == Mt - 1 && c == 0) *total = (int64_t)pos[r] + flag[r];
 }
 
 PanoCam make_cam(const Handle* h) {
@@ -292,14 +324,15 @@ int evaluate_slot(Handle* h, int slot, int cost_type, double eta, double alpha) 
   EMBA_TRY(dev_reserve(h, &h->d_part, &h->part_cap, (int64_t)2 * grid + rgrid + 16));
   EMBA_CUDA(cudaEventRecord(h->ev[0], h->stream));
   EMBA_TRY(prepare_state_tables(h, s));
-  EMBA_CUDA(cudaMemsetAsync(s.hist, 0, sizeof(int32_t) * h->P, h->stream));
+  EMBA_CUDA(cudaMemsetAsync(s.hist_loc, 0, sizeof(int32_t) * h->P, h->stream));
   EMBA_CUDA(cudaMemsetAsync(h->d_flags, 0, sizeof(int32_t) * 16, h->stream));
   const PanoCam cam = make_cam(h);
   EMBA_CUDA(cudaEventRecord(h->ev[1], h->stream));
   if (h->Mc > 0) {
 #define EMBA_EVAL_LAUNCH(C)                                                                                       \
   k_eval<C><<<grid, kEvalThreads, 0, h->stream>>>(h->d_rec, h->Mc, s.Ktab, s.RotTab, s.G2, cam, h->Wp, h->Hp,     \
-                                                  h->C_th, eta, s.dp, s.e, s.pix, s.hist, h->d_part, h->d_flags)
+                                                  h->C_th, eta, s.dp, s.e, s.pix, s.slot, s.hist_loc, h->d_part,   \
+                                                  h->d_flags)
     if (cost_type == EMBA_COST_QUADRATIC) EMBA_EVAL_LAUNCH(EMBA_COST_QUADRATIC);
     else if (cost_type == EMBA_COST_CAUCHY) EMBA_EVAL_LAUNCH(EMBA_COST_CAUCHY);
     else EMBA_EVAL_LAUNCH(EMBA_COST_HUBER);
@@ -322,7 +355,7 @@ int evaluate_slot(Handle* h, int slot, int cost_type, double eta, double alpha) 
     static const bool dbg = getenv("EMBA_DEBUG_TIMING") != nullptr;
     cudaEvent_t d0, d1;
     if (dbg) { cudaEventCreate(&d0); cudaEventCreate(&d1); cudaEventRecord(d0, h->stream); }
-    EMBA_TRY(comm_allreduce_eval(h, s.hist, h->P, h->d_scal));
+    EMBA_TRY(comm_allreduce_eval(h, s.hist_loc, s.hist, h->P, h->d_scal, h->d_flags));
     if (dbg) {
       cudaEventRecord(d1, h->stream); cudaStreamSynchronize(h->stream);
       float ms; cudaEventElapsedTime(&ms, d0, d1);
@@ -343,8 +376,8 @@ int evaluate_slot(Handle* h, int slot, int cost_type, double eta, double alpha) 
   s.M = (int64_t)llround(sc[1]);
   s.cost_reg = 0.5 * alpha * sc[2];
   s.evaluated = true;
-  if (fl & 4) {
-    h->err = "a warped event rounds outside the panorama (out-of-bounds read in the reference, model.cpp:213)";
+  if ((fl & 4) && h->strict_range) {  // with several ranks the flag was max-reduced: every rank takes this branch
+    h->err = "a warped event rounds past the last panorama element (out-of-bounds access in the reference, model.cpp:213)";
     return EMBA_E_RANGE;
   }
   return EMBA_OK;
@@ -364,6 +397,10 @@ int emba_set_state(emba_handle_t hh, int32_t which, int64_t t0_ns, int64_t dt_ns
     h->err = "emba_set_state: bad argument";
     return EMBA_E_ARG;
   }
+  if (n_poses > 65535) {  // control-pose indices travel as 16-bit fields of the Jacobian rows and as 32-bit pair keys
+    h->err = "emba_set_state: more than 65535 control poses per window";
+    return EMBA_E_ARG;
+  }
   EMBA_CUDA(cudaSetDevice(h->device));
   if (t0_ns != h->t0_ns || dt_ns != h->dt_ns || n_poses != h->n) {
     h->t0_ns = t0_ns; h->dt_ns = dt_ns; h->n = n_poses;
@@ -371,9 +408,9 @@ int emba_set_state(emba_handle_t hh, int32_t which, int64_t t0_ns, int64_t dt_ns
     if (rc != EMBA_OK) { h->t0_ns = -1; return rc; }
   }
   StateSlot& s = h->st[which ? 1 - h->cur : h->cur];
-  EMBA_CUDA(cudaMemcpyAsync(s.quat, quat, sizeof(double) * 4 * n_poses, cudaMemcpyHostToDevice, h->stream));
-  EMBA_CUDA(cudaMemcpyAsync(s.Gx, Gx, sizeof(double) * h->P, cudaMemcpyHostToDevice, h->stream));
-  EMBA_CUDA(cudaMemcpyAsync(s.Gy, Gy, sizeof(double) * h->P, cudaMemcpyHostToDevice, h->stream));
+  EMBA_CUDA(upload_bytes(h->up, h->stream, s.quat, quat, sizeof(double) * 4 * n_poses));
+  EMBA_CUDA(upload_bytes(h->up, h->stream, s.Gx, Gx, sizeof(double) * h->P));
+  EMBA_CUDA(upload_bytes(h->up, h->stream, s.Gy, Gy, sizeof(double) * h->P));
   EMBA_CUDA(cudaStreamSynchronize(h->stream));
   s.evaluated = false;
   if (which == EMBA_STATE_CURRENT) h->formed = h->solved = false;
@@ -385,9 +422,9 @@ int emba_get_state(emba_handle_t hh, int32_t which, double* quat, double* Gx, do
   if (!h || (which != 0 && which != 1) || h->n <= 0) return EMBA_E_ARG;
   EMBA_CUDA(cudaSetDevice(h->device));
   StateSlot& s = h->st[which ? 1 - h->cur : h->cur];
-  if (quat) EMBA_CUDA(cudaMemcpyAsync(quat, s.quat, sizeof(double) * 4 * h->n, cudaMemcpyDeviceToHost, h->stream));
-  if (Gx) EMBA_CUDA(cudaMemcpyAsync(Gx, s.Gx, sizeof(double) * h->P, cudaMemcpyDeviceToHost, h->stream));
-  if (Gy) EMBA_CUDA(cudaMemcpyAsync(Gy, s.Gy, sizeof(double) * h->P, cudaMemcpyDeviceToHost, h->stream));
+  if (quat) EMBA_CUDA(download_bytes(h->up, h->stream, quat, s.quat, sizeof(double) * 4 * h->n));
+  if (Gx) EMBA_CUDA(download_bytes(h->up, h->stream, Gx, s.Gx, sizeof(double) * h->P));
+  if (Gy) EMBA_CUDA(download_bytes(h->up, h->stream, Gy, s.Gy, sizeof(double) * h->P));
   EMBA_CUDA(cudaStreamSynchronize(h->stream));
   return EMBA_OK;
 }
@@ -416,37 +453,75 @@ int emba_get_evaluation(emba_handle_t hh, int32_t which, double* ep_out, int32_t
   EMBA_CUDA(cudaSetDevice(h->device));
   StateSlot& s = h->st[which ? 1 - h->cur : h->cur];
   if (!s.evaluated) { h->err = "emba_get_evaluation: state not evaluated"; return EMBA_E_ARG; }
-  if (num_out) EMBA_CUDA(cudaMemcpyAsync(num_out, s.hist, sizeof(int32_t) * h->P, cudaMemcpyDeviceToHost, h->stream));
+  if (num_out) EMBA_CUDA(download_bytes(h->up, h->stream, num_out, s.hist, sizeof(int32_t) * h->P));
   if (ep_out && h->Mc_total > 0) {
+    // residuals in the reference's order (sensor pixel row-major, then time): scatter by the static reference rank,
+    // compact the inliers. No allocation: the scratch arena of the pre-pass is idle between windows.
     const int64_t Mt = h->Mc_total;
-    double *tmp_e = nullptr, *d_out = nullptr;
-    int32_t *flag = nullptr, *pos = nullptr;
-    int rc = EMBA_OK;
-    if ((rc = dev_alloc(h, &tmp_e, Mt)) || (rc = dev_alloc(h, &d_out, Mt)) || (rc = dev_alloc(h, &flag, Mt)) ||
-        (rc = dev_alloc(h, &pos, Mt))) {
-      cudaFree(tmp_e); cudaFree(d_out); cudaFree(flag); cudaFree(pos);
-      return rc;
+    h->ar_tmp.reset();
+    double* tmp_e = h->ar_tmp.take<double>(Mt);
+    double* d_out = h->ar_tmp.take<double>(Mt);
+    int32_t* flag = h->ar_tmp.take<int32_t>(Mt);
+    int32_t* pos = h->ar_tmp.take<int32_t>(Mt);
+    void* scr = h->ar_tmp.take<char>((int64_t)scan_scratch_bytes(Mt));
+    int64_t* d_total = h->ar_tmp.take<int64_t>(2);
+    if (!tmp_e || !d_out || !flag || !pos || !scr || !d_total) { h->err = "emba_get_evaluation: scratch arena too small"; return EMBA_E_CUDA; }
+    EMBA_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t) * Mt, h->stream));
+    if (h->Mc) {
+      k_scatter_ref<<<ceil_div64(h->Mc, 256), 256, 0, h->stream>>>(h->d_refpos, s.pix, s.e, h->Mc, tmp_e, flag);
+      EMBA_LAUNCH_CHECK();
     }
-    cudaMemsetAsync(flag, 0, sizeof(int32_t) * Mt, h->stream);
-    if (h->Mc) k_scatter_ref<<<ceil_div64(h->Mc, 256), 256, 0, h->stream>>>(h->d_refpos, s.pix, s.e, h->Mc, tmp_e, flag);
-    size_t tb = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tb, flag, pos, (int)Mt, h->stream);
-    void* d_tmp = nullptr;
-    cudaMalloc(&d_tmp, tb ? tb : 1);
-    cub::DeviceScan::ExclusiveSum(d_tmp, tb, flag, pos, (int)Mt, h->stream);
-    k_compact_ref<<<ceil_div64(Mt, 256), 256, 0, h->stream>>>(tmp_e, flag, pos, Mt, d_out);
-    h->launches += 4;
-    int32_t lp = 0, lf = 0;
-    cudaMemcpyAsync(&lp, pos + Mt - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
-    cudaMemcpyAsync(&lf, flag + Mt - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
-    cudaError_t e = cudaStreamSynchronize(h->stream);
-    if (e == cudaSuccess && lp + lf > 0)
-      e = cudaMemcpy(ep_out, d_out, sizeof(double) * (size_t)(lp + lf), cudaMemcpyDeviceToHost);
-    cudaFree(tmp_e); cudaFree(d_out); cudaFree(flag); cudaFree(pos); cudaFree(d_tmp);
-    if (e != cudaSuccess) { h->err = std::string("emba_get_evaluation: ") + cudaGetErrorString(e); return EMBA_E_CUDA; }
+    EMBA_TRY(scan_exclusive<int32_t>(h, h->stream, flag, pos, Mt, scr));
+    k_compact_ref<<<ceil_div64(Mt, 256), 256, 0, h->stream>>>(tmp_e, flag, pos, Mt, d_out, d_total);
+    EMBA_LAUNCH_CHECK();
+    EMBA_CUDA(cudaMemcpyAsync(h->h_pin + 12, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    EMBA_CUDA(cudaStreamSynchronize(h->stream));
+    const int64_t cnt = h->h_pin[12];
+    if (cnt > 0) EMBA_CUDA(download_bytes(h->up, h->stream, ep_out, d_out, sizeof(double) * (size_t)cnt));
   }
   EMBA_CUDA(cudaStreamSynchronize(h->stream));
   return EMBA_OK;
+}
+
+int emba_get_jacobian_rows(emba_handle_t hh, double* rows_out, int64_t cap_rows, int64_t* n_rows) {
+  Handle* h = (Handle*)hh;
+  if (!h || !rows_out || !n_rows) return EMBA_E_ARG;
+  if (!h->formed || !h->jrec_valid) { h->err = "emba_get_jacobian_rows: form the normal equations first"; return EMBA_E_ARG; }
+  if (h->world > 1 || h->Mc_total > ((int64_t)1 << 24)) { h->err = "emba_get_jacobian_rows: single GPU, at most 2^24 pairs"; return EMBA_E_SUPPORT; }
+  EMBA_CUDA(cudaSetDevice(h->device));
+  StateSlot& s = h->st[h->cur];
+  const int64_t Mt = h->Mc_total;
+  *n_rows = 0;
+  if (Mt == 0) return EMBA_OK;
+  double *tmp = nullptr, *d_out = nullptr;
+  int32_t *flag = nullptr, *pos = nullptr;
+  void* scr = nullptr;
+  int64_t* d_total = nullptr;
+  int rc = EMBA_OK;
+  do {  // parity-only download: plain allocations, freed below
+    if (cudaMalloc((void**)&tmp, 128 * (size_t)Mt) != cudaSuccess || cudaMalloc((void**)&d_out, 128 * (size_t)Mt) != cudaSuccess ||
+        cudaMalloc((void**)&flag, 4 * (size_t)Mt) != cudaSuccess || cudaMalloc((void**)&pos, 4 * (size_t)Mt) != cudaSuccess ||
+        cudaMalloc(&scr, scan_scratch_bytes(Mt)) != cudaSuccess || cudaMalloc((void**)&d_total, 16) != cudaSuccess) {
+      cudaGetLastError(); h->err = "emba_get_jacobian_rows: out of device memory"; rc = EMBA_E_CUDA; break;
+    }
+    cudaMemsetAsync(flag, 0, 4 * (size_t)Mt, h->stream);
+    k_scatter_rows<<<ceil_div64(h->Mc * 8, 256), 256, 0, h->stream>>>(h->d_refpos, s.pix, h->d_jrec, h->Mc, tmp, flag);
+    h->launches++;
+    if ((rc = scan_exclusive<int32_t>(h, h->stream, flag, pos, Mt, scr))) break;
+    k_compact_rows<<<ceil_div64(Mt * 8, 256), 256, 0, h->stream>>>(tmp, flag, pos, Mt, d_out, d_total);
+    h->launches++;
+    cudaMemcpyAsync(h->h_pin + 12, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { h->err = std::string("emba_get_jacobian_rows: ") + cudaGetErrorString(e); rc = EMBA_E_CUDA; break; }
+    const int64_t cnt = h->h_pin[12];
+    *n_rows = cnt;
+    if (cnt > cap_rows) { h->err = "emba_get_jacobian_rows: output capacity too small"; rc = EMBA_E_ARG; break; }
+    if (cnt > 0 && download_bytes(h->up, h->stream, rows_out, d_out, 128 * (size_t)cnt) != cudaSuccess) {
+      cudaGetLastError(); h->err = "emba_get_jacobian_rows: copy failed"; rc = EMBA_E_CUDA; break;
+    }
+  } while (0);
+  cudaFree(tmp); cudaFree(d_out); cudaFree(flag); cudaFree(pos); cudaFree(scr); cudaFree(d_total);
+  return rc;
 }
 
 int emba_last_timings_ms(emba_handle_t hh, double* out8) {

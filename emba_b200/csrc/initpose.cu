@@ -81,13 +81,13 @@ static double ros_ns_to_sec(int64_t ns) {
 using namespace emba;
 
 extern "C" int emba_fit_control_poses(int32_t device, int64_t n_poses, const int64_t* t_ns, const double* quat_xyzw,
-                                      double t_beg, double t_end, double dt_knots, double* ctrl_quat_out,
+                                      int64_t tb_ns, int64_t te_ns, double dt_knots, double* ctrl_quat_out,
                                       int32_t cap, int32_t* n_ctrl_out) {
-  if (!t_ns || !quat_xyzw || !ctrl_quat_out || !n_ctrl_out || n_poses < 2 || !(dt_knots > 0) || !(t_end > t_beg))
+  if (!t_ns || !quat_xyzw || !ctrl_quat_out || !n_ctrl_out || n_poses < 2 || !(dt_knots > 0) || !(te_ns > tb_ns))
     return EMBA_E_ARG;
   if (cudaSetDevice(device) != cudaSuccess) return EMBA_E_CUDA;
   // host: sub-interval boundaries in ros::Time / ros::Duration arithmetic (trajectory.cpp:263-270)
-  const int64_t tb_ns = ros_duration_ns(t_beg), te_ns = ros_duration_ns(t_end);
+  // t_beg / t_end arrive as the ns-exact ros::Time::toNSec() of the interval (emba.cpp:416)
   const double span = ros_ns_to_sec(te_ns - tb_ns);
   const int n_int = (int)std::floor(span / dt_knots + 1e-6);
   if (n_int < 1) return EMBA_E_ARG;

@@ -1,11 +1,18 @@
-// Static structure of a time window: handle lifetime, event upload, batch mid-times, the per-sensor-pixel
+// Static structure of a time window: handle lifetime, event ingestion, batch mid-times, the per-sensor-pixel
 // pair links that replace the reference's EventMap (include/emba/event_map.h:22-113), and -- once the spline
 // time base is known -- the canonical measurement order (sorted by the control-pose pair a measurement
 // touches) with its work items. Everything here runs once per window / per spline base, never per LM iteration.
+//
+// SURVEY section 8(f) N1. The per-window structures live in two arenas (event level, measurement level) plus a
+// scratch arena, all grow-only: a window no larger than the previous one allocates nothing. Sorts and scans are the
+// library's own (prims.cu). Events come either from host arrays (emba_set_events: pinned sources are copied
+// directly, pageable ones are staged through two pinned buffers) or from a device-resident event sequence
+// (emba_events_*, emba_set_events_dev: no host copy at all).
 #include <algorithm>
+#include <climits>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
-#include <cub/cub.cuh>
 
 #include "emba_internal.cuh"
 
@@ -15,17 +22,40 @@ namespace emba {
 // kernels
 // ---------------------------------------------------------------------------------------------------
 __global__ void k_spix(const uint16_t* __restrict__ x, const uint16_t* __restrict__ y, int Ws, int Hs, int64_t N,
-                       uint32_t* __restrict__ spix, uint32_t* __restrict__ ids, int32_t* __restrict__ flags) {
+                       uint32_t* __restrict__ spix, uint32_t* __restrict__ key, int32_t* __restrict__ flags) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   const uint32_t xi = x[i], yi = y[i];
-  if (xi >= (uint32_t)Ws || yi >= (uint32_t)Hs) {
-    atomicOr(flags, 1);
-    spix[i] = 0;
-  } else {
-    spix[i] = yi * (uint32_t)Ws + xi;
-  }
-  ids[i] = (uint32_t)i;
+  uint32_t s = 0;
+  if (xi >= (uint32_t)Ws || yi >= (uint32_t)Hs) atomicOr(flags, 1);
+  else s = yi * (uint32_t)Ws + xi;
+  spix[i] = s;
+  key[i] = s;
+}
+
+// the two timestamps per batch the mid-time needs (device-resident sequences)
+__global__ void k_batch_tpair(const int64_t* __restrict__ t, int64_t B, int64_t* __restrict__ tpair) {
+  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  tpair[2 * b] = t[b * kBatch];
+  tpair[2 * b + 1] = t[b * kBatch + kBatch - 1];
+}
+
+// ros::Duration(double) rounding of the half span, as the reference evaluates `t_batch_bgn + timespan * 0.5`
+// (src/emba/model.cpp:116-119): Duration::operator*(double) is Duration(toSec()*scale); Duration(double d) is
+// sec = floor(d), nsec = round((d - sec)*1e9). Round-to-nearest intrinsics keep the compiler from contracting the
+// products into FMAs, so odd spans round exactly like the CPU reference.
+__global__ void k_batch_mid(const int64_t* __restrict__ tpair, int64_t B, int64_t* __restrict__ tmid) {
+  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int64_t t_bgn = tpair[2 * b], span = tpair[2 * b + 1] - t_bgn;
+  int64_t sec = span / 1000000000LL, nsec = span % 1000000000LL;
+  if (nsec < 0) { nsec += 1000000000LL; sec -= 1; }
+  const double tosec = __dadd_rn((double)sec, __dmul_rn(1e-9, (double)nsec));
+  const double d = __dmul_rn(tosec, 0.5);
+  const double s = floor(d);
+  const double frac = __dmul_rn(__dsub_rn(d, s), 1e9);
+  tmid[b] = t_bgn + (int64_t)s * 1000000000LL + (int64_t)round(frac);
 }
 
 // sorted order (by sensor pixel, stable in time) -> pair flag per sorted position
@@ -37,7 +67,7 @@ __global__ void k_pair_flags(const uint32_t* __restrict__ skey, int64_t N, int32
 
 __global__ void k_pair_links(const uint32_t* __restrict__ sid, const int32_t* __restrict__ flag,
                              const int32_t* __restrict__ rank, int64_t N, int32_t* __restrict__ prev,
-                             uint32_t* __restrict__ refrank) {
+                             uint32_t* __restrict__ refrank, int64_t* __restrict__ total) {
   int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= N) return;
   const uint32_t ev = sid[j];
@@ -48,6 +78,7 @@ __global__ void k_pair_links(const uint32_t* __restrict__ sid, const int32_t* __
     prev[ev] = -1;
     refrank[ev] = 0xFFFFFFFFu;
   }
+  if (j == N - 1) *total = (int64_t)rank[j] + flag[j];
 }
 
 // knot index and normalised time of every batch mid-time: basalt So3Spline::evaluate,
@@ -67,14 +98,14 @@ __global__ void k_batch_su(const int64_t* __restrict__ tmid, int64_t B, int64_t 
   bu[b] = u;
 }
 
-// per event (time order): is it the current event of a pair, and which control-pose pair does it touch
-__global__ void k_meas_keys(const int32_t* __restrict__ prev, const int32_t* __restrict__ bs, int64_t N, int n,
-                            int32_t* __restrict__ flag) {
+// per event (time order): is it the current event of a pair
+__global__ void k_meas_flags(const int32_t* __restrict__ prev, int64_t N, int32_t* __restrict__ flag) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   flag[i] = prev[i] >= 0 ? 1 : 0;
 }
 
+// compacted (control-pose-pair key, event) list in time order
 __global__ void k_meas_compact(const int32_t* __restrict__ prev, const int32_t* __restrict__ bs,
                                const int32_t* __restrict__ pos, int64_t N, int n, uint32_t* __restrict__ key,
                                uint32_t* __restrict__ ev) {
@@ -85,7 +116,7 @@ __global__ void k_meas_compact(const int32_t* __restrict__ prev, const int32_t* 
   const uint32_t cc = (uint32_t)bs[i / kBatch];
   const uint32_t cp = (uint32_t)bs[p / kBatch];
   const int32_t o = pos[i];
-  key[o] = cc * (uint32_t)n + cp;
+  key[o] = cc * (uint32_t)n + cp;  // n <= 65535 (checked by emba_set_state): fits 32 bits
   ev[o] = (uint32_t)i;
 }
 
@@ -97,13 +128,14 @@ __global__ void k_head_flags(const uint32_t* __restrict__ key, int64_t M, int32_
 
 __global__ void k_head_scatter(const uint32_t* __restrict__ key, const int32_t* __restrict__ flag,
                                const int32_t* __restrict__ gidx, int64_t M, int32_t* __restrict__ gstart,
-                               uint32_t* __restrict__ gkey) {
+                               uint32_t* __restrict__ gkey, int64_t* __restrict__ total) {
   int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= M) return;
   if (flag[j]) {
     gstart[gidx[j]] = (int32_t)j;
     gkey[gidx[j]] = key[j];
   }
+  if (j == M - 1) *total = (int64_t)gidx[j] + flag[j];
 }
 
 __global__ void k_build_recs(const uint32_t* __restrict__ sev, int64_t m_lo, int64_t Mloc,
@@ -134,70 +166,84 @@ static int bits_for(uint64_t maxval) {
   return b;
 }
 
-// stable radix sort of (key, value) pairs; results in the arrays returned through kout/vout
-static int sort_pairs(Handle* h, uint32_t* kin, uint32_t* vin, uint32_t* kalt, uint32_t* valt, int64_t count,
-                      int end_bit, uint32_t** kout, uint32_t** vout) {
-  cub::DoubleBuffer<uint32_t> dk(kin, kalt), dv(vin, valt);
-  size_t tmp = 0;
-  EMBA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)count, 0, end_bit, h->stream));
-  void* d_tmp = nullptr;
-  EMBA_CUDA(cudaMalloc(&d_tmp, tmp ? tmp : 1));
-  cudaError_t e = cub::DeviceRadixSort::SortPairs(d_tmp, tmp, dk, dv, (int)count, 0, end_bit, h->stream);
-  h->launches += 1 + (end_bit + 7) / 8 * 2;
-  cudaStreamSynchronize(h->stream);
-  cudaFree(d_tmp);
-  if (e != cudaSuccess) {
-    h->err = std::string("cub sort: ") + cudaGetErrorString(e);
-    return EMBA_E_CUDA;
-  }
-  *kout = dk.Current();
-  *vout = dv.Current();
-  return EMBA_OK;
-}
-
-static int exclusive_sum(Handle* h, const int32_t* in, int32_t* out, int64_t count) {
-  size_t tmp = 0;
-  EMBA_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, (int)count, h->stream));
-  void* d_tmp = nullptr;
-  EMBA_CUDA(cudaMalloc(&d_tmp, tmp ? tmp : 1));
-  cudaError_t e = cub::DeviceScan::ExclusiveSum(d_tmp, tmp, in, out, (int)count, h->stream);
-  h->launches += 2;
-  cudaStreamSynchronize(h->stream);
-  cudaFree(d_tmp);
-  if (e != cudaSuccess) {
-    h->err = std::string("cub scan: ") + cudaGetErrorString(e);
-    return EMBA_E_CUDA;
-  }
-  return EMBA_OK;
-}
-
-static void free_state(StateSlot& s) {
-  cudaFree(s.quat); cudaFree(s.Gx); cudaFree(s.Gy); cudaFree(s.G2); cudaFree(s.H3); cudaFree(s.Ktab);
-  cudaFree(s.RotTab); cudaFree(s.JacTab); cudaFree(s.dp); cudaFree(s.e); cudaFree(s.pix); cudaFree(s.hist);
-  s = StateSlot();
-}
-
-// ros::Duration(double) rounding of the half span, as the reference evaluates
-// `t_batch_bgn + timespan * 0.5` (src/emba/model.cpp:116-119): Duration::operator*(double) is
-// Duration(toSec()*scale); Duration(double d) is sec=floor(d), nsec=round((d-sec)*1e9).
-// Plain IEEE double arithmetic on the host (no FMA contraction), so odd spans round like the CPU reference.
-static int64_t batch_mid_time(int64_t t_bgn, int64_t t_end) {
-  const int64_t span = t_end - t_bgn;
-  int64_t sec = span / 1000000000LL;
-  int64_t nsec = span % 1000000000LL;
-  if (nsec < 0) { nsec += 1000000000LL; sec -= 1; }
-  volatile double tosec = (double)sec + 1e-9 * (double)nsec;
-  volatile double d = tosec * 0.5;
-  const int64_t s = (int64_t)std::floor(d);
-  volatile double frac = (d - (double)s) * 1e9;
-  const int64_t ns = (int64_t)std::round(frac);
-  return t_bgn + s * 1000000000LL + ns;
-}
-
 int rebuild_static(Handle* h);
 void comm_destroy(Handle* h);
 struct PoissonPlan;
 void poisson_plan_destroy(PoissonPlan* p);
+
+// The per-window pre-pass on device-resident coordinates. d_x / d_y / d_pol_src: Nu entries (device);
+// d_tpair: the first and last timestamp of every batch (device, 2 B entries).
+static int prepass_device(Handle* h, int64_t N, const uint16_t* d_x, const uint16_t* d_y, const uint8_t* d_pol_src,
+                          const int64_t* d_tpair) {
+  const int64_t Nu = h->Nuse, B = h->B;
+  const int T = 256, G = ceil_div64(Nu, T);
+  (void)N;
+  // scratch: sort buffers (4 x u32), pair flags + ranks, radix / scan scratch
+  uint32_t* k0 = h->ar_tmp.take<uint32_t>(Nu);
+  uint32_t* v0 = h->ar_tmp.take<uint32_t>(Nu);
+  uint32_t* k1 = h->ar_tmp.take<uint32_t>(Nu);
+  uint32_t* v1 = h->ar_tmp.take<uint32_t>(Nu);
+  int32_t* d_flag = h->ar_tmp.take<int32_t>(Nu);
+  int32_t* d_rank = h->ar_tmp.take<int32_t>(Nu);
+  void* scr = h->ar_tmp.take<char>((int64_t)std::max(radix_scratch_bytes(Nu), scan_scratch_bytes(Nu)));
+  int64_t* d_total = h->ar_tmp.take<int64_t>(4);
+  if (!k0 || !v0 || !k1 || !v1 || !d_flag || !d_rank || !scr || !d_total) { h->err = "pre-pass scratch arena too small"; return EMBA_E_CUDA; }
+  EMBA_CUDA(cudaMemsetAsync(h->d_flags, 0, sizeof(int32_t) * 16, h->stream));
+  if (d_pol_src != h->d_pol) EMBA_CUDA(cudaMemcpyAsync(h->d_pol, d_pol_src, Nu, cudaMemcpyDeviceToDevice, h->stream));
+  if (B) {
+    k_batch_mid<<<ceil_div64(B, T), T, 0, h->stream>>>(d_tpair, B, h->d_tmid);
+    EMBA_LAUNCH_CHECK();
+  }
+  k_spix<<<G, T, 0, h->stream>>>(d_x, d_y, h->Ws, h->Hs, Nu, h->d_spix_ev, k0, h->d_flags);
+  EMBA_LAUNCH_CHECK();
+  int which = 0;
+  EMBA_TRY(radix_sort_pairs(h, h->stream, k0, v0, k1, v1, Nu, bits_for((uint64_t)h->Ws * h->Hs - 1), scr, true, true, &which));
+  const uint32_t* ks = which ? k1 : k0;
+  const uint32_t* vs = which ? v1 : v0;
+  k_pair_flags<<<G, T, 0, h->stream>>>(ks, Nu, d_flag);
+  EMBA_LAUNCH_CHECK();
+  EMBA_TRY(scan_exclusive<int32_t>(h, h->stream, d_flag, d_rank, Nu, scr));
+  k_pair_links<<<G, T, 0, h->stream>>>(vs, d_flag, d_rank, Nu, h->d_prev, h->d_refrank, d_total);
+  EMBA_LAUNCH_CHECK();
+  EMBA_CUDA(cudaMemcpyAsync(h->h_pin + 8, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+  EMBA_CUDA(cudaMemcpyAsync(h->h_pin + 9, h->d_flags, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  EMBA_CUDA(cudaStreamSynchronize(h->stream));  // the one synchronisation of the event-level pre-pass
+  if (*reinterpret_cast<int32_t*>(h->h_pin + 9) & 1) { h->err = "emba_set_events: event coordinates outside the sensor"; return EMBA_E_ARG; }
+  h->Mc_total = h->h_pin[8];
+  return EMBA_OK;
+}
+
+// sizes the arenas of a window of N events and lays out the event-level arrays
+static int begin_window(Handle* h, int64_t N) {
+  h->N = N;
+  h->Nuse = (N / kBatch) * kBatch;  // integer division at model.cpp:79 drops the tail batch
+  h->B = h->Nuse / kBatch;
+  h->t0_ns = -1;  // forces the spline-dependent structures to be rebuilt
+  h->st[0].evaluated = h->st[1].evaluated = false;
+  h->formed = h->solved = false;
+  h->jrec_valid = false;
+  h->Mc_total = 0;
+  h->Mc = 0;
+  const int64_t Nu = h->Nuse, B = h->B;
+  const size_t ev_bytes = Arena::pad(4 * (size_t)Nu) * 3 + Arena::pad((size_t)Nu) + Arena::pad(8 * (size_t)B) * 3 +
+                          Arena::pad(16 * (size_t)B) + Arena::pad(4 * (size_t)B) + 4096;
+  EMBA_TRY(arena_reserve(h, h->ar_ev, ev_bytes));
+  h->d_spix_ev = h->ar_ev.take<uint32_t>(Nu);
+  h->d_prev = h->ar_ev.take<int32_t>(Nu);
+  h->d_refrank = h->ar_ev.take<uint32_t>(Nu);
+  h->d_pol = h->ar_ev.take<uint8_t>(Nu);
+  h->d_tmid = h->ar_ev.take<int64_t>(B);
+  h->d_bu = h->ar_ev.take<double>(B);
+  h->d_bs = h->ar_ev.take<int32_t>(B);
+  if (!h->d_spix_ev || !h->d_prev || !h->d_refrank || !h->d_pol || !h->d_tmid || !h->d_bu || !h->d_bs) {
+    h->err = "event arena too small"; return EMBA_E_CUDA;
+  }
+  // scratch: the larger of the pairing pass (6 x 4 N + sort scratch + staged x, y) and the static rebuild (below)
+  const size_t tmp_bytes = Arena::pad(4 * (size_t)Nu) * 6 + Arena::pad(2 * (size_t)Nu) * 2 + Arena::pad(16 * (size_t)B) +
+                           Arena::pad(std::max(radix_scratch_bytes(Nu), scan_scratch_bytes(Nu))) + 8192;
+  EMBA_TRY(arena_reserve(h, h->ar_tmp, tmp_bytes));
+  return EMBA_OK;
+}
 
 }  // namespace emba
 
@@ -205,7 +251,7 @@ using namespace emba;
 
 extern "C" {
 
-const char* emba_version(void) { return "emba_b200 0.1 sm_100a"; }
+const char* emba_version(void) { return "emba_b200 0.2 sm_100a"; }
 
 int emba_create(const emba_config_t* cfg, emba_handle_t* out) {
   if (!cfg || !out || !cfg->bearing_lut || cfg->sensor_w <= 0 || cfg->sensor_h <= 0 || cfg->pano_w <= 0 ||
@@ -248,6 +294,7 @@ int emba_create(const emba_config_t* cfg, emba_handle_t* out) {
          cudaMalloc((void**)&st.G2, sizeof(double2) * h->P) == cudaSuccess &&
          cudaMalloc((void**)&st.H3, sizeof(double4) * h->P) == cudaSuccess &&
          cudaMalloc((void**)&st.hist, sizeof(int32_t) * h->P) == cudaSuccess;
+    st.hist_loc = st.hist;
   }
   // per-pixel buffers of the normal equations are sized for the worst case (every pixel active) once, so that
   // forming the equations never allocates
@@ -259,6 +306,9 @@ int emba_create(const emba_config_t* cfg, emba_handle_t* out) {
        cudaMalloc((void**)&h->d_apix, sizeof(int32_t) * P1) == cudaSuccess &&
        cudaMalloc((void**)&h->d_segoff, sizeof(int32_t) * P1) == cudaSuccess &&
        cudaMalloc((void**)&h->d_segend, sizeof(int32_t) * P1) == cudaSuccess &&
+       cudaMalloc((void**)&h->d_segcnt, sizeof(int32_t) * (P1 + 1)) == cudaSuccess &&
+       cudaMalloc((void**)&h->d_longlist, sizeof(int32_t) * (P1 + 1)) == cudaSuccess &&
+       cudaMalloc((void**)&h->d_scan_tmp, scan_scratch_bytes((int64_t)P1 + 1) * 2) == cudaSuccess &&
        cudaMalloc((void**)&h->d_gmask, sizeof(unsigned long long) * 2 * P1) == cudaSuccess &&
        cudaMalloc((void**)&h->d_gmask2, sizeof(unsigned long long) * 2 * P1) == cudaSuccess &&
        cudaMalloc((void**)&h->d_win64, sizeof(int2) * P1) == cudaSuccess &&
@@ -269,7 +319,7 @@ int emba_create(const emba_config_t* cfg, emba_handle_t* out) {
        cudaMalloc((void**)&h->d_b2, sizeof(double) * 2 * P1) == cudaSuccess &&
        cudaMalloc((void**)&h->d_C, sizeof(double) * 3 * P1) == cudaSuccess &&
        cudaMalloc((void**)&h->d_x2, sizeof(double) * 2 * P1) == cudaSuccess;
-  if (!ok) { emba_destroy((emba_handle_t)h); return EMBA_E_CUDA; }
+  if (!ok) { cudaGetLastError(); emba_destroy((emba_handle_t)h); return EMBA_E_CUDA; }
   *out = (emba_handle_t)h;
   return EMBA_OK;
 }
@@ -282,16 +332,22 @@ int emba_destroy(emba_handle_t hh) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   comm_destroy(h);
   if (h->poisson) { poisson_plan_destroy((PoissonPlan*)h->poisson); h->poisson = nullptr; }
-  free_state(h->st[0]); free_state(h->st[1]);
-  void* ptrs[] = {h->d_lut, h->d_tmid, h->d_spix_ev, h->d_pol, h->d_prev, h->d_refrank, h->d_bs, h->d_bu, h->d_rec, h->d_refpos,
-                  h->d_items, h->d_gid, h->d_group_item0, h->d_part, h->d_scal, h->d_flags, h->d_amap, h->d_pflag, h->d_paidx, h->d_len, h->d_apix,
-                  h->d_segoff, h->d_segend, h->d_gmask, h->d_gmask2, h->d_jrec, h->d_skey, h->d_sval, h->d_sval2, h->d_cub_tmp, h->d_sort_tmp, h->d_win64, h->d_winlo,
-                  h->d_winhi, h->d_stripoff, h->d_strip, h->d_A22, h->d_b2, h->d_acc_part, h->d_gsum, h->d_A11,
-                  h->d_b1, h->d_C, h->d_S, h->d_rhs, h->d_x1, h->d_x2, h->d_Spart, h->d_cg, h->d_ldlt_w, h->d_win2, h->d_win_all, h->d_own_len,
-                  h->d_own_off, h->d_gwinlo, h->d_gwinhi, h->d_gstripoff, h->d_gstrip, h->d_recv};
+  for (int s = 0; s < 2; s++) {
+    StateSlot& st = h->st[s];
+    if (st.hist_loc && st.hist_loc != st.hist) cudaFree(st.hist_loc);
+    cudaFree(st.Gx); cudaFree(st.Gy); cudaFree(st.G2); cudaFree(st.H3); cudaFree(st.hist);
+    st = StateSlot();
+  }
+  void* ptrs[] = {h->d_lut, h->ar_ev.base, h->ar_meas.base, h->ar_tmp.base, h->d_part, h->d_scal, h->d_flags, h->d_amap,
+                  h->d_pflag, h->d_paidx, h->d_len, h->d_apix, h->d_segoff, h->d_segend, h->d_segcnt, h->d_longlist,
+                  h->d_scan_tmp, h->d_gmask, h->d_gmask2, h->d_win64, h->d_winlo, h->d_winhi, h->d_stripoff, h->d_strip,
+                  h->d_A22, h->d_b2, h->d_A11, h->d_b1, h->d_C, h->d_S, h->d_rhs, h->d_x1, h->d_x2, h->d_Spart, h->d_cg,
+                  h->d_ldlt_w, h->d_win2, h->d_win_all, h->d_own_len, h->d_gwinlo, h->d_gwinhi, h->d_gstripoff,
+                  h->d_gstrip, h->d_recv};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : {h->ev_fork, h->ev_join, h->ev_fork2, h->ev_join2, h->ev_sort0, h->ev_sort1, h->ev_host}) if (e) cudaEventDestroy(e);
+  uploader_free(h->up);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -308,7 +364,24 @@ int emba_set_shard(emba_handle_t hh, int32_t rank, int32_t world) {
   Handle* h = (Handle*)hh;
   if (!h) return EMBA_E_ARG;
   if (world < 1 || rank < 0 || rank >= world) { h->err = "bad shard"; return EMBA_E_ARG; }
+  EMBA_CUDA(cudaSetDevice(h->device));
   if (rank != h->rank || world != h->world) { h->rank = rank; h->world = world; h->t0_ns = -1; }
+  // several ranks: the evaluation counts into a rank-local histogram (it sizes the rank's row segments), the
+  // all-reduce writes the global one beside it
+  for (int s = 0; s < 2; s++) {
+    StateSlot& st = h->st[s];
+    if (world > 1 && st.hist_loc == st.hist) {
+      st.hist_loc = nullptr;
+      EMBA_TRY(dev_alloc(h, &st.hist_loc, h->P));
+    }
+  }
+  return EMBA_OK;
+}
+
+int emba_set_strict_range(emba_handle_t hh, int32_t on) {
+  Handle* h = (Handle*)hh;
+  if (!h) return EMBA_E_ARG;
+  h->strict_range = on ? 1 : 0;
   return EMBA_OK;
 }
 
@@ -319,67 +392,338 @@ int emba_set_events(emba_handle_t hh, int64_t N, const uint16_t* x, const uint16
   if (N < 0 || (N > 0 && (!x || !y || !t_ns || !pol))) { h->err = "emba_set_events: null input"; return EMBA_E_ARG; }
   if (N >= (int64_t)1 << 31) { h->err = "emba_set_events: more than 2^31-1 events per window"; return EMBA_E_ARG; }
   EMBA_CUDA(cudaSetDevice(h->device));
-  h->N = N;
-  h->Nuse = (N / kBatch) * kBatch;  // integer division at model.cpp:79 drops the tail batch
-  h->B = h->Nuse / kBatch;
-  h->t0_ns = -1;  // forces the spline-dependent structures to be rebuilt
-  h->st[0].evaluated = h->st[1].evaluated = false;
-  h->formed = h->solved = false;
-  h->Mc_total = 0;
-  h->Mc = 0;
-  const int64_t Nu = h->Nuse;
-  // batch mid-times on the host (needs only two timestamps per batch)
-  h->h_tmid.resize(h->B);
-  for (int64_t b = 0; b < h->B; b++) h->h_tmid[b] = batch_mid_time(t_ns[b * kBatch], t_ns[b * kBatch + kBatch - 1]);
-  EMBA_TRY(dev_alloc(h, &h->d_tmid, h->B));
-  if (h->B) EMBA_CUDA(cudaMemcpyAsync(h->d_tmid, h->h_tmid.data(), sizeof(int64_t) * h->B, cudaMemcpyHostToDevice, h->stream));
-  EMBA_TRY(dev_alloc(h, &h->d_spix_ev, Nu));
-  EMBA_TRY(dev_alloc(h, &h->d_pol, Nu));
-  EMBA_TRY(dev_alloc(h, &h->d_prev, Nu));
-  EMBA_TRY(dev_alloc(h, &h->d_refrank, Nu));
-  if (Nu == 0) { EMBA_CUDA(cudaStreamSynchronize(h->stream)); return EMBA_OK; }
-  uint16_t *d_x = nullptr, *d_y = nullptr;
-  uint32_t *d_ids = nullptr, *d_k2 = nullptr, *d_v2 = nullptr, *d_k1 = nullptr;
-  int32_t *d_flag = nullptr, *d_rank = nullptr;
-  int rc = EMBA_OK;
-  do {
-    if ((rc = dev_alloc(h, &d_x, Nu)) || (rc = dev_alloc(h, &d_y, Nu)) || (rc = dev_alloc(h, &d_ids, Nu)) ||
-        (rc = dev_alloc(h, &d_k1, Nu)) || (rc = dev_alloc(h, &d_k2, Nu)) || (rc = dev_alloc(h, &d_v2, Nu)) ||
-        (rc = dev_alloc(h, &d_flag, Nu)) || (rc = dev_alloc(h, &d_rank, Nu)))
-      break;
-    cudaMemcpyAsync(d_x, x, sizeof(uint16_t) * Nu, cudaMemcpyHostToDevice, h->stream);
-    cudaMemcpyAsync(d_y, y, sizeof(uint16_t) * Nu, cudaMemcpyHostToDevice, h->stream);
-    cudaMemcpyAsync(h->d_pol, pol, sizeof(uint8_t) * Nu, cudaMemcpyHostToDevice, h->stream);
-    cudaMemsetAsync(h->d_flags, 0, sizeof(int32_t) * 16, h->stream);
-    const int T = 256, G = ceil_div64(Nu, T);
-    k_spix<<<G, T, 0, h->stream>>>(d_x, d_y, h->Ws, h->Hs, Nu, h->d_spix_ev, d_ids, h->d_flags);
-    h->launches++;
-    cudaMemcpyAsync(d_k1, h->d_spix_ev, sizeof(uint32_t) * Nu, cudaMemcpyDeviceToDevice, h->stream);
-    uint32_t *ks = nullptr, *vs = nullptr;
-    if ((rc = sort_pairs(h, d_k1, d_ids, d_k2, d_v2, Nu, bits_for((uint64_t)h->Ws * h->Hs), &ks, &vs))) break;
-    k_pair_flags<<<G, T, 0, h->stream>>>(ks, Nu, d_flag);
-    h->launches++;
-    if ((rc = exclusive_sum(h, d_flag, d_rank, Nu))) break;
-    k_pair_links<<<G, T, 0, h->stream>>>(vs, d_flag, d_rank, Nu, h->d_prev, h->d_refrank);
-    h->launches++;
-    int32_t last_rank = 0, last_flag = 0, flags0 = 0;
-    cudaMemcpyAsync(&last_rank, d_rank + (Nu - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
-    cudaMemcpyAsync(&last_flag, d_flag + (Nu - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
-    cudaMemcpyAsync(&flags0, h->d_flags, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
-    cudaError_t e = cudaStreamSynchronize(h->stream);
-    if (e != cudaSuccess) { h->err = std::string("emba_set_events: ") + cudaGetErrorString(e); rc = EMBA_E_CUDA; break; }
-    if (flags0 & 1) { h->err = "emba_set_events: event coordinates outside the sensor"; rc = EMBA_E_ARG; break; }
-    h->Mc_total = (int64_t)last_rank + last_flag;
-  } while (0);
-  cudaFree(d_x); cudaFree(d_y); cudaFree(d_ids); cudaFree(d_k1); cudaFree(d_k2); cudaFree(d_v2); cudaFree(d_flag);
-  cudaFree(d_rank);
-  return rc;
+  EMBA_CUDA(cudaEventRecord(h->ev[0], h->stream));
+  EMBA_TRY(begin_window(h, N));
+  const int64_t Nu = h->Nuse, B = h->B;
+  if (Nu == 0) return EMBA_OK;
+  uint16_t* d_x = h->ar_tmp.take<uint16_t>(Nu);
+  uint16_t* d_y = h->ar_tmp.take<uint16_t>(Nu);
+  int64_t* d_tpair = h->ar_tmp.take<int64_t>(2 * B);
+  if (!d_x || !d_y || !d_tpair) { h->err = "pre-pass scratch arena too small"; return EMBA_E_CUDA; }
+  // timestamps stay on the host: only the first and the last stamp of every batch are needed (model.cpp:115-119).
+  // They are gathered into the pinned stage in chunks.
+  EMBA_CUDA(upload_bytes(h->up, h->stream, d_x, x, sizeof(uint16_t) * (size_t)Nu));
+  EMBA_CUDA(upload_bytes(h->up, h->stream, d_y, y, sizeof(uint16_t) * (size_t)Nu));
+  EMBA_CUDA(upload_bytes(h->up, h->stream, h->d_pol, pol, (size_t)Nu));
+  {
+    const int64_t per = (int64_t)(kStageBytes / 16);
+    for (int64_t b0 = 0; b0 < B; b0 += per) {
+      const int64_t nb = std::min(per, B - b0);
+      const int bi = h->up.turn;
+      h->up.turn ^= 1;
+      if (!h->up.stage[bi]) {  // only pinned sources so far: create the stage now
+        EMBA_CUDA(cudaMallocHost(&h->up.stage[bi], kStageBytes));
+        EMBA_CUDA(cudaEventCreateWithFlags(&h->up.ev[bi], cudaEventDisableTiming));
+      }
+      EMBA_CUDA(cudaEventSynchronize(h->up.ev[bi]));
+      int64_t* st = reinterpret_cast<int64_t*>(h->up.stage[bi]);
+      for (int64_t b = 0; b < nb; b++) {
+        st[2 * b] = t_ns[(b0 + b) * kBatch];
+        st[2 * b + 1] = t_ns[(b0 + b) * kBatch + kBatch - 1];
+      }
+      EMBA_CUDA(cudaMemcpyAsync(d_tpair + 2 * b0, st, sizeof(int64_t) * 2 * nb, cudaMemcpyHostToDevice, h->stream));
+      EMBA_CUDA(cudaEventRecord(h->up.ev[bi], h->stream));
+    }
+  }
+  EMBA_TRY(prepass_device(h, N, d_x, d_y, h->d_pol, d_tpair));
+  EMBA_CUDA(cudaEventRecord(h->ev[1], h->stream));
+  EMBA_CUDA(cudaEventSynchronize(h->ev[1]));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+  h->t_setup_ms[0] = ms;
+  return EMBA_OK;
 }
 
 int emba_num_pairs(emba_handle_t hh, int64_t* out) {
   Handle* h = (Handle*)hh;
   if (!h || !out) return EMBA_E_ARG;
   *out = h->Mc_total;
+  return EMBA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// device-resident event sequence (N1)
+// ---------------------------------------------------------------------------------------------------
+#define EV_CUDA(call)                                                                      \
+  do {                                                                                     \
+    cudaError_t _e = (call);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      ev->err = std::string(#call) + ": " + cudaGetErrorString(_e);                        \
+      return EMBA_E_CUDA;                                                                  \
+    }                                                                                      \
+  } while (0)
+
+int emba_events_create(int32_t device, int64_t N, const uint16_t* x, const uint16_t* y, const int64_t* t_ns,
+                       const uint8_t* pol, emba_events_t* out) {
+  if (!out || N < 0 || (N > 0 && (!x || !y || !t_ns || !pol))) return EMBA_E_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return EMBA_E_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return EMBA_E_CUDA;
+  EventStore* ev = new EventStore();
+  ev->device = device;
+  ev->N = N;
+  ev->cap = std::max<int64_t>(N, 1);
+  bool ok = cudaStreamCreateWithFlags(&ev->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaMallocHost((void**)&ev->h_pin, 64 * sizeof(int64_t)) == cudaSuccess &&
+            cudaMalloc((void**)&ev->x, sizeof(uint16_t) * ev->cap) == cudaSuccess &&
+            cudaMalloc((void**)&ev->y, sizeof(uint16_t) * ev->cap) == cudaSuccess &&
+            cudaMalloc((void**)&ev->t, sizeof(int64_t) * ev->cap) == cudaSuccess &&
+            cudaMalloc((void**)&ev->pol, sizeof(uint8_t) * ev->cap) == cudaSuccess;
+  ok = ok && upload_bytes(ev->up, ev->stream, ev->x, x, sizeof(uint16_t) * (size_t)N) == cudaSuccess &&
+       upload_bytes(ev->up, ev->stream, ev->y, y, sizeof(uint16_t) * (size_t)N) == cudaSuccess &&
+       upload_bytes(ev->up, ev->stream, ev->t, t_ns, sizeof(int64_t) * (size_t)N) == cudaSuccess &&
+       upload_bytes(ev->up, ev->stream, ev->pol, pol, (size_t)N) == cudaSuccess &&
+       cudaStreamSynchronize(ev->stream) == cudaSuccess;
+  if (!ok) { cudaGetLastError(); emba_events_destroy((emba_events_t)ev); return EMBA_E_CUDA; }
+  *out = (emba_events_t)ev;
+  return EMBA_OK;
+}
+
+int emba_events_destroy(emba_events_t e) {
+  EventStore* ev = (EventStore*)e;
+  if (!ev) return EMBA_OK;
+  cudaSetDevice(ev->device);
+  if (ev->stream) cudaStreamSynchronize(ev->stream);
+  cudaFree(ev->x); cudaFree(ev->y); cudaFree(ev->t); cudaFree(ev->pol);
+  uploader_free(ev->up);
+  if (ev->h_pin) cudaFreeHost(ev->h_pin);
+  if (ev->stream) cudaStreamDestroy(ev->stream);
+  delete ev;
+  return EMBA_OK;
+}
+
+int emba_events_count(emba_events_t e, int64_t* out) {
+  EventStore* ev = (EventStore*)e;
+  if (!ev || !out) return EMBA_E_ARG;
+  *out = ev->N;
+  return EMBA_OK;
+}
+
+int emba_events_download(emba_events_t e, int64_t i0, int64_t i1, uint16_t* x, uint16_t* y, int64_t* t_ns,
+                         uint8_t* pol) {
+  EventStore* ev = (EventStore*)e;
+  if (!ev || i0 < 0 || i1 < i0 || i1 > ev->N) return EMBA_E_ARG;
+  EV_CUDA(cudaSetDevice(ev->device));
+  const size_t n = (size_t)(i1 - i0);
+  if (n == 0) return EMBA_OK;
+  if (x) EV_CUDA(cudaMemcpyAsync(x, ev->x + i0, sizeof(uint16_t) * n, cudaMemcpyDeviceToHost, ev->stream));
+  if (y) EV_CUDA(cudaMemcpyAsync(y, ev->y + i0, sizeof(uint16_t) * n, cudaMemcpyDeviceToHost, ev->stream));
+  if (t_ns) EV_CUDA(cudaMemcpyAsync(t_ns, ev->t + i0, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, ev->stream));
+  if (pol) EV_CUDA(cudaMemcpyAsync(pol, ev->pol + i0, n, cudaMemcpyDeviceToHost, ev->stream));
+  EV_CUDA(cudaStreamSynchronize(ev->stream));
+  return EMBA_OK;
+}
+
+}  // extern "C"
+
+namespace emba {
+
+// ---- sequence-level kernels
+__global__ void k_time_minmax_sorted(const int64_t* __restrict__ t, int64_t N, unsigned long long* __restrict__ out) {
+  // out[0] = min, out[1] = max, out[2] = number of descents t[i] < t[i-1]
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  long long mn = LLONG_MAX, mx = LLONG_MIN;
+  unsigned long long desc = 0;
+  for (; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    const long long v = t[i];
+    mn = v < mn ? v : mn;
+    mx = v > mx ? v : mx;
+    if (i > 0 && v < t[i - 1]) desc++;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const long long a = __shfl_down_sync(0xffffffffu, mn, o), b = __shfl_down_sync(0xffffffffu, mx, o);
+    mn = a < mn ? a : mn;
+    mx = b > mx ? b : mx;
+    desc += __shfl_down_sync(0xffffffffu, desc, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(reinterpret_cast<long long*>(out), mn);
+    atomicMax(reinterpret_cast<long long*>(out + 1), mx);
+    atomicAdd(out + 2, desc);
+  }
+}
+__global__ void k_time_key(const int64_t* __restrict__ t, const uint32_t* __restrict__ perm, int64_t N, int64_t tmin,
+                           int shift, uint32_t* __restrict__ key) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int64_t src = perm ? perm[i] : i;
+  key[i] = (uint32_t)(((unsigned long long)(t[src] - tmin)) >> shift);
+}
+template <typename T>
+__global__ void k_gather(const T* __restrict__ in, const uint32_t* __restrict__ perm, int64_t N, T* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) out[i] = in[perm[i]];
+}
+template <typename T>
+__global__ void k_stride_pick(const T* __restrict__ in, int64_t Nout, int rate, T* __restrict__ out) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < Nout) out[j] = in[(j + 1) * rate - 1];  // the rate-th, 2 rate-th ... event (emba.cpp:288-300)
+}
+
+// EMBA::getEventSubset (emba.cpp:473-510) on a time-sorted sequence: the two 100-event-stride linear searches stop
+// at the first probe whose stamp exceeds the robust bound, which on sorted stamps is a binary search over the probes.
+__global__ void k_window_search(const int64_t* __restrict__ t, int64_t N, int64_t lo_ns, int64_t hi_ns,
+                                int64_t* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int64_t nprobe = (N + 99) / 100;  // probes at 0, 100, 200, ... < N
+  auto first_above = [&](int64_t from, int64_t bound) {
+    int64_t a = from, b = nprobe;
+    while (a < b) {
+      const int64_t m = (a + b) >> 1;
+      if (t[m * 100] > bound) b = m; else a = m + 1;
+    }
+    return a;  // == nprobe: ran off the end
+  };
+  const int64_t pb = first_above(0, lo_ns);
+  const unsigned long long beg = (unsigned long long)pb * 100ull;  // >= N when no probe lies inside
+  unsigned long long end;
+  const int64_t pe = first_above(pb < nprobe ? pb : nprobe, hi_ns);
+  if (pe < nprobe) end = (unsigned long long)pe * 100ull - 100ull;  // `idx_ev_subset_end -= 100` (size_t: may wrap)
+  else end = (unsigned long long)(pe > pb ? pe : pb) * 100ull;
+  if (end > (unsigned long long)N) end = (unsigned long long)N;     // emba.cpp:503-504
+  out[0] = (int64_t)(beg < (unsigned long long)N ? beg : (unsigned long long)N);
+  out[1] = (int64_t)end;
+}
+
+}  // namespace emba
+
+extern "C" {
+
+int emba_events_sort_by_time(emba_events_t e) {
+  EventStore* ev = (EventStore*)e;
+  if (!ev) return EMBA_E_ARG;
+  EV_CUDA(cudaSetDevice(ev->device));
+  const int64_t N = ev->N;
+  if (N < 2) return EMBA_OK;
+  if (N >= (int64_t)1 << 32) { ev->err = "more than 2^32-1 events"; return EMBA_E_SUPPORT; }
+  Handle hh;  // launch counter / error sink of the primitives
+  Handle* h = &hh;
+  unsigned long long* d_mm = nullptr;
+  EV_CUDA(cudaMalloc((void**)&d_mm, 3 * sizeof(unsigned long long)));
+  const unsigned long long init[3] = {(unsigned long long)LLONG_MAX, (unsigned long long)LLONG_MIN, 0ull};
+  cudaMemcpyAsync(d_mm, init, sizeof(init), cudaMemcpyHostToDevice, ev->stream);
+  k_time_minmax_sorted<<<1184, 256, 0, ev->stream>>>(ev->t, N, d_mm);
+  cudaMemcpyAsync(ev->h_pin, d_mm, sizeof(init), cudaMemcpyDeviceToHost, ev->stream);
+  cudaError_t ce = cudaStreamSynchronize(ev->stream);
+  cudaFree(d_mm);
+  if (ce != cudaSuccess) { ev->err = cudaGetErrorString(ce); return EMBA_E_CUDA; }
+  const int64_t tmin = ev->h_pin[0], tmax = ev->h_pin[1];
+  if (ev->h_pin[2] == 0) return EMBA_OK;  // already sorted (the usual case: bags are recorded in time order)
+  // LSD over the 64-bit span in two 32-bit halves: argsort by the low half, then (stable) by the high half
+  const unsigned long long span = (unsigned long long)(tmax - tmin);
+  const int bits_hi = span >> 32 ? bits_for(span >> 32) : 0;
+  const int bits_lo = bits_hi ? 32 : bits_for(span);
+  uint32_t *k0 = nullptr, *v0 = nullptr, *k1 = nullptr, *v1 = nullptr;
+  void *scr = nullptr, *tmp = nullptr;
+  int rc = EMBA_OK;
+  do {
+    if (cudaMalloc((void**)&k0, 4 * N) != cudaSuccess || cudaMalloc((void**)&v0, 4 * N) != cudaSuccess ||
+        cudaMalloc((void**)&k1, 4 * N) != cudaSuccess || cudaMalloc((void**)&v1, 4 * N) != cudaSuccess ||
+        cudaMalloc(&scr, radix_scratch_bytes(N)) != cudaSuccess || cudaMalloc(&tmp, 8 * N) != cudaSuccess) {
+      cudaGetLastError(); ev->err = "emba_events_sort_by_time: out of device memory"; rc = EMBA_E_CUDA; break;
+    }
+    const int T = 256, G = ceil_div64(N, T);
+    k_time_key<<<G, T, 0, ev->stream>>>(ev->t, nullptr, N, tmin, 0, k0);
+    int which = 0;
+    if ((rc = radix_sort_pairs(h, ev->stream, k0, v0, k1, v1, N, bits_lo, scr, true, false, &which))) break;
+    uint32_t* perm = which ? v1 : v0;
+    if (bits_hi) {
+      uint32_t* ka = which ? k0 : k1;  // the buffer pair not holding the permutation
+      uint32_t* va = which ? v0 : v1;
+      k_time_key<<<G, T, 0, ev->stream>>>(ev->t, perm, N, tmin, 32, which ? k1 : k0);
+      // sort (key_hi, perm) pairs: keys in the perm's own buffer pair, ping-pong with the other pair
+      uint32_t* kin = which ? k1 : k0;
+      int w2 = 0;
+      if ((rc = radix_sort_pairs(h, ev->stream, kin, perm, ka, va, N, bits_hi, scr, false, false, &w2))) break;
+      perm = w2 ? va : perm;
+    }
+    // apply the permutation to the four arrays (through tmp)
+    k_gather<int64_t><<<G, T, 0, ev->stream>>>(ev->t, perm, N, (int64_t*)tmp);
+    cudaMemcpyAsync(ev->t, tmp, 8 * N, cudaMemcpyDeviceToDevice, ev->stream);
+    k_gather<uint16_t><<<G, T, 0, ev->stream>>>(ev->x, perm, N, (uint16_t*)tmp);
+    cudaMemcpyAsync(ev->x, tmp, 2 * N, cudaMemcpyDeviceToDevice, ev->stream);
+    k_gather<uint16_t><<<G, T, 0, ev->stream>>>(ev->y, perm, N, (uint16_t*)tmp);
+    cudaMemcpyAsync(ev->y, tmp, 2 * N, cudaMemcpyDeviceToDevice, ev->stream);
+    k_gather<uint8_t><<<G, T, 0, ev->stream>>>(ev->pol, perm, N, (uint8_t*)tmp);
+    cudaMemcpyAsync(ev->pol, tmp, N, cudaMemcpyDeviceToDevice, ev->stream);
+    ce = cudaStreamSynchronize(ev->stream);
+    if (ce != cudaSuccess) { ev->err = cudaGetErrorString(ce); rc = EMBA_E_CUDA; }
+  } while (0);
+  if (rc != EMBA_OK && ev->err.empty()) ev->err = hh.err;
+  cudaFree(k0); cudaFree(v0); cudaFree(k1); cudaFree(v1); cudaFree(scr); cudaFree(tmp);
+  return rc;
+}
+
+int emba_events_subsample(emba_events_t e, int32_t rate) {
+  EventStore* ev = (EventStore*)e;
+  if (!ev) return EMBA_E_ARG;
+  if (rate < 2) return EMBA_OK;  // emba.cpp:282: only rates >= 2 sample
+  EV_CUDA(cudaSetDevice(ev->device));
+  const int64_t Nout = ev->N / rate;
+  if (Nout > 0) {
+    void* tmp = nullptr;
+    EV_CUDA(cudaMalloc(&tmp, 8 * (size_t)Nout));
+    const int T = 256, G = ceil_div64(Nout, T);
+    k_stride_pick<int64_t><<<G, T, 0, ev->stream>>>(ev->t, Nout, rate, (int64_t*)tmp);
+    cudaMemcpyAsync(ev->t, tmp, 8 * Nout, cudaMemcpyDeviceToDevice, ev->stream);
+    k_stride_pick<uint16_t><<<G, T, 0, ev->stream>>>(ev->x, Nout, rate, (uint16_t*)tmp);
+    cudaMemcpyAsync(ev->x, tmp, 2 * Nout, cudaMemcpyDeviceToDevice, ev->stream);
+    k_stride_pick<uint16_t><<<G, T, 0, ev->stream>>>(ev->y, Nout, rate, (uint16_t*)tmp);
+    cudaMemcpyAsync(ev->y, tmp, 2 * Nout, cudaMemcpyDeviceToDevice, ev->stream);
+    k_stride_pick<uint8_t><<<G, T, 0, ev->stream>>>(ev->pol, Nout, rate, (uint8_t*)tmp);
+    cudaMemcpyAsync(ev->pol, tmp, Nout, cudaMemcpyDeviceToDevice, ev->stream);
+    cudaError_t ce = cudaStreamSynchronize(ev->stream);
+    cudaFree(tmp);
+    if (ce != cudaSuccess) { ev->err = cudaGetErrorString(ce); return EMBA_E_CUDA; }
+  }
+  ev->N = Nout;
+  return EMBA_OK;
+}
+
+int emba_events_window(emba_events_t e, int64_t t_beg_ns, int64_t t_end_ns, int64_t* idx_beg, int64_t* idx_end) {
+  EventStore* ev = (EventStore*)e;
+  if (!ev || !idx_beg || !idx_end) return EMBA_E_ARG;
+  EV_CUDA(cudaSetDevice(ev->device));
+  if (ev->N == 0) { *idx_beg = *idx_end = 0; return EMBA_OK; }
+  int64_t* d_out = nullptr;
+  EV_CUDA(cudaMalloc((void**)&d_out, 2 * sizeof(int64_t)));
+  // t_epsilon = ros::Duration(1e-3) = 1 000 000 ns exactly (emba.cpp:476-478)
+  k_window_search<<<1, 32, 0, ev->stream>>>(ev->t, ev->N, t_beg_ns + 1000000, t_end_ns - 1000000, d_out);
+  cudaMemcpyAsync(ev->h_pin, d_out, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, ev->stream);
+  cudaError_t ce = cudaStreamSynchronize(ev->stream);
+  cudaFree(d_out);
+  if (ce != cudaSuccess) { ev->err = cudaGetErrorString(ce); return EMBA_E_CUDA; }
+  *idx_beg = ev->h_pin[0];
+  *idx_end = ev->h_pin[1];
+  return EMBA_OK;
+}
+
+int emba_set_events_dev(emba_handle_t hh, emba_events_t e, int64_t i0, int64_t i1) {
+  Handle* h = (Handle*)hh;
+  EventStore* ev = (EventStore*)e;
+  if (!h) return EMBA_E_ARG;
+  if (!ev || i0 < 0 || i1 < i0 || i1 > ev->N) { h->err = "emba_set_events_dev: bad range"; return EMBA_E_ARG; }
+  if (ev->device != h->device) { h->err = "emba_set_events_dev: the sequence lives on another device"; return EMBA_E_ARG; }
+  const int64_t N = i1 - i0;
+  if (N >= (int64_t)1 << 31) { h->err = "emba_set_events: more than 2^31-1 events per window"; return EMBA_E_ARG; }
+  EMBA_CUDA(cudaSetDevice(h->device));
+  EMBA_CUDA(cudaStreamSynchronize(ev->stream));
+  EMBA_CUDA(cudaEventRecord(h->ev[0], h->stream));
+  EMBA_TRY(begin_window(h, N));
+  const int64_t B = h->B;
+  if (h->Nuse == 0) return EMBA_OK;
+  int64_t* d_tpair = h->ar_tmp.take<int64_t>(2 * B);
+  if (!d_tpair) { h->err = "pre-pass scratch arena too small"; return EMBA_E_CUDA; }
+  k_batch_tpair<<<ceil_div64(B, 256), 256, 0, h->stream>>>(ev->t + i0, B, d_tpair);
+  EMBA_LAUNCH_CHECK();
+  EMBA_TRY(prepass_device(h, N, ev->x + i0, ev->y + i0, ev->pol + i0, d_tpair));
+  EMBA_CUDA(cudaEventRecord(h->ev[1], h->stream));
+  EMBA_CUDA(cudaEventSynchronize(h->ev[1]));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+  h->t_setup_ms[0] = ms;
   return EMBA_OK;
 }
 
@@ -394,151 +738,166 @@ int rebuild_static(Handle* h) {
   const int n = h->n;
   h->Mc = 0; h->n_items = 0; h->n_groups = 0; h->dmax = 0;
   h->h_items.clear();
-  EMBA_TRY(dev_alloc(h, &h->d_bs, B));
-  EMBA_TRY(dev_alloc(h, &h->d_bu, B));
-  for (int s = 0; s < 2; s++) {
-    EMBA_TRY(dev_alloc(h, &h->st[s].quat, (int64_t)n * 4));
-    EMBA_TRY(dev_alloc(h, &h->st[s].Ktab, (int64_t)n * kKnotStride));
-    EMBA_TRY(dev_alloc(h, &h->st[s].RotTab, B));
-    EMBA_TRY(dev_alloc(h, &h->st[s].JacTab, B));
-    h->st[s].evaluated = false;
-  }
+  h->st[0].evaluated = h->st[1].evaluated = false;
   h->formed = h->solved = false;
-  EMBA_TRY(dev_alloc(h, &h->d_A11, (int64_t)9 * n * n));
-  EMBA_TRY(dev_alloc(h, &h->d_b1, (int64_t)3 * n));
-  EMBA_TRY(dev_alloc(h, &h->d_x1, (int64_t)3 * n));
-  EMBA_TRY(dev_alloc(h, &h->d_S, (int64_t)(3 * n + 1) * (3 * n + 1)));  // bordered with the rhs row
-  EMBA_TRY(dev_alloc(h, &h->d_rhs, (int64_t)3 * n));
-  if (B == 0 || h->Mc_total == 0) {
-    for (int s = 0; s < 2; s++) {
-      EMBA_TRY(dev_alloc(h, &h->st[s].dp, 1)); EMBA_TRY(dev_alloc(h, &h->st[s].e, 1)); EMBA_TRY(dev_alloc(h, &h->st[s].pix, 1));
-    }
-    EMBA_TRY(dev_alloc(h, &h->d_rec, 1));
-    EMBA_TRY(dev_alloc(h, &h->d_refpos, 1));
-    EMBA_TRY(dev_alloc(h, &h->d_gid, (int64_t)n));
-    EMBA_CUDA(cudaMemset(h->d_gid, 0xFF, sizeof(int32_t) * n));
-    return EMBA_OK;
-  }
+  h->jrec_valid = false;
+  EMBA_CUDA(cudaEventRecord(h->ev[0], h->stream));
+  EMBA_TRY(dev_reserve(h, &h->d_A11, &h->A11_cap, (int64_t)9 * n * n));
+  EMBA_TRY(dev_reserve(h, &h->d_b1, &h->b1_cap, (int64_t)3 * n));
+  EMBA_TRY(dev_reserve(h, &h->d_x1, &h->x1_cap, (int64_t)3 * n));
+  EMBA_TRY(dev_reserve(h, &h->d_S, &h->S_cap, (int64_t)(3 * n + 1) * (3 * n + 1)));  // bordered with the rhs row
+  EMBA_TRY(dev_reserve(h, &h->d_rhs, &h->rhs_cap, (int64_t)3 * n));
   const int T = 256;
-  EMBA_CUDA(cudaMemsetAsync(h->d_flags, 0, sizeof(int32_t) * 16, h->stream));
-  k_batch_su<<<ceil_div64(B, T), T, 0, h->stream>>>(h->d_tmid, B, h->t0_ns, h->dt_ns, n, h->d_bs, h->d_bu, h->d_flags);
-  EMBA_LAUNCH_CHECK();
-  int32_t flags0 = 0;
-  EMBA_CUDA(cudaMemcpyAsync(&flags0, h->d_flags, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-  EMBA_CUDA(cudaStreamSynchronize(h->stream));
-  if (flags0 & 2) {
-    h->err = "batch mid-time outside the spline support (the reference aborts here: so3_spline.h:221-230)";
-    return EMBA_E_SUPPORT;
-  }
   const int64_t Mt = h->Mc_total;
-  int32_t *d_flag = nullptr, *d_pos = nullptr, *d_gidx = nullptr, *d_gstart = nullptr;
-  uint32_t *d_key = nullptr, *d_ev = nullptr, *d_key2 = nullptr, *d_ev2 = nullptr, *d_gkey = nullptr;
-  int rc = EMBA_OK;
+  // scratch of the rebuild (the scratch arena was sized for the pairing pass, which is larger: Mt <= Nu)
+  h->ar_tmp.reset();
+  int32_t* d_flag = h->ar_tmp.take<int32_t>(std::max(Nu, Mt));
+  int32_t* d_pos = h->ar_tmp.take<int32_t>(std::max(Nu, Mt));
+  uint32_t* d_key = h->ar_tmp.take<uint32_t>(Mt);
+  uint32_t* d_ev = h->ar_tmp.take<uint32_t>(Mt);
+  uint32_t* d_key2 = h->ar_tmp.take<uint32_t>(Mt);
+  uint32_t* d_ev2 = h->ar_tmp.take<uint32_t>(Mt);
+  void* scr = h->ar_tmp.take<char>((int64_t)std::max(radix_scratch_bytes(std::max(Nu, Mt)), scan_scratch_bytes(std::max(Nu, Mt))));
+  int64_t* d_total = h->ar_tmp.take<int64_t>(4);
+  if (Nu > 0 && (!d_flag || !d_pos || !d_key || !d_ev || !d_key2 || !d_ev2 || !scr || !d_total)) {
+    h->err = "static rebuild: scratch arena too small"; return EMBA_E_CUDA;
+  }
   std::vector<int32_t> gstart;
   std::vector<uint32_t> gkey;
-  uint32_t *ks = nullptr, *vs = nullptr;
-  do {
-    if ((rc = dev_alloc(h, &d_flag, std::max(Nu, Mt))) || (rc = dev_alloc(h, &d_pos, std::max(Nu, Mt))) ||
-        (rc = dev_alloc(h, &d_key, Mt)) || (rc = dev_alloc(h, &d_ev, Mt)) || (rc = dev_alloc(h, &d_key2, Mt)) ||
-        (rc = dev_alloc(h, &d_ev2, Mt)))
-      break;
-    k_meas_keys<<<ceil_div64(Nu, T), T, 0, h->stream>>>(h->d_prev, h->d_bs, Nu, n, d_flag);
-    h->launches++;
-    if ((rc = exclusive_sum(h, d_flag, d_pos, Nu))) break;
+  const uint32_t* vs = nullptr;
+  if (B > 0 && Mt > 0) {
+    EMBA_CUDA(cudaMemsetAsync(h->d_flags, 0, sizeof(int32_t) * 16, h->stream));
+    k_batch_su<<<ceil_div64(B, T), T, 0, h->stream>>>(h->d_tmid, B, h->t0_ns, h->dt_ns, n, h->d_bs, h->d_bu, h->d_flags);
+    EMBA_LAUNCH_CHECK();
+    k_meas_flags<<<ceil_div64(Nu, T), T, 0, h->stream>>>(h->d_prev, Nu, d_flag);
+    EMBA_LAUNCH_CHECK();
+    EMBA_TRY(scan_exclusive<int32_t>(h, h->stream, d_flag, d_pos, Nu, scr));
     k_meas_compact<<<ceil_div64(Nu, T), T, 0, h->stream>>>(h->d_prev, h->d_bs, d_pos, Nu, n, d_key, d_ev);
-    h->launches++;
-    if ((rc = sort_pairs(h, d_key, d_ev, d_key2, d_ev2, Mt, bits_for((uint64_t)n * n), &ks, &vs))) break;
+    EMBA_LAUNCH_CHECK();
+    int which = 0;
+    EMBA_TRY(radix_sort_pairs(h, h->stream, d_key, d_ev, d_key2, d_ev2, Mt, bits_for((uint64_t)n * n - 1), scr, false, true, &which));
+    const uint32_t* ks = which ? d_key2 : d_key;
+    vs = which ? d_ev2 : d_ev;
     // group heads
     k_head_flags<<<ceil_div64(Mt, T), T, 0, h->stream>>>(ks, Mt, d_flag);
-    h->launches++;
-    if ((rc = exclusive_sum(h, d_flag, d_pos, Mt))) break;
-    int32_t lastpos = 0, lastflag = 0;
-    cudaMemcpyAsync(&lastpos, d_pos + (Mt - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
-    cudaMemcpyAsync(&lastflag, d_flag + (Mt - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
-    if (cudaStreamSynchronize(h->stream) != cudaSuccess) { h->err = "rebuild_static: sync failed"; rc = EMBA_E_CUDA; break; }
-    const int G = lastpos + lastflag;
-    if ((rc = dev_alloc(h, &d_gstart, G)) || (rc = dev_alloc(h, &d_gkey, G))) break;
-    k_head_scatter<<<ceil_div64(Mt, T), T, 0, h->stream>>>(ks, d_flag, d_pos, Mt, d_gstart, d_gkey);
-    h->launches++;
+    EMBA_LAUNCH_CHECK();
+    EMBA_TRY(scan_exclusive<int32_t>(h, h->stream, d_flag, d_pos, Mt, scr));
+    // group starts and keys go to the buffers of the sort's other half (free now)
+    int32_t* d_gstart = reinterpret_cast<int32_t*>(which ? d_key : d_key2);
+    uint32_t* d_gkey = which ? d_ev : d_ev2;
+    k_head_scatter<<<ceil_div64(Mt, T), T, 0, h->stream>>>(ks, d_flag, d_pos, Mt, d_gstart, d_gkey, d_total);
+    EMBA_LAUNCH_CHECK();
+    EMBA_CUDA(cudaMemcpyAsync(h->h_pin + 8, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    EMBA_CUDA(cudaMemcpyAsync(h->h_pin + 9, h->d_flags, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    EMBA_CUDA(cudaStreamSynchronize(h->stream));
+    if (*reinterpret_cast<int32_t*>(h->h_pin + 9) & 2) {
+      h->err = "batch mid-time outside the spline support (the reference aborts here: so3_spline.h:221-230)";
+      return EMBA_E_SUPPORT;
+    }
+    const int64_t G = h->h_pin[8];
     gstart.resize(G); gkey.resize(G);
-    cudaMemcpyAsync(gstart.data(), d_gstart, sizeof(int32_t) * G, cudaMemcpyDeviceToHost, h->stream);
-    cudaMemcpyAsync(gkey.data(), d_gkey, sizeof(uint32_t) * G, cudaMemcpyDeviceToHost, h->stream);
-    if (cudaStreamSynchronize(h->stream) != cudaSuccess) { h->err = "rebuild_static: sync failed"; rc = EMBA_E_CUDA; break; }
-  } while (0);
-  if (rc == EMBA_OK) {
-    // host: split groups into work items, pick this rank's contiguous slice (time sharding: groups are ordered by
-    // cp_c, i.e. by time), build the lookup tables
-    const int G = (int)gstart.size();
-    std::vector<WorkItem> all;
-    for (int g = 0; g < G; g++) {
-      const int64_t s0 = gstart[g], s1 = (g + 1 < G) ? gstart[g + 1] : Mt;
-      const int cc = (int)(gkey[g] / (uint32_t)n), cp = (int)(gkey[g] % (uint32_t)n);
-      h->dmax = std::max(h->dmax, cc - cp);
-      static const int64_t item_max = getenv("EMBA_ITEM_MAX") ? atoll(getenv("EMBA_ITEM_MAX")) : kItemMax;
-      for (int64_t s = s0; s < s1; s += item_max) {
-        WorkItem w;
-        w.cp_c = cc; w.cp_p = cp; w.start = (int32_t)s; w.count = (int32_t)std::min<int64_t>(item_max, s1 - s); w.group = g;
-        all.push_back(w);
-      }
-    }
-    // shard boundaries in measurements, snapped to item starts
-    const int64_t lo_t = Mt * h->rank / h->world, hi_t = Mt * (h->rank + 1) / h->world;
-    int64_t m_lo = -1, m_hi = -1;
-    for (const WorkItem& w : all) {
-      if (w.start >= lo_t && w.start < hi_t) {
-        if (m_lo < 0) m_lo = w.start;
-        m_hi = (int64_t)w.start + w.count;
-        h->h_items.push_back(w);
-      }
-    }
-    if (m_lo < 0) { m_lo = m_hi = 0; }
-    h->Mc = m_hi - m_lo;
-    // renumber groups locally (dense ids in order of appearance)
-    std::vector<int32_t> item0;
-    int lastg = -1, ng = 0;
-    for (size_t i = 0; i < h->h_items.size(); i++) {
-      WorkItem& w = h->h_items[i];
-      w.start -= (int32_t)m_lo;
-      if (w.group != lastg) { lastg = w.group; item0.push_back((int32_t)i); ng++; }
-      w.group = ng - 1;
-    }
-    item0.push_back((int32_t)h->h_items.size());
-    h->n_items = (int)h->h_items.size();
-    h->n_groups = ng;
-    h->iota_len = 0;
-    std::vector<int32_t> gid((size_t)n * (h->dmax + 1), -1);
-    for (const WorkItem& w : h->h_items) gid[(size_t)w.cp_c * (h->dmax + 1) + (w.cp_c - w.cp_p)] = w.group;
-    do {
-      if ((rc = dev_alloc(h, &h->d_items, h->n_items)) || (rc = dev_alloc(h, &h->d_gid, (int64_t)gid.size())) ||
-          (rc = dev_alloc(h, &h->d_group_item0, (int64_t)item0.size())) || (rc = dev_alloc(h, &h->d_rec, h->Mc)) ||
-          (rc = dev_alloc(h, &h->d_refpos, h->Mc)) ||
-          (rc = dev_alloc(h, &h->d_acc_part, (int64_t)h->n_items * kAccN)) ||
-          (rc = dev_alloc(h, &h->d_skey, h->Mc)) || (rc = dev_alloc(h, &h->d_sval, h->Mc)) ||
-          (rc = dev_alloc(h, &h->d_sval2, h->Mc)) ||
-          (rc = dev_reserve(h, &h->d_jrec, &h->jrec_cap, h->Mc * kRecDoubles)) ||
-          (rc = dev_alloc(h, &h->d_gsum, (int64_t)h->n_groups * kAccN)))
-        break;
-      for (int s = 0; s < 2 && rc == EMBA_OK; s++) {
-        if ((rc = dev_alloc(h, &h->st[s].dp, h->Mc)) || (rc = dev_alloc(h, &h->st[s].e, h->Mc)) ||
-            (rc = dev_alloc(h, &h->st[s].pix, h->Mc)))
-          break;
-      }
-      if (rc) break;
-      if (h->n_items) cudaMemcpyAsync(h->d_items, h->h_items.data(), sizeof(WorkItem) * h->n_items, cudaMemcpyHostToDevice, h->stream);
-      cudaMemcpyAsync(h->d_gid, gid.data(), sizeof(int32_t) * gid.size(), cudaMemcpyHostToDevice, h->stream);
-      cudaMemcpyAsync(h->d_group_item0, item0.data(), sizeof(int32_t) * item0.size(), cudaMemcpyHostToDevice, h->stream);
-      if (h->Mc) {
-        k_build_recs<<<ceil_div64(h->Mc, T), T, 0, h->stream>>>(vs, m_lo, h->Mc, h->d_spix_ev, h->d_pol, h->d_prev,
-                                                                h->d_refrank, h->d_lut, h->d_rec, h->d_refpos);
-        h->launches++;
-      }
-      cudaError_t e = cudaStreamSynchronize(h->stream);
-      if (e != cudaSuccess) { h->err = std::string("rebuild_static: ") + cudaGetErrorString(e); rc = EMBA_E_CUDA; }
-    } while (0);
+    EMBA_CUDA(cudaMemcpyAsync(gstart.data(), d_gstart, sizeof(int32_t) * G, cudaMemcpyDeviceToHost, h->stream));
+    EMBA_CUDA(cudaMemcpyAsync(gkey.data(), d_gkey, sizeof(uint32_t) * G, cudaMemcpyDeviceToHost, h->stream));
+    EMBA_CUDA(cudaStreamSynchronize(h->stream));
   }
-  cudaFree(d_flag); cudaFree(d_pos); cudaFree(d_key); cudaFree(d_ev); cudaFree(d_key2); cudaFree(d_ev2);
-  cudaFree(d_gstart); cudaFree(d_gkey); cudaFree(d_gidx);
-  return rc;
+  // host: split groups into work items, pick this rank's contiguous slice (time sharding: groups are ordered by
+  // cp_c, i.e. by time), build the lookup tables
+  const int G = (int)gstart.size();
+  std::vector<WorkItem> all;
+  static const int64_t item_max = getenv("EMBA_ITEM_MAX") ? atoll(getenv("EMBA_ITEM_MAX")) : kItemMax;
+  for (int g = 0; g < G; g++) {
+    const int64_t s0 = gstart[g], s1 = (g + 1 < G) ? gstart[g + 1] : Mt;
+    const int cc = (int)(gkey[g] / (uint32_t)n), cp = (int)(gkey[g] % (uint32_t)n);
+    h->dmax = std::max(h->dmax, cc - cp);
+    for (int64_t s = s0; s < s1; s += item_max) {
+      WorkItem w;
+      w.cp_c = cc; w.cp_p = cp; w.start = (int32_t)s; w.count = (int32_t)std::min<int64_t>(item_max, s1 - s); w.group = g;
+      all.push_back(w);
+    }
+  }
+  // shard boundaries in measurements, snapped to item starts
+  const int64_t lo_t = Mt * h->rank / h->world, hi_t = Mt * (h->rank + 1) / h->world;
+  int64_t m_lo = -1, m_hi = -1;
+  for (const WorkItem& w : all) {
+    if (w.start >= lo_t && w.start < hi_t) {
+      if (m_lo < 0) m_lo = w.start;
+      m_hi = (int64_t)w.start + w.count;
+      h->h_items.push_back(w);
+    }
+  }
+  if (m_lo < 0) { m_lo = m_hi = 0; }
+  h->Mc = m_hi - m_lo;
+  // renumber groups locally (dense ids in order of appearance)
+  std::vector<int32_t> item0;
+  int lastg = -1, ng = 0;
+  for (size_t i = 0; i < h->h_items.size(); i++) {
+    WorkItem& w = h->h_items[i];
+    w.start -= (int32_t)m_lo;
+    if (w.group != lastg) { lastg = w.group; item0.push_back((int32_t)i); ng++; }
+    w.group = ng - 1;
+  }
+  item0.push_back((int32_t)h->h_items.size());
+  h->n_items = (int)h->h_items.size();
+  h->n_groups = ng;
+  std::vector<int32_t> gid((size_t)n * (h->dmax + 1), -1);
+  for (const WorkItem& w : h->h_items) gid[(size_t)w.cp_c * (h->dmax + 1) + (w.cp_c - w.cp_p)] = w.group;
+  // ---- measurement-level arena
+  const int64_t Mc = h->Mc;
+  const size_t Mp = (size_t)std::max<int64_t>(Mc, 1);
+  size_t mb = 0;
+  mb += Arena::pad(sizeof(MeasRec) * Mp) + Arena::pad(4 * Mp);                     // rec, refpos
+  mb += 2 * (Arena::pad(16 * Mp) + Arena::pad(8 * Mp) + 2 * Arena::pad(4 * Mp));   // dp, e, pix, slot  x 2 states
+  mb += Arena::pad(8 * (size_t)kRecDoubles * Mp) + Arena::pad(4 * Mp);             // Jacobian rows, sorted row ids
+  mb += 2 * (Arena::pad(32 * (size_t)n) + Arena::pad(8 * (size_t)kKnotStride * n) + 2 * Arena::pad(32 * (size_t)std::max<int64_t>(B, 1)));
+  mb += Arena::pad(sizeof(WorkItem) * (size_t)std::max(1, h->n_items)) + Arena::pad(4 * gid.size()) +
+        Arena::pad(4 * item0.size()) + Arena::pad(8 * (size_t)kAccN * std::max(1, h->n_items)) +
+        Arena::pad(8 * (size_t)kAccN * std::max(1, h->n_groups)) + 8192;
+  // the arena may move: the static rebuild must not lose the canonical event list, which lives in the scratch arena
+  EMBA_TRY(arena_reserve(h, h->ar_meas, mb));
+  Arena& A = h->ar_meas;
+  h->d_rec = A.take<MeasRec>(Mc);
+  h->d_refpos = A.take<uint32_t>(Mc);
+  for (int s = 0; s < 2; s++) {
+    StateSlot& st = h->st[s];
+    st.dp = A.take<double2>(Mc); st.e = A.take<double>(Mc); st.pix = A.take<int32_t>(Mc); st.slot = A.take<int32_t>(Mc);
+    st.quat = A.take<double>((int64_t)n * 4);
+    st.Ktab = A.take<double>((int64_t)n * kKnotStride);
+    st.RotTab = A.take<double4>(B);
+    st.JacTab = A.take<double4>(B);
+  }
+  h->d_jrec = A.take<double>(Mc * kRecDoubles);
+  h->jrec_cap = Mc * kRecDoubles;
+  h->d_sval = A.take<uint32_t>(Mc);
+  h->d_items = A.take<WorkItem>(h->n_items);
+  h->d_gid = A.take<int32_t>((int64_t)gid.size());
+  h->d_group_item0 = A.take<int32_t>((int64_t)item0.size());
+  h->d_acc_part = A.take<double>((int64_t)h->n_items * kAccN);
+  h->d_gsum = A.take<double>((int64_t)h->n_groups * kAccN);
+  if (!h->d_gsum || !h->d_acc_part || !h->d_group_item0 || !h->d_gid || !h->d_items || !h->d_sval || !h->d_jrec) {
+    h->err = "measurement arena too small"; return EMBA_E_CUDA;
+  }
+  if (h->n_items) EMBA_CUDA(cudaMemcpyAsync(h->d_items, h->h_items.data(), sizeof(WorkItem) * h->n_items, cudaMemcpyHostToDevice, h->stream));
+  if (!gid.empty()) EMBA_CUDA(cudaMemcpyAsync(h->d_gid, gid.data(), sizeof(int32_t) * gid.size(), cudaMemcpyHostToDevice, h->stream));
+  EMBA_CUDA(cudaMemcpyAsync(h->d_group_item0, item0.data(), sizeof(int32_t) * item0.size(), cudaMemcpyHostToDevice, h->stream));
+  if (Mc) {
+    k_build_recs<<<ceil_div64(Mc, T), T, 0, h->stream>>>(vs, m_lo, Mc, h->d_spix_ev, h->d_pol, h->d_prev,
+                                                        h->d_refrank, h->d_lut, h->d_rec, h->d_refpos);
+    EMBA_LAUNCH_CHECK();
+  }
+  EMBA_CUDA(cudaEventRecord(h->ev[1], h->stream));
+  EMBA_CUDA(cudaStreamSynchronize(h->stream));  // the host vectors above go out of scope
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+  h->t_setup_ms[1] = ms;
+  return EMBA_OK;
 }
 
 }  // namespace emba
+
+extern "C" int emba_last_setup_ms(emba_handle_t hh, double* out2) {
+  Handle* h = (Handle*)hh;
+  if (!h || !out2) return EMBA_E_ARG;
+  out2[0] = h->t_setup_ms[0];
+  out2[1] = h->t_setup_ms[1];
+  return EMBA_OK;
+}

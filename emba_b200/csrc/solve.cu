@@ -295,8 +295,10 @@ __device__ __forceinline__ void ldlt_panel_body(int d, int k0, int nb, double* _
       ycol[lane] = a[j];  // y_ij = a_ij (lanes i >= j)
       __syncwarp();
       const double dj = ycol[j];
-      bad = bad || (k0 + j < ncheck && (dj == 0.0 || !isfinite(dj)));
-      const double lij = a[j] / dj;  // l_ij
+      // an exactly zero pivot (a control pose no active measurement touches: its whole row and column are zero) is
+      // treated like Eigen's LDLT::solve treats it -- that component of the solution is 0 (model.cpp:789)
+      bad = bad || (k0 + j < ncheck && !isfinite(dj));
+      const double lij = dj != 0.0 ? a[j] / dj : 0.0;  // l_ij
 #pragma unroll
       for (int m = j + 1; m < kNB; m++) a[m] -= lij * ycol[m];  // a_im -= l_ij * y_mj (used for j < m <= i)
       if (lane > j) a[j] = lij;
@@ -349,7 +351,7 @@ __device__ __forceinline__ void ldlt_panel_body(int d, int k0, int nb, double* _
       double y = 0.0;
       for (int m = 0; m <= j; m++) y += As[rr][m] * Li[j][m];
       W[(size_t)(r0 + rr) * kNB + j] = y;
-      S[(size_t)(r0 + rr) * d + k0 + j] = y / Dk[j][j];
+      S[(size_t)(r0 + rr) * d + k0 + j] = Dk[j][j] != 0.0 ? y / Dk[j][j] : 0.0;
     }
   }
 }
@@ -481,7 +483,7 @@ __global__ void __launch_bounds__(1024) k_ldlt_subst(int d, int ld, const double
 __global__ void k_solve_x2(int64_t Np, const int32_t* __restrict__ winlo, const int32_t* __restrict__ winhi,
                            const int64_t* __restrict__ stripoff, const double* __restrict__ strip,
                            const double* __restrict__ C, const double* __restrict__ b2,
-                           const double* __restrict__ x1full, double* __restrict__ x2) {
+                           const double* __restrict__ x1full, double* __restrict__ x2, int64_t own0, int64_t own1) {
   // 8 lanes per pixel walk its strip as (column 0, column 1) pairs: pair e multiplies x1[3*lo + e]; coalesced
   const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t a = gt >> 3;
@@ -508,11 +510,12 @@ __global__ void k_solve_x2(int64_t Np, const int32_t* __restrict__ winlo, const 
     t1 += __shfl_xor_sync(0xffffffffu, t1, o);
   }
   if (a >= Np || sub != 0) return;
-  if (hi < lo) {  // pixel owned by another rank (multi-GPU): its owner computes x2, combined by all-reduce
+  if (a < own0 || a >= own1) {  // pixel owned by another rank (multi-GPU): its owner computes x2, combined by all-reduce
     x2[2 * a] = 0.0;
     x2[2 * a + 1] = 0.0;
     return;
   }
+  // (an owned pixel with an empty pose window -- thres_valid_pixel <= 0 -- still gets x2 = C b2, model.cpp:791)
   const double r0 = b2[2 * a] - t0, r1 = b2[2 * a + 1] - t1;
   const double c00 = C[3 * a], c01 = C[3 * a + 1], c11 = C[3 * a + 2];
   x2[2 * a] = c00 * r0 + c01 * r1;
@@ -816,8 +819,9 @@ int solve_schur(Handle* h, double lambda, int fix) {
   k_expand_x1<<<ceil_div64(3 * n, T), T, 0, h->stream>>>(n, fix, h->d_rhs, h->d_x1);
   EMBA_LAUNCH_CHECK();
   if (Np > 0) {
+    const int64_t own0 = h->world > 1 ? Np * h->rank / h->world : 0, own1 = h->world > 1 ? Np * (h->rank + 1) / h->world : Np;
     k_solve_x2<<<ceil_div64(Np * 8, 256), 256, 0, h->stream>>>(Np, h->sv_winlo, h->sv_winhi, h->sv_stripoff, h->sv_strip,
-                                                           h->d_C, h->d_b2, h->d_x1, h->d_x2);
+                                                           h->d_C, h->d_b2, h->d_x1, h->d_x2, own0, own1);
     EMBA_LAUNCH_CHECK();
     if (h->world > 1) EMBA_TRY(comm_allreduce(h, h->d_x2, 2 * Np, 1));  // owners contribute, the others hold zeros
   }
@@ -832,7 +836,7 @@ int solve_schur(Handle* h, double lambda, int fix) {
     fprintf(stderr, "[emba solve] d=%d a22inv+tiles %.3f finish %.3f ldlt %.3f subst %.3f x2 %.3f ms\n", d, a, b, c, e2, f);
     for (auto& e : de) cudaEventDestroy(e);
   }
-  if (fl & 8) { h->err = "zero or non-finite pivot in the LDL^T factorisation of the Schur complement"; return EMBA_E_NUMERIC; }
+  if (fl & 8) { h->err = "non-finite pivot in the LDL^T factorisation of the Schur complement"; return EMBA_E_NUMERIC; }
   return EMBA_OK;
 }
 

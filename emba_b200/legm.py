@@ -25,16 +25,25 @@ def spline_base_ns(t_beg: float, dt_knots: float):
     return int(np.int64(np.float64(1e9) * np.float64(t_beg))), int(np.int64(np.float64(1e9) * np.float64(dt_knots)))
 
 
+def ros_time_ns(t_sec: float) -> int:
+    """ros::Time(double).toNSec(): sec = floor(t), nsec = round((t - sec) * 1e9) (rostime)."""
+    s = np.floor(np.float64(t_sec))
+    return int(s) * 1_000_000_000 + int(np.round((np.float64(t_sec) - s) * 1e9))
+
+
 def fit_control_poses(t_ns, quat_xyzw, t_beg, t_end, dt_knots, device=0):
     """LinearTrajectory::generateCtrlPosesLong (src/utils/trajectory.cpp:258-294) on the GPU: initial control poses
-    from a dense front-end trajectory (time-sorted t_ns, xyzw quaternions)."""
+    from a dense front-end trajectory (time-sorted t_ns, xyzw quaternions). t_beg / t_end: seconds (converted like
+    ros::Time(double)) or integer nanoseconds."""
     L = capi.load()
     t = np.ascontiguousarray(t_ns, dtype=np.int64)
     q = np.ascontiguousarray(quat_xyzw, dtype=np.float64)
-    cap = int(round((t_end - t_beg) / dt_knots)) + 8
-    out = np.empty((cap, 4))
     n = C.c_int32(0)
-    rc = L.emba_fit_control_poses(device, t.size, ptr(t, C.c_int64), ptr(q), float(t_beg), float(t_end),
+    tb = int(t_beg) if isinstance(t_beg, (int, np.integer)) else ros_time_ns(t_beg)
+    te = int(t_end) if isinstance(t_end, (int, np.integer)) else ros_time_ns(t_end)
+    cap = int(round((te - tb) * 1e-9 / dt_knots)) + 8
+    out = np.empty((cap, 4))
+    rc = L.emba_fit_control_poses(device, t.size, ptr(t, C.c_int64), ptr(q), tb, te,
                                   float(dt_knots), ptr(out), cap, C.byref(n))
     if rc != 0:
         raise EmbaError(rc, "emba_fit_control_poses")
@@ -93,6 +102,66 @@ def reconstructFromGradient(gradients, device=0):
         plan.close()
 
 
+class EventSequence:
+    """Device-resident event recording (include/emba_b200.h: emba_events_*): the steps the reference runs on the host
+    before every window -- time sort (src/utils/rosbag_loading.cpp:61-65), subsampling (src/emba/emba.cpp:281-304),
+    robust window extraction EMBA::getEventSubset (src/emba/emba.cpp:473-510) -- on the GPU."""
+
+    def __init__(self, x, y, t_ns, pol, device=0):
+        self.L = capi.load()
+        x = np.ascontiguousarray(x, dtype=np.uint16)
+        y = np.ascontiguousarray(y, dtype=np.uint16)
+        t = np.ascontiguousarray(t_ns, dtype=np.int64)
+        p = np.ascontiguousarray(pol, dtype=np.uint8)
+        self.h = C.c_void_p()
+        rc = self.L.emba_events_create(int(device), x.size, ptr(x, C.c_uint16), ptr(y, C.c_uint16), ptr(t, C.c_int64),
+                                       ptr(p, C.c_uint8), C.byref(self.h))
+        if rc != 0:
+            raise EmbaError(rc, "emba_events_create")
+
+    def _chk(self, rc, what):
+        if rc != 0:
+            raise EmbaError(rc, what)
+
+    def count(self):
+        v = C.c_int64(0)
+        self._chk(self.L.emba_events_count(self.h, C.byref(v)), "emba_events_count")
+        return v.value
+
+    def sort_by_time(self):
+        self._chk(self.L.emba_events_sort_by_time(self.h), "emba_events_sort_by_time")
+
+    def subsample(self, event_sampling_rate):
+        self._chk(self.L.emba_events_subsample(self.h, int(event_sampling_rate)), "emba_events_subsample")
+
+    def window(self, t_beg_ns, t_end_ns):
+        """EMBA::getEventSubset: returns (idx_beg, idx_end) of the event subset."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._chk(self.L.emba_events_window(self.h, int(t_beg_ns), int(t_end_ns), C.byref(a), C.byref(b)),
+                  "emba_events_window")
+        return a.value, b.value
+
+    def download(self, i0=0, i1=None):
+        i1 = self.count() if i1 is None else i1
+        n = max(0, i1 - i0)
+        x, y = np.empty(n, np.uint16), np.empty(n, np.uint16)
+        t, p = np.empty(n, np.int64), np.empty(n, np.uint8)
+        self._chk(self.L.emba_events_download(self.h, i0, i1, ptr(x, C.c_uint16), ptr(y, C.c_uint16),
+                                              ptr(t, C.c_int64), ptr(p, C.c_uint8)), "emba_events_download")
+        return x, y, t, p
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.emba_events_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Engine:
     def __init__(self, sensor_w, sensor_h, bearing_lut, C_th, pano_w, pano_h, device=0):
         self.L = capi.load()
@@ -132,6 +201,28 @@ class Engine:
         self.N = x.size
         self._chk(self.L.emba_set_events(self.h, x.size, ptr(x, C.c_uint16), ptr(y, C.c_uint16), ptr(t, C.c_int64),
                                          ptr(p, C.c_uint8)))
+
+    def set_events_dev(self, seq: "EventSequence", idx_beg, idx_end):
+        """per-window pre-pass straight from a device-resident sequence (no host copy)"""
+        self.N = int(idx_end - idx_beg)
+        self._chk(self.L.emba_set_events_dev(self.h, seq.h, int(idx_beg), int(idx_end)))
+
+    def setup_ms(self):
+        """device ms of the last (set_events, static rebuild)"""
+        out = np.zeros(2)
+        self._chk(self.L.emba_last_setup_ms(self.h, ptr(out)))
+        return float(out[0]), float(out[1])
+
+    def set_strict_range(self, on):
+        self._chk(self.L.emba_set_strict_range(self.h, int(bool(on))))
+
+    def get_jacobian_rows(self):
+        """[M, 16] rows [Jc(6) Jp(6) e dp(2) 0] of the last assembly in the reference's measurement order"""
+        cap = max(self.num_pairs(), 1)
+        rows = np.empty((cap, 16))
+        n = C.c_int64(0)
+        self._chk(self.L.emba_get_jacobian_rows(self.h, ptr(rows), cap, C.byref(n)))
+        return rows[: n.value].copy()
 
     def num_pairs(self):
         v = C.c_int64(0)
@@ -236,15 +327,26 @@ class Engine:
         self._chk(self.L.emba_accept_candidate(self.h))
 
     def solve_time_window(self, *, max_num_iter=50, tol_fun=1e-3, num_times_tol_fun_sat=2, use_cg=False, cost_type=0,
-                          eta=1.0, thres=5, damping=1.0, alpha=5.0, first_window=True):
+                          eta=1.0, thres=5, damping=1.0, alpha=5.0, first_window=True, callback=None):
+        """EMBA::solveTimeWindow on the device. Returns (log rows, final cost); row columns: iter, lambda, cost_min,
+        cost_new, accepted, active pixels, measurements, cg_iters, cg_error, ms_form, ms_solve, ms_evaluate.
+        callback(row_dict) is called after every solve (solver.cpp:170-179); a truthy return stops the loop."""
         s = LMSettings(max_num_iter, tol_fun, num_times_tol_fun_sat, int(use_cg), cost_type, eta, thres, damping,
                        alpha, int(first_window))
         cap = max_num_iter + 8
         log = (LMLog * cap)()
         nlog, fc = C.c_int32(0), C.c_double(0)
-        self._chk(self.L.emba_solve_time_window(self.h, C.byref(s), log, cap, C.byref(nlog), C.byref(fc)))
+
+        def _cb(rowp, _user):
+            r = rowp.contents
+            return 1 if callback({"iter": r.iter, "lambda": r.lambda_, "cost_min": r.cost_min, "cost_new": r.cost_new,
+                                  "accepted": r.accepted, "cg_iters": r.cg_iters, "cg_error": r.cg_error}) else 0
+
+        cfn = capi.LM_CALLBACK(_cb) if callback is not None else C.cast(None, capi.LM_CALLBACK)
+        self._chk(self.L.emba_solve_time_window_cb(self.h, C.byref(s), log, cap, C.byref(nlog), C.byref(fc), cfn, None))
         rows = np.array([[r.iter, r.lambda_, r.cost_min, r.cost_new, r.accepted, r.num_active_pixels,
-                          r.num_measurements] for r in log[: nlog.value]], dtype=np.float64).reshape(-1, 7)
+                          r.num_measurements, r.cg_iters, r.cg_error, r.ms_form, r.ms_solve, r.ms_evaluate]
+                         for r in log[: nlog.value]], dtype=np.float64).reshape(-1, 12)
         return rows, fc.value
 
     def timings_ms(self):

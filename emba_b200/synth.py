@@ -87,10 +87,15 @@ def make_texture(pano_w, pano_h, seed=1, std=1.5):
     return L
 
 
+YAW0 = 0.0  # yaw offset of the ground-truth trajectory (make_scene sets it; pi-ish values look at the panorama seam)
+
+
 def gt_rotvec(t, yaw_rate=0.35, periodic=False):
     """Ground-truth rotation vector phi(t) = (0.25 sin 1.3t, 0.35 t, 0.08 cos 0.7t) rad; with
     periodic=True the yaw is a bounded triangle wave with the same rate (for spans > 10 s)."""
     t = np.asarray(t, dtype=np.float64)
+    if YAW0 != 0.0:
+        return np.stack([0.25 * np.sin(1.3 * t), YAW0 + yaw_rate * t, 0.08 * np.cos(0.7 * t)], -1)
     if periodic:
         # triangle wave: constant |yaw rate|, bounded to +-1.6 rad (keeps the view away from the seam for any span)
         A = 1.6
@@ -259,9 +264,11 @@ def simulate_events_cuda(L, scene: Scene, t_start, t_stop, *, dt_sim=0.25e-3, ya
 def make_scene(sensor_w=128, sensor_h=128, fx=91.4014729896821, fy=None, cx=None, cy=None, pano_w=1024, pano_h=512,
                C_th=0.45, t_beg=0.1, t_end=2.4, dt_knots=0.05, texture_std=1.5, seed=1, dt_sim=0.25e-3,
                yaw_rate=0.35, periodic=False, device="cpu", pose_noise_deg=0.3, map_scale=0.7, map_noise=0.02,
-               max_events=None, guard=1e-3) -> Scene:
+               max_events=None, guard=1e-3, yaw0=0.0) -> Scene:
     """Build a full seeded problem instance. Defaults are config C1 of SURVEY.md section 8(d)
     (calib/DVS-playroom.yaml intrinsics, launch/playroom.launch parameters)."""
+    global YAW0
+    YAW0 = float(yaw0)
     fy = fx if fy is None else fy
     cx = sensor_w / 2.0 if cx is None else cx
     cy = sensor_h / 2.0 if cy is None else cy
@@ -292,6 +299,7 @@ def make_scene(sensor_w=128, sensor_h=128, fx=91.4014729896821, fy=None, cx=None
     rng7 = np.random.default_rng(seed + 6)
     sc.Gx_init = map_scale * sc.Gx_gt + map_noise * rng7.standard_normal(sc.Gx_gt.shape)
     sc.Gy_init = map_scale * sc.Gy_gt + map_noise * rng7.standard_normal(sc.Gy_gt.shape)
+    YAW0 = 0.0
     return sc
 
 
@@ -300,6 +308,9 @@ CONFIGS = {
     # tiny: CPU-second test case
     "tiny": dict(sensor_w=32, sensor_h=24, fx=30.0, pano_w=256, pano_h=128, C_th=0.3, t_beg=0.1, t_end=0.6,
                  dt_knots=0.05, texture_std=1.5, dt_sim=0.5e-3),
+    # seam: the tiny scene looking at the phi = +-pi seam of the panorama (warped events round to column pano_w)
+    "seam": dict(sensor_w=32, sensor_h=24, fx=30.0, pano_w=256, pano_h=128, C_th=0.3, t_beg=0.1, t_end=0.6,
+                 dt_knots=0.05, texture_std=1.5, dt_sim=0.5e-3, yaw0=3.0),
     # small: a few 10k events
     "small": dict(sensor_w=64, sensor_h=48, fx=60.0, pano_w=512, pano_h=256, C_th=0.3, t_beg=0.1, t_end=1.1,
                   dt_knots=0.05, texture_std=1.5, dt_sim=0.5e-3),

@@ -49,9 +49,11 @@ enum {
   EMBA_E_ARG = -1,      /* bad argument / call order */
   EMBA_E_CUDA = -2,     /* CUDA runtime error */
   EMBA_E_SUPPORT = -3,  /* batch time outside the spline support (basalt so3_spline.h:221-230 asserts) */
-  EMBA_E_RANGE = -4,    /* warped event rounds outside the panorama (UB in the reference, model.cpp:213) */
+  EMBA_E_RANGE = -4,    /* strict mode only (emba_set_strict_range): a warped event rounds past the last panorama
+                           element (out-of-bounds read/write in the reference, model.cpp:213,227) */
   EMBA_E_NCCL = -5,     /* collective error */
-  EMBA_E_NUMERIC = -6   /* zero pivot in the Schur factorisation */
+  EMBA_E_NUMERIC = -6   /* non-finite pivot in the Schur factorisation (exactly zero pivots are handled like Eigen's
+                           LDLT::solve: that component of the solution is 0) */
 };
 
 /* which device-resident state a call refers to (solver.cpp keeps traj_ptr/Gx/Gy and traj_new_ptr/Gx_new/Gy_new) */
@@ -83,7 +85,8 @@ typedef struct {
   int32_t first_time_window;       /* EMBA::first_time_window_: fix the first control pose (solver.cpp:156-165) */
 } emba_lm_settings_t;
 
-/* one row per LM solve, the content of the reference's iteration log line (solver.cpp:170-171) */
+/* one row per LM solve, the content of the reference's iteration log line (solver.cpp:170-171) and of its CG log
+ * (solver.cpp:198-201) */
 typedef struct {
   int32_t iter;
   double lambda;
@@ -92,12 +95,46 @@ typedef struct {
   int32_t accepted;
   int64_t num_active_pixels;
   int64_t num_measurements;  /* inlier measurements M at the candidate */
+  int32_t cg_iters;          /* solveNormalEqCG's pair (iterations, error); 0 / 0.0 for the Schur solve */
+  double cg_error;
+  double ms_form, ms_solve, ms_evaluate;  /* device time of this iteration's three regions, the ones the reference
+                                             instruments (solver.cpp:105-151, 181-222, 242-294); ms_form = 0 after a
+                                             rejected step (the equations are reused) */
 } emba_lm_log_t;
+
+/* optional per-iteration hook of emba_solve_time_window_cb: called on the host after every LM solve with that
+ * iteration's log row (the point where the reference prints its log line and, with record_data, dumps the evolution
+ * images, solver.cpp:170-179). The callback may call emba_get_state / emba_reconstruct_map on the handle (which = 1
+ * is the candidate just evaluated); returning non-zero stops the loop after this iteration. */
+typedef int (*emba_lm_callback_t)(const emba_lm_log_t* row, void* user);
 
 /* ---- lifetime: replaces LEGM::LEGM / ~LEGM (model.cpp:56-70, model.h:80) ---- */
 EMBA_API int emba_create(const emba_config_t* cfg, emba_handle_t* out);
 EMBA_API int emba_destroy(emba_handle_t h);
 EMBA_API const char* emba_last_error(emba_handle_t h);
+
+/* ---- "next" row N1: device-resident event sequence. The whole recording is uploaded once
+ * (pinned, chunked staging); the steps the reference does on the host before every window run on the device:
+ *   emba_events_sort_by_time : std::sort by timestamp after parsing the bag (src/utils/rosbag_loading.cpp:61-65;
+ *                              stable here, std::sort's order of equal stamps is unspecified)
+ *   emba_events_subsample    : keep every rate-th event, the rate-th first (src/emba/emba.cpp:281-304)
+ *   emba_events_window       : EMBA::getEventSubset (src/emba/emba.cpp:473-510): 1 ms robust margins, 100-event
+ *                              stride search, including its unsigned wrap-around when the first probe already lies
+ *                              past the window end; t_beg_ns / t_end_ns are ros::Time::toNSec()
+ *   emba_set_events_dev      : the per-window pre-pass (what emba_set_events does) straight from the sequence,
+ *                              events [idx_beg, idx_end), no host copy */
+typedef struct emba_events_s* emba_events_t;
+EMBA_API int emba_events_create(int32_t device, int64_t n_events, const uint16_t* x, const uint16_t* y,
+                                const int64_t* t_ns, const uint8_t* polarity, emba_events_t* out);
+EMBA_API int emba_events_destroy(emba_events_t ev);
+EMBA_API int emba_events_count(emba_events_t ev, int64_t* out);
+EMBA_API int emba_events_sort_by_time(emba_events_t ev);
+EMBA_API int emba_events_subsample(emba_events_t ev, int32_t event_sampling_rate);
+EMBA_API int emba_events_window(emba_events_t ev, int64_t t_beg_ns, int64_t t_end_ns, int64_t* idx_beg,
+                                int64_t* idx_end);
+EMBA_API int emba_events_download(emba_events_t ev, int64_t idx_beg, int64_t idx_end, uint16_t* x, uint16_t* y,
+                                  int64_t* t_ns, uint8_t* polarity);
+EMBA_API int emba_set_events_dev(emba_handle_t h, emba_events_t ev, int64_t idx_beg, int64_t idx_end);
 
 /* ---- events: replaces the `const EventPacket& events` argument of evaluateDataError (model.h:83-84) and the
  * per-pixel EventMap pairing structure (include/emba/event_map.h:22-113). Called once per time window: uploads
@@ -131,6 +168,12 @@ EMBA_API int emba_evaluate(emba_handle_t h, int32_t which, int32_t cost_type, do
  * ep_out [M] in the reference's order (sensor pixel row-major, then time; model.cpp:179-246),
  * num_ev_map_out [pano_h*pano_w] int32 (model.cpp:227). Either may be NULL. */
 EMBA_API int emba_get_evaluation(emba_handle_t h, int32_t which, double* ep_out, int32_t* num_ev_map_out);
+/* A warped event can round to column pano_w (within half a pixel of the phi = +-pi seam). The reference's release
+ * build then reads and writes element (y, pano_w) of its row-major cv::Mat, i.e. (y + 1, 0) (model.cpp:213-227,
+ * 396-412): the default here reproduces exactly that linear index. Only an index past the LAST element (row
+ * pano_h - 1 at the seam, or row pano_h at the pole) is undefined in the reference; such pairs are dropped as
+ * outliers. on != 0 makes emba_evaluate fail with EMBA_E_RANGE on those instead (all ranks agree on it). */
+EMBA_API int emba_set_strict_range(emba_handle_t h, int32_t on);
 
 /* ---- LEGM::formNormalEq / formNormalEqIRLS (model.cpp:316-687) fused with applyL2Reg (:689-719), on the last
  * evaluation of the CURRENT state. */
@@ -150,6 +193,12 @@ EMBA_API int emba_apply_l2_reg(emba_handle_t h, double alpha);
  * [3n * 2Np] exactly like the reference's MatXd (model.cpp:358) -- only for small problems. Any may be NULL. */
 EMBA_API int emba_get_normal_eq(emba_handle_t h, double* A11, double* b1, double* A22, double* b2, int64_t* active,
                        double* A12_dense);
+/* parity download of the per-measurement Jacobian rows of the last emba_form_normal_eq, in the reference's
+ * measurement order (inlier index = position in ep; model.cpp:179-246): 16 doubles per row
+ * [Jc(6) = temp*dpm_ddrot_cp (model.cpp:449) | Jp(6) = -Gpm*dpm_ddrot_cp (model.cpp:459) | e | dp(2) | 0].
+ * Rows of measurements on inactive pixels are zero (the reference skips them, model.cpp:409-412): form with
+ * thres_valid_pixel = 1 to get every inlier's row. Single GPU, windows of at most 2^24 pairs (EMBA_E_SUPPORT). */
+EMBA_API int emba_get_jacobian_rows(emba_handle_t h, double* rows_out, int64_t cap_rows, int64_t* n_rows);
 /* number of structurally non-zero A12 entries held on the device (windowed per-pixel strips) */
 EMBA_API int emba_a12_entries(emba_handle_t h, int64_t* out);
 
@@ -168,14 +217,20 @@ EMBA_API int emba_accept_candidate(emba_handle_t h);
  * Starts from the CURRENT state; on return the CURRENT state is the refined one. log may be NULL. */
 EMBA_API int emba_solve_time_window(emba_handle_t h, const emba_lm_settings_t* s, emba_lm_log_t* log, int32_t log_cap,
                            int32_t* n_log, double* final_cost);
+/* the same with the per-iteration hook (cb may be NULL) */
+EMBA_API int emba_solve_time_window_cb(emba_handle_t h, const emba_lm_settings_t* s, emba_lm_log_t* log,
+                                       int32_t log_cap, int32_t* n_log, double* final_cost, emba_lm_callback_t cb,
+                                       void* user);
 
 /* ---- "next" row N2: control-pose initialisation from a dense front-end trajectory,
  * LinearTrajectory::generateCtrlPosesLong (src/utils/trajectory.cpp:258-294; generateCtrlPoses :245-256,
  * fitCtrlPoses :149-229) as EMBA::Run calls it (src/emba/emba.cpp:416, sub-interval = dt_knots). poses: time-sorted
- * (t_ns, quaternion xyzw). Writes floor((t_end - t_beg)/dt_knots + 1e-6) + 1 control poses (capacity cap).
+ * (t_ns, quaternion xyzw). t_beg_ns / t_end_ns are the ns-exact ros::Time::toNSec() of the interval the reference
+ * passes (a double second at epoch scale resolves only ~240 ns). Writes floor((t_end - t_beg)/dt_knots + 1e-6) + 1
+ * control poses (capacity cap).
  * EMBA_E_SUPPORT if a knot interval holds fewer than 2 front-end poses (the reference aborts there). No handle. */
 EMBA_API int emba_fit_control_poses(int32_t device, int64_t n_poses, const int64_t* t_ns, const double* quat_xyzw,
-                                    double t_beg, double t_end, double dt_knots, double* ctrl_quat_xyzw_out,
+                                    int64_t t_beg_ns, int64_t t_end_ns, double dt_knots, double* ctrl_quat_xyzw_out,
                                     int32_t cap, int32_t* n_ctrl_out);
 
 /* ---- "next" row N3: intensity map from the gradient map,
@@ -201,6 +256,9 @@ EMBA_API int emba_reconstruct_map(emba_handle_t h, int32_t which, double* img_ou
  * out[5]=solve total, out[6]=map-block assembly kernel alone (k_pix), out[7]=row sort on its side stream (it runs
  * beside k_asm_pose, so its elapsed time includes the contention and is not additive) */
 EMBA_API int emba_last_timings_ms(emba_handle_t h, double* out8);
+/* device time (ms) of the last window set-up: out[0] = emba_set_events / emba_set_events_dev (upload + pair links),
+ * out[1] = the static rebuild the first emba_set_state of a window triggers (canonical order, work items) */
+EMBA_API int emba_last_setup_ms(emba_handle_t h, double* out2);
 /* number of kernel launches issued by this handle so far */
 EMBA_API int emba_launch_count(emba_handle_t h, int64_t* out);
 EMBA_API int emba_synchronize(emba_handle_t h);

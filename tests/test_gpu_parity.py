@@ -38,7 +38,7 @@ def _base(sc):
     return spline_base_ns(sc.t_beg, sc.dt_knots)
 
 
-@pytest.fixture(scope="module", params=["tiny", "small"])
+@pytest.fixture(scope="module", params=["tiny", "small", "seam"])
 def case(request):
     from conftest import GoldenScene, load_golden_ref
 
@@ -411,37 +411,195 @@ def test_small_angle_branches_vs_oracle(tiny):
     eng.close()
 
 
+def test_jacobian_rows_vs_golden(case):
+    """Per-measurement Jacobian rows against the compiled reference (north star: residuals AND Jacobians within
+    1e-6): Jc = temp*dpm_ddrot_cp (model.cpp:449), Jp = -Gpm*dpm_ddrot_cp (model.cpp:459), e, dp -- every inlier
+    (thres_valid_pixel = 1 makes every hit pixel active), in the reference's measurement order."""
+    sc, ref, eng = case
+    t0, dt = _base(sc)
+    eng.set_state(0, t0, dt, sc.quat_init, sc.Gx_init, sc.Gy_init)
+    cd, cr, M = eng.evaluate(0, 0, 1.0, ALPHA)
+    eng.form_normal_eq(1, 0, 1.0, ALPHA)
+    rows = eng.get_jacobian_rows()
+    assert rows.shape == (M, 16)
+    rec, idx = ref["rec"], ref["rec_idx"]
+    sub = rows[idx]
+    assert rel(rec[:, 9:15], sub[:, 0:6]) < 1e-9 and rel(rec[:, 15:21], sub[:, 6:12]) < 1e-9  # spec 1e-6
+    scale = np.abs(rec[:, 9:21]).max()
+    assert np.max(np.abs(rec[:, 9:21] - sub[:, 0:12])) < 1e-9 * scale  # element-wise, not only in norm
+    assert rel(rec[:, 0], sub[:, 12]) < 1e-10 and rel(rec[:, 1:3], sub[:, 13:15]) < 1e-10
+    assert rel(ref["rec_jsum"], rows[:, 0:12].sum(0)) < 1e-9  # checksum over EVERY measurement
+    # with the production threshold the rows of measurements on inactive pixels are zero (model.cpp:409-412)
+    eng.form_normal_eq(THRES, 0, 1.0, ALPHA)
+    rows5 = eng.get_jacobian_rows()
+    num = ref["num_ev_map"].reshape(-1)
+    px = np.round(rec[:, 3]).astype(np.int64) + sc.pano_w * np.round(rec[:, 4]).astype(np.int64)
+    act = num[px] >= THRES
+    assert np.all(rows5[idx][~act, 0:12] == 0.0) and rel(rec[act, 9:21], rows5[idx][act, 0:12]) < 1e-9
+
+
+def test_seam_column_aliases_like_the_reference():
+    """A warped event that rounds to column pano_w is counted in element (y + 1, 0) -- the linear index the
+    reference's release build addresses (model.cpp:213-227): the seam fixture holds such events and the compiled
+    reference's histogram shows them in column 0."""
+    from conftest import GoldenScene, load_golden_ref
+
+    sc, ref = GoldenScene("seam"), load_golden_ref("seam")
+    rec = ref["rec"]
+    at_w = np.round(rec[:, 3]).astype(np.int64) == sc.pano_w
+    assert at_w.sum() > 50
+    eng = _engine(sc)
+    t0, dt = _base(sc)
+    eng.set_state(0, t0, dt, sc.quat_init, sc.Gx_init, sc.Gy_init)
+    cd, cr, M = eng.evaluate(0, 0, 1.0, ALPHA)
+    _, num = eng.get_evaluation(0, None, False, True)
+    assert M == ref["ep"].size and np.array_equal(num, ref["num_ev_map"])
+    rows = np.round(rec[at_w, 4]).astype(np.int64) + 1
+    assert np.all(num[rows, 0] > 0)
+    # the full LM run crosses the seam at every iteration and still follows the reference
+    log, fcost = eng.solve_time_window(alpha=ALPHA, thres=THRES)
+    rlog = ref["lm_log"]
+    assert log.shape[0] == rlog.shape[0] and np.array_equal(log[:, 4], rlog[:, 4])
+    assert abs(fcost - float(ref["lm_final_cost"])) < 1e-7 * float(ref["lm_final_cost"])
+    eng.close()
+
+
 def test_error_codes_range_and_numeric(tiny):
-    """EMBA_E_RANGE where the reference would read the map out of bounds (a warped event rounds to column W: camera
-    looking at the panorama seam, model.cpp:209-213), EMBA_E_NUMERIC for a singular Schur complement (a control pose
-    no measurement touches; Eigen's LDLT would return garbage there)."""
+    """Past the LAST panorama element the reference reads and writes out of bounds (a warped event on the seam in
+    the last row, model.cpp:209-227): such pairs are dropped as outliers by default and reported as EMBA_E_RANGE in
+    strict mode, where a candidate step that causes it counts as a rejected LM step. A control pose no measurement
+    touches gives an exactly zero pivot, which Eigen's LDLT::solve turns into a zero solution component: so does
+    the device solve (EMBA_E_NUMERIC is kept for non-finite pivots)."""
     from emba_b200.capi import EmbaError
     from oracle import emba_oracle as O
 
     sc = tiny
     t0, dt = _base(sc)
     eng = _engine(sc)
-    # yaw by pi: the optical axis points at the seam phi = +-pi, half of the sensor lands within 0.5 px of column W
+    # pitch down by ~75 deg and yaw by pi: the view covers the bottom rows of the panorama at the seam, some events
+    # round to (pano_h - 1, pano_w) or beyond
+    th = np.deg2rad(75.0)
+    pitch = np.array([[np.sin(th / 2), 0.0, 0.0, np.cos(th / 2)]])
     half_turn = np.array([[0.0, 1.0, 0.0, 0.0]])  # xyzw: rotation by pi about y
-    q_seam = O.quat_normalize(O.quat_mul(np.repeat(half_turn, sc.n_poses, 0), sc.quat_init))
+    q_off = O.quat_mul(half_turn, pitch)
+    q_seam = O.quat_normalize(O.quat_mul(np.repeat(q_off, sc.n_poses, 0), sc.quat_init))
+    orc = _oracle(sc)
+    ep_o, num_o = orc.evaluate(q_seam, t0, dt, sc.Gx_init, sc.Gy_init, False)
+    n_drop = orc.cur.size - ep_o.size
     eng.set_state(0, t0, dt, q_seam, sc.Gx_init, sc.Gy_init)
-    with pytest.raises(EmbaError) as ei:
+    cd, cr, M = eng.evaluate(0, 0, 1.0, ALPHA)  # default: no failure, same inlier set as the oracle
+    _, num = eng.get_evaluation(0, None, False, True)
+    assert M == ep_o.size and np.array_equal(num, num_o) and n_drop > 0
+    orc.strict_range = True
+    strict_raises = False
+    try:
+        orc.evaluate(q_seam, t0, dt, sc.Gx_init, sc.Gy_init, False)
+    except ValueError:
+        strict_raises = True
+    eng.set_strict_range(True)
+    if strict_raises:
+        with pytest.raises(EmbaError) as ei:
+            eng.evaluate(0, 0, 1.0, ALPHA)
+        assert ei.value.code == -4
+    else:
         eng.evaluate(0, 0, 1.0, ALPHA)
-    assert ei.value.code == -4
-    # one more control pose than the events reach: its rows of A11 are zero
+    eng.set_strict_range(False)
+    # one more control pose than the events reach: its rows of A11 are zero -> zero pivot -> zero update of that pose
     q_ext = np.concatenate([sc.quat_init, sc.quat_init[-1:], sc.quat_init[-1:]], 0)
     eng.set_state(0, t0, dt, q_ext, sc.Gx_init, sc.Gy_init)
     eng.evaluate(0, 0, 1.0, ALPHA)
     eng.form_normal_eq(THRES, 0, 1.0, ALPHA)
-    A11, _, _, _, _, _ = eng.get_normal_eq(False)
+    A11, A12, A22, b1, b2, act = eng.get_normal_eq(True)
     assert np.all(A11[-3:, :] == 0.0)
-    with pytest.raises(EmbaError) as ei:
-        eng.solve(LAM, False, True)
-    assert ei.value.code == -6
+    x1, x2, _, _ = eng.solve(LAM, False, True)
+    dead = np.nonzero(np.diag(A11)[3:] == 0.0)[0]
+    live = np.nonzero(np.diag(A11)[3:] != 0.0)[0]
+    assert dead.size >= 3 and np.all(x1[dead] == 0.0) and np.isfinite(x1).all() and np.isfinite(x2).all()
+    # the non-degenerate part solves the reduced system exactly like the oracle's dense solve
+    k = live + 3
+    y1, y2 = orc.solve_normal_eq(A11[np.ix_(k, k)], A12[k], A22, b1[k], b2, LAM)
+    assert rel(y1, x1[live]) < 1e-7 and rel(y2, x2) < 1e-7
     # the handle stays usable
     eng.set_state(0, t0, dt, sc.quat_init, sc.Gx_init, sc.Gy_init)
     cd, cr, M = eng.evaluate(0, 0, 1.0, ALPHA)
     assert M > 0
+    eng.close()
+
+
+def test_event_sequence_on_device(tiny):
+    """"next" row N1: time sort (rosbag_loading.cpp:61-65), subsampling (emba.cpp:281-304), robust window extraction
+    (emba.cpp:473-510) on a device-resident recording, then the per-window pre-pass straight from it: identical to
+    the host-array path."""
+    from emba_b200.legm import EventSequence
+    from oracle import emba_oracle as O
+
+    sc = tiny
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(sc.t_ns.size)
+    seq = EventSequence(sc.x[perm], sc.y[perm], sc.t_ns[perm], sc.pol[perm])
+    seq.sort_by_time()
+    x, y, t, p = seq.download()
+    assert np.array_equal(t, np.sort(sc.t_ns))
+    # equal stamps may swap (std::sort is not stable either): compare as multisets of (t, x, y, pol)
+    key = lambda x_, y_, t_, p_: np.lexsort((p_, y_, x_, t_))
+    k0, k1 = key(sc.x, sc.y, sc.t_ns, sc.pol), key(x, y, t, p)
+    assert np.array_equal(sc.x[k0], x[k1]) and np.array_equal(sc.y[k0], y[k1]) and np.array_equal(sc.pol[k0], p[k1])
+    seq.close()
+    # subsampling and windows on the (already sorted) fixture
+    for rate in (1, 2, 3, 7):
+        s2 = EventSequence(sc.x, sc.y, sc.t_ns, sc.pol)
+        s2.sort_by_time()  # no-op: sorted
+        s2.subsample(rate)
+        keep = O.subsample_events(sc.t_ns.size, rate)
+        x, y, t, p = s2.download()
+        assert np.array_equal(t, sc.t_ns[keep]) and np.array_equal(x, sc.x[keep]) and np.array_equal(p, sc.pol[keep])
+        tk = sc.t_ns[keep]
+        lo, hi = int(tk[0]), int(tk[-1])
+        for tb, te in ((lo - 5_000_000, hi + 5_000_000), (lo + 37_000_000, lo + 200_000_000), (lo, lo + 3_000_000),
+                       (hi + 1_000_000_000, hi + 2_000_000_000), (lo - 2_000_000_000, lo - 1_000_000_000)):
+            assert s2.window(tb, te) == O.get_event_subset(tk, tb, te), (rate, tb, te)
+        s2.close()
+    # pre-pass from the device-resident sequence == pre-pass from host arrays
+    seq = EventSequence(sc.x, sc.y, sc.t_ns, sc.pol)
+    i0, i1 = seq.window(int(sc.t_ns[0]) - 2_000_000, int(sc.t_ns[-1]) + 2_000_000)
+    assert (i0, i1) == (0, sc.t_ns.size)
+    t0, dt = _base(sc)
+    outs = []
+    for mode in ("host", "dev"):
+        from emba_b200.legm import Engine
+
+        eng = Engine(sc.sensor_w, sc.sensor_h, sc.bearing_lut(), sc.C_th, sc.pano_w, sc.pano_h)
+        if mode == "host":
+            eng.set_events(sc.x, sc.y, sc.t_ns, sc.pol)
+        else:
+            eng.set_events_dev(seq, i0, i1)
+        eng.set_state(0, t0, dt, sc.quat_init, sc.Gx_init, sc.Gy_init)
+        cd, cr, M = eng.evaluate(0, 0, 1.0, ALPHA)
+        ep, num = eng.get_evaluation(0, M)
+        outs.append((cd, M, ep, num, eng.num_pairs()))
+        eng.close()
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    seq.close()
+
+
+def test_lm_callback_and_cg_log(tiny, tiny_ref):
+    """Per-iteration hook of the device LM loop (the point of solver.cpp:170-179) and the CG log (solver.cpp:198-201)."""
+    sc = tiny
+    eng = _engine(sc)
+    t0, dt = _base(sc)
+    eng.set_state(0, t0, dt, sc.quat_init, sc.Gx_init, sc.Gy_init)
+    seen = []
+    log, fc = eng.solve_time_window(alpha=ALPHA, thres=THRES, use_cg=True, callback=lambda r: seen.append(r) and False)
+    assert len(seen) == log.shape[0] and [r["iter"] for r in seen] == list(range(log.shape[0]))
+    assert np.all(log[:, 7] > 0) and np.all(log[:, 7] <= 100) and np.all(log[:, 8] < 1e-5)  # cg_iters, cg_error
+    assert int(log[0, 7]) == int(tiny_ref["cg_iters"])  # first solve = the golden CG solve (same lambda, same system)
+    assert np.all(log[:, 10] > 0) and np.all(log[:, 11] > 0)  # device ms of solve / evaluate
+    assert np.all((log[:, 9] > 0) == np.concatenate([[True], log[:-1, 4] == 1]))  # form only after an accepted step
+    # a truthy return stops the loop after that iteration
+    eng.set_state(0, t0, dt, sc.quat_init, sc.Gx_init, sc.Gy_init)
+    log2, _ = eng.solve_time_window(alpha=ALPHA, thres=THRES, callback=lambda r: r["iter"] >= 2)
+    assert log2.shape[0] == 3
     eng.close()
 
 
