@@ -65,18 +65,6 @@ __global__ void k_active_fill(const int32_t* __restrict__ flag, const int32_t* _
   }
 }
 
-// every inlier row on an active pixel goes to its slot of the pixel's segment
-__global__ void __launch_bounds__(256)
-k_place(int64_t Mc, const int32_t* __restrict__ pix, const int32_t* __restrict__ slot,
-        const int32_t* __restrict__ rowbase, uint32_t* __restrict__ sval) {
-  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= Mc) return;
-  const int32_t p = pix[m];
-  if (p < 0) return;
-  const int32_t base = rowbase[p];
-  if (base >= 0) sval[(int64_t)base + slot[m]] = (uint32_t)m;
-}
-
 // ---------------------------------------------------------------------------------------------------
 // Segment sort: ascending row ids inside every pixel's segment. "Normalised" bitonic network (every
 // compare-exchange puts the minimum at the lower index: first step of a merge of size k pairs i with i ^ (k-1), the
@@ -100,11 +88,18 @@ __device__ __forceinline__ void warp_bitonic(uint32_t (&a)[K], int lane) {
     } else {
       const int lm = k / K - 1;  // lane ^= lm, r -> K - 1 - r
       const bool lower = (lane & ((lm + 1) >> 1)) == 0;  // the top flipped lane bit decides who is the lower index
-      uint32_t t[K];
+      if (K == 1) {
+        const uint32_t o = __shfl_xor_sync(0xffffffffu, a[0], lm);
+        a[0] = lower ? min(a[0], o) : max(a[0], o);
+      } else {
 #pragma unroll
-      for (int r = 0; r < K; r++) t[r] = __shfl_xor_sync(0xffffffffu, a[K - 1 - r], lm);
-#pragma unroll
-      for (int r = 0; r < K; r++) a[r] = lower ? min(a[r], t[r]) : max(a[r], t[r]);
+        for (int r = 0; r < K / 2; r++) {  // my a[r] meets the partner's a[K-1-r] and vice versa
+          const uint32_t ox = __shfl_xor_sync(0xffffffffu, a[K - 1 - r], lm);
+          const uint32_t oy = __shfl_xor_sync(0xffffffffu, a[r], lm);
+          a[r] = lower ? min(a[r], ox) : max(a[r], ox);
+          a[K - 1 - r] = lower ? min(a[K - 1 - r], oy) : max(a[K - 1 - r], oy);
+        }
+      }
     }
 #pragma unroll
     for (int j = k >> 2; j >= 1; j >>= 1) {
@@ -163,10 +158,29 @@ k_seg_sort(int64_t Np, const int32_t* __restrict__ segoff, const int32_t* __rest
   }
 }
 
-// segments above kSegRegCap rows: one CTA each, network in shared memory (up to cap_smem ids) or, beyond that, in
-// place in global memory
-__global__ void __launch_bounds__(512)
+// segments of 1025 .. 4096 rows: still one warp each, 64 or 128 keys per lane in registers (a rare path: a few per
+// cent of the pixels; the register budget of this kernel does not burden k_seg_sort). Longer ones are left to k_seg_sort_huge.
+constexpr int kSegLongWarps = 2;
+constexpr int kSegLongCap = 4096;
+__global__ void __launch_bounds__(kSegLongWarps * 32)
 k_seg_sort_long(const int32_t* __restrict__ longlist, const int32_t* __restrict__ segoff,
+                const int32_t* __restrict__ segend, uint32_t* __restrict__ sval) {
+  const int lane = threadIdx.x & 31;
+  const int nlong = longlist[0];
+  const int nw = gridDim.x * kSegLongWarps;
+  for (int li = blockIdx.x * kSegLongWarps + (threadIdx.x >> 5); li < nlong; li += nw) {
+    const int a = longlist[1 + li];
+    const int s0 = segoff[a];
+    const int L = segend[a] - s0;
+    if (L <= 2048) seg_sort_regs<64>(sval + s0, L, lane);
+    else if (L <= kSegLongCap) seg_sort_regs<128>(sval + s0, L, lane);
+  }
+}
+
+// segments above 4096 rows (none in the benchmark workloads): one CTA each, network in shared memory (up to
+// cap_smem ids) or, beyond that, in place in global memory
+__global__ void __launch_bounds__(512)
+k_seg_sort_huge(const int32_t* __restrict__ longlist, const int32_t* __restrict__ segoff,
                 const int32_t* __restrict__ segend, uint32_t* __restrict__ sval, int cap_smem) {
   extern __shared__ uint32_t sbuf[];
   const int nlong = longlist[0];
@@ -174,6 +188,7 @@ k_seg_sort_long(const int32_t* __restrict__ longlist, const int32_t* __restrict_
     const int a = longlist[1 + li];
     const int s0 = segoff[a];
     const int L = segend[a] - s0;
+    if (L <= kSegLongCap) continue;
     uint32_t* seg = sval + s0;
     const bool in_smem = L <= cap_smem;
     uint32_t* d = in_smem ? sbuf : seg;
@@ -241,6 +256,7 @@ k_asm_pose(const __grid_constant__ CUtensorMap jmap, const WorkItem* __restrict_
            const MeasRec* __restrict__ rec, const double* __restrict__ Ktab, const double4* __restrict__ RotTab,
            const double4* __restrict__ JacTab, const double2* __restrict__ G2, const double4* __restrict__ H3,
            const double2* __restrict__ dp_in, const double* __restrict__ e_in, const int32_t* __restrict__ pix_in,
+           const int32_t* __restrict__ slot_in, const int32_t* __restrict__ segoff, uint32_t* __restrict__ sval,
            PanoCam cam, double eta, double* __restrict__ jrec, int2* __restrict__ win,
            double* __restrict__ acc_part) {
   __shared__ __align__(1024) double tile[kAsmThreads * kRecDoubles];  // [row][16], chunk-swizzled
@@ -298,6 +314,9 @@ k_asm_pose(const __grid_constant__ CUtensorMap jmap, const WorkItem* __restrict_
         a = (int32_t)__double_as_longlong(Hh.w);
       }
       if (a >= 0) {
+        // the row's place in its pixel's segment of the map side: segment start + the slot the evaluation's
+        // counting atomic handed out (one scattered 4-byte store, nothing waits for it)
+        if (sval) sval[(int64_t)segoff[a] + slot_in[m]] = (uint32_t)m;
         const double4 r0 = r0_n;
         const double bx = r0.x, by = r0.y, bz = r0.z;
         const unsigned long long rw = (unsigned long long)__double_as_longlong(r0.w);
@@ -818,20 +837,6 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   h->launches++;
   EMBA_CUDAC(cudaMemcpyAsync(h->h_pin, d_totals, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
   EMBA_CUDAC(cudaEventRecord(h->ev_host, h->stream));
-  // ---- 1b. side stream: rows -> pixel segments (k_place) and the per-segment ordering (k_seg_sort). They need only
-  // the evaluation and the segment offsets, so they run beside the pose-side kernel; the main stream joins them
-  // before the map-side kernel. The grid of k_seg_sort is sized for the worst case (every pixel active), warps past
-  // the real count find empty segments.
-  if (!atomic_path && h->Mc > 0) {
-    const int64_t Mc = h->Mc;
-    EMBA_CUDAC(cudaEventRecord(h->ev_fork, h->stream));
-    EMBA_CUDAC(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
-    EMBA_CUDAC(cudaEventRecord(h->ev_sort0, h->stream2));
-    EMBA_CUDAC(cudaMemsetAsync(h->d_longlist, 0, sizeof(int32_t), h->stream2));
-    k_place<<<ceil_div64(Mc, T), T, 0, h->stream2>>>(Mc, s.pix, s.slot, d_rowbase, h->d_sval);
-    h->launches++;
-    EMBA_CUDAC(cudaGetLastError());
-  }
   // ---- 2. pose side + Jacobian rows
   const int64_t Mc = h->Mc;
   const PanoCam cam = make_cam(h);
@@ -842,7 +847,8 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
 #define EMBA_ASM_LAUNCH(C)                                                                                         \
   k_asm_pose<C><<<h->n_items, kAsmThreads, 0, h->stream>>>(jmap, h->d_items, h->d_rec, s.Ktab, s.RotTab,          \
                                                            s.JacTab, s.G2,                                        \
-                                                           s.H3, s.dp, s.e, s.pix, cam, eta,                       \
+                                                           s.H3, s.dp, s.e, s.pix, s.slot, h->d_segoff,            \
+                                                           atomic_path ? nullptr : h->d_sval, cam, eta,            \
                                                            h->d_jrec,                                              \
                                                            h->d_win64, h->d_acc_part)
     if (cost_type == EMBA_COST_QUADRATIC) EMBA_ASM_LAUNCH(EMBA_COST_QUADRATIC);
@@ -857,20 +863,23 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   const int64_t Np = h->h_pin[0];
   h->Np = Np;
   h->Ma = h->h_pin[1];
-  if (!atomic_path && Mc > 0) {
-    if (Np > 0) {
-      const int sgrid = (int)std::max<int64_t>(1, std::min<int64_t>((Np + kSegWarps - 1) / kSegWarps, (int64_t)h->sm_count * 32));
-      k_seg_sort<<<sgrid, kSegWarps * 32, 0, h->stream2>>>(Np, h->d_segoff, h->d_segend, h->d_sval, h->d_longlist);
-      h->launches++;
-      const int long_smem = 160 * 1024;
-      EMBA_CUDAC(cudaFuncSetAttribute(k_seg_sort_long, cudaFuncAttributeMaxDynamicSharedMemorySize, long_smem));
-      k_seg_sort_long<<<h->sm_count, 512, long_smem, h->stream2>>>(h->d_longlist, h->d_segoff, h->d_segend, h->d_sval, long_smem / 4);
-      h->launches++;
-      EMBA_CUDAC(cudaGetLastError());
-    }
-    EMBA_CUDAC(cudaEventRecord(h->ev_sort1, h->stream2));
-    EMBA_CUDAC(cudaEventRecord(h->ev_join, h->stream2));
+  // ---- 2b. per-segment ordering of the row ids k_asm_pose has just placed (warp per pixel; the rare segments
+  // above 1024 rows go through the list k_seg_sort builds)
+  EMBA_CUDAC(cudaEventRecord(h->ev_sort0, h->stream));
+  if (!atomic_path && Mc > 0 && Np > 0) {
+    EMBA_CUDAC(cudaMemsetAsync(h->d_longlist, 0, sizeof(int32_t), h->stream));
+    const int sgrid = (int)std::max<int64_t>(1, std::min<int64_t>((Np + kSegWarps - 1) / kSegWarps, (int64_t)h->sm_count * 32));
+    k_seg_sort<<<sgrid, kSegWarps * 32, 0, h->stream>>>(Np, h->d_segoff, h->d_segend, h->d_sval, h->d_longlist);
+    h->launches++;
+    k_seg_sort_long<<<h->sm_count * 4, kSegLongWarps * 32, 0, h->stream>>>(h->d_longlist, h->d_segoff, h->d_segend, h->d_sval);
+    h->launches++;
+    const int huge_smem = 200 * 1024;
+    EMBA_CUDAC(cudaFuncSetAttribute(k_seg_sort_huge, cudaFuncAttributeMaxDynamicSharedMemorySize, huge_smem));
+    k_seg_sort_huge<<<h->sm_count, 512, huge_smem, h->stream>>>(h->d_longlist, h->d_segoff, h->d_segend, h->d_sval, huge_smem / 4);
+    h->launches++;
+    EMBA_CUDAC(cudaGetLastError());
   }
+  EMBA_CUDAC(cudaEventRecord(h->ev_sort1, h->stream));
   // ---- 3. map side: pose windows -> strip offsets. The strip total is read back while the A11 / b1 gather runs.
   EMBA_CUDAC(cudaMemsetAsync(d_len, 0, sizeof(int64_t) * (Np + 1), h->stream));
   if (Np) { k_strip_len<<<ceil_div64(Np, T), T, 0, h->stream>>>(h->d_win64, h->d_winlo, h->d_winhi, Np, d_len); h->launches++; }
@@ -919,8 +928,6 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
                                                           h->d_A22, h->d_b2);
       h->launches++;
     }
-  } else if (Mc > 0) {
-    EMBA_CUDAC(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
   }
   if (!atomic_path) EMBA_CUDAC(cudaEventRecord(h->ev[9], h->stream));
   int strip_cap_used = kStripCap;
@@ -1059,6 +1066,20 @@ int emba_get_normal_eq(emba_handle_t hh, double* A11, double* b1, double* A22, d
     cudaFree(tmp);
     if (e != cudaSuccess) { h->err = "emba_get_normal_eq: A12 copy failed"; return EMBA_E_CUDA; }
   }
+  return EMBA_OK;
+}
+
+int emba_get_counters(emba_handle_t hh, int64_t* out) {
+  Handle* h = (Handle*)hh;
+  if (!h || !out) return EMBA_E_ARG;
+  int32_t nlong = 0;
+  if (h->formed && h->map_path == EMBA_MAP_SORTED && h->Mc > 0 && h->Np > 0) {
+    cudaSetDevice(h->device);
+    cudaMemcpy(&nlong, h->d_longlist, sizeof(int32_t), cudaMemcpyDeviceToHost);
+  }
+  out[0] = h->Mc; out[1] = h->Mc_total; out[2] = h->formed ? h->Np : 0; out[3] = h->formed ? h->Ma : 0;
+  out[4] = h->formed ? h->strip_total * 6 : 0; out[5] = h->formed ? h->sv_strip_total * 6 : 0;
+  out[6] = h->n_items; out[7] = nlong;
   return EMBA_OK;
 }
 

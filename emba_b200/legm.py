@@ -213,6 +213,13 @@ class Engine:
         self._chk(self.L.emba_last_setup_ms(self.h, ptr(out)))
         return float(out[0]), float(out[1])
 
+    def counters(self):
+        out = np.zeros(8, dtype=np.int64)
+        self._chk(self.L.emba_get_counters(self.h, ptr(out, C.c_int64)))
+        return dict(measurements_rank=int(out[0]), pairs_window=int(out[1]), active_pixels=int(out[2]),
+                    rows_on_active_rank=int(out[3]), a12_entries_local=int(out[4]), a12_entries_solve=int(out[5]),
+                    work_items=int(out[6]), long_segments=int(out[7]))
+
     def set_strict_range(self, on):
         self._chk(self.L.emba_set_strict_range(self.h, int(bool(on))))
 

@@ -259,6 +259,12 @@ EMBA_API int emba_last_timings_ms(emba_handle_t h, double* out8);
 /* device time (ms) of the last window set-up: out[0] = emba_set_events / emba_set_events_dev (upload + pair links),
  * out[1] = the static rebuild the first emba_set_state of a window triggers (canonical order, work items) */
 EMBA_API int emba_last_setup_ms(emba_handle_t h, double* out2);
+/* sizes of the last assembly on this handle (this rank): out[0] = measurements (pairs) of this rank's time slice,
+ * out[1] = pairs of the whole window, out[2] = active pixels, out[3] = this rank's rows on active pixels,
+ * out[4] = A12 entries this rank's own rows produced (local strips), out[5] = A12 entries it holds for the solve
+ * (== out[4] with one GPU; with several, the merged strips of the pixels it owns), out[6] = work items,
+ * out[7] = pixel segments longer than the warp sort's 1024 rows */
+EMBA_API int emba_get_counters(emba_handle_t h, int64_t* out8);
 /* number of kernel launches issued by this handle so far */
 EMBA_API int emba_launch_count(emba_handle_t h, int64_t* out);
 EMBA_API int emba_synchronize(emba_handle_t h);
