@@ -92,6 +92,21 @@ SIGNATURES = {
     "emba_events_download": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_uint16), C.POINTER(C.c_uint16),
                                        C.POINTER(C.c_int64), C.POINTER(C.c_uint8)]),
     "emba_set_events_dev": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_int64]),
+    "emba_ext_create": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]),
+    "emba_ext_destroy": (C.c_int, [C.c_void_p]),
+    "emba_ext_num_pairs": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "emba_ext_set_state": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, _dp, _dp, _dp]),
+    "emba_ext_get_state": (C.c_int, [C.c_void_p, _dp, _dp, _dp]),
+    "emba_ext_evaluate": (C.c_int, [C.c_void_p, C.c_double, _dp, _dp, C.POINTER(C.c_int64)]),
+    "emba_ext_form": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "emba_ext_get_rows": (C.c_int, [C.c_void_p, C.c_int64, _dp, _dp, _dp, _dp, _dp, C.POINTER(C.c_int32),
+                                    C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                    C.POINTER(C.c_int64)]),
+    "emba_ext_get_normal_eq": (C.c_int, [C.c_void_p, _dp, _dp, _dp, C.POINTER(C.c_int32)]),
+    "emba_ext_matvec": (C.c_int, [C.c_void_p, C.c_double, C.c_double, _dp, _dp]),
+    "emba_ext_solve": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int32, C.c_double, _dp, C.POINTER(C.c_int32), _dp]),
+    "emba_ext_apply": (C.c_int, [C.c_void_p, C.c_double]),
+    "emba_ext_last_ms": (C.c_int, [C.c_void_p, _dp]),
     "emba_fit_control_poses": (C.c_int, [C.c_int32, C.c_int64, C.POINTER(C.c_int64), _dp, C.c_int64, C.c_int64,
                                          C.c_double, _dp, C.c_int32, C.POINTER(C.c_int32)]),
     "emba_poisson_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),

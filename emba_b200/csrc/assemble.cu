@@ -18,13 +18,18 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include "emba_internal.cuh"
 
 namespace emba {
 
 PanoCam make_cam(const Handle* h);
 int comm_allreduce(Handle* h, void* buf, int64_t count, int dtype);
-int comm_exchange_strips(Handle* h);
+int comm_exchange_prepare(Handle* h);
+int comm_exchange_sizes(Handle* h);
+int comm_exchange_step(Handle* h, int step, cudaStream_t st);
+int comm_exchange_finish(Handle* h);
 
 // ---------------------------------------------------------------------------------------------------
 // flag = pixel active (global count >= thres, model.cpp:333); segcnt = this rank's rows on it if active, else 0
@@ -63,6 +68,19 @@ __global__ void k_active_fill(const int32_t* __restrict__ flag, const int32_t* _
     amap[p] = -1;
     rowbase[p] = -1;
   }
+}
+
+// every inlier row on an active pixel goes to its slot of the pixel's segment (a separate pass: fused into the
+// pose-side kernel the scattered 4-byte stores cost that HBM-bound kernel 2.8 ms on C4, alone they take 1.7 ms)
+__global__ void __launch_bounds__(256)
+k_place(int64_t Mc, const int32_t* __restrict__ pix, const int32_t* __restrict__ slot,
+        const int32_t* __restrict__ rowbase, uint32_t* __restrict__ sval) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= Mc) return;
+  const int32_t p = pix[m];
+  if (p < 0) return;
+  const int32_t base = rowbase[p];
+  if (base >= 0) sval[(int64_t)base + slot[m]] = (uint32_t)m;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -122,6 +140,9 @@ __device__ __forceinline__ void warp_bitonic(uint32_t (&a)[K], int lane) {
   }
 }
 
+// (An adaptive front end -- a few odd-even transposition passes while the segment is unsorted -- was measured and
+// dropped: rows reach their segment through atomics of ~300 k measurements in flight, and not one C4 segment in 350 k
+// was sorted after 6 passes.)
 template <int K>
 __device__ __forceinline__ void seg_sort_regs(uint32_t* __restrict__ seg, int L, int lane) {
   uint32_t a[K];
@@ -139,9 +160,10 @@ __device__ __forceinline__ void seg_sort_regs(uint32_t* __restrict__ seg, int L,
 }
 
 __global__ void __launch_bounds__(kSegWarps * 32)
-k_seg_sort(int64_t Np, const int32_t* __restrict__ segoff, const int32_t* __restrict__ segend,
+k_seg_sort(const int64_t* __restrict__ np_dev, const int32_t* __restrict__ segoff, const int32_t* __restrict__ segend,
            uint32_t* __restrict__ sval, int32_t* __restrict__ longlist) {
   const int lane = threadIdx.x & 31;
+  const int64_t Np = np_dev[0];  // the active-pixel count is still on its way to the host when this is enqueued
   const int64_t nw = (int64_t)gridDim.x * kSegWarps;
   for (int64_t a = (int64_t)blockIdx.x * kSegWarps + (threadIdx.x >> 5); a < Np; a += nw) {
     const int s0 = segoff[a];
@@ -256,7 +278,6 @@ k_asm_pose(const __grid_constant__ CUtensorMap jmap, const WorkItem* __restrict_
            const MeasRec* __restrict__ rec, const double* __restrict__ Ktab, const double4* __restrict__ RotTab,
            const double4* __restrict__ JacTab, const double2* __restrict__ G2, const double4* __restrict__ H3,
            const double2* __restrict__ dp_in, const double* __restrict__ e_in, const int32_t* __restrict__ pix_in,
-           const int32_t* __restrict__ slot_in, const int32_t* __restrict__ segoff, uint32_t* __restrict__ sval,
            PanoCam cam, double eta, double* __restrict__ jrec, int2* __restrict__ win,
            double* __restrict__ acc_part) {
   __shared__ __align__(1024) double tile[kAsmThreads * kRecDoubles];  // [row][16], chunk-swizzled
@@ -314,9 +335,6 @@ k_asm_pose(const __grid_constant__ CUtensorMap jmap, const WorkItem* __restrict_
         a = (int32_t)__double_as_longlong(Hh.w);
       }
       if (a >= 0) {
-        // the row's place in its pixel's segment of the map side: segment start + the slot the evaluation's
-        // counting atomic handed out (one scattered 4-byte store, nothing waits for it)
-        if (sval) sval[(int64_t)segoff[a] + slot_in[m]] = (uint32_t)m;
         const double4 r0 = r0_n;
         const double bx = r0.x, by = r0.y, bz = r0.z;
         const unsigned long long rw = (unsigned long long)__double_as_longlong(r0.w);
@@ -662,7 +680,7 @@ __device__ __forceinline__ void pix_one(int64_t seg0, int64_t seg1, int qlo, int
 }
 
 __global__ void __launch_bounds__(kPixWarps * 32)
-k_pix(int64_t Np, const int32_t* __restrict__ segoff, const int32_t* __restrict__ segend,
+k_pix(int64_t a_begin, int64_t a_end, const int32_t* __restrict__ segoff, const int32_t* __restrict__ segend,
       const uint32_t* __restrict__ sval,
       const double* __restrict__ jrec, const int32_t* __restrict__ winlo, const int32_t* __restrict__ winhi,
       const int64_t* __restrict__ stripoff, double* __restrict__ strip, const int32_t* __restrict__ apix,
@@ -683,7 +701,7 @@ k_pix(int64_t Np, const int32_t* __restrict__ segoff, const int32_t* __restrict_
   else if (lane == 26) { ia = 14; ib = 14; }
   else if (lane == 27) { ia = 13; ib = 12; }
   else if (lane == 28) { ia = 14; ib = 12; }
-  for (int64_t a = (int64_t)blockIdx.x * kPixWarps + warp; a < Np; a += nw) {
+  for (int64_t a = a_begin + (int64_t)blockIdx.x * kPixWarps + warp; a < a_end; a += nw) {
     const int64_t seg0 = segoff[a];
     const int64_t seg1 = segend[a];
     const int qlo = winlo[a];
@@ -837,6 +855,26 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   h->launches++;
   EMBA_CUDAC(cudaMemcpyAsync(h->h_pin, d_totals, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
   EMBA_CUDAC(cudaEventRecord(h->ev_host, h->stream));
+  // ---- 1b. side stream: rows -> pixel segments (k_place) and the per-segment ordering (k_seg_sort*). They need only
+  // the evaluation and the segment offsets; they are submitted before the pose-side kernel and the main stream joins
+  // them before the map-side kernel.
+  if (!atomic_path && h->Mc > 0) {
+    const int64_t Mc = h->Mc;
+    EMBA_CUDAC(cudaEventRecord(h->ev_fork, h->stream));
+    EMBA_CUDAC(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+    EMBA_CUDAC(cudaEventRecord(h->ev_sort0, h->stream2));
+    EMBA_CUDAC(cudaMemsetAsync(h->d_longlist, 0, sizeof(int32_t), h->stream2));
+    k_place<<<ceil_div64(Mc, T), T, 0, h->stream2>>>(Mc, s.pix, s.slot, d_rowbase, h->d_sval);
+    k_seg_sort<<<h->sm_count * 32, kSegWarps * 32, 0, h->stream2>>>(d_totals, h->d_segoff, h->d_segend, h->d_sval, h->d_longlist);
+    k_seg_sort_long<<<h->sm_count * 16, kSegLongWarps * 32, 0, h->stream2>>>(h->d_longlist, h->d_segoff, h->d_segend, h->d_sval);
+    const int huge_smem = 200 * 1024;
+    EMBA_CUDAC(cudaFuncSetAttribute(k_seg_sort_huge, cudaFuncAttributeMaxDynamicSharedMemorySize, huge_smem));
+    k_seg_sort_huge<<<h->sm_count, 512, huge_smem, h->stream2>>>(h->d_longlist, h->d_segoff, h->d_segend, h->d_sval, huge_smem / 4);
+    h->launches += 4;
+    EMBA_CUDAC(cudaGetLastError());
+    EMBA_CUDAC(cudaEventRecord(h->ev_sort1, h->stream2));
+    EMBA_CUDAC(cudaEventRecord(h->ev_join, h->stream2));
+  }
   // ---- 2. pose side + Jacobian rows
   const int64_t Mc = h->Mc;
   const PanoCam cam = make_cam(h);
@@ -847,8 +885,7 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
 #define EMBA_ASM_LAUNCH(C)                                                                                         \
   k_asm_pose<C><<<h->n_items, kAsmThreads, 0, h->stream>>>(jmap, h->d_items, h->d_rec, s.Ktab, s.RotTab,          \
                                                            s.JacTab, s.G2,                                        \
-                                                           s.H3, s.dp, s.e, s.pix, s.slot, h->d_segoff,            \
-                                                           atomic_path ? nullptr : h->d_sval, cam, eta,            \
+                                                           s.H3, s.dp, s.e, s.pix, cam, eta,                       \
                                                            h->d_jrec,                                              \
                                                            h->d_win64, h->d_acc_part)
     if (cost_type == EMBA_COST_QUADRATIC) EMBA_ASM_LAUNCH(EMBA_COST_QUADRATIC);
@@ -863,23 +900,6 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   const int64_t Np = h->h_pin[0];
   h->Np = Np;
   h->Ma = h->h_pin[1];
-  // ---- 2b. per-segment ordering of the row ids k_asm_pose has just placed (warp per pixel; the rare segments
-  // above 1024 rows go through the list k_seg_sort builds)
-  EMBA_CUDAC(cudaEventRecord(h->ev_sort0, h->stream));
-  if (!atomic_path && Mc > 0 && Np > 0) {
-    EMBA_CUDAC(cudaMemsetAsync(h->d_longlist, 0, sizeof(int32_t), h->stream));
-    const int sgrid = (int)std::max<int64_t>(1, std::min<int64_t>((Np + kSegWarps - 1) / kSegWarps, (int64_t)h->sm_count * 32));
-    k_seg_sort<<<sgrid, kSegWarps * 32, 0, h->stream>>>(Np, h->d_segoff, h->d_segend, h->d_sval, h->d_longlist);
-    h->launches++;
-    k_seg_sort_long<<<h->sm_count * 4, kSegLongWarps * 32, 0, h->stream>>>(h->d_longlist, h->d_segoff, h->d_segend, h->d_sval);
-    h->launches++;
-    const int huge_smem = 200 * 1024;
-    EMBA_CUDAC(cudaFuncSetAttribute(k_seg_sort_huge, cudaFuncAttributeMaxDynamicSharedMemorySize, huge_smem));
-    k_seg_sort_huge<<<h->sm_count, 512, huge_smem, h->stream>>>(h->d_longlist, h->d_segoff, h->d_segend, h->d_sval, huge_smem / 4);
-    h->launches++;
-    EMBA_CUDAC(cudaGetLastError());
-  }
-  EMBA_CUDAC(cudaEventRecord(h->ev_sort1, h->stream));
   // ---- 3. map side: pose windows -> strip offsets. The strip total is read back while the A11 / b1 gather runs.
   EMBA_CUDAC(cudaMemsetAsync(d_len, 0, sizeof(int64_t) * (Np + 1), h->stream));
   if (Np) { k_strip_len<<<ceil_div64(Np, T), T, 0, h->stream>>>(h->d_win64, h->d_winlo, h->d_winhi, Np, d_len); h->launches++; }
@@ -906,9 +926,18 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   // rank subtracts its Schur contributions from its OWN partial and one all-reduce in the solve combines both
   // (saves a 72 n^2-byte all-reduce per assembly); emba_get_normal_eq combines them on demand.
   h->a11_partial = h->world > 1;
+  // several GPUs: the pose windows are final now -- exchange them and size the strip transfers BEFORE the map-side
+  // kernel, so that the transfers can overlap it (the host reads those numbers with the same synchronisation as
+  // the strip total)
+  const bool exchange = h->world > 1 && Np > 0 && !atomic_path;
+  if (exchange) {
+    EMBA_TRYC(comm_exchange_prepare(h));
+    EMBA_CUDAC(cudaEventRecord(h->ev_host, h->stream));
+  }
   EMBA_CUDAC(cudaEventSynchronize(h->ev_host));
   const int64_t tot = h->h_pin[2];
   h->strip_total = tot;
+  if (exchange) EMBA_TRYC(comm_exchange_sizes(h));
   EMBA_TRYC(dev_reserve(h, &h->d_strip, &h->strip_cap, tot * 6 + tot * 3));  // +50 %: windows drift between iterations
   EMBA_CUDAC(cudaEventRecord(h->ev[8], h->stream));
   if (atomic_path) {
@@ -929,6 +958,7 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
       h->launches++;
     }
   }
+  if (!atomic_path && Mc > 0) EMBA_CUDAC(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
   if (!atomic_path) EMBA_CUDAC(cudaEventRecord(h->ev[9], h->stream));
   int strip_cap_used = kStripCap;
   if (Np > 0 && !atomic_path) {
@@ -941,12 +971,33 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
     const int pix_smem = kPixWarps * (kPixStages * kPixTile * kRecDoubles + strip_cap * 6) * 8;
     EMBA_CUDAC(cudaFuncSetAttribute(k_pix, cudaFuncAttributeMaxDynamicSharedMemorySize, pix_smem));
     const int ctas_per_sm = std::max(1, std::min(4, (227 * 1024) / (pix_smem + 1024)));
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((Np + kPixWarps - 1) / kPixWarps, (int64_t)h->sm_count * 4 * ctas_per_sm));
-    k_pix<<<grid, kPixWarps * 32, pix_smem, h->stream>>>(Np, h->d_segoff, h->d_segend, vs, h->d_jrec, h->d_winlo, h->d_winhi,
-                                                  h->d_stripoff, h->d_strip, h->d_apix, s.Gx, s.Gy,
-                                                  h->rank == 0 ? alpha : 0.0, h->d_A22, h->d_b2, h->pose_group, h->d_gmask, strip_cap);
-    h->launches++;
-    EMBA_CUDAC(cudaGetLastError());
+    auto launch_pix = [&](int64_t a_begin, int64_t a_end) -> int {
+      if (a_end <= a_begin) return EMBA_OK;
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((a_end - a_begin + kPixWarps - 1) / kPixWarps, (int64_t)h->sm_count * 4 * ctas_per_sm));
+      k_pix<<<grid, kPixWarps * 32, pix_smem, h->stream>>>(a_begin, a_end, h->d_segoff, h->d_segend, vs, h->d_jrec, h->d_winlo, h->d_winhi,
+                                                    h->d_stripoff, h->d_strip, h->d_apix, s.Gx, s.Gy,
+                                                    h->rank == 0 ? alpha : 0.0, h->d_A22, h->d_b2, h->pose_group, h->d_gmask, strip_cap);
+      h->launches++;
+      EMBA_CUDAC(cudaGetLastError());
+      return EMBA_OK;
+    };
+    if (!exchange || h->world > 64) {
+      EMBA_TRYC(launch_pix(0, Np));
+    } else {
+      // one launch per owner's pixel range, in ring order: the strips of rank r+1's pixels first -- they leave on the
+      // communication stream while the next range is being reduced -- my own range last
+      const int W = h->world, r = h->rank;
+      for (int st = 1; st <= W; st++) {
+        const int q = (r + st) % W;
+        EMBA_TRYC(launch_pix(Np * q / W, Np * (q + 1) / W));
+        if (st < W) {
+          EMBA_CUDAC(cudaEventRecord(h->ev_chunk[st], h->stream));
+          EMBA_CUDAC(cudaStreamWaitEvent(h->stream3, h->ev_chunk[st], 0));
+          EMBA_TRYC(comm_exchange_step(h, st, h->stream3));
+        }
+      }
+      EMBA_CUDAC(cudaEventRecord(h->ev_comm, h->stream3));
+    }
   }
   EMBA_CUDAC(cudaEventRecord(h->ev[10], h->stream));
   EMBA_CUDAC(cudaStreamWaitEvent(h->stream, h->ev_join2, 0));
@@ -958,7 +1009,17 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
     // A22 / b2 are small: all-reduce. A12: every rank's strips cover (almost) disjoint pose ranges, so they are not
     // summed everywhere; each rank becomes the owner of a contiguous range of pixels and receives only the
     // sub-strips of those pixels (1/world of the volume), see comm.cu
-    EMBA_TRYC(comm_exchange_strips(h));  // (the A22 / b2 all-reduces are grouped with its window all-gather)
+    if (!exchange) {  // fp64-atomic map path: nothing was overlapped, run the exchange back to back
+      EMBA_TRYC(comm_exchange_prepare(h));
+      EMBA_CUDAC(cudaStreamSynchronize(h->stream));
+      EMBA_TRYC(comm_exchange_sizes(h));
+    }
+    if (!exchange || h->world > 64) {
+      for (int st = 1; st < h->world; st++) EMBA_TRYC(comm_exchange_step(h, st, h->stream));
+    } else {
+      EMBA_CUDAC(cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
+    }
+    EMBA_TRYC(comm_exchange_finish(h));
   }
   EMBA_CUDAC(cudaEventRecord(h->ev[7], h->stream));
   EMBA_CUDAC(cudaStreamSynchronize(h->stream));

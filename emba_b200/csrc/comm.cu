@@ -217,17 +217,22 @@ __global__ void k_gather_meta(int W, int64_t Np, int64_t n_own, const int64_t* _
   if (t == 0) meta[2 * W + 1] = gstripoff[Np];
 }
 
-int comm_exchange_strips(Handle* h) {
+// The exchange in three parts, so that the transfers overlap the map-side kernel (assemble.cu):
+//   comm_exchange_prepare : (before k_pix; the pose windows are final once k_asm_pose is done) window all-gather,
+//                           sub-strip lengths / offsets / merged windows, the few numbers the host needs
+//   comm_exchange_step    : step s of a ring-shift all-to-all on the communication stream: my chunk for rank r+s
+//                           leaves as soon as k_pix has finished that owner's pixel range, the chunk of rank r-s
+//                           for me arrives
+//   comm_exchange_finish  : A22 / b2 all-reduce, deterministic merge of the received sub-strips
+int comm_exchange_prepare(Handle* h) {
   NcclApi* api = nccl_api();
   if (!api || !h->nccl_comm) { h->err = "multi-GPU shard without a communicator: call emba_comm_init"; return EMBA_E_NCCL; }
   const int W = h->world, r = h->rank;
   const int64_t Np = h->Np;
   const int T = 256;
-  static const bool dbg = getenv("EMBA_DEBUG_TIMING") != nullptr;
-  cudaEvent_t de[5];
-  if (dbg) { for (auto& e : de) cudaEventCreate(&e); cudaEventRecord(de[0], h->stream); }
   auto own0 = [&](int q) { return Np * q / W; };
   const int64_t a0 = own0(r), n_own = own0(r + 1) - a0;
+  if (2 * W + 2 > 900) { h->err = "world size too large"; return EMBA_E_SUPPORT; }
   EMBA_TRY(dev_reserve(h, &h->d_win_all, &h->win_all_cap, (int64_t)W * Np * 2 + 2 * Np));
   EMBA_TRY(dev_reserve(h, &h->d_own_len, &h->own_cap, (int64_t)2 * W * (n_own + 1) + 8 * W + 32));
   if (!h->d_win2) {
@@ -235,68 +240,82 @@ int comm_exchange_strips(Handle* h) {
     EMBA_TRY(dev_alloc(h, &h->d_gwinlo, h->P + 1));
     EMBA_TRY(dev_alloc(h, &h->d_gwinhi, h->P + 1));
     EMBA_TRY(dev_alloc(h, &h->d_gstripoff, h->P + 2));
+    EMBA_TRY(dev_alloc(h, &h->d_glen, h->P + 2));
   }
   int64_t* own_len = h->d_own_len;
   int64_t* own_off = own_len + (size_t)W * (n_own + 1);
-  int64_t* recvbase_dev = own_off + (size_t)W * (n_own + 1);
+  int64_t* meta_dev = own_off + (size_t)W * (n_own + 1) + (W + 1);
   k_pack_win<<<ceil_div64(Np, T), T, 0, h->stream>>>(Np, h->d_winlo, h->d_winhi, h->d_win2);
   EMBA_LAUNCH_CHECK();
-  // one NCCL group (= one launch): the small A22 / b2 all-reduces ride with the window all-gather
-  // (ncclInt32 = 2, ncclFloat64 = 8, ncclSum = 0)
-  if (api->group_start() != 0) { h->err = "ncclGroupStart failed"; return EMBA_E_NCCL; }
-  int rc = api->allreduce(h->d_A22, h->d_A22, (size_t)(3 * Np), 8, 0, h->nccl_comm, h->stream);
-  rc |= api->allreduce(h->d_b2, h->d_b2, (size_t)(2 * Np), 8, 0, h->nccl_comm, h->stream);
-  rc |= api->allgather(h->d_win2, h->d_win_all, (size_t)Np * 2, 2, h->nccl_comm, h->stream);
-  if (api->group_end() != 0 || rc != 0) { h->err = "ncclAllReduce/ncclAllGather (A22, b2, windows) failed"; return EMBA_E_NCCL; }
+  // ncclInt32 = 2
+  if (api->allgather(h->d_win2, h->d_win_all, (size_t)Np * 2, 2, h->nccl_comm, h->stream) != 0) {
+    h->err = "ncclAllGather (pose windows) failed"; return EMBA_E_NCCL;
+  }
   h->launches++;
   k_own_len<<<ceil_div64(Np + 1, T), T, 0, h->stream>>>(W, Np, a0, n_own, h->d_win_all, own_len, h->d_gwinlo,
-                                                        h->d_gwinhi, h->d_len);
+                                                        h->d_gwinhi, h->d_glen);
   EMBA_LAUNCH_CHECK();
   k_zero_tail<<<1, 64, 0, h->stream>>>(W, n_own, own_len);
   EMBA_LAUNCH_CHECK();
-  // scans: per source rank over my pixels; merged strip offsets over all pixels
-  auto scan64 = [&](const int64_t* in, int64_t* out, int64_t count) -> int {
-    return scan_exclusive<int64_t>(h, h->stream, in, out, count, h->d_scan_tmp);
-  };
   // ONE scan over the flattened [source][pixel] lengths (each source's tail entry is 0): own_off[s][i] is then the
   // offset of pixel i's sub-strip from source s in the receive buffer, chunk base included
-  EMBA_TRY(scan64(own_len, own_off, (int64_t)W * (n_own + 1)));
-  EMBA_TRY(scan64(h->d_len, h->d_gstripoff, Np + 1));
-  if (dbg) cudaEventRecord(de[1], h->stream);
-  // host needs: recv counts (W), my local strip offsets at the ownership boundaries (W+1), merged total (1)
-  // gathered on the device and read back with ONE copy into pinned memory
-  std::vector<int64_t> recv_cnt(W), send_off(W + 1), recvbase(W + 1);
-  int64_t gtot = 0;
-  if (2 * W + 2 > 1000) { h->err = "world size too large"; return EMBA_E_SUPPORT; }
-  int64_t* meta_dev = recvbase_dev + (W + 1);
+  EMBA_TRY(scan_exclusive<int64_t>(h, h->stream, own_len, own_off, (int64_t)W * (n_own + 1), h->d_scan_tmp));
+  EMBA_TRY(scan_exclusive<int64_t>(h, h->stream, h->d_glen, h->d_gstripoff, Np + 1, h->d_scan_tmp));
+  // host needs: recv counts (W), my local strip offsets at the ownership boundaries (W+1), merged total (1):
+  // gathered on the device, read back with ONE copy into pinned memory (the caller synchronises)
   k_gather_meta<<<1, 64, 0, h->stream>>>(W, Np, n_own, own_off, h->d_stripoff, h->d_gstripoff, meta_dev);
   EMBA_LAUNCH_CHECK();
-  int64_t* meta = h->h_pin + 16;
-  EMBA_CUDA(cudaMemcpyAsync(meta, meta_dev, sizeof(int64_t) * (2 * W + 2), cudaMemcpyDeviceToHost, h->stream));
-  EMBA_CUDA(cudaStreamSynchronize(h->stream));
-  for (int s = 0; s < W; s++) recv_cnt[s] = meta[s];
-  for (int q = 0; q <= W; q++) send_off[q] = meta[W + q];
-  gtot = meta[2 * W + 1];
-  recvbase[0] = 0;
-  for (int s = 0; s < W; s++) recvbase[s + 1] = recvbase[s] + recv_cnt[s];
-  EMBA_TRY(dev_reserve(h, &h->d_recv, &h->recv_cap, recvbase[W] * 6 + recvbase[W] * 3));
-  EMBA_TRY(dev_reserve(h, &h->d_gstrip, &h->gstrip_cap, gtot * 6 + gtot * 3));
-  if (dbg) cudaEventRecord(de[2], h->stream);
-  // all-to-all of contiguous chunks (ncclFloat64 = 8)
+  EMBA_CUDA(cudaMemcpyAsync(h->h_pin + 32, meta_dev, sizeof(int64_t) * (2 * W + 2), cudaMemcpyDeviceToHost, h->stream));
+  return EMBA_OK;
+}
+
+// after the caller's synchronisation: sizes the receive / merged buffers
+int comm_exchange_sizes(Handle* h) {
+  const int W = h->world;
+  const int64_t* meta = h->h_pin + 32;
+  h->x_recv_cnt.assign(meta, meta + W);
+  h->x_send_off.assign(meta + W, meta + 2 * W + 1);
+  h->x_gtot = meta[2 * W + 1];
+  h->x_recvbase.assign(W + 1, 0);
+  for (int s = 0; s < W; s++) h->x_recvbase[s + 1] = h->x_recvbase[s] + h->x_recv_cnt[s];
+  EMBA_TRY(dev_reserve(h, &h->d_recv, &h->recv_cap, h->x_recvbase[W] * 6 + h->x_recvbase[W] * 3));
+  EMBA_TRY(dev_reserve(h, &h->d_gstrip, &h->gstrip_cap, h->x_gtot * 6 + h->x_gtot * 3));
+  return EMBA_OK;
+}
+
+// step s = 1 .. W-1 on stream st: send my sub-strips of rank (r + s)'s pixels, receive rank (r - s)'s for mine
+int comm_exchange_step(Handle* h, int step, cudaStream_t st) {
+  NcclApi* api = nccl_api();
+  const int W = h->world, r = h->rank;
+  const int to = (r + step) % W, from = (r - step + W) % W;
+  const int64_t scount = (h->x_send_off[to + 1] - h->x_send_off[to]) * 6;
+  const int64_t rcount = h->x_recv_cnt[from] * 6;
   if (api->group_start() != 0) { h->err = "ncclGroupStart failed"; return EMBA_E_NCCL; }
-  for (int q = 0; q < W; q++) {
-    if (q == r) continue;
-    const int64_t scount = (send_off[q + 1] - send_off[q]) * 6;
-    const int64_t rcount = recv_cnt[q] * 6;
-    if (scount > 0) rc |= api->send(h->d_strip + send_off[q] * 6, (size_t)scount, 8, q, h->nccl_comm, h->stream);
-    if (rcount > 0) rc |= api->recv(h->d_recv + recvbase[q] * 6, (size_t)rcount, 8, q, h->nccl_comm, h->stream);
-  }
+  int rc = 0;  // ncclFloat64 = 8
+  if (scount > 0) rc |= api->send(h->d_strip + h->x_send_off[to] * 6, (size_t)scount, 8, to, h->nccl_comm, st);
+  if (rcount > 0) rc |= api->recv(h->d_recv + h->x_recvbase[from] * 6, (size_t)rcount, 8, from, h->nccl_comm, st);
   if (api->group_end() != 0 || rc != 0) { h->err = "ncclSend/ncclRecv failed"; return EMBA_E_NCCL; }
   h->launches++;
-  if (recv_cnt[r] > 0)
-    EMBA_CUDA(cudaMemcpyAsync(h->d_recv + recvbase[r] * 6, h->d_strip + send_off[r] * 6, sizeof(double) * recv_cnt[r] * 6,
-                              cudaMemcpyDeviceToDevice, h->stream));
-  if (dbg) cudaEventRecord(de[3], h->stream);
+  return EMBA_OK;
+}
+
+int comm_exchange_finish(Handle* h) {
+  NcclApi* api = nccl_api();
+  const int W = h->world, r = h->rank;
+  const int64_t Np = h->Np;
+  const int T = 256;
+  const int64_t a0 = Np * r / W, n_own = Np * (r + 1) / W - a0;
+  int64_t* own_off = h->d_own_len + (size_t)W * (n_own + 1);
+  // my own sub-strips do not travel
+  if (h->x_recv_cnt[r] > 0)
+    EMBA_CUDA(cudaMemcpyAsync(h->d_recv + h->x_recvbase[r] * 6, h->d_strip + h->x_send_off[r] * 6,
+                              sizeof(double) * h->x_recv_cnt[r] * 6, cudaMemcpyDeviceToDevice, h->stream));
+  // one NCCL group (= one launch) for the two small all-reduces (ncclFloat64 = 8, ncclSum = 0)
+  if (api->group_start() != 0) { h->err = "ncclGroupStart failed"; return EMBA_E_NCCL; }
+  int rc = api->allreduce(h->d_A22, h->d_A22, (size_t)(3 * Np), 8, 0, h->nccl_comm, h->stream);
+  rc |= api->allreduce(h->d_b2, h->d_b2, (size_t)(2 * Np), 8, 0, h->nccl_comm, h->stream);
+  if (api->group_end() != 0 || rc != 0) { h->err = "ncclAllReduce (A22, b2) failed"; return EMBA_E_NCCL; }
+  h->launches++;
   if (n_own > 0) {
     if (W <= 8)
       k_merge_strips<8><<<ceil_div64(n_own * 32, T), T, 0, h->stream>>>(W, Np, a0, n_own, h->d_win_all, own_off,
@@ -308,20 +327,10 @@ int comm_exchange_strips(Handle* h) {
                                                                        h->pose_group, h->d_gmask2);
     EMBA_LAUNCH_CHECK();
   }
-  if (dbg) {
-    cudaEventRecord(de[4], h->stream);
-    cudaStreamSynchronize(h->stream);
-    float a, b, c, d2;
-    cudaEventElapsedTime(&a, de[0], de[1]); cudaEventElapsedTime(&b, de[1], de[2]); cudaEventElapsedTime(&c, de[2], de[3]);
-    cudaEventElapsedTime(&d2, de[3], de[4]);
-    if (r == 0) fprintf(stderr, "[emba exchange] windows+scans %.3f host-roundtrip %.3f send/recv %.3f merge %.3f ms (recv %.1f MB)\n",
-                        a, b, c, d2, recvbase[W] * 48.0 / 1e6);
-    for (auto& e : de) cudaEventDestroy(e);
-  }
   h->sv_winlo = h->d_gwinlo; h->sv_winhi = h->d_gwinhi; h->sv_stripoff = h->d_gstripoff; h->sv_strip = h->d_gstrip;
   h->sv_gmask = h->d_gmask2;
   h->mask_min_len = -1;  // the merge wrote every owned pixel's masks
-  h->sv_strip_total = gtot;
+  h->sv_strip_total = h->x_gtot;
   return EMBA_OK;
 }
 

@@ -98,6 +98,12 @@ struct Handle {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // side stream: the row sort runs beside the pose-side assembly
+  cudaStream_t stream3 = nullptr;  // communication stream of the pipelined strip exchange (several GPUs)
+  cudaEvent_t ev_chunk[64] = {};   // k_pix finished the pixel range of owner (rank + s)
+  cudaEvent_t ev_comm = nullptr;
+  std::vector<int64_t> x_recv_cnt, x_send_off, x_recvbase;  // strip exchange: poses received per source rank, my
+  int64_t x_gtot = 0;                                        // strip offsets at the ownership boundaries, merged total
+  int64_t* d_glen = nullptr;       // [P+2] merged strip lengths
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sort0 = nullptr, ev_sort1 = nullptr;
   cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
   cudaEvent_t ev_host = nullptr;   // marks a small device->host read-back the host waits for while later launches queue

@@ -274,6 +274,9 @@ int emba_create(const emba_config_t* cfg, emba_handle_t* out) {
   cudaEventCreateWithFlags(&h->ev_fork2, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->ev_host, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming);
+  if (cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking) != cudaSuccess) { delete h; return EMBA_E_CUDA; }
+  for (auto& e : h->ev_chunk) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   if (cudaMallocHost((void**)&h->h_pin, 1024 * sizeof(int64_t)) != cudaSuccess) { delete h; return EMBA_E_CUDA; }
   cudaEventCreate(&h->ev_sort0);
   cudaEventCreate(&h->ev_sort1);
@@ -328,6 +331,7 @@ int emba_destroy(emba_handle_t hh) {
   Handle* h = (Handle*)hh;
   if (!h) return EMBA_OK;
   cudaSetDevice(h->device);
+  if (h->stream3) cudaStreamSynchronize(h->stream3);
   if (h->stream2) cudaStreamSynchronize(h->stream2);
   if (h->stream) cudaStreamSynchronize(h->stream);
   comm_destroy(h);
@@ -348,7 +352,11 @@ int emba_destroy(emba_handle_t hh) {
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : {h->ev_fork, h->ev_join, h->ev_fork2, h->ev_join2, h->ev_sort0, h->ev_sort1, h->ev_host}) if (e) cudaEventDestroy(e);
   uploader_free(h->up);
+  for (auto& e : h->ev_chunk) if (e) cudaEventDestroy(e);
+  if (h->ev_comm) cudaEventDestroy(h->ev_comm);
+  if (h->d_glen) cudaFree(h->d_glen);
   if (h->h_pin) cudaFreeHost(h->h_pin);
+  if (h->stream3) cudaStreamDestroy(h->stream3);
   if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;

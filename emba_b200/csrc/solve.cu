@@ -716,15 +716,6 @@ __global__ void k_update_map(int64_t P, const int32_t* __restrict__ amap, const 
   }
 }
 
-static int dot(Handle* h, int64_t n, const double* a, const double* b, double* out_dev, int slot) {
-  const int grid = h->sm_count * 2;
-  double* part = h->d_part;
-  k_dot_partial<<<grid, 256, 0, h->stream>>>(n, a, b, part + 4096 * slot);
-  k_dot_final<<<1, 256, 0, h->stream>>>(grid, part + 4096 * slot, out_dev);
-  h->launches += 2;
-  return EMBA_OK;
-}
-
 int solve_schur(Handle* h, double lambda, int fix) {
   static const bool dbg = getenv("EMBA_DEBUG_TIMING") != nullptr;
   cudaEvent_t de[6];
@@ -840,6 +831,118 @@ int solve_schur(Handle* h, double lambda, int fix) {
   return EMBA_OK;
 }
 
+// ---- device-resident CG control: the scalars of Eigen's loop (ConjugateGradient.h:26-96) live in one small
+// struct on the device; every kernel of an iteration reads what it needs from there and returns at once when the
+// stopping test has fired, so the host only enqueues iterations (in chunks) and looks at the flag once per chunk.
+struct CgScal {
+  double rhs2, thr, absNew, absOld, ptmp, rn2, beta;
+  int done, iters;
+};
+
+__global__ void k_cg_init(CgScal* sc, double tol) {
+  // rhsNorm2 == 0 -> x = 0, 0 iterations; threshold = max(tol^2 rhsNorm2, smallest normal); residual = rhs (x0 = 0)
+  const double rhs2 = sc->rhs2;
+  sc->thr = fmax(tol * tol * rhs2, 2.2250738585072014e-308);
+  sc->rn2 = rhs2;
+  sc->iters = 0;
+  sc->done = (rhs2 == 0.0 || rhs2 < sc->thr) ? 1 : 0;
+}
+
+// out = sum of the per-block partials (fixed order), written to a field of the control struct; which: 0 rhs2,
+// 1 absNew (first), 2 ptmp, 3 rn2 + stopping test, 4 absNew (in the loop) + beta + iteration count
+__global__ void k_cg_reduce(int nblk, const double* __restrict__ part, CgScal* sc, int which, int max_iter) {
+  __shared__ double sh[256];
+  if (which >= 2 && sc->done) return;
+  double s = 0;
+  for (int b = threadIdx.x; b < nblk; b += 256) s += part[b];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x != 0) return;
+  const double v = sh[0];
+  if (which == 0) sc->rhs2 = v;
+  else if (which == 1) sc->absNew = v;
+  else if (which == 2) sc->ptmp = v;
+  else if (which == 3) { sc->rn2 = v; if (v < sc->thr) sc->done = 1; }  // `break` before i++ (ConjugateGradient.h:78-79)
+  else {
+    sc->absOld = sc->absNew;
+    sc->absNew = v;
+    sc->beta = v / sc->absOld;
+  }
+}
+__global__ void k_cg_next(CgScal* sc, int max_iter) {  // i++ ; while (i < maxIters)
+  if (sc->done) return;
+  sc->iters += 1;
+  if (sc->iters >= max_iter) sc->done = 1;
+}
+
+// the vector kernels keep k_dot_partial's grid-stride order, so every dot product sums in the same order as before
+__global__ void __launch_bounds__(256) k_cg_dot(int64_t n, const double* __restrict__ a, const double* __restrict__ b,
+                                                double* __restrict__ part, const CgScal* sc, int check) {
+  if (check && sc->done) return;
+  double s = 0;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) s += a[i] * b[i];
+  __shared__ double sh[256];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+}
+// x += alpha p, r -= alpha tmp, partials of r.r   (alpha = absNew / p.tmp)
+__global__ void __launch_bounds__(256) k_cg_step1(int64_t n, const double* __restrict__ p, const double* __restrict__ tmp,
+                                                  double* __restrict__ x, double* __restrict__ r,
+                                                  double* __restrict__ part, const CgScal* sc) {
+  if (sc->done) return;
+  const double alpha = sc->absNew / sc->ptmp;
+  double s = 0;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    x[i] += alpha * p[i];
+    const double ri = r[i] + (-alpha) * tmp[i];
+    r[i] = ri;
+    s += ri * ri;
+  }
+  __shared__ double sh[256];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+}
+// z = invd .* r, partials of r.z
+__global__ void __launch_bounds__(256) k_cg_step2(int64_t n, const double* __restrict__ invd, const double* __restrict__ r,
+                                                  double* __restrict__ z, double* __restrict__ part, const CgScal* sc) {
+  if (sc->done) return;
+  double s = 0;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const double zi = invd[i] * r[i];
+    z[i] = zi;
+    s += r[i] * zi;
+  }
+  __shared__ double sh[256];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+}
+// p = z + beta p
+__global__ void k_cg_step3(int64_t n, const double* __restrict__ z, double* __restrict__ p, const CgScal* sc) {
+  if (sc->done) return;
+  const double beta = sc->beta;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = z[i] + beta * p[i];
+}
+
 int solve_pcg(Handle* h, double lambda, int fix, int* iters_out, double* err_out) {
   const int n = h->n;
   const int d = 3 * (n - fix);
@@ -847,8 +950,9 @@ int solve_pcg(Handle* h, double lambda, int fix, int* iters_out, double* err_out
   // Several GPUs: every vector is replicated; the matrix is not. A12 lives with the pixel owners (solve view), A11 /
   // b1 are combined here once if they are still per-rank partials, A22 / b2 are already global. A product y = A v
   // is then a sum of per-rank partial vectors -- rank 0 adds the A11m block, owners add their A22m blocks and their
-  // strips' contributions -- combined by ONE all-reduce of (d + 2 Np) doubles per iteration. All ranks see the
-  // same y, so the scalars (dot products) need no communication and every rank takes the same decisions.
+  // strips' contributions -- combined by ONE all-reduce of (d + 2 Np) doubles per iteration, issued from the device
+  // timeline like every other step. All ranks see the same y, so the scalars need no communication and every rank
+  // takes the same decisions.
   const int W = h->world;
   if (W > 1 && h->a11_partial) {
     EMBA_TRY(comm_allreduce(h, h->d_A11, (int64_t)9 * n * n, 1));
@@ -872,17 +976,13 @@ int solve_pcg(Handle* h, double lambda, int fix, int* iters_out, double* err_out
   double* z = p + tot;
   double* tmp = z + tot;
   double* ypart = tmp + tot;
-  double* sc = h->d_scal + 8;
+  CgScal* sc = reinterpret_cast<CgScal*>(h->d_scal + 8);
+  double* part = h->d_part;
+  const int dgrid = h->sm_count * 2;
   k_cg_setup<<<G, T, 0, h->stream>>>(d, fix, n, Np, h->d_A11, h->d_b1, h->d_A22, h->d_b2, lambda, b, invd);
   EMBA_LAUNCH_CHECK();
   EMBA_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * tot, h->stream));
   EMBA_CUDA(cudaMemcpyAsync(r, b, sizeof(double) * tot, cudaMemcpyDeviceToDevice, h->stream));  // x0 = 0
-  auto hdot = [&](const double* a, const double* c, double* out) -> int {
-    EMBA_TRY(dot(h, tot, a, c, sc, 0));
-    EMBA_CUDA(cudaMemcpyAsync(out, sc, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    EMBA_CUDA(cudaStreamSynchronize(h->stream));
-    return EMBA_OK;
-  };
   auto matvec = [&](const double* v, double* y) -> int {
     if (h->rank == 0) {
       k_cg_a11<<<d, 128, 0, h->stream>>>(d, fix, n, h->d_A11, lambda, v, y);
@@ -903,50 +1003,44 @@ int solve_pcg(Handle* h, double lambda, int fix, int* iters_out, double* err_out
     if (W > 1) EMBA_TRY(comm_allreduce(h, y, tot, 1));
     return EMBA_OK;
   };
-  double rhs2 = 0, rn2 = 0;
-  EMBA_TRY(hdot(b, b, &rhs2));
-  int it = 0;
-  double err = 0;
-  if (rhs2 == 0) {
-    it = 0; err = 0;
-  } else {
-    const double thr = std::max(tol * tol * rhs2, 2.2250738585072014e-308);
-    rn2 = rhs2;
-    if (rn2 < thr) {
-      err = sqrt(rn2 / rhs2);
-    } else {
-      k_mul<<<G, T, 0, h->stream>>>(tot, invd, r, p);
-      h->launches++;
-      double absNew = 0;
-      EMBA_TRY(hdot(r, p, &absNew));
-      while (it < max_iter) {
-        EMBA_TRY(matvec(p, tmp));
-        double ptmp = 0;
-        EMBA_TRY(hdot(p, tmp, &ptmp));
-        const double alpha = absNew / ptmp;
-        k_axpy<<<G, T, 0, h->stream>>>(tot, alpha, p, x);
-        k_axpy<<<G, T, 0, h->stream>>>(tot, -alpha, tmp, r);
-        h->launches += 2;
-        EMBA_TRY(hdot(r, r, &rn2));
-        if (rn2 < thr) break;
-        k_mul<<<G, T, 0, h->stream>>>(tot, invd, r, z);
-        h->launches++;
-        const double absOld = absNew;
-        EMBA_TRY(hdot(r, z, &absNew));
-        const double beta = absNew / absOld;
-        k_xpby<<<G, T, 0, h->stream>>>(tot, z, beta, p);
-        h->launches++;
-        it++;
-      }
-      err = sqrt(rn2 / rhs2);
+  // rhsNorm2, stopping threshold, first search direction
+  k_cg_dot<<<dgrid, 256, 0, h->stream>>>(tot, b, b, part, sc, 0);
+  k_cg_reduce<<<1, 256, 0, h->stream>>>(dgrid, part, sc, 0, max_iter);
+  k_cg_init<<<1, 1, 0, h->stream>>>(sc, tol);
+  k_mul<<<G, T, 0, h->stream>>>(tot, invd, r, p);
+  k_cg_dot<<<dgrid, 256, 0, h->stream>>>(tot, r, p, part, sc, 0);
+  k_cg_reduce<<<1, 256, 0, h->stream>>>(dgrid, part, sc, 1, max_iter);
+  h->launches += 6;
+  EMBA_CUDA(cudaGetLastError());
+  // iterations: enqueued in chunks, the flag is looked at once per chunk (kernels after the stop are no-ops)
+  int64_t* hflag = h->h_pin + 20;
+  const int chunk = 10;
+  for (int it0 = 0; it0 < max_iter; it0 += chunk) {
+    for (int k = 0; k < chunk && it0 + k < max_iter; k++) {
+      EMBA_TRY(matvec(p, tmp));
+      k_cg_dot<<<dgrid, 256, 0, h->stream>>>(tot, p, tmp, part, sc, 1);
+      k_cg_reduce<<<1, 256, 0, h->stream>>>(dgrid, part, sc, 2, max_iter);
+      k_cg_step1<<<dgrid, 256, 0, h->stream>>>(tot, p, tmp, x, r, part, sc);
+      k_cg_reduce<<<1, 256, 0, h->stream>>>(dgrid, part, sc, 3, max_iter);
+      k_cg_step2<<<dgrid, 256, 0, h->stream>>>(tot, invd, r, z, part, sc);
+      k_cg_reduce<<<1, 256, 0, h->stream>>>(dgrid, part, sc, 4, max_iter);
+      k_cg_step3<<<G, T, 0, h->stream>>>(tot, z, p, sc);
+      k_cg_next<<<1, 1, 0, h->stream>>>(sc, max_iter);
+      h->launches += 8;
     }
+    EMBA_CUDA(cudaGetLastError());
+    EMBA_CUDA(cudaMemcpyAsync(hflag, &sc->done, sizeof(int) * 2, cudaMemcpyDeviceToHost, h->stream));
+    EMBA_CUDA(cudaStreamSynchronize(h->stream));
+    if (reinterpret_cast<int*>(hflag)[0]) break;
   }
+  CgScal hs;
+  EMBA_CUDA(cudaMemcpyAsync(&hs, sc, sizeof(CgScal), cudaMemcpyDeviceToHost, h->stream));
   k_expand_x1<<<ceil_div64(3 * n, T), T, 0, h->stream>>>(n, fix, x, h->d_x1);
   EMBA_LAUNCH_CHECK();
   if (Np > 0) EMBA_CUDA(cudaMemcpyAsync(h->d_x2, x + d, sizeof(double) * 2 * Np, cudaMemcpyDeviceToDevice, h->stream));
   EMBA_CUDA(cudaStreamSynchronize(h->stream));
-  if (iters_out) *iters_out = it;
-  if (err_out) *err_out = err;
+  if (iters_out) *iters_out = hs.iters;
+  if (err_out) *err_out = hs.rhs2 == 0.0 ? 0.0 : sqrt(hs.rn2 / hs.rhs2);
   return EMBA_OK;
 }
 

@@ -371,6 +371,94 @@ class Engine:
         self._chk(self.L.emba_synchronize(self.h))
 
 
+class ExtEngine:
+    """Extension mode (include/emba_b200.h: emba_ext_*): cubic per-event SO(3) spline, bilinear map sampling,
+    normal equations in Jacobian form solved by block-Jacobi PCG. `engine` provides the pairing, `seq` the timestamps."""
+
+    def __init__(self, engine: Engine, seq: EventSequence, idx_beg, idx_end):
+        self.L, self.eng, self.seq = engine.L, engine, seq
+        self.h = C.c_void_p()
+        engine._chk(self.L.emba_ext_create(engine.h, seq.h, int(idx_beg), int(idx_end), C.byref(self.h)))
+        self.n, self.Np = 0, 0
+
+    def _chk(self, rc):
+        self.eng._chk(rc)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.emba_ext_destroy(self.h)
+            self.h = None
+
+    def num_pairs(self):
+        v = C.c_int64(0)
+        self._chk(self.L.emba_ext_num_pairs(self.h, C.byref(v)))
+        return v.value
+
+    def set_state(self, t0_ns, dt_ns, quat, Gx, Gy):
+        q = np.ascontiguousarray(quat, dtype=np.float64)
+        gx = np.ascontiguousarray(Gx, dtype=np.float64)
+        gy = np.ascontiguousarray(Gy, dtype=np.float64)
+        self.n = q.shape[0]
+        self._chk(self.L.emba_ext_set_state(self.h, int(t0_ns), int(dt_ns), self.n, ptr(q), ptr(gx), ptr(gy)))
+
+    def get_state(self):
+        q = np.empty((self.n, 4))
+        gx = np.empty((self.eng.pano_h, self.eng.pano_w))
+        gy = np.empty((self.eng.pano_h, self.eng.pano_w))
+        self._chk(self.L.emba_ext_get_state(self.h, ptr(q), ptr(gx), ptr(gy)))
+        return q, gx, gy
+
+    def evaluate(self, alpha=0.0):
+        cd, cr, M = C.c_double(0), C.c_double(0), C.c_int64(0)
+        self._chk(self.L.emba_ext_evaluate(self.h, float(alpha), C.byref(cd), C.byref(cr), C.byref(M)))
+        return cd.value, cr.value, M.value
+
+    def form(self, thres, alpha):
+        Np, Mu = C.c_int64(0), C.c_int64(0)
+        self._chk(self.L.emba_ext_form(self.h, int(thres), float(alpha), C.byref(Np), C.byref(Mu)))
+        self.Np = Np.value
+        return Np.value, Mu.value
+
+    def get_rows(self):
+        M = self.num_pairs()
+        cap = max(M, 1)
+        out = dict(e=np.empty(cap), dp=np.empty((cap, 2)), pm=np.empty((cap, 2)), J=np.empty((cap, 24)),
+                   axy=np.empty((cap, 2)), cp=np.empty((cap, 2), np.int32), pix=np.empty((cap, 4), np.int32),
+                   ev=np.empty(cap, np.int32), flag=np.empty(cap, np.int32))
+        n = C.c_int64(0)
+        self._chk(self.L.emba_ext_get_rows(self.h, cap, ptr(out["e"]), ptr(out["dp"]), ptr(out["pm"]), ptr(out["J"]),
+                                           ptr(out["axy"]), ptr(out["cp"], C.c_int32), ptr(out["pix"], C.c_int32),
+                                           ptr(out["ev"], C.c_int32), ptr(out["flag"], C.c_int32), C.byref(n)))
+        return {k: v[: n.value] for k, v in out.items()}
+
+    def get_normal_eq(self):
+        d = 3 * self.n + 2 * self.Np
+        g, Bp, Bm, act = np.empty(d), np.empty((self.n, 3, 3)), np.empty((max(self.Np, 1), 3)), np.empty(max(self.Np, 1), np.int32)
+        self._chk(self.L.emba_ext_get_normal_eq(self.h, ptr(g), ptr(Bp), ptr(Bm), ptr(act, C.c_int32)))
+        return g, Bp, Bm[: self.Np], act[: self.Np]
+
+    def matvec(self, lam, alpha, v):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        y = np.empty_like(v)
+        self._chk(self.L.emba_ext_matvec(self.h, float(lam), float(alpha), ptr(v), ptr(y)))
+        return y
+
+    def solve(self, lam, alpha, max_iter=100, tol=1e-6):
+        x = np.empty(3 * self.n + 2 * self.Np)
+        it, err = C.c_int32(0), C.c_double(0)
+        self._chk(self.L.emba_ext_solve(self.h, float(lam), float(alpha), int(max_iter), float(tol), ptr(x), C.byref(it),
+                                        C.byref(err)))
+        return x, it.value, err.value
+
+    def apply(self, damping=1.0):
+        self._chk(self.L.emba_ext_apply(self.h, float(damping)))
+
+    def last_ms(self):
+        out = np.zeros(3)
+        self._chk(self.L.emba_ext_last_ms(self.h, ptr(out)))
+        return dict(evaluate=out[0], form=out[1], solve=out[2])
+
+
 # ------------------------------------------------------------------------------------------------
 # reference-shaped interface
 # ------------------------------------------------------------------------------------------------

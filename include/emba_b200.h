@@ -249,6 +249,46 @@ EMBA_API int emba_poisson_last_ms(emba_poisson_t p, double* ms_out, int64_t* lau
  * image crosses PCIe */
 EMBA_API int emba_reconstruct_map(emba_handle_t h, int32_t which, double* img_out);
 
+/* ---- "next" row N4: EXTENSION MODE, the variant BASELINE.json's north star words literally --
+ * cubic cumulative SO(3) B-spline evaluated PER EVENT with its 4 active control poses (re-derived from
+ * basalt::So3Spline<4>::evaluate, thirdparty/basalt-headers/include/basalt/spline/so3_spline.h:218-274, which the
+ * reference wraps in CubicTrajectory::evaluate, src/utils/trajectory.cpp:453-479), bilinear sampling of the gradient
+ * map (8 map Jacobian entries instead of the nearest pixel's 2, model.cpp:209-214), 2 x 12 rotation Jacobian
+ * entries per event pair (parity mode: 2 x 6, model.cpp:449,459). The reference has no implementation of this mode:
+ * it is checked against oracle/ext_capi.cpp (the same model on the reference's vendored basalt) and reported
+ * separately from the parity mode. The pairing of events comes from `h` (emba_ext_create runs emba_set_events_dev on
+ * it), timestamps from the device-resident sequence, which must outlive the extension handle.
+ *   emba_ext_evaluate : residuals, cost, the explicit sparse Jacobian rows, footprint counts
+ *   emba_ext_form     : active pixels (footprint hits >= thres; a row is used iff its 4 pixels are active),
+ *                       g = J^T e (- alpha G), block diagonal of H = J^T J (+ alpha I on the map block)
+ *   emba_ext_solve    : block-Jacobi PCG on (H + lambda diag H) x = g, matrix free through the stored rows
+ *   emba_ext_apply    : R_i <- Exp(x1_i) R_i, G[active] += damping * x2, G[inactive] = 0
+ * Unknown order: 3 n_poses rotation components, then (Gx, Gy) per ACTIVE pixel in ascending pixel index. */
+typedef struct emba_ext_s* emba_ext_t;
+EMBA_API int emba_ext_create(emba_handle_t h, emba_events_t ev, int64_t idx_beg, int64_t idx_end, emba_ext_t* out);
+EMBA_API int emba_ext_destroy(emba_ext_t x);
+EMBA_API int emba_ext_num_pairs(emba_ext_t x, int64_t* out);
+EMBA_API int emba_ext_set_state(emba_ext_t x, int64_t t0_ns, int64_t dt_ns, int32_t n_poses, const double* quat_xyzw,
+                                const double* Gx, const double* Gy);
+EMBA_API int emba_ext_get_state(emba_ext_t x, double* quat_xyzw_out, double* Gx_out, double* Gy_out);
+EMBA_API int emba_ext_evaluate(emba_ext_t x, double alpha, double* cost_data, double* cost_reg, int64_t* num_measurements);
+EMBA_API int emba_ext_form(emba_ext_t x, int32_t thres_valid_pixel, double alpha, int64_t* num_active_pixels,
+                           int64_t* num_rows_used);
+/* parity downloads: one row per event pair in time order of the current event (cap rows each, any may be NULL):
+ * e, dp[2], pm[2] (warped current event), J[24] = Jc(12) | Jp(12), axy[2] (bilinear fractions), cp[2] (first control
+ * pose of the current / previous event), pix[4] (footprint), ev (current event), flag (0 outlier, 1 inlier, 3 used) */
+EMBA_API int emba_ext_get_rows(emba_ext_t x, int64_t cap, double* e, double* dp, double* pm, double* J24, double* axy,
+                               int32_t* cp, int32_t* pix, int32_t* ev, int32_t* flag, int64_t* n_rows);
+/* g [3n + 2Np], pose_blocks [n][9], pixel_blocks [Np][3] (xx, xy, yy), active [Np] */
+EMBA_API int emba_ext_get_normal_eq(emba_ext_t x, double* g, double* pose_blocks, double* pixel_blocks, int32_t* active);
+/* y = (J^T J + alpha I_map + lambda diag H) v, the operator emba_ext_solve iterates with (v, y: 3n + 2Np, host) */
+EMBA_API int emba_ext_matvec(emba_ext_t x, double lambda, double alpha, const double* v, double* y);
+EMBA_API int emba_ext_solve(emba_ext_t x, double lambda, double alpha, int32_t max_iter, double tol, double* x_out,
+                            int32_t* iters, double* error);
+EMBA_API int emba_ext_apply(emba_ext_t x, double damping_factor);
+/* device ms of the last evaluate / form / solve */
+EMBA_API int emba_ext_last_ms(emba_ext_t x, double* out3);
+
 /* ---- measurement hooks used by bench.py (CUDA events on the handle's stream) */
 /* elapsed device time (CUDA events on the handle's stream) of the last emba_evaluate / emba_form_normal_eq /
  * emba_solve, ms: out[0]=evaluate total, out[1]=per-measurement residual kernel (k_eval), out[2]=form total,

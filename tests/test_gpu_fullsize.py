@@ -1,6 +1,8 @@
 """GPU tests at BASELINE.json's sizes: configuration C1 (~0.93 M events, playroom.launch shape) against the CPU
-oracle element by element, and configuration C2 (~10 M events) through size-independent properties (bitwise
-determinism, count conservation, symmetry, two independent solvers agreeing, monotone LM)."""
+oracle element by element, configuration C2 (~10 M events) element by element against the compiled reference
+(oracle/_ref) and through size-independent properties (bitwise determinism, count conservation, symmetry, two
+independent solvers agreeing, monotone LM), C3 and the headline configuration C4 (~120 M events, 2048x1024, n = 201)
+through the same properties."""
 import numpy as np
 import pytest
 
@@ -45,6 +47,34 @@ def test_c1_against_oracle():
     G11, G12, g1 = orc.gauge_fix(B11, B12, c1)
     y1, y2 = orc.solve_normal_eq(G11, G12, B22, g1, c2, 1e-3)
     assert rel(y1, x1) < 1e-6 and rel(y2, x2) < 1e-6
+    eng.close()
+
+
+def test_c2_elementwise_vs_compiled_reference():
+    """C2 (10.4 M events, 240x180, 1024x512, n = 97) against the UNMODIFIED reference sources compiled into
+    oracle/_ref/libemba_ref.so: integer outputs identical, residuals 1e-10, assembled H / g 1e-9 (BASELINE.json)."""
+    from oracle import ref_binding as RB
+
+    if not RB.available():
+        pytest.skip("oracle/_ref/libemba_ref.so not built")
+    sc, eng, t0, dt = _setup("C2")
+    ref = RB.RefLEGM(sc.sensor_w, sc.sensor_h, sc.fx, sc.fy, sc.cx, sc.cy, sc.C_th, sc.pano_w, sc.pano_h)
+    ref.set_events(sc.x, sc.y, sc.t_ns, sc.pol)
+    tr = RB.RefTraj(sc.t_beg, sc.dt_knots, sc.quat_init)
+    ep_r, num_r = ref.evaluate(tr, sc.Gx_init, sc.Gy_init, True)
+    cd, cr, M = eng.evaluate(0, 0, 1.0, ALPHA)
+    ep, num = eng.get_evaluation(0, M)
+    assert M == ep_r.size and np.array_equal(num, num_r)
+    assert rel(ep_r, ep) < 1e-10 and np.max(np.abs(ep_r - ep)) < 1e-9
+    assert abs(cd - 0.5 * float(ep_r @ ep_r)) < 1e-11 * cd
+    assert abs(cr - ref.reg_cost(sc.Gx_init, sc.Gy_init, ALPHA)) < 1e-12 * cr
+    B11, _, B22, c1, c2, act_r = ref.form(sc.n_poses, THRES, sc.Gx_init, sc.Gy_init, ALPHA, want_A12=False)
+    Np = eng.form_normal_eq(THRES, 0, 1.0, ALPHA)
+    A11, _, A22, b1, b2, act = eng.get_normal_eq(False)
+    assert Np == act_r.size and np.array_equal(act, act_r)
+    for a, b in ((B11, A11), (B22, A22), (c1, b1), (c2, b2)):
+        assert rel(a, b) < 1e-9
+    assert np.max(np.abs(B11 - A11)) < 1e-9 * np.abs(B11).max()
     eng.close()
 
 
@@ -151,4 +181,51 @@ def test_c3_properties():
     log, fc = eng.solve_time_window(max_num_iter=3, alpha=ALPHA, thres=THRES)
     acc = log[log[:, 4] == 1]
     assert acc.shape[0] >= 1 and np.all(np.diff(acc[:, 3]) < 0) and fc < log[0, 2]
+    eng.close()
+
+
+def test_c4_headline_properties():
+    """Configuration C4, the one the metric is quoted on (~120 M events, 2048x1024 panorama, n = 201, one GPU):
+    size-independent properties. Bitwise equality of two passes is also the test of the per-pixel row ordering -- the
+    rows reach their pixel segments through atomics in a different order every run, only the segment sort makes the
+    summation order (and with it every bit of A12 / A22 / b2 / x) reproducible."""
+    sc, eng, t0, dt = _setup("C4")
+    assert 90_000_000 < sc.n_events < 140_000_000 and sc.n_poses == 201 and (sc.pano_w, sc.pano_h) == (2048, 1024)
+    out = []
+    for _ in range(2):
+        eng.set_state(0, t0, dt, sc.quat_init, sc.Gx_init, sc.Gy_init)
+        cd, cr, M = eng.evaluate(0, 0, 1.0, ALPHA)
+        Np = eng.form_normal_eq(THRES, 0, 1.0, ALPHA)
+        A11, _, A22, b1, b2, act = eng.get_normal_eq(False)
+        x1, x2, _, _ = eng.solve(1e-3, False, True)
+        out.append((cd, cr, M, Np, A11, A22, b1, b2, act, x1, x2))
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    cd, cr, M, Np, A11, A22, b1, b2, act, x1, x2 = out[0]
+    _, num = eng.get_evaluation(0, None, False, True)
+    c = eng.counters()
+    assert int(num.sum()) == M and M <= eng.num_pairs() == c["pairs_window"]
+    assert np.array_equal(act, np.nonzero(num.reshape(-1) >= THRES)[0]) and Np == act.size
+    assert c["rows_on_active_rank"] == int(num.reshape(-1)[act].sum())  # every row of an active pixel has a segment slot
+    assert num.max() > 1024 and c["long_segments"] == int((num.reshape(-1)[act] > 1024).sum())  # long-segment path exercised
+    assert np.max(np.abs(A11 - A11.T)) <= 1e-12 * np.abs(A11).max() and np.all(np.diag(A11)[3:] > 0)
+    assert np.all(A22[:, 0, 0] >= ALPHA) and np.all(A22[:, 0, 0] * A22[:, 1, 1] - A22[:, 0, 1] ** 2 > 0)
+    assert np.isfinite(x1).all() and np.isfinite(x2).all()
+    # linearity of the assembly in the residual: the map-side right-hand side of the atomic path (different kernel,
+    # different order) agrees to rounding
+    eng.set_map_path(1)
+    eng.form_normal_eq(THRES, 0, 1.0, ALPHA)
+    _, _, A22a, _, b2a, _ = eng.get_normal_eq(False)
+    eng.set_map_path(0)
+    assert rel(A22, A22a) < 1e-12 and rel(b2, b2a) < 1e-11
+    # two independent solvers agree on the step; LM decreases the cost
+    eng.form_normal_eq(THRES, 0, 1.0, ALPHA)
+    y1, y2, it, err = eng.solve(1e-1, True, True)
+    z1, z2, _, _ = eng.solve(1e-1, False, True)
+    assert err < 1e-4 and rel(z1, y1) < 5e-2 and rel(z2, y2) < 5e-2
+    log, fc = eng.solve_time_window(max_num_iter=3, alpha=ALPHA, thres=THRES)
+    acc = log[log[:, 4] == 1]
+    assert acc.shape[0] >= 1 and np.all(np.diff(acc[:, 3]) < 0) and fc < log[0, 2]
+    q, gx, gy = eng.get_state(0)
+    assert np.array_equal(q[0], sc.quat_init[0]) and np.all(np.abs(np.linalg.norm(q, axis=1) - 1) < 1e-12)
     eng.close()
