@@ -11,8 +11,8 @@
 //     system (H + lambda diag H) x = g is solved by block-Jacobi PCG with the matrix-free product J^T (J v).
 //     With bilinear sampling the map block of H is no longer block diagonal, so the reference's Schur complement
 //     onto the control poses (model.cpp:721-792) has no cheap analogue here; PCG is its counterpart (model.cpp:794-840).
-// There is no reference implementation of this mode: results are checked against oracle/ext_capi.cpp (the same model
-// on the reference's vendored basalt / Sophus, itself checked against finite differences) and are reported separately
+// There is no reference implementation of this mode: results are checked (tests/test_ext.py) against an fp64 CPU restatement of the same model
+// on the reference's vendored basalt / Sophus, itself checked against finite differences, and are reported separately
 // from the parity mode.
 #include <algorithm>
 #include <cmath>
