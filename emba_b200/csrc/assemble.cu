@@ -39,7 +39,7 @@ __global__ void k_active_flags(const int32_t* __restrict__ hist, const int32_t* 
   if (p >= P) return;
   const int f = hist[p] >= thres ? 1 : 0;
   flag[p] = f;
-  segcnt[p] = f ? hist_loc[p] : 0;
+  segcnt[p] = f ? ((hist_loc[p] + 7) & ~7) : 0;  // segments start on 32-byte boundaries (vector loads of the segment sort)
 }
 
 // aidx / rowbase: exclusive scans of flag / segcnt. rowbase is rewritten in place to "first row of the pixel's
@@ -50,20 +50,29 @@ __global__ void k_active_fill(const int32_t* __restrict__ flag, const int32_t* _
                               double4* __restrict__ H3, int32_t* __restrict__ segoff, int32_t* __restrict__ segend,
                               int64_t* __restrict__ totals) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
+  const bool valid = p < P;
   // the active index also rides in the spare lane of the Hessian entry, so the assembly kernel gets it with the
   // gather it does anyway
-  const int f = flag[p];
-  const int32_t a = aidx[p];
-  const int32_t base = rowbase[p];
+  const int f = valid ? flag[p] : 0;
+  const int32_t a = valid ? aidx[p] : 0;
+  const int32_t base = valid ? rowbase[p] : 0;
+  const int32_t cnt = f ? hist_loc[p] : 0;
+  // rows on active pixels (this rank): one atomic per warp
+  {
+    long long cntw = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cntw += __shfl_xor_sync(0xffffffffu, cntw, o);
+    if ((threadIdx.x & 31) == 0 && cntw) atomicAdd(reinterpret_cast<unsigned long long*>(totals + 1), (unsigned long long)cntw);
+  }
+  if (!valid) return;
   reinterpret_cast<double*>(H3 + p)[3] = __longlong_as_double((long long)(f ? a : -1));
-  if (p == P - 1) { totals[0] = (int64_t)a + f; totals[1] = (int64_t)base + (f ? hist_loc[p] : 0); }
+  if (p == P - 1) totals[0] = (int64_t)a + f;
   if (f) {
     amap[p] = a;
     apix[a] = (int32_t)p;
     win[a] = make_int2(INT_MAX, -1);
     segoff[a] = base;
-    segend[a] = base + hist_loc[p];
+    segend[a] = base + cnt;
   } else {
     amap[p] = -1;
     rowbase[p] = -1;
@@ -143,19 +152,48 @@ __device__ __forceinline__ void warp_bitonic(uint32_t (&a)[K], int lane) {
 // (An adaptive front end -- a few odd-even transposition passes while the segment is unsorted -- was measured and
 // dropped: rows reach their segment through atomics of ~300 k measurements in flight, and not one C4 segment in 350 k
 // was sorted after 6 passes.)
+// a lane's K consecutive keys travel as 32-byte (K >= 8), 16-byte (K = 4) or 8-byte (K = 2) vectors: segments start
+// on 32-byte boundaries, so a K-key group costs K/8 load instructions instead of K scalar ones that each touch 32
+// sectors (the scalar version was LSU-bound). Reads may run past the segment's end (masked; the buffer has a tail
+// pad), stores never do.
 template <int K>
 __device__ __forceinline__ void seg_sort_regs(uint32_t* __restrict__ seg, int L, int lane) {
   uint32_t a[K];
+  const int i0 = lane * K;
+  if (K >= 8) {
 #pragma unroll
-  for (int r = 0; r < K; r++) {
-    const int i = lane * K + r;
-    a[r] = i < L ? seg[i] : 0xFFFFFFFFu;
+    for (int v = 0; v < K / 8; v++) {
+      const uint4 lo = *reinterpret_cast<const uint4*>(seg + i0 + 8 * v);
+      const uint4 hi = *reinterpret_cast<const uint4*>(seg + i0 + 8 * v + 4);
+      a[8 * v] = lo.x; a[8 * v + 1] = lo.y; a[8 * v + 2] = lo.z; a[8 * v + 3] = lo.w;
+      a[8 * v + 4] = hi.x; a[8 * v + 5] = hi.y; a[8 * v + 6] = hi.z; a[8 * v + 7] = hi.w;
+    }
+  } else if (K == 4) {
+    const uint4 q = *reinterpret_cast<const uint4*>(seg + i0);
+    a[0] = q.x; a[1] = q.y; a[2] = q.z; a[3] = q.w;
+  } else if (K == 2) {
+    const uint2 q = *reinterpret_cast<const uint2*>(seg + i0);
+    a[0] = q.x; a[1] = q.y;
+  } else {
+    a[0] = seg[i0];
   }
-  warp_bitonic<K>(a, lane);
 #pragma unroll
-  for (int r = 0; r < K; r++) {
-    const int i = lane * K + r;
-    if (i < L) seg[i] = a[r];
+  for (int r = 0; r < K; r++)
+    if (i0 + r >= L) a[r] = 0xFFFFFFFFu;
+  warp_bitonic<K>(a, lane);
+  if (K >= 4) {
+#pragma unroll
+    for (int v = 0; v < K / 4; v++) {
+      const int i = i0 + 4 * v;
+      if (i + 4 <= L) *reinterpret_cast<uint4*>(seg + i) = make_uint4(a[4 * v], a[4 * v + 1], a[4 * v + 2], a[4 * v + 3]);
+      else {
+#pragma unroll
+        for (int r = 0; r < 4; r++) if (i + r < L) seg[i + r] = a[4 * v + r];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < K; r++) if (i0 + r < L) seg[i0 + r] = a[r];
   }
 }
 
@@ -843,13 +881,14 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   void* scan_tmp2 = reinterpret_cast<char*>(h->d_scan_tmp) + scan_scratch_bytes(P + 2);
 #define EMBA_TRYC(x) do { int _r = (x); if (_r != EMBA_OK) return _r; } while (0)
 #define EMBA_CUDAC(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { h->err = std::string(#x) + ": " + cudaGetErrorString(_e); return EMBA_E_CUDA; } } while (0)
+  int64_t* d_totals = reinterpret_cast<int64_t*>(h->d_scal + 32);
+  EMBA_CUDAC(cudaMemsetAsync(d_totals, 0, 2 * sizeof(int64_t), h->stream));
   k_active_flags<<<ceil_div64(P, T), T, 0, h->stream>>>(s.hist, s.hist_loc, P, thres, d_flag, d_rowbase);
   h->launches++;
   EMBA_TRYC(scan_exclusive<int32_t>(h, h->stream, d_flag, d_aidx, P, h->d_scan_tmp));
   EMBA_TRYC(scan_exclusive<int32_t>(h, h->stream, d_rowbase, d_rowbase, P, scan_tmp2));
   // Np goes back to the host through pinned memory; the host waits for it only after the pose-side kernel (which
   // does not need it) has been queued, so the round trip hides behind that kernel
-  int64_t* d_totals = reinterpret_cast<int64_t*>(h->d_scal + 32);
   k_active_fill<<<ceil_div64(P, T), T, 0, h->stream>>>(d_flag, d_aidx, s.hist_loc, d_rowbase, P, h->d_amap, h->d_apix,
                                                       h->d_win64, s.H3, h->d_segoff, h->d_segend, d_totals);
   h->launches++;

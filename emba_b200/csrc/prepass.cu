@@ -855,7 +855,8 @@ int rebuild_static(Handle* h) {
   size_t mb = 0;
   mb += Arena::pad(sizeof(MeasRec) * Mp) + Arena::pad(4 * Mp);                     // rec, refpos
   mb += 2 * (Arena::pad(16 * Mp) + Arena::pad(8 * Mp) + 2 * Arena::pad(4 * Mp));   // dp, e, pix, slot  x 2 states
-  mb += Arena::pad(8 * (size_t)kRecDoubles * Mp) + Arena::pad(4 * Mp);             // Jacobian rows, sorted row ids
+  const size_t sval_len = Mp + 8 * std::min<size_t>((size_t)h->P, Mp) + 8192;      // segments padded to 8 ids + tail pad
+  mb += Arena::pad(8 * (size_t)kRecDoubles * Mp) + Arena::pad(4 * sval_len);       // Jacobian rows, sorted row ids
   mb += 2 * (Arena::pad(32 * (size_t)n) + Arena::pad(8 * (size_t)kKnotStride * n) + 2 * Arena::pad(32 * (size_t)std::max<int64_t>(B, 1)));
   mb += Arena::pad(sizeof(WorkItem) * (size_t)std::max(1, h->n_items)) + Arena::pad(4 * gid.size()) +
         Arena::pad(4 * item0.size()) + Arena::pad(8 * (size_t)kAccN * std::max(1, h->n_items)) +
@@ -875,7 +876,7 @@ int rebuild_static(Handle* h) {
   }
   h->d_jrec = A.take<double>(Mc * kRecDoubles);
   h->jrec_cap = Mc * kRecDoubles;
-  h->d_sval = A.take<uint32_t>(Mc);
+  h->d_sval = A.take<uint32_t>((int64_t)sval_len);
   h->d_items = A.take<WorkItem>(h->n_items);
   h->d_gid = A.take<int32_t>((int64_t)gid.size());
   h->d_group_item0 = A.take<int32_t>((int64_t)item0.size());

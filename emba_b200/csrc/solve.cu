@@ -559,13 +559,30 @@ __global__ void k_cg_a11(int d, int fix, int n, const double* __restrict__ A11, 
 // into a per-WARP accumulator in shared memory (lanes own distinct rows, pixels come in a fixed order), so the
 // summation order is fixed: warp accumulators -> CTA partial (fixed order) -> k_cg_y1 (fixed order over chunks).
 __global__ void __launch_bounds__(256)
-k_cg_pix(int64_t Np, int d, int fix, int nwarps, const int32_t* __restrict__ winlo, const int32_t* __restrict__ winhi,
+k_cg_pix(int64_t Np, int d, int fix, int n, int nwarps, const int32_t* __restrict__ winlo, const int32_t* __restrict__ winhi,
          const int64_t* __restrict__ stripoff, const double* __restrict__ strip, const double* __restrict__ A22,
-         double lambda, const double* __restrict__ p, double* __restrict__ y, double* __restrict__ part,
-         int64_t own0, int64_t own1) {
+         const double* __restrict__ A11, double lambda, const double* __restrict__ p, double* __restrict__ y,
+         double* __restrict__ part, int64_t own0, int64_t own1, const int* __restrict__ done) {
   extern __shared__ double y1s[];  // [nwarps][d]
+  if (*done) return;
   const int chunk = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // y1 = A11m p1: one warp per row, rows dealt round-robin over the grid (A11 == nullptr on the ranks that do not
+  // hold the pose block: their rows start from zero)
+  for (int i = chunk * 8 + warp; i < d; i += gridDim.x * 8) {
+    double s = 0.0;
+    if (A11) {
+      const double* row = A11 + (size_t)(3 * fix + i) * (3 * n) + 3 * fix;
+      for (int j = lane; j < d; j += 32) {
+        double a = row[j];
+        if (j == i) a += lambda * a;
+        s += a * p[j];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    }
+    if (lane == 0) y[i] = s;
+  }
   const int64_t a0 = Np * chunk / gridDim.x, a1 = Np * (chunk + 1) / gridDim.x;
   for (int i = threadIdx.x; i < nwarps * d; i += blockDim.x) y1s[i] = 0.0;
   __syncthreads();
@@ -832,60 +849,31 @@ int solve_schur(Handle* h, double lambda, int fix) {
 }
 
 // ---- device-resident CG control: the scalars of Eigen's loop (ConjugateGradient.h:26-96) live in one small
-// struct on the device; every kernel of an iteration reads what it needs from there and returns at once when the
-// stopping test has fired, so the host only enqueues iterations (in chunks) and looks at the flag once per chunk.
+// struct on the device. An iteration is FIVE launches (product, dot, and the three vector updates); every kernel sums
+// the previous kernel's per-block partials itself (all blocks in the same fixed order, so they agree bit for bit),
+// reads the stopping flag a PREVIOUS kernel wrote and returns at once when it has fired. The host only enqueues
+// iterations (in chunks) and looks at the flag once per chunk.
 struct CgScal {
-  double rhs2, thr, absNew, absOld, ptmp, rn2, beta;
+  double rhs2, thr, absNew[2], rn2;
   int done, iters;
 };
+constexpr int kCgDotGrid = 296;
 
-__global__ void k_cg_init(CgScal* sc, double tol) {
-  // rhsNorm2 == 0 -> x = 0, 0 iterations; threshold = max(tol^2 rhsNorm2, smallest normal); residual = rhs (x0 = 0)
-  const double rhs2 = sc->rhs2;
-  sc->thr = fmax(tol * tol * rhs2, 2.2250738585072014e-308);
-  sc->rn2 = rhs2;
-  sc->iters = 0;
-  sc->done = (rhs2 == 0.0 || rhs2 < sc->thr) ? 1 : 0;
-}
-
-// out = sum of the per-block partials (fixed order), written to a field of the control struct; which: 0 rhs2,
-// 1 absNew (first), 2 ptmp, 3 rn2 + stopping test, 4 absNew (in the loop) + beta + iteration count
-__global__ void k_cg_reduce(int nblk, const double* __restrict__ part, CgScal* sc, int which, int max_iter) {
-  __shared__ double sh[256];
-  if (which >= 2 && sc->done) return;
+__device__ __forceinline__ double cg_sum_partials(const double* __restrict__ part, double* sh) {
+  // fixed-order sum of the kCgDotGrid partials, by every block alike
   double s = 0;
-  for (int b = threadIdx.x; b < nblk; b += 256) s += part[b];
+  for (int b = threadIdx.x; b < kCgDotGrid; b += 256) s += part[b];
   sh[threadIdx.x] = s;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
     if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x != 0) return;
   const double v = sh[0];
-  if (which == 0) sc->rhs2 = v;
-  else if (which == 1) sc->absNew = v;
-  else if (which == 2) sc->ptmp = v;
-  else if (which == 3) { sc->rn2 = v; if (v < sc->thr) sc->done = 1; }  // `break` before i++ (ConjugateGradient.h:78-79)
-  else {
-    sc->absOld = sc->absNew;
-    sc->absNew = v;
-    sc->beta = v / sc->absOld;
-  }
+  __syncthreads();
+  return v;
 }
-__global__ void k_cg_next(CgScal* sc, int max_iter) {  // i++ ; while (i < maxIters)
-  if (sc->done) return;
-  sc->iters += 1;
-  if (sc->iters >= max_iter) sc->done = 1;
-}
-
-// the vector kernels keep k_dot_partial's grid-stride order, so every dot product sums in the same order as before
-__global__ void __launch_bounds__(256) k_cg_dot(int64_t n, const double* __restrict__ a, const double* __restrict__ b,
-                                                double* __restrict__ part, const CgScal* sc, int check) {
-  if (check && sc->done) return;
-  double s = 0;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) s += a[i] * b[i];
-  __shared__ double sh[256];
+__device__ __forceinline__ void cg_block_partial(double s, double* sh, double* __restrict__ part) {
   sh[threadIdx.x] = s;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
@@ -894,12 +882,50 @@ __global__ void __launch_bounds__(256) k_cg_dot(int64_t n, const double* __restr
   }
   if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
 }
+
+// rhsNorm2 == 0 -> x = 0, 0 iterations; threshold = max(tol^2 rhsNorm2, smallest normal); residual = rhs (x0 = 0);
+// absNew = r . (M^-1 r)
+__global__ void __launch_bounds__(256) k_cg_init(const double* __restrict__ part_bb, const double* __restrict__ part_rp,
+                                                 CgScal* sc, double tol) {
+  __shared__ double sh[256];
+  const double rhs2 = cg_sum_partials(part_bb, sh);
+  const double absNew = cg_sum_partials(part_rp, sh);
+  if (threadIdx.x == 0) {
+    sc->rhs2 = rhs2;
+    sc->thr = fmax(tol * tol * rhs2, 2.2250738585072014e-308);
+    sc->rn2 = rhs2;
+    sc->absNew[0] = absNew;
+    sc->iters = 0;
+    sc->done = (rhs2 == 0.0 || rhs2 < sc->thr) ? 1 : 0;
+  }
+}
+
+// partials of a . b (k_dot_partial's grid-stride order). fold_y1: the pose part of b is completed on the fly from
+// the per-chunk partials of the strip product (one GPU; with several the completed vector is all-reduced first)
+__global__ void __launch_bounds__(256) k_cg_dot(int64_t n, const double* __restrict__ a, double* __restrict__ b,
+                                                double* __restrict__ part, const CgScal* sc, int check, int d,
+                                                int chunks, const double* __restrict__ ypart) {
+  __shared__ double sh[256];
+  if (check && sc->done) return;
+  double s = 0;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    double bi = b[i];
+    if (ypart && i < d) {
+      for (int c = 0; c < chunks; c++) bi += ypart[(size_t)c * d + i];
+      b[i] = bi;
+    }
+    s += a[i] * bi;
+  }
+  cg_block_partial(s, sh, part);
+}
 // x += alpha p, r -= alpha tmp, partials of r.r   (alpha = absNew / p.tmp)
 __global__ void __launch_bounds__(256) k_cg_step1(int64_t n, const double* __restrict__ p, const double* __restrict__ tmp,
                                                   double* __restrict__ x, double* __restrict__ r,
-                                                  double* __restrict__ part, const CgScal* sc) {
+                                                  const double* __restrict__ part_in, double* __restrict__ part_out,
+                                                  const CgScal* sc, int par) {
+  __shared__ double sh[256];
   if (sc->done) return;
-  const double alpha = sc->absNew / sc->ptmp;
+  const double alpha = sc->absNew[par] / cg_sum_partials(part_in, sh);
   double s = 0;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
     x[i] += alpha * p[i];
@@ -907,40 +933,43 @@ __global__ void __launch_bounds__(256) k_cg_step1(int64_t n, const double* __res
     r[i] = ri;
     s += ri * ri;
   }
-  __shared__ double sh[256];
-  sh[threadIdx.x] = s;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+  cg_block_partial(s, sh, part_out);
 }
-// z = invd .* r, partials of r.z
+// stopping test on r.r (`break` before i++, ConjugateGradient.h:78-79); z = invd .* r, partials of r.z
 __global__ void __launch_bounds__(256) k_cg_step2(int64_t n, const double* __restrict__ invd, const double* __restrict__ r,
-                                                  double* __restrict__ z, double* __restrict__ part, const CgScal* sc) {
+                                                  double* __restrict__ z, const double* __restrict__ part_in,
+                                                  double* __restrict__ part_out, CgScal* sc) {
+  __shared__ double sh[256];
   if (sc->done) return;
+  const double rn2 = cg_sum_partials(part_in, sh);
+  const bool stop = rn2 < sc->thr;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { sc->rn2 = rn2; if (stop) sc->done = 1; }  // read by LATER kernels only
+  if (stop) return;
   double s = 0;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
     const double zi = invd[i] * r[i];
     z[i] = zi;
     s += r[i] * zi;
   }
-  __shared__ double sh[256];
-  sh[threadIdx.x] = s;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+  cg_block_partial(s, sh, part_out);
 }
-// p = z + beta p
-__global__ void k_cg_step3(int64_t n, const double* __restrict__ z, double* __restrict__ p, const CgScal* sc) {
+// beta = absNew' / absNew; p = z + beta p; i++ ; while (i < maxIters)
+__global__ void __launch_bounds__(256) k_cg_step3(int64_t n, const double* __restrict__ z, double* __restrict__ p,
+                                                  const double* __restrict__ part_in, CgScal* sc, int par, int max_iter) {
+  __shared__ double sh[256];
   if (sc->done) return;
-  const double beta = sc->beta;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = z[i] + beta * p[i];
+  const double absNew = cg_sum_partials(part_in, sh);
+  const double beta = absNew / sc->absNew[par];
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) p[i] = z[i] + beta * p[i];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    sc->absNew[par ^ 1] = absNew;  // the other parity: nobody reads it in this launch
+    sc->iters += 1;
+  }
+}
+// the iteration bound is applied by the first kernel of the NEXT iteration's chain (so that `done` is never written and
+// read inside one launch): folded into the product kernel's guard below
+__global__ void k_cg_bound(CgScal* sc, int max_iter) {
+  if (!sc->done && sc->iters >= max_iter) sc->done = 1;
 }
 
 int solve_pcg(Handle* h, double lambda, int fix, int* iters_out, double* err_out) {
@@ -977,57 +1006,50 @@ int solve_pcg(Handle* h, double lambda, int fix, int* iters_out, double* err_out
   double* tmp = z + tot;
   double* ypart = tmp + tot;
   CgScal* sc = reinterpret_cast<CgScal*>(h->d_scal + 8);
-  double* part = h->d_part;
-  const int dgrid = h->sm_count * 2;
+  double* pa = h->d_part;         // three partial buffers, used round robin by the chain
+  double* pb = h->d_part + 1024;
+  double* pc = h->d_part + 2048;
   k_cg_setup<<<G, T, 0, h->stream>>>(d, fix, n, Np, h->d_A11, h->d_b1, h->d_A22, h->d_b2, lambda, b, invd);
   EMBA_LAUNCH_CHECK();
   EMBA_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * tot, h->stream));
   EMBA_CUDA(cudaMemcpyAsync(r, b, sizeof(double) * tot, cudaMemcpyDeviceToDevice, h->stream));  // x0 = 0
+  // y = A v. One GPU: the pose rows of the result are left as per-chunk partials, the dot kernel completes them.
   auto matvec = [&](const double* v, double* y) -> int {
-    if (h->rank == 0) {
-      k_cg_a11<<<d, 128, 0, h->stream>>>(d, fix, n, h->d_A11, lambda, v, y);
-      h->launches++;
-    } else {
-      EMBA_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * d, h->stream));
-    }
-    if (Np > 0) {
-      const int nwarps = std::max(1, std::min(8, (int)((48 * 1024) / (sizeof(double) * (size_t)d))));
-      const size_t shm = sizeof(double) * (size_t)d * nwarps;
-      if (shm > 48 * 1024) EMBA_CUDA(cudaFuncSetAttribute(k_cg_pix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-      k_cg_pix<<<kCgChunks, 256, shm, h->stream>>>(Np, d, fix, nwarps, h->sv_winlo, h->sv_winhi, h->sv_stripoff,
-                                                   h->sv_strip, h->d_A22, lambda, v, y, ypart, own0, own1);
-      k_cg_y1<<<ceil_div64(d, 128), 128, 0, h->stream>>>(d, kCgChunks, ypart, y);
-      h->launches += 2;
-    }
+    const int nwarps = std::max(1, std::min(8, (int)((48 * 1024) / (sizeof(double) * (size_t)d))));
+    const size_t shm = sizeof(double) * (size_t)d * nwarps;
+    if (shm > 48 * 1024) EMBA_CUDA(cudaFuncSetAttribute(k_cg_pix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+    k_cg_pix<<<kCgChunks, 256, shm, h->stream>>>(Np, d, fix, n, nwarps, h->sv_winlo, h->sv_winhi, h->sv_stripoff,
+                                                 h->sv_strip, h->d_A22, h->rank == 0 ? h->d_A11 : nullptr, lambda, v, y,
+                                                 ypart, own0, own1, &sc->done);
+    h->launches++;
     EMBA_CUDA(cudaGetLastError());
-    if (W > 1) EMBA_TRY(comm_allreduce(h, y, tot, 1));
+    if (W > 1) {
+      k_cg_y1<<<ceil_div64(d, 128), 128, 0, h->stream>>>(d, kCgChunks, ypart, y);
+      h->launches++;
+      EMBA_TRY(comm_allreduce(h, y, tot, 1));
+    }
     return EMBA_OK;
   };
   // rhsNorm2, stopping threshold, first search direction
-  k_cg_dot<<<dgrid, 256, 0, h->stream>>>(tot, b, b, part, sc, 0);
-  k_cg_reduce<<<1, 256, 0, h->stream>>>(dgrid, part, sc, 0, max_iter);
-  k_cg_init<<<1, 1, 0, h->stream>>>(sc, tol);
+  k_cg_dot<<<kCgDotGrid, 256, 0, h->stream>>>(tot, b, b, pa, sc, 0, 0, 0, nullptr);
   k_mul<<<G, T, 0, h->stream>>>(tot, invd, r, p);
-  k_cg_dot<<<dgrid, 256, 0, h->stream>>>(tot, r, p, part, sc, 0);
-  k_cg_reduce<<<1, 256, 0, h->stream>>>(dgrid, part, sc, 1, max_iter);
-  h->launches += 6;
+  k_cg_dot<<<kCgDotGrid, 256, 0, h->stream>>>(tot, r, p, pb, sc, 0, 0, 0, nullptr);
+  k_cg_init<<<1, 256, 0, h->stream>>>(pa, pb, sc, tol);
+  h->launches += 4;
   EMBA_CUDA(cudaGetLastError());
   // iterations: enqueued in chunks, the flag is looked at once per chunk (kernels after the stop are no-ops)
   int64_t* hflag = h->h_pin + 20;
   const int chunk = 10;
   for (int it0 = 0; it0 < max_iter; it0 += chunk) {
-    for (int k = 0; k < chunk && it0 + k < max_iter; k++) {
+    for (int k = it0; k < it0 + chunk && k < max_iter; k++) {
       EMBA_TRY(matvec(p, tmp));
-      k_cg_dot<<<dgrid, 256, 0, h->stream>>>(tot, p, tmp, part, sc, 1);
-      k_cg_reduce<<<1, 256, 0, h->stream>>>(dgrid, part, sc, 2, max_iter);
-      k_cg_step1<<<dgrid, 256, 0, h->stream>>>(tot, p, tmp, x, r, part, sc);
-      k_cg_reduce<<<1, 256, 0, h->stream>>>(dgrid, part, sc, 3, max_iter);
-      k_cg_step2<<<dgrid, 256, 0, h->stream>>>(tot, invd, r, z, part, sc);
-      k_cg_reduce<<<1, 256, 0, h->stream>>>(dgrid, part, sc, 4, max_iter);
-      k_cg_step3<<<G, T, 0, h->stream>>>(tot, z, p, sc);
-      k_cg_next<<<1, 1, 0, h->stream>>>(sc, max_iter);
-      h->launches += 8;
+      k_cg_dot<<<kCgDotGrid, 256, 0, h->stream>>>(tot, p, tmp, pa, sc, 1, d, kCgChunks, W > 1 ? nullptr : ypart);
+      k_cg_step1<<<kCgDotGrid, 256, 0, h->stream>>>(tot, p, tmp, x, r, pa, pb, sc, k & 1);
+      k_cg_step2<<<kCgDotGrid, 256, 0, h->stream>>>(tot, invd, r, z, pb, pc, sc);
+      k_cg_step3<<<kCgDotGrid, 256, 0, h->stream>>>(tot, z, p, pc, sc, k & 1, max_iter);
+      h->launches += 4;
     }
+    k_cg_bound<<<1, 1, 0, h->stream>>>(sc, max_iter);
     EMBA_CUDA(cudaGetLastError());
     EMBA_CUDA(cudaMemcpyAsync(hflag, &sc->done, sizeof(int) * 2, cudaMemcpyDeviceToHost, h->stream));
     EMBA_CUDA(cudaStreamSynchronize(h->stream));

@@ -150,10 +150,13 @@ def test_ext_cuda_rows_and_normal_equations_vs_oracle():
     v = rng.standard_normal(H.shape[0])
     Hd = H + lam * np.diag(np.diag(H))
     assert rel(Hd @ v, ext.matvec(lam, ALPHA, v)) < 1e-9
-    # gauge: the window's first control poses are only weakly observed; the damped system is still SPD
-    x, it, err = ext.solve(lam, ALPHA, max_iter=500, tol=1e-10)
-    x_ref = np.linalg.solve(Hd, gv)
-    assert err < 1e-9 and rel(x_ref, x) < 1e-6
+    # control poses no event reaches (the padding knots at both ends) have zero rows: their update is zero, the rest
+    # of the damped system is SPD
+    x, it, err = ext.solve(lam, ALPHA, max_iter=2000, tol=1e-11)
+    live = np.nonzero(np.diag(Hd) != 0.0)[0]
+    dead = np.nonzero(np.diag(Hd) == 0.0)[0]
+    x_ref = np.linalg.solve(Hd[np.ix_(live, live)], gv[live])
+    assert err < 1e-9 and np.all(x[dead] == 0.0) and rel(x_ref, x[live]) < 1e-5
     ext.close(); seq.close(); eng.close()
 
 
