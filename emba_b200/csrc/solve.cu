@@ -629,12 +629,20 @@ k_cg_pix(int64_t Np, int d, int fix, int n, int nwarps, const int32_t* __restric
   }
 }
 
-__global__ void k_cg_y1(int d, int chunks, const double* __restrict__ part, double* __restrict__ y) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// y1 += sum over the chunks' partial rows: one WARP per row (lane l takes chunks l, l + 32, ... then a fixed shuffle
+// tree), so the ~600 loads of a row are independent and in flight together; a thread walking them one after the other
+// was 2/3 of a PCG iteration on C2
+__global__ void __launch_bounds__(256) k_cg_y1(int d, int chunks, const double* __restrict__ part, double* __restrict__ y,
+                                               const int* __restrict__ done) {
+  if (*done) return;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (i >= d) return;
-  double s = y[i];
-  for (int c = 0; c < chunks; c++) s += part[(size_t)c * d + i];
-  y[i] = s;
+  double s = 0.0;
+  for (int c = lane; c < chunks; c += 32) s += part[(size_t)c * d + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) y[i] += s;
 }
 
 // deterministic dot products: out[0] = a.b with fixed-grid partials
@@ -900,22 +908,13 @@ __global__ void __launch_bounds__(256) k_cg_init(const double* __restrict__ part
   }
 }
 
-// partials of a . b (k_dot_partial's grid-stride order). fold_y1: the pose part of b is completed on the fly from
-// the per-chunk partials of the strip product (one GPU; with several the completed vector is all-reduced first)
-__global__ void __launch_bounds__(256) k_cg_dot(int64_t n, const double* __restrict__ a, double* __restrict__ b,
-                                                double* __restrict__ part, const CgScal* sc, int check, int d,
-                                                int chunks, const double* __restrict__ ypart) {
+// partials of a . b (k_dot_partial's grid-stride order)
+__global__ void __launch_bounds__(256) k_cg_dot(int64_t n, const double* __restrict__ a, const double* __restrict__ b,
+                                                double* __restrict__ part, const CgScal* sc, int check) {
   __shared__ double sh[256];
   if (check && sc->done) return;
   double s = 0;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
-    double bi = b[i];
-    if (ypart && i < d) {
-      for (int c = 0; c < chunks; c++) bi += ypart[(size_t)c * d + i];
-      b[i] = bi;
-    }
-    s += a[i] * bi;
-  }
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) s += a[i] * b[i];
   cg_block_partial(s, sh, part);
 }
 // x += alpha p, r -= alpha tmp, partials of r.r   (alpha = absNew / p.tmp)
@@ -1013,7 +1012,7 @@ int solve_pcg(Handle* h, double lambda, int fix, int* iters_out, double* err_out
   EMBA_LAUNCH_CHECK();
   EMBA_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * tot, h->stream));
   EMBA_CUDA(cudaMemcpyAsync(r, b, sizeof(double) * tot, cudaMemcpyDeviceToDevice, h->stream));  // x0 = 0
-  // y = A v. One GPU: the pose rows of the result are left as per-chunk partials, the dot kernel completes them.
+  // y = A v
   auto matvec = [&](const double* v, double* y) -> int {
     const int nwarps = std::max(1, std::min(8, (int)((48 * 1024) / (sizeof(double) * (size_t)d))));
     const size_t shm = sizeof(double) * (size_t)d * nwarps;
@@ -1023,17 +1022,15 @@ int solve_pcg(Handle* h, double lambda, int fix, int* iters_out, double* err_out
                                                  ypart, own0, own1, &sc->done);
     h->launches++;
     EMBA_CUDA(cudaGetLastError());
-    if (W > 1) {
-      k_cg_y1<<<ceil_div64(d, 128), 128, 0, h->stream>>>(d, kCgChunks, ypart, y);
-      h->launches++;
-      EMBA_TRY(comm_allreduce(h, y, tot, 1));
-    }
+    k_cg_y1<<<ceil_div64(d, 8), 256, 0, h->stream>>>(d, kCgChunks, ypart, y, &sc->done);
+    h->launches++;
+    if (W > 1) EMBA_TRY(comm_allreduce(h, y, tot, 1));
     return EMBA_OK;
   };
   // rhsNorm2, stopping threshold, first search direction
-  k_cg_dot<<<kCgDotGrid, 256, 0, h->stream>>>(tot, b, b, pa, sc, 0, 0, 0, nullptr);
+  k_cg_dot<<<kCgDotGrid, 256, 0, h->stream>>>(tot, b, b, pa, sc, 0);
   k_mul<<<G, T, 0, h->stream>>>(tot, invd, r, p);
-  k_cg_dot<<<kCgDotGrid, 256, 0, h->stream>>>(tot, r, p, pb, sc, 0, 0, 0, nullptr);
+  k_cg_dot<<<kCgDotGrid, 256, 0, h->stream>>>(tot, r, p, pb, sc, 0);
   k_cg_init<<<1, 256, 0, h->stream>>>(pa, pb, sc, tol);
   h->launches += 4;
   EMBA_CUDA(cudaGetLastError());
@@ -1043,7 +1040,7 @@ int solve_pcg(Handle* h, double lambda, int fix, int* iters_out, double* err_out
   for (int it0 = 0; it0 < max_iter; it0 += chunk) {
     for (int k = it0; k < it0 + chunk && k < max_iter; k++) {
       EMBA_TRY(matvec(p, tmp));
-      k_cg_dot<<<kCgDotGrid, 256, 0, h->stream>>>(tot, p, tmp, pa, sc, 1, d, kCgChunks, W > 1 ? nullptr : ypart);
+      k_cg_dot<<<kCgDotGrid, 256, 0, h->stream>>>(tot, p, tmp, pa, sc, 1);
       k_cg_step1<<<kCgDotGrid, 256, 0, h->stream>>>(tot, p, tmp, x, r, pa, pb, sc, k & 1);
       k_cg_step2<<<kCgDotGrid, 256, 0, h->stream>>>(tot, invd, r, z, pb, pc, sc);
       k_cg_step3<<<kCgDotGrid, 256, 0, h->stream>>>(tot, z, p, pc, sc, k & 1, max_iter);

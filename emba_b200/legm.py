@@ -284,7 +284,7 @@ class Engine:
         num = np.empty((self.pano_h, self.pano_w), dtype=np.int32) if want_num else None
         self._chk(self.L.emba_get_evaluation(self.h, which, ptr(ep), ptr(num, C.c_int32)))
         if ep is not None and M is not None:
-            ep = ep[:M].copy()
+            ep = ep[:M]
         return ep, num
 
     # -- normal equations ----------------------------------------------------------------------------
