@@ -618,9 +618,7 @@ def main():
             k_ev, k_as, k_px, Mr, nnz_loc, nnz_solve, k_so, k_mp = allr[r]
             Nr = N / world
             kern_ranks.append({
-                # k_proj (24 B per event of the slice: list id, sensor pixel, warped position written) + k_eval (per pair:
-                # 8 event ids, 16 + 32 warped positions -- the previous event's is a lone 32-byte sector --, 32 written)
-                "k_proj+k_eval": (k_ev, 24.0 * Nr + 88.0 * Mr + 20.0 * P + 0.64 * Nr),
+                "k_eval": (k_ev, 64.0 * Mr + 20.0 * P + 0.64 * Nr),
                 "k_asm_pose": (k_as, 188.0 * Mr + 48.0 * P + 0.64 * Nr),
                 "k_pix": (k_px, 132.0 * Mr + 8.0 * nnz_loc + 40.0 * Np)})
         # the slowest rank decides the step: report its kernels

@@ -101,10 +101,11 @@ constexpr int kSegWarps = 4;
 constexpr int kSegRegCap = 1024;   // longest segment a single warp sorts in registers (32 per lane)
 
 // element i = lane * K + r  (blocked: a lane's K keys are consecutive)
-template <int K>
+// KMIN = 2: full sort. KMIN = 32 K: only the last merge (the two halves are already sorted).
+template <int K, int KMIN = 2>
 __device__ __forceinline__ void warp_bitonic(uint32_t (&a)[K], int lane) {
 #pragma unroll
-  for (int k = 2; k <= 32 * K; k <<= 1) {
+  for (int k = KMIN; k <= 32 * K; k <<= 1) {
     // flip step: i <-> i ^ (k - 1)
     if (k <= K) {
 #pragma unroll
@@ -156,7 +157,7 @@ __device__ __forceinline__ void warp_bitonic(uint32_t (&a)[K], int lane) {
 // on 32-byte boundaries, so a K-key group costs K/8 load instructions instead of K scalar ones that each touch 32
 // sectors (the scalar version was LSU-bound). Reads may run past the segment's end (masked; the buffer has a tail
 // pad), stores never do.
-template <int K>
+template <int K, int KMIN = 2>
 __device__ __forceinline__ void seg_sort_regs(uint32_t* __restrict__ seg, int L, int lane) {
   uint32_t a[K];
   const int i0 = lane * K;
@@ -180,7 +181,7 @@ __device__ __forceinline__ void seg_sort_regs(uint32_t* __restrict__ seg, int L,
 #pragma unroll
   for (int r = 0; r < K; r++)
     if (i0 + r >= L) a[r] = 0xFFFFFFFFu;
-  warp_bitonic<K>(a, lane);
+  warp_bitonic<K, KMIN>(a, lane);
   if (K >= 4) {
 #pragma unroll
     for (int v = 0; v < K / 4; v++) {
@@ -197,7 +198,7 @@ __device__ __forceinline__ void seg_sort_regs(uint32_t* __restrict__ seg, int L,
   }
 }
 
-__global__ void __launch_bounds__(kSegWarps * 32)
+__global__ void __launch_bounds__(kSegWarps * 32, 6)
 k_seg_sort(const int64_t* __restrict__ np_dev, const int32_t* __restrict__ segoff, const int32_t* __restrict__ segend,
            uint32_t* __restrict__ sval, int32_t* __restrict__ longlist) {
   const int lane = threadIdx.x & 31;
@@ -218,8 +219,10 @@ k_seg_sort(const int64_t* __restrict__ np_dev, const int32_t* __restrict__ segof
   }
 }
 
-// segments of 1025 .. 4096 rows: still one warp each, 64 or 128 keys per lane in registers (a rare path: a few per
-// cent of the pixels; the register budget of this kernel does not burden k_seg_sort). Longer ones are left to k_seg_sort_huge.
+// segments of 1025 .. 4096 rows (a few per cent of the pixels): still one warp each. The 1024-key chunks are sorted
+// with the register network above, then merged pairwise by the LAST stage of the same network over 64 and 128 keys
+// per lane (a full 2048 / 4096-key network does not unroll into registers; one merge stage does). Chunks and merged
+// blocks pass through global memory (L1) because the blocked layouts of the three key counts differ.
 constexpr int kSegLongWarps = 2;
 constexpr int kSegLongCap = 4096;
 __global__ void __launch_bounds__(kSegLongWarps * 32)
@@ -232,8 +235,17 @@ k_seg_sort_long(const int32_t* __restrict__ longlist, const int32_t* __restrict_
     const int a = longlist[1 + li];
     const int s0 = segoff[a];
     const int L = segend[a] - s0;
-    if (L <= 2048) seg_sort_regs<64>(sval + s0, L, lane);
-    else if (L <= kSegLongCap) seg_sort_regs<128>(sval + s0, L, lane);
+    if (L > kSegLongCap) continue;
+    uint32_t* seg = sval + s0;
+    for (int c = 0; c < L; c += kSegRegCap) seg_sort_regs<32>(seg + c, min(kSegRegCap, L - c), lane);
+    __syncwarp();
+    seg_sort_regs<64, 2048>(seg, min(2048, L), lane);
+    if (L > 2048) {
+      if (L > 3072) seg_sort_regs<64, 2048>(seg + 2048, L - 2048, lane);
+      __syncwarp();
+      seg_sort_regs<128, 4096>(seg, L, lane);
+    }
+    __syncwarp();
   }
 }
 
@@ -894,12 +906,41 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   h->launches++;
   EMBA_CUDAC(cudaMemcpyAsync(h->h_pin, d_totals, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
   EMBA_CUDAC(cudaEventRecord(h->ev_host, h->stream));
+  // ---- 2. pose side + Jacobian rows
+  const int64_t Mc = h->Mc;
+  const PanoCam cam = make_cam(h);
+  EMBA_CUDAC(cudaEventRecord(h->ev_fork, h->stream));  // the side stream's kernels need everything up to here
+  EMBA_CUDAC(cudaEventRecord(h->ev[5], h->stream));
+  if (h->n_items > 0) {
+    EMBA_TRYC(jrec_tensor_map(h));
+    // The pose-side kernel is HBM-bound and would fill every SM (3 CTAs of 80 registers x 256 threads); padding its
+    // shared-memory request caps it at 2 CTAs per SM, and the row placement / segment sort of the side stream --
+    // compute- and latency-bound -- run in the third that is left instead of queueing behind it.
+    static const int asm_pad = getenv("EMBA_ASM_PAD") ? atoi(getenv("EMBA_ASM_PAD")) : 48 * 1024;
+    if (asm_pad > 48 * 1024 - 33 * 1024) {
+      EMBA_CUDAC(cudaFuncSetAttribute(k_asm_pose<EMBA_COST_QUADRATIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, asm_pad));
+      EMBA_CUDAC(cudaFuncSetAttribute(k_asm_pose<EMBA_COST_CAUCHY>, cudaFuncAttributeMaxDynamicSharedMemorySize, asm_pad));
+      EMBA_CUDAC(cudaFuncSetAttribute(k_asm_pose<EMBA_COST_HUBER>, cudaFuncAttributeMaxDynamicSharedMemorySize, asm_pad));
+    }
+    const CUtensorMap jmap = *reinterpret_cast<const CUtensorMap*>(h->jrec_tmap);
+#define EMBA_ASM_LAUNCH(C)                                                                                         \
+  k_asm_pose<C><<<h->n_items, kAsmThreads, asm_pad, h->stream>>>(jmap, h->d_items, h->d_rec, s.Ktab, s.RotTab,          \
+                                                           s.JacTab, s.G2,                                        \
+                                                           s.H3, s.dp, s.e, s.pix, cam, eta,                       \
+                                                           h->d_jrec,                                              \
+                                                           h->d_win64, h->d_acc_part)
+    if (cost_type == EMBA_COST_QUADRATIC) EMBA_ASM_LAUNCH(EMBA_COST_QUADRATIC);
+    else if (cost_type == EMBA_COST_CAUCHY) EMBA_ASM_LAUNCH(EMBA_COST_CAUCHY);
+    else EMBA_ASM_LAUNCH(EMBA_COST_HUBER);
+#undef EMBA_ASM_LAUNCH
+    h->launches++;
+    EMBA_CUDAC(cudaGetLastError());
+  }
   // ---- 1b. side stream: rows -> pixel segments (k_place) and the per-segment ordering (k_seg_sort*). They need only
   // the evaluation and the segment offsets; they are submitted before the pose-side kernel and the main stream joins
   // them before the map-side kernel.
   if (!atomic_path && h->Mc > 0) {
     const int64_t Mc = h->Mc;
-    EMBA_CUDAC(cudaEventRecord(h->ev_fork, h->stream));
     EMBA_CUDAC(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
     EMBA_CUDAC(cudaEventRecord(h->ev_sort0, h->stream2));
     EMBA_CUDAC(cudaMemsetAsync(h->d_longlist, 0, sizeof(int32_t), h->stream2));
@@ -913,26 +954,6 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
     EMBA_CUDAC(cudaGetLastError());
     EMBA_CUDAC(cudaEventRecord(h->ev_sort1, h->stream2));
     EMBA_CUDAC(cudaEventRecord(h->ev_join, h->stream2));
-  }
-  // ---- 2. pose side + Jacobian rows
-  const int64_t Mc = h->Mc;
-  const PanoCam cam = make_cam(h);
-  EMBA_CUDAC(cudaEventRecord(h->ev[5], h->stream));
-  if (h->n_items > 0) {
-    EMBA_TRYC(jrec_tensor_map(h));
-    const CUtensorMap jmap = *reinterpret_cast<const CUtensorMap*>(h->jrec_tmap);
-#define EMBA_ASM_LAUNCH(C)                                                                                         \
-  k_asm_pose<C><<<h->n_items, kAsmThreads, 0, h->stream>>>(jmap, h->d_items, h->d_rec, s.Ktab, s.RotTab,          \
-                                                           s.JacTab, s.G2,                                        \
-                                                           s.H3, s.dp, s.e, s.pix, cam, eta,                       \
-                                                           h->d_jrec,                                              \
-                                                           h->d_win64, h->d_acc_part)
-    if (cost_type == EMBA_COST_QUADRATIC) EMBA_ASM_LAUNCH(EMBA_COST_QUADRATIC);
-    else if (cost_type == EMBA_COST_CAUCHY) EMBA_ASM_LAUNCH(EMBA_COST_CAUCHY);
-    else EMBA_ASM_LAUNCH(EMBA_COST_HUBER);
-#undef EMBA_ASM_LAUNCH
-    h->launches++;
-    EMBA_CUDAC(cudaGetLastError());
   }
   EMBA_CUDAC(cudaEventRecord(h->ev[6], h->stream));
   EMBA_CUDAC(cudaEventSynchronize(h->ev_host));

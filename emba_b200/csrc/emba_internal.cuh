@@ -81,7 +81,6 @@ struct StateSlot {
   double* Ktab = nullptr;    // [n*kKnotStride] per knot interval s: R_s (9, row-major), delta_w = Log(R_{s+1} R_s^-1) (3)
   double4* RotTab = nullptr; // [B] per batch: (s1, s2, knot index s, 0): R_batch = (I + s1 K + s2 K^2) R_s, K = [delta_w]x
   double4* JacTab = nullptr; // [B] per batch: (alpha, beta, gamma, 0): A = alpha I + beta K + gamma K^2
-  double2* pm = nullptr;     // [Nuse] warped position of every event the shard touches (indexed by event)
   double2* dp = nullptr;     // [Mc] displacement pm_c - pm_p
   double* e = nullptr;       // [Mc] residual
   int32_t* pix = nullptr;    // [Mc] pano pixel index of the current event, -1 = outlier
@@ -120,7 +119,6 @@ struct Handle {
   int64_t P = 0;
   double C_th = 0;
   double* d_lut = nullptr;  // [Ws*Hs*3]
-  double* d_lut_unit = nullptr;  // [Ws*Hs*3] the same bearings normalised (the projection is homogeneous of degree 0)
   // events
   int64_t N = 0, Nuse = 0, B = 0;
   int64_t* d_tmid = nullptr;     // [B]
@@ -135,9 +133,6 @@ struct Handle {
   int32_t* d_bs = nullptr;    // [B] knot index s of the batch mid-time
   double* d_bu = nullptr;     // [B] u in [0,1)
   MeasRec* d_rec = nullptr;   // [Mc] canonical order, this shard only (32 B, read as two coalesced 16 B loads)
-  uint2* d_mpair = nullptr;   // [Mc] (current event | polarity << 31, previous event) of the measurement
-  uint32_t* d_projlist = nullptr;  // [n_proj] events this shard's measurements touch (ascending): the ones k_proj warps
-  int64_t n_proj = 0;
   uint32_t* d_refpos = nullptr;  // [Mc] rank of the pair in the reference's order (sensor pixel row-major, then time)
   int64_t Mc = 0;             // measurements of this shard
   std::vector<WorkItem> h_items;

@@ -131,45 +131,43 @@ __device__ __forceinline__ double rho_of(double e, double a) {
   return ab < a ? 0.5 * ab * ab : a * ab - 0.5 * a * a;
 }
 
+// (Projecting every EVENT once into a 16-byte array and forming the pairs from it -- half the atan2 / asin -- was
+// built and measured on C4: 1.47 ms projection + 2.81 ms pair kernel against 3.7 ms for this fused kernel. The pair
+// kernel is bound by its gathers and the counting atomic, not by the fp64 pipe, so the split only added traffic.)
 constexpr int kEvalThreads = 256;
-
-// warped position of every event the shard's measurements touch, ONCE per event: an event is the current event of one
-// pair and the previous event of the next pair of its sensor pixel, so projecting per measurement did every
-// atan2 / asin twice (k_eval was fp64-ALU bound on exactly those). Events of one batch share the batch pose: the two
-// table reads are warp-uniform almost always.
-__global__ void __launch_bounds__(256)
-k_proj(const uint32_t* __restrict__ list, int64_t n_list, const uint32_t* __restrict__ spix,
-       const double* __restrict__ lut_unit, const double* __restrict__ Ktab, const double4* __restrict__ RotTab,
-       PanoCam cam, double2* __restrict__ pm) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_list) return;
-  const uint32_t ev = list[i];
-  const size_t sp = spix[ev];
-  const double bx = lut_unit[3 * sp], by = lut_unit[3 * sp + 1], bz = lut_unit[3 * sp + 2];
-  const double4 rt = ldg256(RotTab + ev / kBatch);
-  const int sk = (int)__double_as_longlong(rt.z);
-  double X, Y, Z, px, py;
-  rotate_bearing(Ktab + (size_t)sk * kKnotStride, rt.x, rt.y, bx, by, bz, X, Y, Z);
-  project_pm_unit(cam, X, Y, Z, px, py);
-  pm[ev] = make_double2(px, py);
-}
 
 template <int COST>
 __global__ void __launch_bounds__(kEvalThreads)
-k_eval(const uint2* __restrict__ mpair, int64_t Mc, const double2* __restrict__ pm, const double2* __restrict__ G2,
-       int W, int H, double C_th, double eta,
+k_eval(const MeasRec* __restrict__ rec, int64_t Mc, const double* __restrict__ Ktab,
+       const double4* __restrict__ RotTab, const double2* __restrict__ G2, PanoCam cam, int W, int H, double C_th, double eta,
        double2* __restrict__ dp_out, double* __restrict__ e_out, int32_t* __restrict__ pix_out,
        int32_t* __restrict__ slot_out, int32_t* __restrict__ hist, double* __restrict__ part,
        int32_t* __restrict__ flags) {
   double cost = 0.0;
   double cnt = 0.0;
   for (int64_t m = (int64_t)blockIdx.x * kEvalThreads + threadIdx.x; m < Mc; m += (int64_t)gridDim.x * kEvalThreads) {
-    const uint2 pr = mpair[m];
-    const double pol = (pr.x >> 31) ? 1.0 : 0.0;
-    const double2 pc = pm[pr.x & 0x7FFFFFFFu];
-    const double2 pp = pm[pr.y];
-    const double pcx = pc.x, pcy = pc.y;
-    const double dx = pcx - pp.x, dy = pcy - pp.y;
+    const double4 r0 = ldg256(rec + m);
+    const double bx = r0.x, by = r0.y, bz = r0.z;
+    const unsigned long long w = (unsigned long long)__double_as_longlong(r0.w);
+    const uint32_t bcp = (uint32_t)w, bp = (uint32_t)(w >> 32);
+    const uint32_t bc = bcp & 0x7FFFFFFFu;
+    const double pol = (bcp >> 31) ? 1.0 : 0.0;
+    double pcx, pcy, ppx, ppy;
+    {
+      const double4 rt = ldg256(RotTab + bc);
+      const int sk = (int)__double_as_longlong(rt.z);
+      double X, Y, Z;
+      rotate_bearing(Ktab + (size_t)sk * kKnotStride, rt.x, rt.y, bx, by, bz, X, Y, Z);
+      project_pm_unit(cam, X, Y, Z, pcx, pcy);
+    }
+    {
+      const double4 rt = ldg256(RotTab + bp);
+      const int sk = (int)__double_as_longlong(rt.z);
+      double X, Y, Z;
+      rotate_bearing(Ktab + (size_t)sk * kKnotStride, rt.x, rt.y, bx, by, bz, X, Y, Z);
+      project_pm_unit(cam, X, Y, Z, ppx, ppy);
+    }
+    const double dx = pcx - ppx, dy = pcy - ppy;
     // dp.norm() > 10 (model.cpp:199-200), evaluated without FMA contraction like the CPU build
     const double nrm = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
     int32_t pix = -1, slot = -1;
@@ -334,11 +332,8 @@ int evaluate_slot(Handle* h, int slot, int cost_type, double eta, double alpha) 
   const PanoCam cam = make_cam(h);
   EMBA_CUDA(cudaEventRecord(h->ev[1], h->stream));
   if (h->Mc > 0) {
-    k_proj<<<ceil_div64(h->n_proj, 256), 256, 0, h->stream>>>(h->d_projlist, h->n_proj, h->d_spix_ev, h->d_lut_unit,
-                                                              s.Ktab, s.RotTab, cam, s.pm);
-    h->launches++;
 #define EMBA_EVAL_LAUNCH(C)                                                                                       \
-  k_eval<C><<<grid, kEvalThreads, 0, h->stream>>>(h->d_mpair, h->Mc, s.pm, s.G2, h->Wp, h->Hp,                    \
+  k_eval<C><<<grid, kEvalThreads, 0, h->stream>>>(h->d_rec, h->Mc, s.Ktab, s.RotTab, s.G2, cam, h->Wp, h->Hp,     \
                                                   h->C_th, eta, s.dp, s.e, s.pix, s.slot, s.hist_loc, h->d_part,   \
                                                   h->d_flags)
     if (cost_type == EMBA_COST_QUADRATIC) EMBA_EVAL_LAUNCH(EMBA_COST_QUADRATIC);

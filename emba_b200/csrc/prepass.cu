@@ -138,45 +138,26 @@ __global__ void k_head_scatter(const uint32_t* __restrict__ key, const int32_t* 
   if (j == M - 1) *total = (int64_t)gidx[j] + flag[j];
 }
 
-// unit bearings: rotations keep the norm, and both the projection (atan2 of a ratio, asin of y / norm) and its
-// Jacobian are homogeneous of degree 0 in the bearing, so the per-projection norm and division
-// (equirectangular_camera.h:22-24) are done once per sensor pixel here
-__global__ void k_unit_lut(const double* __restrict__ lut, int64_t S, double* __restrict__ out) {
-  const int64_t sp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (sp >= S) return;
-  const double lx = lut[3 * sp], ly = lut[3 * sp + 1], lz = lut[3 * sp + 2];
-  const double inv = 1.0 / sqrt(lx * lx + ly * ly + lz * lz);
-  out[3 * sp] = lx * inv; out[3 * sp + 1] = ly * inv; out[3 * sp + 2] = lz * inv;
-}
-
 __global__ void k_build_recs(const uint32_t* __restrict__ sev, int64_t m_lo, int64_t Mloc,
                              const uint32_t* __restrict__ spix, const uint8_t* __restrict__ pol,
                              const int32_t* __restrict__ prev, const uint32_t* __restrict__ refrank,
-                             const double* __restrict__ lut_unit, MeasRec* __restrict__ rec,
-                             uint32_t* __restrict__ refpos, uint2* __restrict__ mpair, int32_t* __restrict__ need) {
+                             const double* __restrict__ lut, MeasRec* __restrict__ rec,
+                             uint32_t* __restrict__ refpos) {
   int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= Mloc) return;
   const uint32_t ev = sev[m_lo + j];
-  const uint32_t pv = (uint32_t)prev[ev];
   MeasRec r;
   const size_t sp = spix[ev];
-  r.bx = lut_unit[3 * sp]; r.by = lut_unit[3 * sp + 1]; r.bz = lut_unit[3 * sp + 2];
-  const uint32_t pbit = (uint32_t)(pol[ev] ? 1u : 0u) << 31;
-  r.bc_pol = (ev / kBatch) | pbit;
-  r.bp = pv / kBatch;
+  // unit bearing: rotations keep the norm, and both the projection (atan2 of a ratio, asin of y / norm) and its
+  // Jacobian are homogeneous of degree 0 in the bearing, so the per-measurement norm and division
+  // (equirectangular_camera.h:22-24) are done once here instead of twice per evaluation
+  const double lx = lut[3 * sp], ly = lut[3 * sp + 1], lz = lut[3 * sp + 2];
+  const double inv = 1.0 / sqrt(lx * lx + ly * ly + lz * lz);
+  r.bx = lx * inv; r.by = ly * inv; r.bz = lz * inv;
+  r.bc_pol = (ev / kBatch) | ((uint32_t)(pol[ev] ? 1u : 0u) << 31);
+  r.bp = (uint32_t)prev[ev] / kBatch;
   rec[j] = r;
   refpos[j] = refrank[ev];
-  mpair[j] = make_uint2(ev | pbit, pv);
-  need[ev] = 1;   // events whose warped position the evaluation needs (benign races: everybody writes 1)
-  need[pv] = 1;
-}
-
-__global__ void k_proj_list(const int32_t* __restrict__ need, const int32_t* __restrict__ pos, int64_t N,
-                            uint32_t* __restrict__ list, int64_t* __restrict__ total) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  if (need[i]) list[pos[i]] = (uint32_t)i;
-  if (i == N - 1) *total = (int64_t)pos[i] + need[i];
 }
 
 static int bits_for(uint64_t maxval) {
@@ -306,15 +287,9 @@ int emba_create(const emba_config_t* cfg, emba_handle_t* out) {
   const size_t lut_bytes = sizeof(double) * 3 * (size_t)h->Ws * h->Hs;
   bool ok = cudaMalloc((void**)&h->d_lut, lut_bytes) == cudaSuccess &&
             cudaMemcpy(h->d_lut, cfg->bearing_lut, lut_bytes, cudaMemcpyHostToDevice) == cudaSuccess &&
-            cudaMalloc((void**)&h->d_lut_unit, lut_bytes) == cudaSuccess &&
             cudaMalloc((void**)&h->d_scal, sizeof(double) * 64) == cudaSuccess &&
             cudaMalloc((void**)&h->d_flags, sizeof(int32_t) * 16) == cudaSuccess &&
             cudaMemset(h->d_flags, 0, sizeof(int32_t) * 16) == cudaSuccess;
-  if (ok) {
-    const int64_t S = (int64_t)h->Ws * h->Hs;
-    k_unit_lut<<<ceil_div64(S, 256), 256, 0, h->stream>>>(h->d_lut, S, h->d_lut_unit);
-    ok = cudaStreamSynchronize(h->stream) == cudaSuccess;
-  }
   for (int s = 0; s < 2 && ok; s++) {
     StateSlot& st = h->st[s];
     ok = ok && cudaMalloc((void**)&st.Gx, sizeof(double) * h->P) == cudaSuccess &&
@@ -367,7 +342,7 @@ int emba_destroy(emba_handle_t hh) {
     cudaFree(st.Gx); cudaFree(st.Gy); cudaFree(st.G2); cudaFree(st.H3); cudaFree(st.hist);
     st = StateSlot();
   }
-  void* ptrs[] = {h->d_lut, h->d_lut_unit, h->ar_ev.base, h->ar_meas.base, h->ar_tmp.base, h->d_part, h->d_scal, h->d_flags, h->d_amap,
+  void* ptrs[] = {h->d_lut, h->ar_ev.base, h->ar_meas.base, h->ar_tmp.base, h->d_part, h->d_scal, h->d_flags, h->d_amap,
                   h->d_pflag, h->d_paidx, h->d_len, h->d_apix, h->d_segoff, h->d_segend, h->d_segcnt, h->d_longlist,
                   h->d_scan_tmp, h->d_gmask, h->d_gmask2, h->d_win64, h->d_winlo, h->d_winhi, h->d_stripoff, h->d_strip,
                   h->d_A22, h->d_b2, h->d_A11, h->d_b1, h->d_C, h->d_S, h->d_rhs, h->d_x1, h->d_x2, h->d_Spart, h->d_cg,
@@ -878,8 +853,7 @@ int rebuild_static(Handle* h) {
   const int64_t Mc = h->Mc;
   const size_t Mp = (size_t)std::max<int64_t>(Mc, 1);
   size_t mb = 0;
-  mb += Arena::pad(sizeof(MeasRec) * Mp) + Arena::pad(4 * Mp) + Arena::pad(8 * Mp);  // rec, refpos, mpair
-  mb += Arena::pad(4 * (size_t)std::max<int64_t>(Nu, 1)) + 2 * Arena::pad(16 * (size_t)std::max<int64_t>(Nu, 1));  // projection list, pm x 2 states
+  mb += Arena::pad(sizeof(MeasRec) * Mp) + Arena::pad(4 * Mp);                     // rec, refpos
   mb += 2 * (Arena::pad(16 * Mp) + Arena::pad(8 * Mp) + 2 * Arena::pad(4 * Mp));   // dp, e, pix, slot  x 2 states
   const size_t sval_len = Mp + 8 * std::min<size_t>((size_t)h->P, Mp) + 8192;      // segments padded to 8 ids + tail pad
   mb += Arena::pad(8 * (size_t)kRecDoubles * Mp) + Arena::pad(4 * sval_len);       // Jacobian rows, sorted row ids
@@ -892,11 +866,8 @@ int rebuild_static(Handle* h) {
   Arena& A = h->ar_meas;
   h->d_rec = A.take<MeasRec>(Mc);
   h->d_refpos = A.take<uint32_t>(Mc);
-  h->d_mpair = A.take<uint2>(Mc);
-  h->d_projlist = A.take<uint32_t>(Nu);
   for (int s = 0; s < 2; s++) {
     StateSlot& st = h->st[s];
-    st.pm = A.take<double2>(Nu);
     st.dp = A.take<double2>(Mc); st.e = A.take<double>(Mc); st.pix = A.take<int32_t>(Mc); st.slot = A.take<int32_t>(Mc);
     st.quat = A.take<double>((int64_t)n * 4);
     st.Ktab = A.take<double>((int64_t)n * kKnotStride);
@@ -917,21 +888,10 @@ int rebuild_static(Handle* h) {
   if (h->n_items) EMBA_CUDA(cudaMemcpyAsync(h->d_items, h->h_items.data(), sizeof(WorkItem) * h->n_items, cudaMemcpyHostToDevice, h->stream));
   if (!gid.empty()) EMBA_CUDA(cudaMemcpyAsync(h->d_gid, gid.data(), sizeof(int32_t) * gid.size(), cudaMemcpyHostToDevice, h->stream));
   EMBA_CUDA(cudaMemcpyAsync(h->d_group_item0, item0.data(), sizeof(int32_t) * item0.size(), cudaMemcpyHostToDevice, h->stream));
-  h->n_proj = 0;
   if (Mc) {
-    // (the scratch arena's flag / position arrays are free again: the sorted event list lives in the key buffers)
-    int32_t* d_need = d_flag;
-    EMBA_CUDA(cudaMemsetAsync(d_need, 0, sizeof(int32_t) * Nu, h->stream));
     k_build_recs<<<ceil_div64(Mc, T), T, 0, h->stream>>>(vs, m_lo, Mc, h->d_spix_ev, h->d_pol, h->d_prev,
-                                                        h->d_refrank, h->d_lut_unit, h->d_rec, h->d_refpos, h->d_mpair,
-                                                        d_need);
+                                                        h->d_refrank, h->d_lut, h->d_rec, h->d_refpos);
     EMBA_LAUNCH_CHECK();
-    EMBA_TRY(scan_exclusive<int32_t>(h, h->stream, d_need, d_pos, Nu, scr));
-    k_proj_list<<<ceil_div64(Nu, T), T, 0, h->stream>>>(d_need, d_pos, Nu, h->d_projlist, d_total);
-    EMBA_LAUNCH_CHECK();
-    EMBA_CUDA(cudaMemcpyAsync(h->h_pin + 8, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
-    EMBA_CUDA(cudaStreamSynchronize(h->stream));
-    h->n_proj = h->h_pin[8];
   }
   EMBA_CUDA(cudaEventRecord(h->ev[1], h->stream));
   EMBA_CUDA(cudaStreamSynchronize(h->stream));  // the host vectors above go out of scope
