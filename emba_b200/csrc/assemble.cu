@@ -81,15 +81,24 @@ __global__ void k_active_fill(const int32_t* __restrict__ flag, const int32_t* _
 
 // every inlier row on an active pixel goes to its slot of the pixel's segment (a separate pass: fused into the
 // pose-side kernel the scattered 4-byte stores cost that HBM-bound kernel 2.8 ms on C4, alone they take 1.7 ms)
+constexpr int kPlaceRows = 4;  // rows per thread: the dependent gather chain pix -> rowbase[pix] -> store of four rows
+                               // is in flight at once (the one-row version issued 7 % of the time: pure latency)
 __global__ void __launch_bounds__(256)
 k_place(int64_t Mc, const int32_t* __restrict__ pix, const int32_t* __restrict__ slot,
         const int32_t* __restrict__ rowbase, uint32_t* __restrict__ sval) {
-  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= Mc) return;
-  const int32_t p = pix[m];
-  if (p < 0) return;
-  const int32_t base = rowbase[p];
-  if (base >= 0) sval[(int64_t)base + slot[m]] = (uint32_t)m;
+  const int64_t m0 = (int64_t)blockIdx.x * (256 * kPlaceRows) + threadIdx.x;
+  int32_t p[kPlaceRows], sl[kPlaceRows], base[kPlaceRows];
+#pragma unroll
+  for (int k = 0; k < kPlaceRows; k++) {
+    const int64_t m = m0 + k * 256;
+    p[k] = m < Mc ? pix[m] : -1;
+    sl[k] = m < Mc ? slot[m] : 0;
+  }
+#pragma unroll
+  for (int k = 0; k < kPlaceRows; k++) base[k] = p[k] >= 0 ? rowbase[p[k]] : -1;
+#pragma unroll
+  for (int k = 0; k < kPlaceRows; k++)
+    if (base[k] >= 0) sval[(int64_t)base[k] + sl[k]] = (uint32_t)(m0 + k * 256);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -913,16 +922,16 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   EMBA_CUDAC(cudaEventRecord(h->ev[5], h->stream));
   if (h->n_items > 0) {
     EMBA_TRYC(jrec_tensor_map(h));
-    // The pose-side kernel is HBM-bound and would fill every SM (3 CTAs of 80 registers x 256 threads); padding its
-    // shared-memory request caps it at 2 CTAs per SM, and the row placement / segment sort of the side stream --
-    // compute- and latency-bound -- run in the third that is left instead of queueing behind it.
-    static const int asm_pad = getenv("EMBA_ASM_PAD") ? atoi(getenv("EMBA_ASM_PAD")) : 48 * 1024;
+    // (Capping this HBM-bound kernel at 2 CTAs per SM with a shared-memory pad, to leave a third of every SM to the
+    // side stream's placement / segment sort, was measured on C4: form 14.3 ms against 13.3 ms without the pad. What
+    // matters is the submission order -- this kernel first, the side stream's kernels behind it: they then fill the
+    // SMs as its CTAs retire instead of delaying its start. EMBA_ASM_PAD keeps the experiment reachable.)
+    static const int asm_pad = getenv("EMBA_ASM_PAD") ? atoi(getenv("EMBA_ASM_PAD")) : 0;
     if (asm_pad > 48 * 1024 - 33 * 1024) {
       EMBA_CUDAC(cudaFuncSetAttribute(k_asm_pose<EMBA_COST_QUADRATIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, asm_pad));
       EMBA_CUDAC(cudaFuncSetAttribute(k_asm_pose<EMBA_COST_CAUCHY>, cudaFuncAttributeMaxDynamicSharedMemorySize, asm_pad));
       EMBA_CUDAC(cudaFuncSetAttribute(k_asm_pose<EMBA_COST_HUBER>, cudaFuncAttributeMaxDynamicSharedMemorySize, asm_pad));
     }
-    const CUtensorMap jmap = *reinterpret_cast<const CUtensorMap*>(h->jrec_tmap);
 #define EMBA_ASM_LAUNCH(C)                                                                                         \
   k_asm_pose<C><<<h->n_items, kAsmThreads, asm_pad, h->stream>>>(jmap, h->d_items, h->d_rec, s.Ktab, s.RotTab,          \
                                                            s.JacTab, s.G2,                                        \
@@ -944,7 +953,7 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
     EMBA_CUDAC(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
     EMBA_CUDAC(cudaEventRecord(h->ev_sort0, h->stream2));
     EMBA_CUDAC(cudaMemsetAsync(h->d_longlist, 0, sizeof(int32_t), h->stream2));
-    k_place<<<ceil_div64(Mc, T), T, 0, h->stream2>>>(Mc, s.pix, s.slot, d_rowbase, h->d_sval);
+    k_place<<<ceil_div64(Mc, 256 * kPlaceRows), 256, 0, h->stream2>>>(Mc, s.pix, s.slot, d_rowbase, h->d_sval);
     k_seg_sort<<<h->sm_count * 32, kSegWarps * 32, 0, h->stream2>>>(d_totals, h->d_segoff, h->d_segend, h->d_sval, h->d_longlist);
     k_seg_sort_long<<<h->sm_count * 16, kSegLongWarps * 32, 0, h->stream2>>>(h->d_longlist, h->d_segoff, h->d_segend, h->d_sval);
     const int huge_smem = 200 * 1024;

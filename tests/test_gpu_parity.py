@@ -255,7 +255,10 @@ def test_lm_variants_vs_oracle(tiny):
         log, fc = eng.solve_time_window(max_num_iter=6, alpha=ALPHA, thres=THRES, **kw_e)
         assert log.shape[0] == log_o.shape[0]
         assert np.array_equal(log[:, 4], log_o[:, 4])
-        assert np.max(np.abs(log[:, 3] - log_o[:, 3]) / log_o[:, 3]) < 1e-6
+        # the direct solve agrees to rounding; PCG stops at a relative residual of 1e-6 (model.cpp:828-831), so two
+        # implementations that sum in different orders agree on the step -- and on the cost -- only to about that
+        cost_tol = 2e-5 if kw_e.get("use_cg") else 1e-6
+        assert np.max(np.abs(log[:, 3] - log_o[:, 3]) / log_o[:, 3]) < cost_tol
         q, gx, gy = eng.get_state(0)
         ang = 2 * np.arccos(np.abs(np.sum(q * q_o, -1)).clip(0, 1))
         assert np.max(ang) < 1e-5 and rel(gx_o, gx) < 1e-4 and rel(gy_o, gy) < 1e-4
