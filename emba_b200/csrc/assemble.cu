@@ -932,6 +932,7 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
       EMBA_CUDAC(cudaFuncSetAttribute(k_asm_pose<EMBA_COST_CAUCHY>, cudaFuncAttributeMaxDynamicSharedMemorySize, asm_pad));
       EMBA_CUDAC(cudaFuncSetAttribute(k_asm_pose<EMBA_COST_HUBER>, cudaFuncAttributeMaxDynamicSharedMemorySize, asm_pad));
     }
+    const CUtensorMap jmap = *reinterpret_cast<const CUtensorMap*>(h->jrec_tmap);
 #define EMBA_ASM_LAUNCH(C)                                                                                         \
   k_asm_pose<C><<<h->n_items, kAsmThreads, asm_pad, h->stream>>>(jmap, h->d_items, h->d_rec, s.Ktab, s.RotTab,          \
                                                            s.JacTab, s.G2,                                        \
