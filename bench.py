@@ -404,6 +404,7 @@ def main():
     launches = eng.launch_count() - l0
     clk = clocks.stop()
     cnt = eng.counters()
+    comm = eng.comm_ms() if world > 1 else None
     ms_dev = float(np.mean(dev_ms))
     t_red = torch.tensor([ms_dev, wall], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -672,6 +673,8 @@ def main():
         }
         if parity_mgpu is not None:
             out["parity_multi_gpu"] = parity_mgpu
+        if comm is not None:
+            out["comm_ms_rank0_last_step"] = comm
         if world == 1 and not args.no_cpu_baseline:
             # bounded sample: ~10-30 s of single-thread CPU work on a prefix of the same window; its outputs double as
             # a parity check of the device path on the same prefix

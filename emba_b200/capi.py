@@ -81,6 +81,7 @@ SIGNATURES = {
     "emba_set_strict_range": (C.c_int, [_H, C.c_int32]),
     "emba_get_jacobian_rows": (C.c_int, [_H, _dp, C.c_int64, C.POINTER(C.c_int64)]),
     "emba_last_setup_ms": (C.c_int, [_H, _dp]),
+    "emba_last_comm_ms": (C.c_int, [_H, _dp]),
     "emba_get_counters": (C.c_int, [_H, C.POINTER(C.c_int64)]),
     "emba_events_create": (C.c_int, [C.c_int32, C.c_int64, C.POINTER(C.c_uint16), C.POINTER(C.c_uint16),
                                      C.POINTER(C.c_int64), C.POINTER(C.c_uint8), C.POINTER(C.c_void_p)]),

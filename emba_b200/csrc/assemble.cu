@@ -29,6 +29,7 @@ int comm_allreduce(Handle* h, void* buf, int64_t count, int dtype);
 int comm_exchange_prepare(Handle* h);
 int comm_exchange_sizes(Handle* h);
 int comm_exchange_step(Handle* h, int step, cudaStream_t st);
+int comm_exchange_all(Handle* h, cudaStream_t st);
 int comm_exchange_finish(Handle* h);
 
 // ---------------------------------------------------------------------------------------------------
@@ -1000,9 +1001,13 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   // kernel, so that the transfers can overlap it (the host reads those numbers with the same synchronisation as
   // the strip total)
   const bool exchange = h->world > 1 && Np > 0 && !atomic_path;
+  static const bool pipe_env = !(getenv("EMBA_XCHG_PIPELINE") && atoi(getenv("EMBA_XCHG_PIPELINE")) == 0);
+  const bool pipelined = pipe_env && h->world <= 64;
   if (exchange) {
+    EMBA_CUDAC(cudaEventRecord(h->ev_x[2], h->stream));
     EMBA_TRYC(comm_exchange_prepare(h));
     EMBA_CUDAC(cudaEventRecord(h->ev_host, h->stream));
+    EMBA_CUDAC(cudaEventRecord(h->ev_x[3], h->stream));
   }
   EMBA_CUDAC(cudaEventSynchronize(h->ev_host));
   const int64_t tot = h->h_pin[2];
@@ -1051,7 +1056,7 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
       EMBA_CUDAC(cudaGetLastError());
       return EMBA_OK;
     };
-    if (!exchange || h->world > 64) {
+    if (!exchange || !pipelined) {
       EMBA_TRYC(launch_pix(0, Np));
     } else {
       // one launch per owner's pixel range, in ring order: the strips of rank r+1's pixels first -- they leave on the
@@ -1084,12 +1089,14 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
       EMBA_CUDAC(cudaStreamSynchronize(h->stream));
       EMBA_TRYC(comm_exchange_sizes(h));
     }
-    if (!exchange || h->world > 64) {
-      for (int st = 1; st < h->world; st++) EMBA_TRYC(comm_exchange_step(h, st, h->stream));
+    if (!exchange || !pipelined) {
+      EMBA_TRYC(comm_exchange_all(h, h->stream));
     } else {
       EMBA_CUDAC(cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
     }
+    EMBA_CUDAC(cudaEventRecord(h->ev_x[4], h->stream));
     EMBA_TRYC(comm_exchange_finish(h));
+    EMBA_CUDAC(cudaEventRecord(h->ev_x[5], h->stream));
   }
   EMBA_CUDAC(cudaEventRecord(h->ev[7], h->stream));
   EMBA_CUDAC(cudaStreamSynchronize(h->stream));
@@ -1100,6 +1107,11 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   cudaEventElapsedTime(&ms, h->ev[9], h->ev[10]); h->t_ms[6] = ms;
   h->t_ms[7] = 0.0;
   if (!atomic_path && Mc > 0) { cudaEventElapsedTime(&ms, h->ev_sort0, h->ev_sort1); h->t_ms[7] = ms; }
+  if (exchange) {
+    cudaEventElapsedTime(&ms, h->ev_x[2], h->ev_x[3]); h->t_comm_ms[1] = ms;
+    cudaEventElapsedTime(&ms, h->ev[9], h->ev_x[4]); h->t_comm_ms[2] = ms;
+    cudaEventElapsedTime(&ms, h->ev_x[4], h->ev_x[5]); h->t_comm_ms[3] = ms;
+  }
 #undef EMBA_TRYC
 #undef EMBA_CUDAC
   h->formed = true;

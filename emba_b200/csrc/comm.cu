@@ -299,6 +299,24 @@ int comm_exchange_step(Handle* h, int step, cudaStream_t st) {
   return EMBA_OK;
 }
 
+// all steps as ONE NCCL group (one launch): the unpipelined exchange, after the map-side kernel has finished
+int comm_exchange_all(Handle* h, cudaStream_t st) {
+  NcclApi* api = nccl_api();
+  const int W = h->world, r = h->rank;
+  if (api->group_start() != 0) { h->err = "ncclGroupStart failed"; return EMBA_E_NCCL; }
+  int rc = 0;
+  for (int q = 0; q < W; q++) {
+    if (q == r) continue;
+    const int64_t scount = (h->x_send_off[q + 1] - h->x_send_off[q]) * 6;
+    const int64_t rcount = h->x_recv_cnt[q] * 6;
+    if (scount > 0) rc |= api->send(h->d_strip + h->x_send_off[q] * 6, (size_t)scount, 8, q, h->nccl_comm, st);
+    if (rcount > 0) rc |= api->recv(h->d_recv + h->x_recvbase[q] * 6, (size_t)rcount, 8, q, h->nccl_comm, st);
+  }
+  if (api->group_end() != 0 || rc != 0) { h->err = "ncclSend/ncclRecv failed"; return EMBA_E_NCCL; }
+  h->launches++;
+  return EMBA_OK;
+}
+
 int comm_exchange_finish(Handle* h) {
   NcclApi* api = nccl_api();
   const int W = h->world, r = h->rank;

@@ -101,6 +101,8 @@ struct Handle {
   cudaStream_t stream3 = nullptr;  // communication stream of the pipelined strip exchange (several GPUs)
   cudaEvent_t ev_chunk[64] = {};   // k_pix finished the pixel range of owner (rank + s)
   cudaEvent_t ev_comm = nullptr;
+  cudaEvent_t ev_x[8] = {};        // timing marks of the multi-GPU exchange phases
+  double t_comm_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   std::vector<int64_t> x_recv_cnt, x_send_off, x_recvbase;  // strip exchange: poses received per source rank, my
   int64_t x_gtot = 0;                                        // strip offsets at the ownership boundaries, merged total
   int64_t* d_glen = nullptr;       // [P+2] merged strip lengths

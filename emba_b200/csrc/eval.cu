@@ -355,16 +355,9 @@ int evaluate_slot(Handle* h, int slot, int cost_type, double eta, double alpha) 
   EMBA_LAUNCH_CHECK();
   if (h->world > 1) {
     // the active-pixel decision is global: combine the histogram and the scalars
-    static const bool dbg = getenv("EMBA_DEBUG_TIMING") != nullptr;
-    cudaEvent_t d0, d1;
-    if (dbg) { cudaEventCreate(&d0); cudaEventCreate(&d1); cudaEventRecord(d0, h->stream); }
+    EMBA_CUDA(cudaEventRecord(h->ev_x[0], h->stream));
     EMBA_TRY(comm_allreduce_eval(h, s.hist_loc, s.hist, h->P, h->d_scal, h->d_flags));
-    if (dbg) {
-      cudaEventRecord(d1, h->stream); cudaStreamSynchronize(h->stream);
-      float ms; cudaEventElapsedTime(&ms, d0, d1);
-      if (h->rank == 0) fprintf(stderr, "[emba evaluate] hist+scalar all-reduce %.3f ms\n", ms);
-      cudaEventDestroy(d0); cudaEventDestroy(d1);
-    }
+    EMBA_CUDA(cudaEventRecord(h->ev_x[1], h->stream));
   }
   EMBA_CUDA(cudaEventRecord(h->ev[3], h->stream));
   double sc[3];
@@ -375,6 +368,7 @@ int evaluate_slot(Handle* h, int slot, int cost_type, double eta, double alpha) 
   float ms = 0;
   cudaEventElapsedTime(&ms, h->ev[0], h->ev[3]); h->t_ms[0] = ms;
   cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->t_ms[1] = ms;
+  if (h->world > 1) { cudaEventElapsedTime(&ms, h->ev_x[0], h->ev_x[1]); h->t_comm_ms[0] = ms; }
   s.cost_data = sc[0];
   s.M = (int64_t)llround(sc[1]);
   s.cost_reg = 0.5 * alpha * sc[2];

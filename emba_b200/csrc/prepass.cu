@@ -277,6 +277,7 @@ int emba_create(const emba_config_t* cfg, emba_handle_t* out) {
   cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming);
   if (cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking) != cudaSuccess) { delete h; return EMBA_E_CUDA; }
   for (auto& e : h->ev_chunk) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+  for (auto& e : h->ev_x) cudaEventCreate(&e);
   if (cudaMallocHost((void**)&h->h_pin, 1024 * sizeof(int64_t)) != cudaSuccess) { delete h; return EMBA_E_CUDA; }
   cudaEventCreate(&h->ev_sort0);
   cudaEventCreate(&h->ev_sort1);
@@ -353,6 +354,7 @@ int emba_destroy(emba_handle_t hh) {
   for (cudaEvent_t e : {h->ev_fork, h->ev_join, h->ev_fork2, h->ev_join2, h->ev_sort0, h->ev_sort1, h->ev_host}) if (e) cudaEventDestroy(e);
   uploader_free(h->up);
   for (auto& e : h->ev_chunk) if (e) cudaEventDestroy(e);
+  for (auto& e : h->ev_x) if (e) cudaEventDestroy(e);
   if (h->ev_comm) cudaEventDestroy(h->ev_comm);
   if (h->d_glen) cudaFree(h->d_glen);
   if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -902,6 +904,13 @@ int rebuild_static(Handle* h) {
 }
 
 }  // namespace emba
+
+extern "C" int emba_last_comm_ms(emba_handle_t hh, double* out8) {
+  Handle* h = (Handle*)hh;
+  if (!h || !out8) return EMBA_E_ARG;
+  for (int i = 0; i < 8; i++) out8[i] = h->t_comm_ms[i];
+  return EMBA_OK;
+}
 
 extern "C" int emba_last_setup_ms(emba_handle_t hh, double* out2) {
   Handle* h = (Handle*)hh;

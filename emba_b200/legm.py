@@ -220,6 +220,11 @@ class Engine:
                     rows_on_active_rank=int(out[3]), a12_entries_local=int(out[4]), a12_entries_solve=int(out[5]),
                     work_items=int(out[6]), long_segments=int(out[7]))
 
+    def comm_ms(self):
+        out = np.zeros(8)
+        self._chk(self.L.emba_last_comm_ms(self.h, ptr(out)))
+        return dict(eval_allreduce=out[0], exchange_prepare=out[1], pix_and_sends=out[2], allreduce_and_merge=out[3])
+
     def set_strict_range(self, on):
         self._chk(self.L.emba_set_strict_range(self.h, int(bool(on))))
 

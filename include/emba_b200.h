@@ -305,6 +305,11 @@ EMBA_API int emba_last_setup_ms(emba_handle_t h, double* out2);
  * (== out[4] with one GPU; with several, the merged strips of the pixels it owns), out[6] = work items,
  * out[7] = pixel segments longer than the warp sort's 1024 rows */
 EMBA_API int emba_get_counters(emba_handle_t h, int64_t* out8);
+/* several GPUs: device ms of the collective phases of the last pass on this rank. out[0] = histogram / cost
+ * all-reduce of emba_evaluate, out[1] = window all-gather + exchange bookkeeping (before the map-side kernel),
+ * out[2] = map-side kernel with the overlapped strip sends (until the last chunk has arrived), out[3] = A22 / b2
+ * all-reduce + merge of the received sub-strips; the rest 0 */
+EMBA_API int emba_last_comm_ms(emba_handle_t h, double* out8);
 /* number of kernel launches issued by this handle so far */
 EMBA_API int emba_launch_count(emba_handle_t h, int64_t* out);
 EMBA_API int emba_synchronize(emba_handle_t h);
