@@ -1001,7 +1001,12 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   // kernel, so that the transfers can overlap it (the host reads those numbers with the same synchronisation as
   // the strip total)
   const bool exchange = h->world > 1 && Np > 0 && !atomic_path;
-  static const bool pipe_env = !(getenv("EMBA_XCHG_PIPELINE") && atoi(getenv("EMBA_XCHG_PIPELINE")) == 0);
+  // The ring-pipelined variant (one map-side launch per owner's pixel range, each range leaving on a communication
+  // stream while the next is reduced) is kept behind EMBA_XCHG_PIPELINE=1: measured on C4 it LOSES to one grouped
+  // all-to-all after the map-side kernel (8 GPUs: pass 4.57 vs 3.16 ms; 4 GPUs: 5.77 vs 5.33 ms) -- seven small
+  // send/recv launches with their rendezvous cost more than the transfer they hide, and the chunked map-side
+  // launches lose 0.2 ms to their tails.
+  static const bool pipe_env = getenv("EMBA_XCHG_PIPELINE") && atoi(getenv("EMBA_XCHG_PIPELINE")) == 1;
   const bool pipelined = pipe_env && h->world <= 64;
   if (exchange) {
     EMBA_CUDAC(cudaEventRecord(h->ev_x[2], h->stream));
