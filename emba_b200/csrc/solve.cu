@@ -62,7 +62,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait_s() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(kSchurThreads, 4)
-k_schur_tiles(int64_t Np, int d, int fix, int nt, int Z, const int32_t* __restrict__ winlo,
+k_schur_tiles(int64_t own0, int64_t own1, int d, int fix, int nt, int Z, const int32_t* __restrict__ winlo,
               const int32_t* __restrict__ winhi, const int64_t* __restrict__ stripoff,
               const double* __restrict__ strip, const double* __restrict__ C, const double* __restrict__ b2,
               const unsigned long long* __restrict__ gmask, int group, double* __restrict__ Spart) {
@@ -74,7 +74,9 @@ k_schur_tiles(int64_t Np, int d, int fix, int nt, int Z, const int32_t* __restri
   int pair_lin = dgl;  // index of (I, J) in the I-major numbering k_schur_finish uses
   for (int k = 0; k < I; k++) pair_lin += nt - k;
   const int z = blockIdx.x;
-  const int64_t a0 = Np * z / Z, a1 = Np * (z + 1) / Z;
+  // pixel chunks of the range this rank OWNS (all active pixels with one GPU): chunking the whole pixel range left
+  // (world - 1) / world of the CTAs with nothing but empty windows and the rest with single-GPU-sized chunks
+  const int64_t a0 = own0 + (own1 - own0) * z / Z, a1 = own0 + (own1 - own0) * (z + 1) / Z;
   const int rowI0 = I * kST, rowJ0 = J * kST;
   const bool Jhas_rhs = (d >= rowJ0 && d < rowJ0 + kST);
   // pose ranges covered by the tiles (poses are >= fix)
@@ -583,7 +585,8 @@ k_cg_pix(int64_t Np, int d, int fix, int n, int nwarps, const int32_t* __restric
     }
     if (lane == 0) y[i] = s;
   }
-  const int64_t a0 = Np * chunk / gridDim.x, a1 = Np * (chunk + 1) / gridDim.x;
+  // chunks of the pixel range this rank owns (the map rows of the other pixels were zeroed by the caller)
+  const int64_t a0 = own0 + (own1 - own0) * chunk / gridDim.x, a1 = own0 + (own1 - own0) * (chunk + 1) / gridDim.x;
   for (int i = threadIdx.x; i < nwarps * d; i += blockDim.x) y1s[i] = 0.0;
   __syncthreads();
   const double* p1 = p;
@@ -613,8 +616,7 @@ k_cg_pix(int64_t Np, int d, int fix, int n, int nwarps, const int32_t* __restric
       if (lane == 0) {
         // several GPUs: A22 is replicated, so only the pixel's owner adds the A22m term (the strips of the other
         // pixels are empty here and t0 = t1 = 0); the partial vectors are summed by one all-reduce
-        double xx = 0.0, xy = 0.0, yy = 0.0;
-        if (a >= own0 && a < own1) { xx = A22[3 * a]; xy = A22[3 * a + 1]; yy = A22[3 * a + 2]; }
+        const double xx = A22[3 * a], xy = A22[3 * a + 1], yy = A22[3 * a + 2];
         y[d + 2 * a] = t0 + (xx + lambda * xx) * pa + xy * pb;
         y[d + 2 * a + 1] = t1 + xy * pa + (yy + lambda * yy) * pb;
       }
@@ -753,12 +755,13 @@ int solve_schur(Handle* h, double lambda, int fix) {
   const int nt = (d + 1 + kST - 1) / kST;
   const int npairs = nt * (nt + 1) / 2;
   static const int zmult = getenv("EMBA_SCHUR_ZMULT") ? atoi(getenv("EMBA_SCHUR_ZMULT")) : 16;
+  const int64_t own0 = h->world > 1 ? Np * h->rank / h->world : 0, own1 = h->world > 1 ? Np * (h->rank + 1) / h->world : Np;
   int Z = std::max(1, (h->sm_count * zmult) / npairs);
-  Z = (int)std::min<int64_t>(Z, std::max<int64_t>(1, (Np + kSchurThreads - 1) / kSchurThreads));
+  Z = (int)std::min<int64_t>(Z, std::max<int64_t>(1, (own1 - own0 + kSchurThreads - 1) / kSchurThreads));
   EMBA_TRY(dev_reserve(h, &h->d_Spart, &h->Spart_cap, (int64_t)Z * npairs * kST * kST));
   EMBA_TRY(fill_strip_masks(h));  // occupancy masks of the strips k_pix left in global memory (once per assembly)
   dim3 grid(Z, npairs);
-  k_schur_tiles<<<grid, kSchurThreads, 0, h->stream>>>(Np, d, fix, nt, Z, h->sv_winlo, h->sv_winhi, h->sv_stripoff, h->sv_strip,
+  k_schur_tiles<<<grid, kSchurThreads, 0, h->stream>>>(own0, own1, d, fix, nt, Z, h->sv_winlo, h->sv_winhi, h->sv_stripoff, h->sv_strip,
                                              h->d_C, h->d_b2, h->sv_gmask, h->pose_group, h->d_Spart);
   EMBA_LAUNCH_CHECK();
   const int64_t tot = (int64_t)d * (d + 1);
@@ -835,7 +838,6 @@ int solve_schur(Handle* h, double lambda, int fix) {
   k_expand_x1<<<ceil_div64(3 * n, T), T, 0, h->stream>>>(n, fix, h->d_rhs, h->d_x1);
   EMBA_LAUNCH_CHECK();
   if (Np > 0) {
-    const int64_t own0 = h->world > 1 ? Np * h->rank / h->world : 0, own1 = h->world > 1 ? Np * (h->rank + 1) / h->world : Np;
     k_solve_x2<<<ceil_div64(Np * 8, 256), 256, 0, h->stream>>>(Np, h->sv_winlo, h->sv_winhi, h->sv_stripoff, h->sv_strip,
                                                            h->d_C, h->d_b2, h->d_x1, h->d_x2, own0, own1);
     EMBA_LAUNCH_CHECK();
@@ -1017,6 +1019,7 @@ int solve_pcg(Handle* h, double lambda, int fix, int* iters_out, double* err_out
     const int nwarps = std::max(1, std::min(8, (int)((48 * 1024) / (sizeof(double) * (size_t)d))));
     const size_t shm = sizeof(double) * (size_t)d * nwarps;
     if (shm > 48 * 1024) EMBA_CUDA(cudaFuncSetAttribute(k_cg_pix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+    if (W > 1) EMBA_CUDA(cudaMemsetAsync(y + d, 0, sizeof(double) * 2 * Np, h->stream));
     k_cg_pix<<<kCgChunks, 256, shm, h->stream>>>(Np, d, fix, n, nwarps, h->sv_winlo, h->sv_winhi, h->sv_stripoff,
                                                  h->sv_strip, h->d_A22, h->rank == 0 ? h->d_A11 : nullptr, lambda, v, y,
                                                  ypart, own0, own1, &sc->done);
