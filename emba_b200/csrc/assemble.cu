@@ -29,8 +29,8 @@ int comm_allreduce(Handle* h, void* buf, int64_t count, int dtype);
 int comm_exchange_prepare(Handle* h);
 int comm_exchange_sizes(Handle* h);
 int comm_exchange_step(Handle* h, int step, cudaStream_t st);
-int comm_exchange_all(Handle* h, cudaStream_t st);
-int comm_exchange_finish(Handle* h);
+int comm_exchange_all(Handle* h, cudaStream_t st, bool with_a22);
+int comm_exchange_finish(Handle* h, bool a22_done);
 
 // ---------------------------------------------------------------------------------------------------
 // flag = pixel active (global count >= thres, model.cpp:333); segcnt = this rank's rows on it if active, else 0
@@ -1095,12 +1095,12 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
       EMBA_TRYC(comm_exchange_sizes(h));
     }
     if (!exchange || !pipelined) {
-      EMBA_TRYC(comm_exchange_all(h, h->stream));
+      EMBA_TRYC(comm_exchange_all(h, h->stream, true));
     } else {
       EMBA_CUDAC(cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
     }
     EMBA_CUDAC(cudaEventRecord(h->ev_x[4], h->stream));
-    EMBA_TRYC(comm_exchange_finish(h));
+    EMBA_TRYC(comm_exchange_finish(h, !exchange || !pipelined));
     EMBA_CUDAC(cudaEventRecord(h->ev_x[5], h->stream));
   }
   EMBA_CUDAC(cudaEventRecord(h->ev[7], h->stream));

@@ -299,12 +299,17 @@ int comm_exchange_step(Handle* h, int step, cudaStream_t st) {
   return EMBA_OK;
 }
 
-// all steps as ONE NCCL group (one launch): the unpipelined exchange, after the map-side kernel has finished
-int comm_exchange_all(Handle* h, cudaStream_t st) {
+// all steps as ONE NCCL group (one launch): the unpipelined exchange, after the map-side kernel has finished. The
+// two small all-reduces of the map blocks ride in the same group (with_a22).
+int comm_exchange_all(Handle* h, cudaStream_t st, bool with_a22) {
   NcclApi* api = nccl_api();
   const int W = h->world, r = h->rank;
   if (api->group_start() != 0) { h->err = "ncclGroupStart failed"; return EMBA_E_NCCL; }
   int rc = 0;
+  if (with_a22) {
+    rc |= api->allreduce(h->d_A22, h->d_A22, (size_t)(3 * h->Np), 8, 0, h->nccl_comm, st);
+    rc |= api->allreduce(h->d_b2, h->d_b2, (size_t)(2 * h->Np), 8, 0, h->nccl_comm, st);
+  }
   for (int q = 0; q < W; q++) {
     if (q == r) continue;
     const int64_t scount = (h->x_send_off[q + 1] - h->x_send_off[q]) * 6;
@@ -317,7 +322,7 @@ int comm_exchange_all(Handle* h, cudaStream_t st) {
   return EMBA_OK;
 }
 
-int comm_exchange_finish(Handle* h) {
+int comm_exchange_finish(Handle* h, bool a22_done) {
   NcclApi* api = nccl_api();
   const int W = h->world, r = h->rank;
   const int64_t Np = h->Np;
@@ -328,12 +333,14 @@ int comm_exchange_finish(Handle* h) {
   if (h->x_recv_cnt[r] > 0)
     EMBA_CUDA(cudaMemcpyAsync(h->d_recv + h->x_recvbase[r] * 6, h->d_strip + h->x_send_off[r] * 6,
                               sizeof(double) * h->x_recv_cnt[r] * 6, cudaMemcpyDeviceToDevice, h->stream));
-  // one NCCL group (= one launch) for the two small all-reduces (ncclFloat64 = 8, ncclSum = 0)
-  if (api->group_start() != 0) { h->err = "ncclGroupStart failed"; return EMBA_E_NCCL; }
-  int rc = api->allreduce(h->d_A22, h->d_A22, (size_t)(3 * Np), 8, 0, h->nccl_comm, h->stream);
-  rc |= api->allreduce(h->d_b2, h->d_b2, (size_t)(2 * Np), 8, 0, h->nccl_comm, h->stream);
-  if (api->group_end() != 0 || rc != 0) { h->err = "ncclAllReduce (A22, b2) failed"; return EMBA_E_NCCL; }
-  h->launches++;
+  if (!a22_done) {
+    // one NCCL group (= one launch) for the two small all-reduces (ncclFloat64 = 8, ncclSum = 0)
+    if (api->group_start() != 0) { h->err = "ncclGroupStart failed"; return EMBA_E_NCCL; }
+    int rc = api->allreduce(h->d_A22, h->d_A22, (size_t)(3 * Np), 8, 0, h->nccl_comm, h->stream);
+    rc |= api->allreduce(h->d_b2, h->d_b2, (size_t)(2 * Np), 8, 0, h->nccl_comm, h->stream);
+    if (api->group_end() != 0 || rc != 0) { h->err = "ncclAllReduce (A22, b2) failed"; return EMBA_E_NCCL; }
+    h->launches++;
+  }
   if (n_own > 0) {
     if (W <= 8)
       k_merge_strips<8><<<ceil_div64(n_own * 32, T), T, 0, h->stream>>>(W, Np, a0, n_own, h->d_win_all, own_off,

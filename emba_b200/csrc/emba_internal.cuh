@@ -384,6 +384,14 @@ __device__ __forceinline__ double4 so3_exp(const Vec3& o) {
   return q;
 }
 
+// 256-bit read-only global load (sm_100: LDG.E.ENL2.256): one instruction per 32-byte table entry / record, half
+// the L1TEX wavefronts of two 128-bit gathers. The address must be 32-byte aligned.
+__device__ __forceinline__ double4 ldg256(const void* p) {
+  double4 r;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+}
+
 // Batch pose applied to a bearing vector. The linear SO(3) spline gives R_batch = Exp(u delta_w) R_s with
 // delta_w = Log(R_{s+1} R_s^-1) (so3_spline.h:218-274 in world-frame form), i.e. Rodrigues with the per-batch
 // scalars s1 = sin(u th)/th, s2 = (1 - cos(u th))/th^2 and the per-knot-interval matrix K = [delta_w]x:
@@ -401,6 +409,22 @@ __device__ __forceinline__ void rotate_bearing(const double* __restrict__ kt, do
   Z = z0 + s1 * z1 + s2 * z2;
 }
 
+// the same with the knot-interval entry fetched as three 256-bit loads (the entry is 96 bytes, 32-byte aligned): 3 LSU
+// instructions instead of 12 scalar ones -- k_eval was bound by L1TEX wavefronts
+__device__ __forceinline__ void rotate_bearing_v(const double* __restrict__ kt, double s1, double s2, double bx,
+                                                 double by, double bz, double& X, double& Y, double& Z) {
+  const double4 a = ldg256(kt), b = ldg256(kt + 4), c = ldg256(kt + 8);
+  const double x0 = a.x * bx + a.y * by + a.z * bz;
+  const double y0 = a.w * bx + b.x * by + b.y * bz;
+  const double z0 = b.z * bx + b.w * by + c.x * bz;
+  const double dx = c.y, dy = c.z, dz = c.w;
+  const double x1 = dy * z0 - dz * y0, y1 = dz * x0 - dx * z0, z1 = dx * y0 - dy * x0;
+  const double x2 = dy * z1 - dz * y1, y2 = dz * x1 - dx * z1, z2 = dx * y1 - dy * x1;
+  X = x0 + s1 * x1 + s2 * x2;
+  Y = y0 + s1 * y1 + s2 * y2;
+  Z = z0 + s1 * z1 + s2 * z2;
+}
+
 // w = v A for a row vector v, A = alpha I + beta K + gamma K^2, K = [delta]x:  v K = v x delta
 __device__ __forceinline__ void row_times_A(const double* __restrict__ kt, double al, double be, double ga,
                                             const double v[3], double w[3]) {
@@ -410,14 +434,6 @@ __device__ __forceinline__ void row_times_A(const double* __restrict__ kt, doubl
   w[0] = al * v[0] + be * a0 + ga * b0;
   w[1] = al * v[1] + be * a1 + ga * b1;
   w[2] = al * v[2] + be * a2 + ga * b2;
-}
-
-// 256-bit read-only global load (sm_100: LDG.E.ENL2.256): one instruction per 32-byte table entry / record, half
-// the L1TEX wavefronts of two 128-bit gathers. The address must be 32-byte aligned.
-__device__ __forceinline__ double4 ldg256(const void* p) {
-  double4 r;
-  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
-  return r;
 }
 
 struct PanoCam {

@@ -157,14 +157,14 @@ k_eval(const MeasRec* __restrict__ rec, int64_t Mc, const double* __restrict__ K
       const double4 rt = ldg256(RotTab + bc);
       const int sk = (int)__double_as_longlong(rt.z);
       double X, Y, Z;
-      rotate_bearing(Ktab + (size_t)sk * kKnotStride, rt.x, rt.y, bx, by, bz, X, Y, Z);
+      rotate_bearing_v(Ktab + (size_t)sk * kKnotStride, rt.x, rt.y, bx, by, bz, X, Y, Z);
       project_pm_unit(cam, X, Y, Z, pcx, pcy);
     }
     {
       const double4 rt = ldg256(RotTab + bp);
       const int sk = (int)__double_as_longlong(rt.z);
       double X, Y, Z;
-      rotate_bearing(Ktab + (size_t)sk * kKnotStride, rt.x, rt.y, bx, by, bz, X, Y, Z);
+      rotate_bearing_v(Ktab + (size_t)sk * kKnotStride, rt.x, rt.y, bx, by, bz, X, Y, Z);
       project_pm_unit(cam, X, Y, Z, ppx, ppy);
     }
     const double dx = pcx - ppx, dy = pcy - ppy;

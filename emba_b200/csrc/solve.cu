@@ -65,15 +65,19 @@ __global__ void __launch_bounds__(kSchurThreads, 4)
 k_schur_tiles(int64_t own0, int64_t own1, int d, int fix, int nt, int Z, const int32_t* __restrict__ winlo,
               const int32_t* __restrict__ winhi, const int64_t* __restrict__ stripoff,
               const double* __restrict__ strip, const double* __restrict__ C, const double* __restrict__ b2,
-              const unsigned long long* __restrict__ gmask, int group, double* __restrict__ Spart) {
-  // CTAs are ordered heaviest first: blockIdx.y walks the tile pairs diagonal by diagonal (pairs on and near the
-  // diagonal meet the most pose windows), blockIdx.x the pixel chunks; the light far-off-diagonal pairs fill the tail
-  int I = blockIdx.y, dgl = 0;
+              const unsigned long long* __restrict__ gmask, int group, double* __restrict__ Spart, int order) {
+  // CTA order: `order` 0 = pixel chunk fastest (heaviest tile pairs first over the whole grid), 1 = tile pair fastest:
+  // the CTAs in flight together then work on the SAME few pixel chunks, whose strips every tile pair re-reads -- with
+  // chunks small enough they stay in the 126 MB L2 instead of being streamed from HBM once per pair. Within a chunk
+  // the pairs still go diagonal by diagonal (pairs on and near the diagonal meet the most pose windows).
+  const int npairs_ = nt * (nt + 1) / 2;
+  const int pair_idx = order ? (int)(blockIdx.x % npairs_) : (int)blockIdx.y;
+  const int z = order ? (int)(blockIdx.x / npairs_) : (int)blockIdx.x;
+  int I = pair_idx, dgl = 0;
   while (I >= nt - dgl) { I -= nt - dgl; dgl++; }
   const int J = I + dgl;
   int pair_lin = dgl;  // index of (I, J) in the I-major numbering k_schur_finish uses
   for (int k = 0; k < I; k++) pair_lin += nt - k;
-  const int z = blockIdx.x;
   // pixel chunks of the range this rank OWNS (all active pixels with one GPU): chunking the whole pixel range left
   // (world - 1) / world of the CTAs with nothing but empty windows and the rest with single-GPU-sized chunks
   const int64_t a0 = own0 + (own1 - own0) * z / Z, a1 = own0 + (own1 - own0) * (z + 1) / Z;
@@ -196,7 +200,7 @@ k_schur_tiles(int64_t own0, int64_t own1, int d, int fix, int nt, int Z, const i
     }
     cp_async_wait_s<0>();
   }
-  double* out = Spart + ((size_t)z * gridDim.y + pair_lin) * (kST * kST);
+  double* out = Spart + ((size_t)z * npairs_ + pair_lin) * (kST * kST);
 #pragma unroll
   for (int r = 0; r < 3; r++)
 #pragma unroll
@@ -760,9 +764,11 @@ int solve_schur(Handle* h, double lambda, int fix) {
   Z = (int)std::min<int64_t>(Z, std::max<int64_t>(1, (own1 - own0 + kSchurThreads - 1) / kSchurThreads));
   EMBA_TRY(dev_reserve(h, &h->d_Spart, &h->Spart_cap, (int64_t)Z * npairs * kST * kST));
   EMBA_TRY(fill_strip_masks(h));  // occupancy masks of the strips k_pix left in global memory (once per assembly)
+  static const int order = getenv("EMBA_SCHUR_ORDER") ? atoi(getenv("EMBA_SCHUR_ORDER")) : 0;
   dim3 grid(Z, npairs);
+  if (order) grid = dim3((unsigned)((int64_t)Z * npairs), 1);
   k_schur_tiles<<<grid, kSchurThreads, 0, h->stream>>>(own0, own1, d, fix, nt, Z, h->sv_winlo, h->sv_winhi, h->sv_stripoff, h->sv_strip,
-                                             h->d_C, h->d_b2, h->sv_gmask, h->pose_group, h->d_Spart);
+                                             h->d_C, h->d_b2, h->sv_gmask, h->pose_group, h->d_Spart, order);
   EMBA_LAUNCH_CHECK();
   const int64_t tot = (int64_t)d * (d + 1);
   if (dbg) cudaEventRecord(de[1], h->stream);
