@@ -84,14 +84,15 @@ json.dump({wl: traffic}, open(tj_path, "w"), indent=1)
 
 with open(os.path.join(out_dir, f"{tag}_ncu_summary.txt"), "w") as f:
     c = bench["config"]
-    f.write(f"profiles/{tag} -- NVIDIA B200 (sm_100a), workload {wl}: {c['events']} events, {c['measurements']} measurements, "
+    ws = bench.get("workload_stats", c)
+    f.write(f"profiles/{tag} -- NVIDIA B200 (sm_100a), workload {wl}: {c['events']} events, {ws['measurements']} measurements, "
             f"{c['sensor'][0]}x{c['sensor'][1]} sensor, {c['panorama'][0]}x{c['panorama'][1]} panorama, n = {c['control_poses']} "
-            f"control poses, Np = {c['active_pixels']} active pixels\n\n")
+            f"control poses, Np = {ws['active_pixels']} active pixels\n\n")
     f.write("Commands (each ncu pass only after the same command exited 0 without ncu, same gpurun call):\n"
-            "  python bench.py --steps 3 --warmup 2 --no-cpu-baseline --lm-iters 3\n"
-            f"  ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv   -> {tag}_launches_bench_{wl}.csv\n"
-            "  ncu --set full --clock-control none --import-source on -k regex:\"k_eval|k_asm_pose|k_pix\" -s 12 -c 3\n"
-            "  ncu --set full --clock-control none --import-source on -k regex:\"k_schur_tiles|k_ldlt_fused|k_gemm_f64\" -c 6\n"
+            "  python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras\n"
+            f"  ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv   -> {tag}_launches_bench_{wl}.csv\n"
+            "  ncu --set full --clock-control none --import-source on -k regex:\"k_eval|k_asm_pose|k_pix|k_place|k_seg_sort\" (second pass)\n"
+            "  ncu --set full --clock-control none --import-source on -k regex:\"k_schur_tiles|k_ldlt_fused|k_cg_pix\"\n"
             f"Default bench of the same build (python bench.py): {tag}_bench_default_{wl}.json\n")
     rf = bench["roofline"]
     f.write(f"  value {bench['value']:.4g} events/s ({bench['ms_per_step']:.3f} ms per pass), e2e {bench['e2e']['value']:.4g} events/s, "
@@ -101,7 +102,7 @@ with open(os.path.join(out_dir, f"{tag}_ncu_summary.txt"), "w") as f:
     f.write("  live kernel times (ms): " + ", ".join(f"{k} {v:.3f}" for k, v in rf["kernels_ms"].items()) + "\n")
     f.write("  algorithmic GB/s: " + ", ".join(f"{k} {v:.0f}" for k, v in rf["kernels_alg_gbs"].items()) + "\n")
     if "lm" in bench and bench["lm"] and "ms_per_iteration" in bench["lm"]:
-        f.write(f"  LM: {bench['lm']['ms_per_iteration']:.3f} ms per iteration ({bench['lm']['iterations']} solves, {bench['lm']['accepted']} accepted)\n")
+        f.write(f"  LM: {bench['lm']['ms_per_iteration']:.3f} ms per iteration ({bench['lm'].get('solves', bench['lm'].get('iterations'))} solves, {bench['lm']['accepted']} accepted)\n")
     if "cpu_baseline" in bench:
         cb = bench["cpu_baseline"]
         f.write(f"  CPU {cb['kind']}: {cb['value']:.4g} {cb['unit']} on {cb['cores']} core(s)\n")
