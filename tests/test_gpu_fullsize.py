@@ -229,3 +229,39 @@ def test_c4_headline_properties():
     q, gx, gy = eng.get_state(0)
     assert np.array_equal(q[0], sc.quat_init[0]) and np.all(np.abs(np.linalg.norm(q, axis=1) - 1) < 1e-12)
     eng.close()
+
+
+def test_long_and_huge_pixel_segments_vs_oracle():
+    """C1's trajectory over a 48x24 panorama: ~170 panorama pixels share 0.26 M measurements, so every row segment of the map
+    side is thousands of rows long -- the register merge path (1025 .. 4096 rows) and the CTA-wide path (> 4096 rows)
+    of the segment sort, which the benchmark workloads hardly reach. Element-wise against the numpy oracle."""
+    from emba_b200 import synth
+    from emba_b200.legm import Engine, spline_base_ns
+    from oracle import emba_oracle as O
+
+    sc = synth.make_config("C1", pano_w=48, pano_h=24, device="cuda")
+    eng = Engine(sc.sensor_w, sc.sensor_h, sc.bearing_lut(), sc.C_th, sc.pano_w, sc.pano_h)
+    eng.set_events(sc.x, sc.y, sc.t_ns, sc.pol)
+    t0, dt = spline_base_ns(sc.t_beg, sc.dt_knots)
+    eng.set_state(0, t0, dt, sc.quat_init, sc.Gx_init, sc.Gy_init)
+    orc = O.Oracle(sc.sensor_w, sc.sensor_h, sc.bearing_lut(), sc.pano_w, sc.pano_h, sc.C_th)
+    orc.set_events(sc.x, sc.y, sc.t_ns, sc.pol)
+    ep_o, num_o = orc.evaluate(sc.quat_init, t0, dt, sc.Gx_init, sc.Gy_init, True)
+    cd, cr, M = eng.evaluate(0, 0, 1.0, ALPHA)
+    _, num = eng.get_evaluation(0, None, False, True)
+    assert M == ep_o.size and np.array_equal(num, num_o)
+    assert (num > 4096).sum() >= 3 and ((num > 1024) & (num <= 4096)).sum() >= 3  # both long paths really run
+    outs = []
+    for _ in range(2):
+        Np = eng.form_normal_eq(THRES, 0, 1.0, ALPHA)
+        outs.append(eng.get_normal_eq(True))
+    for a, b in zip(outs[0], outs[1]):  # bit-reproducible although the rows reach their segments in a different order
+        assert np.array_equal(a, b)
+    A11, A12, A22, b1, b2, act = outs[0]
+    assert eng.counters()["long_segments"] == int((num.reshape(-1)[act] > 1024).sum())
+    B11, B12, B22, c1, c2, act_o = orc.form_normal_eq(sc.n_poses, THRES)
+    B22, c2 = orc.apply_l2_reg(B22, c2, act_o, ALPHA, sc.Gx_init, sc.Gy_init)
+    assert np.array_equal(act, act_o)
+    for a, b in ((B11, A11), (B12, A12), (B22, A22), (c1, b1), (c2, b2)):
+        assert rel(a, b) < 1e-9
+    eng.close()

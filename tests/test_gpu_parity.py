@@ -548,6 +548,15 @@ def test_event_sequence_on_device(tiny):
     k0, k1 = key(sc.x, sc.y, sc.t_ns, sc.pol), key(x, y, t, p)
     assert np.array_equal(sc.x[k0], x[k1]) and np.array_equal(sc.y[k0], y[k1]) and np.array_equal(sc.pol[k0], p[k1])
     seq.close()
+    # a recording longer than 2^32 ns: the sort's second (high 32 bits) stage
+    t_long = sc.t_ns.astype(np.int64) * 20 + 1_600_000_000_000_000_000  # epoch-scale stamps, 10 s span
+    seq = EventSequence(sc.x[perm], sc.y[perm], t_long[perm], sc.pol[perm])
+    seq.sort_by_time()
+    x, y, t, p = seq.download()
+    assert np.array_equal(t, np.sort(t_long)) and int(t[-1] - t[0]) > (1 << 32)
+    k0, k1 = key(sc.x, sc.y, t_long, sc.pol), key(x, y, t, p)
+    assert np.array_equal(sc.x[k0], x[k1]) and np.array_equal(sc.y[k0], y[k1]) and np.array_equal(sc.pol[k0], p[k1])
+    seq.close()
     # subsampling and windows on the (already sorted) fixture
     for rate in (1, 2, 3, 7):
         s2 = EventSequence(sc.x, sc.y, sc.t_ns, sc.pol)
