@@ -257,7 +257,7 @@ def run_reference(args, workload, rank, world):
         dev = "cuda" if torch.cuda.is_available() else "cpu"
     except Exception:
         dev = "cpu"
-    sc = synth.make_scene(**kw, device=dev)
+    sc = synth.make_scene(**kw, device=dev, sort_on_device=False)  # the product library stays out of this process
     # bounded sample per step: a prefix of the window sized so that the whole run stays within a few minutes
     n_sample = min(sc.n_events, max(200_000, min(2_000_000, int(6e7 / max(1, args.steps + args.warmup)))))
     times, last = [], None

@@ -316,6 +316,7 @@ size_t scan_scratch_bytes(int64_t count);
 template <typename T>
 int scan_exclusive(Handle* h, cudaStream_t st, const T* in, T* out, int64_t count, void* scratch);
 bool is_pinned(const void* p);
+cudaError_t uploader_init(Uploader& up);
 cudaError_t upload_bytes(Uploader& up, cudaStream_t st, void* dst, const void* src, size_t bytes);
 cudaError_t download_bytes(Uploader& up, cudaStream_t st, void* dst, const void* src, size_t bytes);
 void uploader_free(Uploader& up);

@@ -279,6 +279,7 @@ int emba_create(const emba_config_t* cfg, emba_handle_t* out) {
   for (auto& e : h->ev_chunk) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   for (auto& e : h->ev_x) cudaEventCreate(&e);
   if (cudaMallocHost((void**)&h->h_pin, 1024 * sizeof(int64_t)) != cudaSuccess) { delete h; return EMBA_E_CUDA; }
+  if (uploader_init(h->up) != cudaSuccess) { delete h; return EMBA_E_CUDA; }
   cudaEventCreate(&h->ev_sort0);
   cudaEventCreate(&h->ev_sort1);
   for (auto& e : h->ev) cudaEventCreate(&e);
@@ -421,10 +422,7 @@ int emba_set_events(emba_handle_t hh, int64_t N, const uint16_t* x, const uint16
       const int64_t nb = std::min(per, B - b0);
       const int bi = h->up.turn;
       h->up.turn ^= 1;
-      if (!h->up.stage[bi]) {  // only pinned sources so far: create the stage now
-        EMBA_CUDA(cudaMallocHost(&h->up.stage[bi], kStageBytes));
-        EMBA_CUDA(cudaEventCreateWithFlags(&h->up.ev[bi], cudaEventDisableTiming));
-      }
+      EMBA_CUDA(uploader_init(h->up));
       EMBA_CUDA(cudaEventSynchronize(h->up.ev[bi]));
       int64_t* st = reinterpret_cast<int64_t*>(h->up.stage[bi]);
       for (int64_t b = 0; b < nb; b++) {

@@ -260,6 +260,18 @@ bool is_pinned(const void* p) {
   return at.type == cudaMemoryTypeHost;
 }
 
+// both pinned stages and their events, created together on first use
+cudaError_t uploader_init(Uploader& up) {
+  cudaError_t e;
+  for (int i = 0; i < 2; i++) {
+    if (!up.stage[i]) {
+      if ((e = cudaMallocHost(&up.stage[i], kStageBytes)) != cudaSuccess) return e;
+      if ((e = cudaEventCreateWithFlags(&up.ev[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+  }
+  return cudaSuccess;
+}
+
 // returns a cudaError_t; every copy is checked
 cudaError_t upload_bytes(Uploader& up, cudaStream_t st, void* dst, const void* src, size_t bytes) {
   if (bytes == 0) return cudaSuccess;

@@ -1,6 +1,5 @@
 // GPU event simulator for synthetic benchmark input (include/emba_synth.h). Not on the measured path.
 #include <cuda_runtime.h>
-#include <cub/cub.cuh>
 #include <stdint.h>
 
 #include "../../include/emba_synth.h"
@@ -74,18 +73,28 @@ __global__ void k_sim(int S, const double* __restrict__ lut, const double* __res
   if (!FILL) count[p] = c;
 }
 
-__global__ void k_widen(const int32_t* in, int64_t* out, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = in[i];
-}
-__global__ void k_iota(uint32_t* v, int64_t n) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) v[i] = (uint32_t)i;
-}
-__global__ void k_gather(const uint32_t* __restrict__ idx, int64_t n, const uint8_t* __restrict__ pol,
-                         const uint32_t* __restrict__ pix, uint8_t* __restrict__ pol_o, uint32_t* __restrict__ pix_o) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { pol_o[i] = pol[idx[i]]; pix_o[i] = pix[idx[i]]; }
+// exclusive scan of the per-pixel event counts (a few 10^4 entries): one block, chunks of 1024
+__global__ void k_scan_counts(const int32_t* __restrict__ in, int64_t* __restrict__ out, int n) {
+  __shared__ int64_t sh[1024];
+  __shared__ int64_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n + 1; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int64_t v = i < n ? in[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const int64_t u = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += u;
+      __syncthreads();
+    }
+    if (i < n + 1) out[i] = carry + sh[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += sh[1023];
+    __syncthreads();
+  }
 }
 __global__ void k_xy(const uint32_t* __restrict__ pix, int64_t n, int Ws, uint16_t* __restrict__ x, uint16_t* __restrict__ y) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -104,11 +113,9 @@ extern "C" int emba_synth_simulate(int device, int Ws, int Hs, const double* lut
   const int S = Ws * Hs;
   double *d_lut = nullptr, *d_L = nullptr, *d_R = nullptr;
   int32_t* d_cnt = nullptr;
-  int64_t *d_cnt64 = nullptr, *d_off = nullptr, *d_t = nullptr, *d_t2 = nullptr;
-  uint8_t *d_pol = nullptr, *d_pol2 = nullptr;
-  uint32_t *d_pix = nullptr, *d_pix2 = nullptr, *d_idx = nullptr, *d_idx2 = nullptr;
-  void* d_tmp = nullptr;
-  size_t tb = 0;
+  int64_t *d_off = nullptr, *d_t = nullptr;
+  uint8_t* d_pol = nullptr;
+  uint32_t* d_pix = nullptr;
   int64_t total = 0;
   emba_synth_s* s = nullptr;
   const int T = 128, G = (S + T - 1) / T;
@@ -117,52 +124,34 @@ extern "C" int emba_synth_simulate(int device, int Ws, int Hs, const double* lut
   SY(cudaMalloc(&d_L, sizeof(double) * (size_t)Wp * Hp));
   SY(cudaMalloc(&d_R, sizeof(double) * 9 * (size_t)(n_steps + 1)));
   SY(cudaMalloc(&d_cnt, sizeof(int32_t) * S));
-  SY(cudaMalloc(&d_cnt64, sizeof(int64_t) * (S + 1)));
   SY(cudaMalloc(&d_off, sizeof(int64_t) * (S + 1)));
   SY(cudaMemcpy(d_lut, lut, sizeof(double) * 3 * S, cudaMemcpyHostToDevice));
   SY(cudaMemcpy(d_L, L, sizeof(double) * (size_t)Wp * Hp, cudaMemcpyHostToDevice));
   SY(cudaMemcpy(d_R, R_steps, sizeof(double) * 9 * (size_t)(n_steps + 1), cudaMemcpyHostToDevice));
   k_sim<false><<<G, T>>>(S, d_lut, d_L, Wp, Hp, C_th, n_steps, d_R, t_start, dt_sim, d_cnt, nullptr, nullptr, nullptr, nullptr);
-  SY(cudaMemset(d_cnt64, 0, sizeof(int64_t) * (S + 1)));
-  k_widen<<<G, T>>>(d_cnt, d_cnt64, S);
-  SY(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_cnt64, d_off, S + 1));
-  SY(cudaMalloc(&d_tmp, tb));
-  SY(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_cnt64, d_off, S + 1));
+  k_scan_counts<<<1, 1024>>>(d_cnt, d_off, S);
   SY(cudaMemcpy(&total, d_off + S, sizeof(int64_t), cudaMemcpyDeviceToHost));
-  cudaFree(d_tmp); d_tmp = nullptr;
   if (total >= ((int64_t)1 << 31)) { rc = -1; goto done; }
   {
     const int64_t n = total > 0 ? total : 1;
-    SY(cudaMalloc(&d_t, sizeof(int64_t) * n)); SY(cudaMalloc(&d_t2, sizeof(int64_t) * n));
-    SY(cudaMalloc(&d_pol, n)); SY(cudaMalloc(&d_pol2, n));
-    SY(cudaMalloc(&d_pix, sizeof(uint32_t) * n)); SY(cudaMalloc(&d_pix2, sizeof(uint32_t) * n));
-    SY(cudaMalloc(&d_idx, sizeof(uint32_t) * n)); SY(cudaMalloc(&d_idx2, sizeof(uint32_t) * n));
+    SY(cudaMalloc(&d_t, sizeof(int64_t) * n));
+    SY(cudaMalloc(&d_pol, n));
+    SY(cudaMalloc(&d_pix, sizeof(uint32_t) * n));
   }
+  // events come out sensor-pixel major (every pixel's own events in time order); the caller sorts them by time with
+  // the library's own event-sequence sort (emba_events_sort_by_time), the step the reference does after parsing a bag
   k_sim<true><<<G, T>>>(S, d_lut, d_L, Wp, Hp, C_th, n_steps, d_R, t_start, dt_sim, nullptr, d_off, d_t, d_pol, d_pix);
-  if (total > 0) {
-    const int G2 = (int)((total + 255) / 256);
-    k_iota<<<G2, 256>>>(d_idx, total);
-    cub::DoubleBuffer<int64_t> dk(d_t, d_t2);
-    cub::DoubleBuffer<uint32_t> dv(d_idx, d_idx2);
-    SY(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int)total, 0, 48));
-    SY(cudaMalloc(&d_tmp, tb));
-    SY(cub::DeviceRadixSort::SortPairs(d_tmp, tb, dk, dv, (int)total, 0, 48));
-    k_gather<<<G2, 256>>>(dv.Current(), total, d_pol, d_pix, d_pol2, d_pix2);
-    SY(cudaDeviceSynchronize());
-    if (dk.Current() != d_t) { int64_t* t = d_t; d_t = d_t2; d_t2 = t; }
-  }
   SY(cudaDeviceSynchronize());
   s = new emba_synth_s();
   s->device = device; s->n = total; s->Ws = Ws;
   s->d_t = d_t; d_t = nullptr;
-  s->d_pol = d_pol2; d_pol2 = nullptr;
-  s->d_pix = d_pix2; d_pix2 = nullptr;
+  s->d_pol = d_pol; d_pol = nullptr;
+  s->d_pix = d_pix; d_pix = nullptr;
   *out = s;
   *n_events = total;
 done:
-  cudaFree(d_lut); cudaFree(d_L); cudaFree(d_R); cudaFree(d_cnt); cudaFree(d_cnt64); cudaFree(d_off); cudaFree(d_t);
-  cudaFree(d_t2); cudaFree(d_pol); cudaFree(d_pol2); cudaFree(d_pix); cudaFree(d_pix2); cudaFree(d_idx);
-  cudaFree(d_idx2); cudaFree(d_tmp);
+  cudaFree(d_lut); cudaFree(d_L); cudaFree(d_R); cudaFree(d_cnt); cudaFree(d_off); cudaFree(d_t); cudaFree(d_pol);
+  cudaFree(d_pix);
   return rc;
 }
 

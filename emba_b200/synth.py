@@ -223,7 +223,7 @@ def _exp_so3_np(phi):
 
 
 def simulate_events_cuda(L, scene: Scene, t_start, t_stop, *, dt_sim=0.25e-3, yaw_rate=0.35, periodic=False,
-                         device_index=0):
+                         device_index=0, sort_on_device=True):
     """Same event model as simulate_events, one CUDA thread per sensor pixel (emba_b200/csrc/synth.cu through
     include/emba_synth.h). Used for the large benchmark configurations."""
     import ctypes as C
@@ -258,13 +258,24 @@ def simulate_events_cuda(L, scene: Scene, t_start, t_stop, *, dt_sim=0.25e-3, ya
     lib.emba_synth_free(h)
     if rc != 0:
         raise RuntimeError(f"emba_synth_fetch failed ({rc})")
+    # the simulator emits sensor-pixel-major streams: sort by time with the library's device-resident event sequence
+    # (stable, so equal stamps keep the simulator's pixel order), like the reference sorts a parsed bag
+    if not sort_on_device:  # bench.py's reference arm: nothing of the product library runs in that process
+        order = np.argsort(t, kind="stable")
+        return x[order], y[order], t[order], p[order]
+    from .legm import EventSequence
+
+    seq = EventSequence(x, y, t, p, device=device_index)
+    seq.sort_by_time()
+    x, y, t, p = seq.download()
+    seq.close()
     return x, y, t, p
 
 
 def make_scene(sensor_w=128, sensor_h=128, fx=91.4014729896821, fy=None, cx=None, cy=None, pano_w=1024, pano_h=512,
                C_th=0.45, t_beg=0.1, t_end=2.4, dt_knots=0.05, texture_std=1.5, seed=1, dt_sim=0.25e-3,
                yaw_rate=0.35, periodic=False, device="cpu", pose_noise_deg=0.3, map_scale=0.7, map_noise=0.02,
-               max_events=None, guard=1e-3, yaw0=0.0) -> Scene:
+               max_events=None, guard=1e-3, yaw0=0.0, sort_on_device=True) -> Scene:
     """Build a full seeded problem instance. Defaults are config C1 of SURVEY.md section 8(d)
     (calib/DVS-playroom.yaml intrinsics, launch/playroom.launch parameters)."""
     global YAW0
@@ -281,7 +292,7 @@ def make_scene(sensor_w=128, sensor_h=128, fx=91.4014729896821, fy=None, cx=None
     if str(device).startswith("cuda"):
         dev_idx = int(str(device).split(":")[1]) if ":" in str(device) else 0
         x, y, t_ns, pol = simulate_events_cuda(L, sc, t_beg + guard, t_end - guard, dt_sim=dt_sim, yaw_rate=yaw_rate,
-                                               periodic=periodic, device_index=dev_idx)
+                                               periodic=periodic, device_index=dev_idx, sort_on_device=sort_on_device)
     else:
         x, y, t_ns, pol = simulate_events(L, sc, t_beg + guard, t_end - guard, dt_sim=dt_sim, yaw_rate=yaw_rate,
                                           periodic=periodic, device=device, max_events=max_events)
