@@ -559,8 +559,8 @@ def main():
         if dist is not None:
             dist.all_reduce(t_red, op=dist.ReduceOp.MAX)
         lm_window = {"ms": float(t_red[0]) * 1e3, "solves": int(log_w.shape[0]),
-                     "h2d_bytes": int(world * (5 * N + 16 * (N // 100) + 32 * n + 16 * P)), "d2h_bytes": int(world * (32 * n + 16 * P)),
-                     "note": "emba_set_events (pinned x, y, polarity + 2 timestamps per batch) + emba_set_state + "
+                     "h2d_bytes": int(5 * N + world * (16 * (N // 100) + 32 * n + 16 * P)), "d2h_bytes": int(world * (32 * n + 16 * P)),
+                     "note": "emba_set_events (pinned x, y, polarity of the rank's own time slice + 2 timestamps per batch) + emba_set_state + "
                              "emba_solve_time_window + emba_get_state"}
     except Exception as ex:
         lm_window = {"error": str(ex)}

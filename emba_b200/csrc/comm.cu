@@ -78,6 +78,15 @@ int comm_allreduce(Handle* h, void* buf, int64_t count, int dtype) {
   return EMBA_OK;
 }
 
+int comm_allgather_i32(Handle* h, const int32_t* send, int32_t* recv, int64_t count) {
+  if (h->world <= 1) return EMBA_OK;
+  NcclApi* api = nccl_api();
+  if (!api || !h->nccl_comm) { h->err = "multi-GPU shard without a communicator: call emba_comm_init before emba_set_events"; return EMBA_E_NCCL; }
+  if (api->allgather(send, recv, (size_t)count, 2, h->nccl_comm, h->stream) != 0) { h->err = "ncclAllGather failed"; return EMBA_E_NCCL; }
+  h->launches++;
+  return EMBA_OK;
+}
+
 // the evaluation's reductions as ONE NCCL group: int32 histogram over the panorama (rank-local counts in, global
 // counts out -- the local ones size the rank's row segments afterwards), fp64 cost and count, and the range flag
 // (max), so that every rank takes the same decision on it

@@ -122,7 +122,11 @@ struct Handle {
   double C_th = 0;
   double* d_lut = nullptr;  // [Ws*Hs*3]
   // events
-  int64_t N = 0, Nuse = 0, B = 0;
+  int64_t N = 0, Nuse = 0, B = 0;  // events of the window, the usable multiple of 100, batches (all GLOBAL)
+  int64_t ev_off = 0, Nloc = 0;    // this rank's slice of the events (whole batches): first global id, count. The
+                                   // per-event arrays below are local (index = global id - ev_off); d_prev holds
+                                   // GLOBAL ids. One GPU: ev_off = 0, Nloc = Nuse.
+  int64_t Mloc_pairs = 0;          // pairs whose current event lies in the slice
   int64_t* d_tmid = nullptr;     // [B]
   uint32_t* d_spix_ev = nullptr; // [Nuse] sensor pixel per event
   uint8_t* d_pol = nullptr;      // [Nuse]

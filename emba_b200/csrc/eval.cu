@@ -451,6 +451,10 @@ int emba_get_evaluation(emba_handle_t hh, int32_t which, double* ep_out, int32_t
   StateSlot& s = h->st[which ? 1 - h->cur : h->cur];
   if (!s.evaluated) { h->err = "emba_get_evaluation: state not evaluated"; return EMBA_E_ARG; }
   if (num_out) EMBA_CUDA(download_bytes(h->up, h->stream, num_out, s.hist, sizeof(int32_t) * h->P));
+  if (ep_out && h->world > 1) {
+    h->err = "emba_get_evaluation: the residual vector in the reference's order is assembled on one GPU only";
+    return EMBA_E_SUPPORT;
+  }
   if (ep_out && h->Mc_total > 0) {
     // residuals in the reference's order (sensor pixel row-major, then time): scatter by the static reference rank,
     // compact the inliers. No allocation: the scratch arena of the pre-pass is idle between windows.

@@ -81,6 +81,70 @@ __global__ void k_pair_links(const uint32_t* __restrict__ sid, const int32_t* __
   if (j == N - 1) *total = (int64_t)rank[j] + flag[j];
 }
 
+// ---- several GPUs: every rank pairs only its own time slice of the events; a pair whose previous event lies in an
+// earlier slice is closed through the per-sensor-pixel "last event" tables of the ranks (halo)
+__global__ void k_pix_tables(const uint32_t* __restrict__ skey, const uint32_t* __restrict__ sid, int64_t N, int64_t ev_off,
+                             int32_t* __restrict__ last, int32_t* __restrict__ firstpos, int32_t* __restrict__ lastpos) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  const uint32_t s = skey[j];
+  if (j == 0 || skey[j - 1] != s) firstpos[s] = (int32_t)j;
+  if (j == N - 1 || skey[j + 1] != s) { lastpos[s] = (int32_t)j; last[s] = (int32_t)(ev_off + sid[j]); }
+}
+// last event of the pixel in the nearest earlier slice that has one
+__global__ void k_halo(int S, int rank, const int32_t* __restrict__ last_all, int32_t* __restrict__ halo) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  int32_t v = -1;
+  for (int r = rank - 1; r >= 0 && v < 0; r--) v = last_all[(size_t)r * (S + 1) + s];
+  halo[s] = v;
+}
+__global__ void k_pair_flags_halo(const uint32_t* __restrict__ skey, int64_t N, const int32_t* __restrict__ halo,
+                                  int32_t* __restrict__ flag) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  const bool first = j == 0 || skey[j] != skey[j - 1];
+  flag[j] = (!first || halo[skey[j]] >= 0) ? 1 : 0;
+}
+// pairs of every sensor pixel in this slice
+__global__ void k_pix_counts(int S, const int32_t* __restrict__ firstpos, const int32_t* __restrict__ lastpos,
+                             const int32_t* __restrict__ flag, const int32_t* __restrict__ rank, int32_t* __restrict__ cnt) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const int f = firstpos[s], l = lastpos[s];
+  cnt[s] = f >= 0 ? rank[l] + flag[l] - rank[f] : 0;
+}
+// tot[s] = pairs of pixel s over all slices, lower[s] = those of the earlier slices
+__global__ void k_pix_totals(int S, int rank, int W, const int32_t* __restrict__ cnt_all, int32_t* __restrict__ tot,
+                             int32_t* __restrict__ lower) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > S) return;
+  int t = 0, lo = 0;
+  if (s < S)
+    for (int r = 0; r < W; r++) { const int c = cnt_all[(size_t)r * (S + 1) + s]; t += c; if (r < rank) lo += c; }
+  tot[s] = t;  // tot[S] = 0: the scan's last entry becomes the window's pair count
+  if (s < S) lower[s] = lo;
+}
+__global__ void k_pair_links_halo(const uint32_t* __restrict__ skey, const uint32_t* __restrict__ sid,
+                                  const int32_t* __restrict__ flag, const int32_t* __restrict__ rank,
+                                  const int32_t* __restrict__ firstpos, const int32_t* __restrict__ halo,
+                                  const int32_t* __restrict__ pixbase, const int32_t* __restrict__ lower, int64_t N,
+                                  int64_t ev_off, int32_t* __restrict__ prev, uint32_t* __restrict__ refrank,
+                                  int64_t* __restrict__ total) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  const uint32_t ev = sid[j], s = skey[j];
+  if (flag[j]) {
+    const bool first = j == 0 || skey[j - 1] != s;
+    prev[ev] = first ? halo[s] : (int32_t)(ev_off + sid[j - 1]);
+    refrank[ev] = (uint32_t)(pixbase[s] + lower[s] + (rank[j] - rank[firstpos[s]]));
+  } else {
+    prev[ev] = -1;
+    refrank[ev] = 0xFFFFFFFFu;
+  }
+  if (j == N - 1) *total = (int64_t)rank[j] + flag[j];
+}
+
 // knot index and normalised time of every batch mid-time: basalt So3Spline::evaluate,
 // reference thirdparty/basalt-headers/include/basalt/spline/so3_spline.h:219-230
 __global__ void k_batch_su(const int64_t* __restrict__ tmid, int64_t B, int64_t t0, int64_t dt, int n,
@@ -107,13 +171,13 @@ __global__ void k_meas_flags(const int32_t* __restrict__ prev, int64_t N, int32_
 
 // compacted (control-pose-pair key, event) list in time order
 __global__ void k_meas_compact(const int32_t* __restrict__ prev, const int32_t* __restrict__ bs,
-                               const int32_t* __restrict__ pos, int64_t N, int n, uint32_t* __restrict__ key,
-                               uint32_t* __restrict__ ev) {
+                               const int32_t* __restrict__ pos, int64_t N, int n, int64_t ev_off,
+                               uint32_t* __restrict__ key, uint32_t* __restrict__ ev) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
-  const int32_t p = prev[i];
+  const int32_t p = prev[i];  // global id
   if (p < 0) return;
-  const uint32_t cc = (uint32_t)bs[i / kBatch];
+  const uint32_t cc = (uint32_t)bs[(ev_off + i) / kBatch];
   const uint32_t cp = (uint32_t)bs[p / kBatch];
   const int32_t o = pos[i];
   key[o] = cc * (uint32_t)n + cp;  // n <= 65535 (checked by emba_set_state): fits 32 bits
@@ -141,11 +205,11 @@ __global__ void k_head_scatter(const uint32_t* __restrict__ key, const int32_t* 
 __global__ void k_build_recs(const uint32_t* __restrict__ sev, int64_t m_lo, int64_t Mloc,
                              const uint32_t* __restrict__ spix, const uint8_t* __restrict__ pol,
                              const int32_t* __restrict__ prev, const uint32_t* __restrict__ refrank,
-                             const double* __restrict__ lut, MeasRec* __restrict__ rec,
+                             const double* __restrict__ lut, int64_t ev_off, MeasRec* __restrict__ rec,
                              uint32_t* __restrict__ refpos) {
   int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= Mloc) return;
-  const uint32_t ev = sev[m_lo + j];
+  const uint32_t ev = sev[m_lo + j];  // local id of the current event; prev[] holds global ids
   MeasRec r;
   const size_t sp = spix[ev];
   // unit bearing: rotations keep the norm, and both the projection (atan2 of a ratio, asin of y / norm) and its
@@ -154,7 +218,7 @@ __global__ void k_build_recs(const uint32_t* __restrict__ sev, int64_t m_lo, int
   const double lx = lut[3 * sp], ly = lut[3 * sp + 1], lz = lut[3 * sp + 2];
   const double inv = 1.0 / sqrt(lx * lx + ly * ly + lz * lz);
   r.bx = lx * inv; r.by = ly * inv; r.bz = lz * inv;
-  r.bc_pol = (ev / kBatch) | ((uint32_t)(pol[ev] ? 1u : 0u) << 31);
+  r.bc_pol = (uint32_t)((ev_off + ev) / kBatch) | ((uint32_t)(pol[ev] ? 1u : 0u) << 31);
   r.bp = (uint32_t)prev[ev] / kBatch;
   rec[j] = r;
   refpos[j] = refrank[ev];
@@ -171,45 +235,93 @@ void comm_destroy(Handle* h);
 struct PoissonPlan;
 void poisson_plan_destroy(PoissonPlan* p);
 
-// The per-window pre-pass on device-resident coordinates. d_x / d_y / d_pol_src: Nu entries (device);
-// d_tpair: the first and last timestamp of every batch (device, 2 B entries).
-static int prepass_device(Handle* h, int64_t N, const uint16_t* d_x, const uint16_t* d_y, const uint8_t* d_pol_src,
+int comm_allgather_i32(Handle* h, const int32_t* send, int32_t* recv, int64_t count);
+
+// The per-window pre-pass on device-resident coordinates. d_x / d_y / d_pol_src: this rank's Nloc events (device);
+// d_tpair: the first and last timestamp of every batch of the WINDOW (device, 2 B entries).
+static int prepass_device(Handle* h, const uint16_t* d_x, const uint16_t* d_y, const uint8_t* d_pol_src,
                           const int64_t* d_tpair) {
-  const int64_t Nu = h->Nuse, B = h->B;
-  const int T = 256, G = ceil_div64(Nu, T);
-  (void)N;
-  // scratch: sort buffers (4 x u32), pair flags + ranks, radix / scan scratch
-  uint32_t* k0 = h->ar_tmp.take<uint32_t>(Nu);
-  uint32_t* v0 = h->ar_tmp.take<uint32_t>(Nu);
-  uint32_t* k1 = h->ar_tmp.take<uint32_t>(Nu);
-  uint32_t* v1 = h->ar_tmp.take<uint32_t>(Nu);
-  int32_t* d_flag = h->ar_tmp.take<int32_t>(Nu);
-  int32_t* d_rank = h->ar_tmp.take<int32_t>(Nu);
-  void* scr = h->ar_tmp.take<char>((int64_t)std::max(radix_scratch_bytes(Nu), scan_scratch_bytes(Nu)));
+  const int64_t Nu = h->Nloc, B = h->B;
+  const int64_t Nu1 = std::max<int64_t>(Nu, 1);
+  const int T = 256, G = ceil_div64(Nu1, T);
+  const int S = h->Ws * h->Hs, W = h->world;
+  // scratch: sort buffers (4 x u32), pair flags + ranks, radix / scan scratch, per-sensor-pixel tables (several GPUs)
+  uint32_t* k0 = h->ar_tmp.take<uint32_t>(Nu1);
+  uint32_t* v0 = h->ar_tmp.take<uint32_t>(Nu1);
+  uint32_t* k1 = h->ar_tmp.take<uint32_t>(Nu1);
+  uint32_t* v1 = h->ar_tmp.take<uint32_t>(Nu1);
+  int32_t* d_flag = h->ar_tmp.take<int32_t>(Nu1);
+  int32_t* d_rank = h->ar_tmp.take<int32_t>(Nu1);
+  void* scr = h->ar_tmp.take<char>((int64_t)std::max(radix_scratch_bytes(Nu1), scan_scratch_bytes(std::max<int64_t>(Nu1, S + 2))));
   int64_t* d_total = h->ar_tmp.take<int64_t>(4);
-  if (!k0 || !v0 || !k1 || !v1 || !d_flag || !d_rank || !scr || !d_total) { h->err = "pre-pass scratch arena too small"; return EMBA_E_CUDA; }
+  int32_t* tab = W > 1 ? h->ar_tmp.take<int32_t>((int64_t)(7 + 2 * W) * (S + 1)) : nullptr;
+  if (!k0 || !v0 || !k1 || !v1 || !d_flag || !d_rank || !scr || !d_total || (W > 1 && !tab)) { h->err = "pre-pass scratch arena too small"; return EMBA_E_CUDA; }
   EMBA_CUDA(cudaMemsetAsync(h->d_flags, 0, sizeof(int32_t) * 16, h->stream));
-  if (d_pol_src != h->d_pol) EMBA_CUDA(cudaMemcpyAsync(h->d_pol, d_pol_src, Nu, cudaMemcpyDeviceToDevice, h->stream));
+  EMBA_CUDA(cudaMemsetAsync(d_total, 0, sizeof(int64_t) * 4, h->stream));
+  if (Nu && d_pol_src != h->d_pol) EMBA_CUDA(cudaMemcpyAsync(h->d_pol, d_pol_src, Nu, cudaMemcpyDeviceToDevice, h->stream));
   if (B) {
     k_batch_mid<<<ceil_div64(B, T), T, 0, h->stream>>>(d_tpair, B, h->d_tmid);
     EMBA_LAUNCH_CHECK();
   }
-  k_spix<<<G, T, 0, h->stream>>>(d_x, d_y, h->Ws, h->Hs, Nu, h->d_spix_ev, k0, h->d_flags);
-  EMBA_LAUNCH_CHECK();
-  int which = 0;
-  EMBA_TRY(radix_sort_pairs(h, h->stream, k0, v0, k1, v1, Nu, bits_for((uint64_t)h->Ws * h->Hs - 1), scr, true, true, &which));
-  const uint32_t* ks = which ? k1 : k0;
-  const uint32_t* vs = which ? v1 : v0;
-  k_pair_flags<<<G, T, 0, h->stream>>>(ks, Nu, d_flag);
-  EMBA_LAUNCH_CHECK();
-  EMBA_TRY(scan_exclusive<int32_t>(h, h->stream, d_flag, d_rank, Nu, scr));
-  k_pair_links<<<G, T, 0, h->stream>>>(vs, d_flag, d_rank, Nu, h->d_prev, h->d_refrank, d_total);
-  EMBA_LAUNCH_CHECK();
-  EMBA_CUDA(cudaMemcpyAsync(h->h_pin + 8, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+  const uint32_t *ks = k0, *vs = v0;
+  if (Nu) {
+    k_spix<<<G, T, 0, h->stream>>>(d_x, d_y, h->Ws, h->Hs, Nu, h->d_spix_ev, k0, h->d_flags);
+    EMBA_LAUNCH_CHECK();
+    int which = 0;
+    EMBA_TRY(radix_sort_pairs(h, h->stream, k0, v0, k1, v1, Nu, bits_for((uint64_t)S - 1), scr, true, true, &which));
+    ks = which ? k1 : k0;
+    vs = which ? v1 : v0;
+  }
+  if (W == 1) {
+    if (Nu) {
+      k_pair_flags<<<G, T, 0, h->stream>>>(ks, Nu, d_flag);
+      EMBA_LAUNCH_CHECK();
+      EMBA_TRY(scan_exclusive<int32_t>(h, h->stream, d_flag, d_rank, Nu, scr));
+      k_pair_links<<<G, T, 0, h->stream>>>(vs, d_flag, d_rank, Nu, h->d_prev, h->d_refrank, d_total);
+      EMBA_LAUNCH_CHECK();
+    }
+    EMBA_CUDA(cudaMemcpyAsync(h->h_pin + 8, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+  } else {
+    // per-sensor-pixel tables: last event / first and last sorted position in my slice; the ranks exchange the
+    // "last event" tables (halo) and, once the halo pairs are known, their per-pixel pair counts (reference-order
+    // ranks of the pairs, window total)
+    const int S1 = S + 1;
+    int32_t *last = tab, *firstpos = tab + S1, *lastpos = tab + 2 * S1, *halo = tab + 3 * S1, *cnt = tab + 4 * S1,
+            *tot = tab + 5 * S1, *lower = tab + 6 * S1, *last_all = tab + 7 * S1, *cnt_all = last_all + (size_t)W * S1;
+    EMBA_CUDA(cudaMemsetAsync(tab, 0xFF, sizeof(int32_t) * 3 * S1, h->stream));  // last, firstpos, lastpos = -1
+    if (Nu) {
+      k_pix_tables<<<G, T, 0, h->stream>>>(ks, vs, Nu, h->ev_off, last, firstpos, lastpos);
+      EMBA_LAUNCH_CHECK();
+    }
+    EMBA_TRY(comm_allgather_i32(h, last, last_all, S1));
+    k_halo<<<ceil_div64(S, T), T, 0, h->stream>>>(S, h->rank, last_all, halo);
+    EMBA_LAUNCH_CHECK();
+    // (the tables above are strided by S + 1: last_all[r * (S + 1) + s])
+    if (Nu) {
+      k_pair_flags_halo<<<G, T, 0, h->stream>>>(ks, Nu, halo, d_flag);
+      EMBA_LAUNCH_CHECK();
+      EMBA_TRY(scan_exclusive<int32_t>(h, h->stream, d_flag, d_rank, Nu, scr));
+    }
+    k_pix_counts<<<ceil_div64(S, T), T, 0, h->stream>>>(S, firstpos, lastpos, d_flag, d_rank, cnt);
+    EMBA_LAUNCH_CHECK();
+    EMBA_CUDA(cudaMemsetAsync(cnt + S, 0, sizeof(int32_t), h->stream));
+    EMBA_TRY(comm_allgather_i32(h, cnt, cnt_all, S1));
+    k_pix_totals<<<ceil_div64(S1, T), T, 0, h->stream>>>(S, h->rank, W, cnt_all, tot, lower);
+    EMBA_LAUNCH_CHECK();
+    EMBA_TRY(scan_exclusive<int32_t>(h, h->stream, tot, tot, S1, scr));  // tot -> first reference rank of the pixel
+    if (Nu) {
+      k_pair_links_halo<<<G, T, 0, h->stream>>>(ks, vs, d_flag, d_rank, firstpos, halo, tot, lower, Nu, h->ev_off, h->d_prev,
+                                                h->d_refrank, d_total);
+      EMBA_LAUNCH_CHECK();
+    }
+    EMBA_CUDA(cudaMemcpyAsync(h->h_pin + 8, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    EMBA_CUDA(cudaMemcpyAsync(h->h_pin + 10, tot + S, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  }
   EMBA_CUDA(cudaMemcpyAsync(h->h_pin + 9, h->d_flags, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   EMBA_CUDA(cudaStreamSynchronize(h->stream));  // the one synchronisation of the event-level pre-pass
   if (*reinterpret_cast<int32_t*>(h->h_pin + 9) & 1) { h->err = "emba_set_events: event coordinates outside the sensor"; return EMBA_E_ARG; }
-  h->Mc_total = h->h_pin[8];
+  h->Mloc_pairs = h->h_pin[8];
+  h->Mc_total = W == 1 ? h->Mloc_pairs : (int64_t)*reinterpret_cast<int32_t*>(h->h_pin + 10);
   return EMBA_OK;
 }
 
@@ -218,13 +330,19 @@ static int begin_window(Handle* h, int64_t N) {
   h->N = N;
   h->Nuse = (N / kBatch) * kBatch;  // integer division at model.cpp:79 drops the tail batch
   h->B = h->Nuse / kBatch;
+  // this rank's slice: whole batches, split by event COUNT (load balance by count, not by time)
+  const int64_t b_lo = h->B * h->rank / h->world, b_hi = h->B * (h->rank + 1) / h->world;
+  h->ev_off = b_lo * kBatch;
+  h->Nloc = (b_hi - b_lo) * kBatch;
   h->t0_ns = -1;  // forces the spline-dependent structures to be rebuilt
   h->st[0].evaluated = h->st[1].evaluated = false;
   h->formed = h->solved = false;
   h->jrec_valid = false;
   h->Mc_total = 0;
+  h->Mloc_pairs = 0;
   h->Mc = 0;
-  const int64_t Nu = h->Nuse, B = h->B;
+  const int64_t Nu = std::max<int64_t>(h->Nloc, 1), B = std::max<int64_t>(h->B, 1);
+  const int64_t S1 = (int64_t)h->Ws * h->Hs + 1;
   const size_t ev_bytes = Arena::pad(4 * (size_t)Nu) * 3 + Arena::pad((size_t)Nu) + Arena::pad(8 * (size_t)B) * 3 +
                           Arena::pad(16 * (size_t)B) + Arena::pad(4 * (size_t)B) + 4096;
   EMBA_TRY(arena_reserve(h, h->ar_ev, ev_bytes));
@@ -238,9 +356,11 @@ static int begin_window(Handle* h, int64_t N) {
   if (!h->d_spix_ev || !h->d_prev || !h->d_refrank || !h->d_pol || !h->d_tmid || !h->d_bu || !h->d_bs) {
     h->err = "event arena too small"; return EMBA_E_CUDA;
   }
-  // scratch: the larger of the pairing pass (6 x 4 N + sort scratch + staged x, y) and the static rebuild (below)
+  // scratch: the larger of the pairing pass (6 x 4 N + sort scratch + staged x, y + sensor-pixel tables) and the
+  // static rebuild (below)
   const size_t tmp_bytes = Arena::pad(4 * (size_t)Nu) * 6 + Arena::pad(2 * (size_t)Nu) * 2 + Arena::pad(16 * (size_t)B) +
-                           Arena::pad(std::max(radix_scratch_bytes(Nu), scan_scratch_bytes(Nu))) + 8192;
+                           Arena::pad(std::max(radix_scratch_bytes(Nu), scan_scratch_bytes(std::max<int64_t>(Nu, S1 + 1)))) +
+                           Arena::pad(4 * (size_t)(7 + 2 * h->world) * (size_t)S1) + 16384;
   EMBA_TRY(arena_reserve(h, h->ar_tmp, tmp_bytes));
   return EMBA_OK;
 }
@@ -402,20 +522,21 @@ int emba_set_events(emba_handle_t hh, int64_t N, const uint16_t* x, const uint16
   if (!h) return EMBA_E_ARG;
   if (N < 0 || (N > 0 && (!x || !y || !t_ns || !pol))) { h->err = "emba_set_events: null input"; return EMBA_E_ARG; }
   if (N >= (int64_t)1 << 31) { h->err = "emba_set_events: more than 2^31-1 events per window"; return EMBA_E_ARG; }
+  if (h->world > 1 && !h->nccl_comm) { h->err = "emba_set_events: several ranks need a communicator first (emba_comm_init)"; return EMBA_E_NCCL; }
   EMBA_CUDA(cudaSetDevice(h->device));
   EMBA_CUDA(cudaEventRecord(h->ev[0], h->stream));
   EMBA_TRY(begin_window(h, N));
-  const int64_t Nu = h->Nuse, B = h->B;
-  if (Nu == 0) return EMBA_OK;
-  uint16_t* d_x = h->ar_tmp.take<uint16_t>(Nu);
-  uint16_t* d_y = h->ar_tmp.take<uint16_t>(Nu);
+  const int64_t Nl = h->Nloc, B = h->B, off = h->ev_off;
+  if (h->Nuse == 0) return EMBA_OK;
+  uint16_t* d_x = h->ar_tmp.take<uint16_t>(std::max<int64_t>(Nl, 1));
+  uint16_t* d_y = h->ar_tmp.take<uint16_t>(std::max<int64_t>(Nl, 1));
   int64_t* d_tpair = h->ar_tmp.take<int64_t>(2 * B);
   if (!d_x || !d_y || !d_tpair) { h->err = "pre-pass scratch arena too small"; return EMBA_E_CUDA; }
-  // timestamps stay on the host: only the first and the last stamp of every batch are needed (model.cpp:115-119).
-  // They are gathered into the pinned stage in chunks.
-  EMBA_CUDA(upload_bytes(h->up, h->stream, d_x, x, sizeof(uint16_t) * (size_t)Nu));
-  EMBA_CUDA(upload_bytes(h->up, h->stream, d_y, y, sizeof(uint16_t) * (size_t)Nu));
-  EMBA_CUDA(upload_bytes(h->up, h->stream, h->d_pol, pol, (size_t)Nu));
+  // a rank uploads only its own slice of the events. Timestamps stay on the host: only the first and the last stamp
+  // of every batch of the window are needed (model.cpp:115-119); they are gathered into the pinned stage in chunks.
+  EMBA_CUDA(upload_bytes(h->up, h->stream, d_x, x + off, sizeof(uint16_t) * (size_t)Nl));
+  EMBA_CUDA(upload_bytes(h->up, h->stream, d_y, y + off, sizeof(uint16_t) * (size_t)Nl));
+  EMBA_CUDA(upload_bytes(h->up, h->stream, h->d_pol, pol + off, (size_t)Nl));
   {
     const int64_t per = (int64_t)(kStageBytes / 16);
     for (int64_t b0 = 0; b0 < B; b0 += per) {
@@ -433,7 +554,7 @@ int emba_set_events(emba_handle_t hh, int64_t N, const uint16_t* x, const uint16
       EMBA_CUDA(cudaEventRecord(h->up.ev[bi], h->stream));
     }
   }
-  EMBA_TRY(prepass_device(h, N, d_x, d_y, h->d_pol, d_tpair));
+  EMBA_TRY(prepass_device(h, d_x, d_y, h->d_pol, d_tpair));
   EMBA_CUDA(cudaEventRecord(h->ev[1], h->stream));
   EMBA_CUDA(cudaEventSynchronize(h->ev[1]));
   float ms = 0;
@@ -716,6 +837,7 @@ int emba_set_events_dev(emba_handle_t hh, emba_events_t e, int64_t i0, int64_t i
   if (ev->device != h->device) { h->err = "emba_set_events_dev: the sequence lives on another device"; return EMBA_E_ARG; }
   const int64_t N = i1 - i0;
   if (N >= (int64_t)1 << 31) { h->err = "emba_set_events: more than 2^31-1 events per window"; return EMBA_E_ARG; }
+  if (h->world > 1 && !h->nccl_comm) { h->err = "emba_set_events_dev: several ranks need a communicator first (emba_comm_init)"; return EMBA_E_NCCL; }
   EMBA_CUDA(cudaSetDevice(h->device));
   EMBA_CUDA(cudaStreamSynchronize(ev->stream));
   EMBA_CUDA(cudaEventRecord(h->ev[0], h->stream));
@@ -726,7 +848,8 @@ int emba_set_events_dev(emba_handle_t hh, emba_events_t e, int64_t i0, int64_t i
   if (!d_tpair) { h->err = "pre-pass scratch arena too small"; return EMBA_E_CUDA; }
   k_batch_tpair<<<ceil_div64(B, 256), 256, 0, h->stream>>>(ev->t + i0, B, d_tpair);
   EMBA_LAUNCH_CHECK();
-  EMBA_TRY(prepass_device(h, N, ev->x + i0, ev->y + i0, ev->pol + i0, d_tpair));
+  const int64_t o = i0 + h->ev_off;
+  EMBA_TRY(prepass_device(h, ev->x + o, ev->y + o, ev->pol + o, d_tpair));
   EMBA_CUDA(cudaEventRecord(h->ev[1], h->stream));
   EMBA_CUDA(cudaEventSynchronize(h->ev[1]));
   float ms = 0;
@@ -742,7 +865,7 @@ namespace emba {
 // Rebuilds everything that depends on the spline time base (t0, dt, n) or on the shard: batch (s, u), the
 // canonical measurement order with its records, groups and work items, and the per-measurement buffers.
 int rebuild_static(Handle* h) {
-  const int64_t Nu = h->Nuse, B = h->B;
+  const int64_t Nu = h->Nloc, B = h->B;
   const int n = h->n;
   h->Mc = 0; h->n_items = 0; h->n_groups = 0; h->dmax = 0;
   h->h_items.clear();
@@ -756,7 +879,7 @@ int rebuild_static(Handle* h) {
   EMBA_TRY(dev_reserve(h, &h->d_S, &h->S_cap, (int64_t)(3 * n + 1) * (3 * n + 1)));  // bordered with the rhs row
   EMBA_TRY(dev_reserve(h, &h->d_rhs, &h->rhs_cap, (int64_t)3 * n));
   const int T = 256;
-  const int64_t Mt = h->Mc_total;
+  const int64_t Mt = h->Mloc_pairs;  // pairs of this rank's slice: every one of them is this rank's measurement
   // scratch of the rebuild (the scratch arena was sized for the pairing pass, which is larger: Mt <= Nu)
   h->ar_tmp.reset();
   int32_t* d_flag = h->ar_tmp.take<int32_t>(std::max(Nu, Mt));
@@ -773,14 +896,16 @@ int rebuild_static(Handle* h) {
   std::vector<int32_t> gstart;
   std::vector<uint32_t> gkey;
   const uint32_t* vs = nullptr;
-  if (B > 0 && Mt > 0) {
+  if (B > 0) {
     EMBA_CUDA(cudaMemsetAsync(h->d_flags, 0, sizeof(int32_t) * 16, h->stream));
     k_batch_su<<<ceil_div64(B, T), T, 0, h->stream>>>(h->d_tmid, B, h->t0_ns, h->dt_ns, n, h->d_bs, h->d_bu, h->d_flags);
     EMBA_LAUNCH_CHECK();
+  }
+  if (B > 0 && Mt > 0) {
     k_meas_flags<<<ceil_div64(Nu, T), T, 0, h->stream>>>(h->d_prev, Nu, d_flag);
     EMBA_LAUNCH_CHECK();
     EMBA_TRY(scan_exclusive<int32_t>(h, h->stream, d_flag, d_pos, Nu, scr));
-    k_meas_compact<<<ceil_div64(Nu, T), T, 0, h->stream>>>(h->d_prev, h->d_bs, d_pos, Nu, n, d_key, d_ev);
+    k_meas_compact<<<ceil_div64(Nu, T), T, 0, h->stream>>>(h->d_prev, h->d_bs, d_pos, Nu, n, h->ev_off, d_key, d_ev);
     EMBA_LAUNCH_CHECK();
     int which = 0;
     EMBA_TRY(radix_sort_pairs(h, h->stream, d_key, d_ev, d_key2, d_ev2, Mt, bits_for((uint64_t)n * n - 1), scr, false, true, &which));
@@ -823,18 +948,10 @@ int rebuild_static(Handle* h) {
       all.push_back(w);
     }
   }
-  // shard boundaries in measurements, snapped to item starts
-  const int64_t lo_t = Mt * h->rank / h->world, hi_t = Mt * (h->rank + 1) / h->world;
-  int64_t m_lo = -1, m_hi = -1;
-  for (const WorkItem& w : all) {
-    if (w.start >= lo_t && w.start < hi_t) {
-      if (m_lo < 0) m_lo = w.start;
-      m_hi = (int64_t)w.start + w.count;
-      h->h_items.push_back(w);
-    }
-  }
-  if (m_lo < 0) { m_lo = m_hi = 0; }
-  h->Mc = m_hi - m_lo;
+  // (with several GPUs the time sharding already happened at the event level: all of the slice's pairs are mine)
+  const int64_t m_lo = 0;
+  h->h_items = all;
+  h->Mc = Mt;
   // renumber groups locally (dense ids in order of appearance)
   std::vector<int32_t> item0;
   int lastg = -1, ng = 0;
@@ -890,7 +1007,7 @@ int rebuild_static(Handle* h) {
   EMBA_CUDA(cudaMemcpyAsync(h->d_group_item0, item0.data(), sizeof(int32_t) * item0.size(), cudaMemcpyHostToDevice, h->stream));
   if (Mc) {
     k_build_recs<<<ceil_div64(Mc, T), T, 0, h->stream>>>(vs, m_lo, Mc, h->d_spix_ev, h->d_pol, h->d_prev,
-                                                        h->d_refrank, h->d_lut, h->d_rec, h->d_refpos);
+                                                        h->d_refrank, h->d_lut, h->ev_off, h->d_rec, h->d_refpos);
     EMBA_LAUNCH_CHECK();
   }
   EMBA_CUDA(cudaEventRecord(h->ev[1], h->stream));
