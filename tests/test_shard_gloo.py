@@ -1,7 +1,9 @@
 """world_size-2 gloo test (CPU) of the time-sharded decomposition the multi-GPU path uses:
 
-  * measurements are partitioned by contiguous control-pose (time) slices; num_ev_map is all-reduced BEFORE the
-    active-pixel decision, the cost is all-reduced;
+  * events are partitioned into contiguous slices of whole batches, a measurement belongs to the rank of its CURRENT
+    event; a pair whose previous event lies in an earlier slice is closed through all-gathered per-sensor-pixel
+    "last event" tables (halo), the reference-order rank of every pair through all-gathered per-pixel pair counts;
+    num_ev_map is all-reduced BEFORE the active-pixel decision, the cost is all-reduced;
   * A11/b1/A22/b2 partials are all-reduced;
   * A12 is exchanged as per-pixel sub-strips: every rank sends, for the pixels another rank owns, only its own
     (pose-window) sub-strip; the owner merges them -- no rank ever holds all of A12;
@@ -38,15 +40,49 @@ def _worker(rank, world, port, out):
     orc.set_events(sc.x, sc.y, sc.t_ns, sc.pol)
     t0, dt = O.spline_base_ns(sc.t_beg, sc.dt_knots)
     n, thres, alpha = sc.n_poses, int(g["thres"]), float(g["alpha"])
-    # full evaluation, then restrict to this rank's slice: canonical order = sorted by (cp_c, cp_p); the slice is a
-    # contiguous range of that order (what rebuild_static() assigns to a rank)
+    # ---- (0) the per-rank pairing pre-pass (emba_b200/csrc/prepass.cu, prepass_device with several ranks), restated:
+    # sort my slice by sensor pixel, exchange the "last event of the pixel" tables, close the halo pairs, exchange the
+    # per-pixel pair counts, derive the reference-order rank of every pair
+    n_used = orc.n_used
+    B = n_used // 100
+    e_lo, e_hi = 100 * (B * rank // world), 100 * (B * (rank + 1) // world)
+    S = sc.sensor_w * sc.sensor_h
+    spix = (sc.y[e_lo:e_hi].astype(np.int64) * sc.sensor_w + sc.x[e_lo:e_hi].astype(np.int64))
+    o = np.argsort(spix, kind="stable")
+    ks, vs = spix[o], o + e_lo
+    first = np.r_[True, ks[1:] != ks[:-1]] if ks.size else np.zeros(0, bool)
+    lastm = np.r_[ks[1:] != ks[:-1], True] if ks.size else np.zeros(0, bool)
+    last = -np.ones(S, dtype=np.int64)
+    last[ks[lastm]] = vs[lastm]
+    tabs = [torch.zeros(S, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(tabs, torch.from_numpy(last))
+    halo = -np.ones(S, dtype=np.int64)
+    for r in range(rank - 1, -1, -1):
+        t = tabs[r].numpy()
+        halo = np.where((halo < 0) & (t >= 0), t, halo)
+    prev_loc = np.where(first, halo[ks], np.r_[-1, vs[:-1]])  # global ids, -1 = no pair
+    is_pair = prev_loc >= 0
+    cnt = np.bincount(ks[is_pair], minlength=S)
+    cnts = [torch.zeros(S, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(cnts, torch.from_numpy(cnt))
+    tot = sum(c.numpy() for c in cnts)
+    lower = sum((cnts[r].numpy() for r in range(rank)), np.zeros(S, dtype=np.int64))
+    pixbase = np.cumsum(tot) - tot
+    within = np.cumsum(is_pair) - is_pair  # pairs before position j in my sorted slice
+    firstpos = np.zeros(S, dtype=np.int64)
+    firstpos[ks[first]] = np.nonzero(first)[0]
+    refrank = pixbase[ks] + lower[ks] + (within - within[firstpos[ks]])
+    # against the unsharded pairing of the oracle (reference order = sensor pixel row-major, then time)
+    gcur, gprev = orc.cur, orc.prev
+    sel = (gcur >= e_lo) & (gcur < e_hi)
+    assert int(tot.sum()) == gcur.size and int(is_pair.sum()) == int(sel.sum())
+    mycur, myprev, myrank = vs[is_pair], prev_loc[is_pair], refrank[is_pair]
+    assert np.array_equal(gcur[myrank], mycur) and np.array_equal(gprev[myrank], myprev)
+    # ---- full evaluation, then restrict to this rank's slice: a measurement belongs to the rank of its current event
     orc.evaluate(sc.quat_init, t0, dt, sc.Gx_init, sc.Gy_init, True)
     st = orc.state
-    # all pairs incl. outliers are sharded in the library; the oracle state only keeps inliers -- same partition rule
-    key = st["cp_c"] * n + st["cp_p"]
-    order = np.argsort(key, kind="stable")
-    M = order.size
-    mine = order[M * rank // world: M * (rank + 1) // world]
+    M = st["cur"].size
+    mine = np.nonzero((st["cur"] >= e_lo) & (st["cur"] < e_hi))[0]
     # (1) histogram + cost all-reduce
     W, H = sc.pano_w, sc.pano_h
     hist = torch.from_numpy(np.bincount(st["pix"][mine], minlength=W * H).astype(np.int32))
