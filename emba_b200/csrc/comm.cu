@@ -404,7 +404,15 @@ int emba_comm_init(emba_handle_t hh, const void* id128, int32_t rank, int32_t wo
   std::memcpy(&id, id128, 128);
   const int r = api->init_rank(&h->nccl_comm, world, id, rank);
   if (r != 0) { h->err = std::string("ncclCommInitRank: ") + (api->errstr ? api->errstr(r) : "error"); h->nccl_comm = nullptr; return EMBA_E_NCCL; }
-  return emba_set_shard(hh, rank, world);
+  EMBA_TRY(emba_set_shard(hh, rank, world));
+  // the first collective on a communicator sets up its channels (seconds): pay for it here, not inside the first
+  // window's pre-pass
+  if (world > 1) {
+    EMBA_CUDA(cudaMemsetAsync(h->d_flags, 0, sizeof(int32_t) * 16, h->stream));
+    EMBA_TRY(comm_allreduce(h, h->d_flags, 16, 0));
+    EMBA_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  return EMBA_OK;
 }
 
 }  // extern "C"
