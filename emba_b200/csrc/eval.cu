@@ -136,8 +136,8 @@ __device__ __forceinline__ double rho_of(double e, double a) {
 // kernel is bound by its gathers and the counting atomic, not by the fp64 pipe, so the split only added traffic.)
 constexpr int kEvalThreads = 256;
 
-template <int COST>
-__global__ void __launch_bounds__(kEvalThreads)
+template <int COST, int MINB>
+__global__ void __launch_bounds__(kEvalThreads, MINB)
 k_eval(const MeasRec* __restrict__ rec, int64_t Mc, const double* __restrict__ Ktab,
        const double4* __restrict__ RotTab, const double2* __restrict__ G2, PanoCam cam, int W, int H, double C_th, double eta,
        double2* __restrict__ dp_out, double* __restrict__ e_out, int32_t* __restrict__ pix_out,
@@ -332,13 +332,23 @@ int evaluate_slot(Handle* h, int slot, int cost_type, double eta, double alpha) 
   const PanoCam cam = make_cam(h);
   EMBA_CUDA(cudaEventRecord(h->ev[1], h->stream));
   if (h->Mc > 0) {
-#define EMBA_EVAL_LAUNCH(C)                                                                                       \
-  k_eval<C><<<grid, kEvalThreads, 0, h->stream>>>(h->d_rec, h->Mc, s.Ktab, s.RotTab, s.G2, cam, h->Wp, h->Hp,     \
-                                                  h->C_th, eta, s.dp, s.e, s.pix, s.slot, s.hist_loc, h->d_part,   \
-                                                  h->d_flags)
+    // resident CTAs per SM the kernel is compiled for: 4 (64 registers, no spills), 5 (48 registers), 6 (40): the
+    // kernel is bound by the latency of its dependent gathers, so occupancy is traded against a few spilled values
+    static const int occ = getenv("EMBA_EVAL_OCC") ? atoi(getenv("EMBA_EVAL_OCC")) : 4;
+#define EMBA_EVAL_LAUNCH2(C, B)                                                                                   \
+  k_eval<C, B><<<grid, kEvalThreads, 0, h->stream>>>(h->d_rec, h->Mc, s.Ktab, s.RotTab, s.G2, cam, h->Wp, h->Hp,  \
+                                                     h->C_th, eta, s.dp, s.e, s.pix, s.slot, s.hist_loc,           \
+                                                     h->d_part, h->d_flags)
+#define EMBA_EVAL_LAUNCH(C)                        \
+  do {                                             \
+    if (occ >= 6) EMBA_EVAL_LAUNCH2(C, 6);         \
+    else if (occ == 5) EMBA_EVAL_LAUNCH2(C, 5);    \
+    else EMBA_EVAL_LAUNCH2(C, 4);                  \
+  } while (0)
     if (cost_type == EMBA_COST_QUADRATIC) EMBA_EVAL_LAUNCH(EMBA_COST_QUADRATIC);
     else if (cost_type == EMBA_COST_CAUCHY) EMBA_EVAL_LAUNCH(EMBA_COST_CAUCHY);
     else EMBA_EVAL_LAUNCH(EMBA_COST_HUBER);
+#undef EMBA_EVAL_LAUNCH2
 #undef EMBA_EVAL_LAUNCH
     EMBA_LAUNCH_CHECK();
   }
