@@ -332,8 +332,8 @@ int evaluate_slot(Handle* h, int slot, int cost_type, double eta, double alpha) 
   const PanoCam cam = make_cam(h);
   EMBA_CUDA(cudaEventRecord(h->ev[1], h->stream));
   if (h->Mc > 0) {
-    // resident CTAs per SM the kernel is compiled for: 4 (64 registers, no spills), 5 (48 registers), 6 (40): the
-    // kernel is bound by the latency of its dependent gathers, so occupancy is traded against a few spilled values
+    // resident CTAs per SM the kernel is compiled for: 4 (64 registers, no spills; the default), 5 (48 registers),
+    // 6 (40). Measured on C4: 3.58 / 3.77 / 4.32 ms -- the spilled values cost more than the extra warps hide.
     static const int occ = getenv("EMBA_EVAL_OCC") ? atoi(getenv("EMBA_EVAL_OCC")) : 4;
 #define EMBA_EVAL_LAUNCH2(C, B)                                                                                   \
   k_eval<C, B><<<grid, kEvalThreads, 0, h->stream>>>(h->d_rec, h->Mc, s.Ktab, s.RotTab, s.G2, cam, h->Wp, h->Hp,  \

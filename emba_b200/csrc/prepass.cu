@@ -388,7 +388,16 @@ int emba_create(const emba_config_t* cfg, emba_handle_t* out) {
   cudaGetDeviceProperties(&prop, h->device);
   h->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return EMBA_E_CUDA; }
-  if (cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess) { delete h; return EMBA_E_CUDA; }
+  {
+    // the side stream (row placement / segment sort beside the pose-side kernel, A11 gather beside the map-side kernel)
+    // has the main stream's priority. Giving it the HIGHER priority (EMBA_SIDE_PRIO=1) was measured on C4: its kernels
+    // then take every SM slot the HBM-bound pose-side kernel frees and stretch that kernel from 7.0 to 11.5 ms
+    // (form 13.4 -> 16.1 ms).
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    const bool hi = getenv("EMBA_SIDE_PRIO") && atoi(getenv("EMBA_SIDE_PRIO")) == 1;
+    if (cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, hi ? prio_hi : prio_lo) != cudaSuccess) { delete h; return EMBA_E_CUDA; }
+  }
   cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->ev_fork2, cudaEventDisableTiming);
