@@ -28,6 +28,7 @@ PanoCam make_cam(const Handle* h);
 int comm_allreduce(Handle* h, void* buf, int64_t count, int dtype);
 int comm_exchange_prepare(Handle* h);
 int comm_exchange_sizes(Handle* h);
+int comm_exchange_dst(Handle* h);
 int comm_exchange_step(Handle* h, int step, cudaStream_t st);
 int comm_exchange_all(Handle* h, cudaStream_t st, bool with_a22);
 int comm_exchange_finish(Handle* h, bool a22_done);
@@ -635,8 +636,10 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 // one pixel: rows [seg0, seg1) of the sorted list. SMEM: the strip accumulates in shared memory (typed shared
 // accesses) and is copied out at the end; otherwise (pose window longer than kStripCap) directly in global memory.
+// gs: the strip's place in the local strip buffer; go: where the finished strip goes (== gs on one GPU; the owner
+// rank's receive buffer, possibly over NVLink, in the peer-memory exchange -- stores only, never read back).
 template <bool SMEM>
-__device__ __forceinline__ void pix_one(int64_t seg0, int64_t seg1, int qlo, int len, double* __restrict__ gs,
+__device__ __forceinline__ void pix_one(int64_t seg0, int64_t seg1, int qlo, int len, double* __restrict__ gs, double* go,
                                         double* s_tile, double* s_strip, const uint32_t* __restrict__ sval,
                                         const double* __restrict__ jrec, int lane, int s, int r, int c, int ia,
                                         int ib, int group, double& acc_out, unsigned long long& mask0, unsigned long long& mask1) {
@@ -726,7 +729,9 @@ __device__ __forceinline__ void pix_one(int64_t seg0, int64_t seg1, int qlo, int
   if (have) flush();
   __syncwarp();
   if (SMEM) {
-    for (int i = lane; i < len * 6; i += 32) gs[i] = sp[i];
+    for (int i = lane; i < len * 6; i += 32) go[i] = sp[i];
+  } else if (go != gs) {
+    for (int i = lane; i < len * 6; i += 32) go[i] = gs[i];
   }
   if (SMEM) {
     strip_mask_warp(sp, len, qlo, group, lane, mask0, mask1);  // occupancy of the finished strip (emba_internal.cuh)
@@ -745,7 +750,8 @@ k_pix(int64_t a_begin, int64_t a_end, const int32_t* __restrict__ segoff, const 
       const double* __restrict__ jrec, const int32_t* __restrict__ winlo, const int32_t* __restrict__ winhi,
       const int64_t* __restrict__ stripoff, double* __restrict__ strip, const int32_t* __restrict__ apix,
       const double* __restrict__ Gx, const double* __restrict__ Gy, double alpha, double* __restrict__ A22,
-      double* __restrict__ b2, int group, unsigned long long* __restrict__ gmask, int strip_cap) {
+      double* __restrict__ b2, int group, unsigned long long* __restrict__ gmask, int strip_cap,
+      const int64_t* __restrict__ dst) {
   extern __shared__ __align__(16) unsigned char pix_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t smem_per_warp = (size_t)(kPixStages * kPixTile * kRecDoubles + strip_cap * 6) * 8;
@@ -767,10 +773,11 @@ k_pix(int64_t a_begin, int64_t a_end, const int32_t* __restrict__ segoff, const 
     const int qlo = winlo[a];
     const int len = winhi[a] >= qlo ? winhi[a] - qlo + 1 : 0;  // empty window: no local rows (multi-GPU)
     double* gs = strip + stripoff[a] * 6;
+    double* go = dst ? reinterpret_cast<double*>((uintptr_t)dst[a]) : gs;
     double acc = 0.0;
     unsigned long long mask0 = 0ull, mask1 = 0ull;
-    if (len <= strip_cap) pix_one<true>(seg0, seg1, qlo, len, gs, s_tile, s_strip, sval, jrec, lane, s, r, c, ia, ib, group, acc, mask0, mask1);
-    else pix_one<false>(seg0, seg1, qlo, len, gs, s_tile, s_strip, sval, jrec, lane, s, r, c, ia, ib, group, acc, mask0, mask1);
+    if (len <= strip_cap) pix_one<true>(seg0, seg1, qlo, len, gs, go, s_tile, s_strip, sval, jrec, lane, s, r, c, ia, ib, group, acc, mask0, mask1);
+    else pix_one<false>(seg0, seg1, qlo, len, gs, go, s_tile, s_strip, sval, jrec, lane, s, r, c, ia, ib, group, acc, mask0, mask1);
     if (lane == 0) { gmask[2 * a] = mask0; gmask[2 * a + 1] = mask1; }
     // applyL2Reg (model.cpp:689-719): A22 += alpha*I, b2 -= alpha * (Gx, Gy)[pixel]
     const int32_t pix = apix[a];
@@ -781,6 +788,7 @@ k_pix(int64_t a_begin, int64_t a_end, const int32_t* __restrict__ segoff, const 
     if (lane == 28) b2[2 * a + 1] = acc - alpha * Gy[pix];
     __syncwarp();
   }
+  if (dst) __threadfence_system();  // remote sub-strips are performed before the kernel counts as finished
 }
 
 // occupancy masks of finished strips with at least min_len poses, one warp per pixel (the solve calls it for the
@@ -797,6 +805,22 @@ __global__ void k_strip_mask(int64_t Np, const int32_t* __restrict__ winlo, cons
   unsigned long long m0, m1;
   strip_mask_warp(strip + stripoff[a] * 6, len, lo, group, lane, m0, m1);
   if (lane == 0) { gmask[2 * a] = m0; gmask[2 * a + 1] = m1; }
+}
+
+// peer-memory exchange behind the fp64-atomic map path: one warp per pixel copies its finished local strip to the
+// owner's receive buffer
+__global__ void k_strip_push(int64_t Np, const int32_t* __restrict__ winlo, const int32_t* __restrict__ winhi,
+                             const int64_t* __restrict__ stripoff, const double* __restrict__ strip,
+                             const int64_t* __restrict__ dst) {
+  const int64_t a = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (a >= Np) return;
+  const int lo = winlo[a], hi = winhi[a];
+  const int len = hi >= lo ? hi - lo + 1 : 0;
+  const double* src = strip + stripoff[a] * 6;
+  double* out = reinterpret_cast<double*>((uintptr_t)dst[a]);
+  for (int i = lane; i < len * 6; i += 32) out[i] = src[i];
+  __threadfence_system();
 }
 
 int fill_strip_masks(Handle* h) {
@@ -1007,7 +1031,7 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   // send/recv launches with their rendezvous cost more than the transfer they hide, and the chunked map-side
   // launches lose 0.2 ms to their tails.
   static const bool pipe_env = getenv("EMBA_XCHG_PIPELINE") && atoi(getenv("EMBA_XCHG_PIPELINE")) == 1;
-  const bool pipelined = pipe_env && h->world <= 64;
+  bool pipelined = pipe_env && h->world <= 64;
   if (exchange) {
     EMBA_CUDAC(cudaEventRecord(h->ev_x[2], h->stream));
     EMBA_TRYC(comm_exchange_prepare(h));
@@ -1017,7 +1041,11 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   EMBA_CUDAC(cudaEventSynchronize(h->ev_host));
   const int64_t tot = h->h_pin[2];
   h->strip_total = tot;
-  if (exchange) EMBA_TRYC(comm_exchange_sizes(h));
+  h->peer_now = false;
+  if (exchange) {
+    EMBA_TRYC(comm_exchange_sizes(h));
+    if (h->peer_now) { pipelined = false; EMBA_TRYC(comm_exchange_dst(h)); }
+  }
   EMBA_TRYC(dev_reserve(h, &h->d_strip, &h->strip_cap, tot * 6 + tot * 3));  // +50 %: windows drift between iterations
   EMBA_CUDAC(cudaEventRecord(h->ev[8], h->stream));
   if (atomic_path) {
@@ -1056,7 +1084,8 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
       const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((a_end - a_begin + kPixWarps - 1) / kPixWarps, (int64_t)h->sm_count * 4 * ctas_per_sm));
       k_pix<<<grid, kPixWarps * 32, pix_smem, h->stream>>>(a_begin, a_end, h->d_segoff, h->d_segend, vs, h->d_jrec, h->d_winlo, h->d_winhi,
                                                     h->d_stripoff, h->d_strip, h->d_apix, s.Gx, s.Gy,
-                                                    h->rank == 0 ? alpha : 0.0, h->d_A22, h->d_b2, h->pose_group, h->d_gmask, strip_cap);
+                                                    h->rank == 0 ? alpha : 0.0, h->d_A22, h->d_b2, h->pose_group, h->d_gmask, strip_cap,
+                                                    h->peer_now ? h->d_dst : nullptr);
       h->launches++;
       EMBA_CUDAC(cudaGetLastError());
       return EMBA_OK;
@@ -1093,6 +1122,12 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
       EMBA_TRYC(comm_exchange_prepare(h));
       EMBA_CUDAC(cudaStreamSynchronize(h->stream));
       EMBA_TRYC(comm_exchange_sizes(h));
+      if (h->peer_now) {  // peer-memory exchange: the finished local strips are pushed to their owners by a copy kernel
+        EMBA_TRYC(comm_exchange_dst(h));
+        k_strip_push<<<ceil_div64(Np * 32, 256), 256, 0, h->stream>>>(Np, h->d_winlo, h->d_winhi, h->d_stripoff, h->d_strip, h->d_dst);
+        h->launches++;
+        EMBA_CUDAC(cudaGetLastError());
+      }
     }
     if (!exchange || !pipelined) {
       EMBA_TRYC(comm_exchange_all(h, h->stream, true));

@@ -9,6 +9,8 @@
 
 #include <cstring>
 
+#include <cuda.h>
+
 #include "emba_internal.cuh"
 
 namespace emba {
@@ -214,6 +216,58 @@ __global__ void k_merge_strips(int W, int64_t Np, int64_t a0, int64_t n_own, con
 }
 
 
+// ---------------------------------------------------------------------------------------------------
+// Peer-memory variant of the exchange (default when every rank can map every other rank's receive buffer with CUDA
+// IPC; NVLink / NVSwitch peers). The all-to-all disappears into the map-side kernel: every warp of k_pix stores its
+// finished sub-strip straight into the owner's receive buffer (posted NVLink stores, 1/W of them local), at the
+// offset the owner's merge expects. All ranks hold all pose windows after the window all-gather, so every rank
+// computes the same [source][owner] volume matrix and from it every receive layout -- no sizes travel. The grouped
+// A22 / b2 all-reduce that follows the map-side kernel is also the barrier: it completes on a rank only after
+// every rank has entered it, i.e. after every rank's map-side kernel (and its remote stores) has finished. The
+// next assembly's window all-gather orders the owner's merge (a read of the receive buffer) before any peer's next
+// map-side kernel writes into it.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int owner_of(int64_t a, int64_t Np, int W) { return (int)(((a + 1) * W - 1) / Np); }
+
+// cnt[s * W + q] = poses of the sub-strips rank s holds for the pixels rank q owns
+__global__ void k_cnt_matrix(int W, int64_t Np, const int32_t* __restrict__ win_all, unsigned long long* __restrict__ cnt) {
+  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = a < Np;
+  const int q = valid ? owner_of(a, Np, W) : -1;
+  const int q0 = __shfl_sync(0xffffffffu, q, 0);
+  const bool uniform = __all_sync(0xffffffffu, q == q0);
+  for (int s = 0; s < W; s++) {
+    long long len = 0;
+    if (valid) {
+      const int lo = win_all[((size_t)s * Np + a) * 2], hi = win_all[((size_t)s * Np + a) * 2 + 1];
+      len = hi >= lo ? (long long)(hi - lo + 1) : 0;
+    }
+    if (uniform) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) len += __shfl_xor_sync(0xffffffffu, len, o);
+      if ((threadIdx.x & 31) == 0 && len) atomicAdd(cnt + (size_t)s * W + q0, (unsigned long long)len);
+    } else if (valid && len) {
+      atomicAdd(cnt + (size_t)s * W + q, (unsigned long long)len);
+    }
+  }
+}
+
+struct PeerTab {
+  double* recv[Handle::kPeerMax];   // receive buffer of owner q as mapped on this rank
+  int64_t base[Handle::kPeerMax];   // poses in front of this rank's chunk in owner q's buffer
+};
+
+// destination of every local sub-strip: owner's buffer + my chunk's base + the strip's offset inside my chunk
+// (local strips are laid out in pixel order, so inside a chunk the offsets are the local ones, shifted)
+__global__ void k_strip_dst(int W, int64_t Np, const int64_t* __restrict__ stripoff, PeerTab tab, int64_t* __restrict__ dst) {
+  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= Np) return;
+  const int q = owner_of(a, Np, W);
+  const int64_t a0 = Np * q / W;
+  double* p = tab.recv[q] + (tab.base[q] + stripoff[a] - stripoff[a0]) * 6;
+  dst[a] = (int64_t)(uintptr_t)p;
+}
+
 // the few numbers the host needs for the exchange: receive counts per source rank, my strip offsets at the
 // ownership boundaries, merged strip total
 __global__ void k_gather_meta(int W, int64_t Np, int64_t n_own, const int64_t* __restrict__ own_off,
@@ -224,6 +278,101 @@ __global__ void k_gather_meta(int W, int64_t Np, int64_t n_own, const int64_t* _
     meta[s] = own_off[(size_t)s * (n_own + 1) + n_own] - own_off[(size_t)s * (n_own + 1)];  // poses received from s
   for (int q = t; q <= W; q += blockDim.x) meta[W + q] = stripoff[Np * q / W];
   if (t == 0) meta[2 * W + 1] = gstripoff[Np];
+}
+
+static bool peer_wanted(const Handle* h) {
+  static const bool off = getenv("EMBA_XCHG_PEER") && atoi(getenv("EMBA_XCHG_PEER")) == 0;
+  return !off && h->world > 1 && h->world <= Handle::kPeerMax && h->peer_mode != 0;
+}
+
+struct PeerMsg {  // what a rank publishes about its receive buffer (80 bytes)
+  cudaIpcMemHandle_t handle;
+  int64_t offset;  // of d_recv inside the allocation the handle names
+  int64_t ok;
+};
+static_assert(sizeof(PeerMsg) == 80, "PeerMsg layout");
+
+// (Re)allocates the receive buffers that have to grow (want[q] > 0: new capacity of rank q's, in doubles) and maps
+// them on every rank. Every rank calls this with the same `want` (it follows from the all-gathered pose windows), so
+// the collectives inside line up. On any failure anywhere, ALL ranks switch to the ncclSend/ncclRecv exchange for
+// good (the decision is taken on all-gathered / all-reduced flags). The caller has synchronised the stream.
+static int peer_remap(Handle* h, const int64_t* want) {
+  NcclApi* api = nccl_api();
+  const int W = h->world, r = h->rank;
+  const int words = (int)(sizeof(PeerMsg) / sizeof(int32_t));
+  if (!h->d_peerx) EMBA_TRY(dev_alloc(h, &h->d_peerx, (int64_t)(Handle::kPeerMax + 2) * 10));
+  for (int q = 0; q < W; q++)
+    if (q != r && want[q] > 0 && h->peer_base[q]) {  // nothing of mine is using the old mapping any more
+      cudaIpcCloseMemHandle(h->peer_base[q]);
+      cudaGetLastError();
+      h->peer_base[q] = nullptr;
+      h->peer_recv[q] = nullptr;
+    }
+  PeerMsg* msg = reinterpret_cast<PeerMsg*>(h->h_pin + 600);
+  PeerMsg* all = reinterpret_cast<PeerMsg*>(h->h_pin + 620);
+  std::memset(msg, 0, sizeof(PeerMsg));
+  msg->ok = 1;
+  double* old = nullptr;
+  if (want[r] > 0) {
+    double* fresh = nullptr;
+    if (cudaMalloc((void**)&fresh, sizeof(double) * (size_t)want[r]) != cudaSuccess) { cudaGetLastError(); msg->ok = 0; }
+    else { old = h->d_recv; h->d_recv = fresh; h->recv_cap = want[r]; }
+  }
+  if (msg->ok && h->d_recv) {
+    if (cudaIpcGetMemHandle(&msg->handle, h->d_recv) != cudaSuccess) { cudaGetLastError(); msg->ok = 0; }
+    else {
+      typedef CUresult (*fn_range)(CUdeviceptr*, size_t*, CUdeviceptr);
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qr;
+      CUdeviceptr base = 0;
+      size_t size = 0;
+      if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn ||
+          ((fn_range)fn)(&base, &size, (CUdeviceptr)(uintptr_t)h->d_recv) != CUDA_SUCCESS) { cudaGetLastError(); msg->ok = 0; }
+      else msg->offset = (int64_t)((uintptr_t)h->d_recv - (uintptr_t)base);
+    }
+  }
+  int32_t* stage = reinterpret_cast<int32_t*>(h->d_peerx);
+  EMBA_CUDA(cudaMemcpyAsync(stage + (size_t)W * words, msg, sizeof(PeerMsg), cudaMemcpyHostToDevice, h->stream));
+  if (api->allgather(stage + (size_t)W * words, stage, (size_t)words, 2, h->nccl_comm, h->stream) != 0) {
+    h->err = "ncclAllGather (receive-buffer handles) failed"; return EMBA_E_NCCL;
+  }
+  h->launches++;
+  EMBA_CUDA(cudaMemcpyAsync(all, stage, sizeof(PeerMsg) * W, cudaMemcpyDeviceToHost, h->stream));
+  EMBA_CUDA(cudaStreamSynchronize(h->stream));
+  // every rank unmapped the buffers that are being replaced BEFORE it contributed to that all-gather
+  if (old) cudaFree(old);
+  bool ok = true;
+  for (int q = 0; q < W; q++) ok = ok && all[q].ok == 1;
+  int32_t mine = ok ? 1 : 0;
+  if (ok) {
+    for (int q = 0; q < W && mine; q++) {
+      if (q == r || want[q] <= 0) continue;
+      void* base = nullptr;
+      if (cudaIpcOpenMemHandle(&base, all[q].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); mine = 0; break; }
+      h->peer_base[q] = base;
+      h->peer_recv[q] = reinterpret_cast<double*>(reinterpret_cast<char*>(base) + all[q].offset);
+    }
+    int32_t* hflag = reinterpret_cast<int32_t*>(h->h_pin + 600);
+    *hflag = mine;
+    EMBA_CUDA(cudaMemcpyAsync(stage, hflag, sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    if (api->allreduce(stage, stage, 1, 2, 3, h->nccl_comm, h->stream) != 0) { h->err = "ncclAllReduce (peer mapping) failed"; return EMBA_E_NCCL; }
+    h->launches++;
+    EMBA_CUDA(cudaMemcpyAsync(hflag, stage, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    EMBA_CUDA(cudaStreamSynchronize(h->stream));
+    ok = *hflag == 1;
+  }
+  if (!ok) {
+    for (int q = 0; q < W; q++) {
+      if (h->peer_base[q]) { cudaIpcCloseMemHandle(h->peer_base[q]); cudaGetLastError(); }
+      h->peer_base[q] = nullptr; h->peer_recv[q] = nullptr; h->peer_cap[q] = 0;
+    }
+    h->peer_mode = 0;
+    return EMBA_OK;
+  }
+  for (int q = 0; q < W; q++) if (want[q] > 0) h->peer_cap[q] = want[q];
+  h->peer_recv[r] = h->d_recv;
+  h->peer_mode = 1;
+  return EMBA_OK;
 }
 
 // The exchange in three parts, so that the transfers overlap the map-side kernel (assemble.cu):
@@ -243,7 +392,7 @@ int comm_exchange_prepare(Handle* h) {
   const int64_t a0 = own0(r), n_own = own0(r + 1) - a0;
   if (2 * W + 2 > 900) { h->err = "world size too large"; return EMBA_E_SUPPORT; }
   EMBA_TRY(dev_reserve(h, &h->d_win_all, &h->win_all_cap, (int64_t)W * Np * 2 + 2 * Np));
-  EMBA_TRY(dev_reserve(h, &h->d_own_len, &h->own_cap, (int64_t)2 * W * (n_own + 1) + 8 * W + 32));
+  EMBA_TRY(dev_reserve(h, &h->d_own_len, &h->own_cap, (int64_t)2 * W * (n_own + 1) + 8 * W + 32 + (int64_t)W * W));
   if (!h->d_win2) {
     EMBA_TRY(dev_alloc(h, &h->d_win2, 2 * (h->P + 1)));
     EMBA_TRY(dev_alloc(h, &h->d_gwinlo, h->P + 1));
@@ -275,6 +424,14 @@ int comm_exchange_prepare(Handle* h) {
   k_gather_meta<<<1, 64, 0, h->stream>>>(W, Np, n_own, own_off, h->d_stripoff, h->d_gstripoff, meta_dev);
   EMBA_LAUNCH_CHECK();
   EMBA_CUDA(cudaMemcpyAsync(h->h_pin + 32, meta_dev, sizeof(int64_t) * (2 * W + 2), cudaMemcpyDeviceToHost, h->stream));
+  if (peer_wanted(h)) {
+    // [source][owner] volumes, identical on every rank: the receive layout of every owner follows from them
+    int64_t* cnt_dev = meta_dev + (2 * W + 2);
+    EMBA_CUDA(cudaMemsetAsync(cnt_dev, 0, sizeof(int64_t) * W * W, h->stream));
+    k_cnt_matrix<<<ceil_div64(Np, T), T, 0, h->stream>>>(W, Np, h->d_win_all, reinterpret_cast<unsigned long long*>(cnt_dev));
+    EMBA_LAUNCH_CHECK();
+    EMBA_CUDA(cudaMemcpyAsync(h->h_pin + 256, cnt_dev, sizeof(int64_t) * W * W, cudaMemcpyDeviceToHost, h->stream));
+  }
   return EMBA_OK;
 }
 
@@ -287,8 +444,41 @@ int comm_exchange_sizes(Handle* h) {
   h->x_gtot = meta[2 * W + 1];
   h->x_recvbase.assign(W + 1, 0);
   for (int s = 0; s < W; s++) h->x_recvbase[s + 1] = h->x_recvbase[s] + h->x_recv_cnt[s];
-  EMBA_TRY(dev_reserve(h, &h->d_recv, &h->recv_cap, h->x_recvbase[W] * 6 + h->x_recvbase[W] * 3));
   EMBA_TRY(dev_reserve(h, &h->d_gstrip, &h->gstrip_cap, h->x_gtot * 6 + h->x_gtot * 3));
+  h->peer_now = false;
+  if (peer_wanted(h)) {
+    const int64_t* cm = h->h_pin + 256;
+    h->x_cnt.assign(cm, cm + (size_t)W * W);
+    int64_t want[Handle::kPeerMax] = {};
+    bool any = false;
+    for (int q = 0; q < W; q++) {
+      int64_t need = 0;
+      for (int s = 0; s < W; s++) need += h->x_cnt[(size_t)s * W + q];
+      need *= 6;
+      if (need > h->peer_cap[q]) { want[q] = need + need / 2 + 1024; any = true; }  // +50 %: windows drift between iterations
+    }
+    if (any) EMBA_TRY(peer_remap(h, want));
+    h->peer_now = h->peer_mode == 1;
+  }
+  if (!h->peer_now) EMBA_TRY(dev_reserve(h, &h->d_recv, &h->recv_cap, h->x_recvbase[W] * 6 + h->x_recvbase[W] * 3));
+  return EMBA_OK;
+}
+
+// peer mode: per-pixel destinations of this assembly's sub-strips (before the map-side kernel)
+int comm_exchange_dst(Handle* h) {
+  const int W = h->world, r = h->rank;
+  const int64_t Np = h->Np;
+  EMBA_TRY(dev_reserve(h, &h->d_dst, &h->dst_cap, Np + 1));
+  PeerTab tab;
+  for (int q = 0; q < Handle::kPeerMax; q++) { tab.recv[q] = nullptr; tab.base[q] = 0; }
+  for (int q = 0; q < W; q++) {
+    tab.recv[q] = q == r ? h->d_recv : h->peer_recv[q];
+    int64_t b = 0;
+    for (int s = 0; s < r; s++) b += h->x_cnt[(size_t)s * W + q];
+    tab.base[q] = b;
+  }
+  k_strip_dst<<<ceil_div64(Np, 256), 256, 0, h->stream>>>(W, Np, h->d_stripoff, tab, h->d_dst);
+  EMBA_LAUNCH_CHECK();
   return EMBA_OK;
 }
 
@@ -319,7 +509,7 @@ int comm_exchange_all(Handle* h, cudaStream_t st, bool with_a22) {
     rc |= api->allreduce(h->d_A22, h->d_A22, (size_t)(3 * h->Np), 8, 0, h->nccl_comm, st);
     rc |= api->allreduce(h->d_b2, h->d_b2, (size_t)(2 * h->Np), 8, 0, h->nccl_comm, st);
   }
-  for (int q = 0; q < W; q++) {
+  for (int q = 0; q < W && !h->peer_now; q++) {
     if (q == r) continue;
     const int64_t scount = (h->x_send_off[q + 1] - h->x_send_off[q]) * 6;
     const int64_t rcount = h->x_recv_cnt[q] * 6;
@@ -327,7 +517,7 @@ int comm_exchange_all(Handle* h, cudaStream_t st, bool with_a22) {
     if (rcount > 0) rc |= api->recv(h->d_recv + h->x_recvbase[q] * 6, (size_t)rcount, 8, q, h->nccl_comm, st);
   }
   if (api->group_end() != 0 || rc != 0) { h->err = "ncclSend/ncclRecv failed"; return EMBA_E_NCCL; }
-  h->launches++;
+  if (with_a22 || !h->peer_now) h->launches++;
   return EMBA_OK;
 }
 
@@ -338,8 +528,8 @@ int comm_exchange_finish(Handle* h, bool a22_done) {
   const int T = 256;
   const int64_t a0 = Np * r / W, n_own = Np * (r + 1) / W - a0;
   int64_t* own_off = h->d_own_len + (size_t)W * (n_own + 1);
-  // my own sub-strips do not travel
-  if (h->x_recv_cnt[r] > 0)
+  // my own sub-strips do not travel (peer mode: the map-side kernel already stored them in place)
+  if (h->x_recv_cnt[r] > 0 && !h->peer_now)
     EMBA_CUDA(cudaMemcpyAsync(h->d_recv + h->x_recvbase[r] * 6, h->d_strip + h->x_send_off[r] * 6,
                               sizeof(double) * h->x_recv_cnt[r] * 6, cudaMemcpyDeviceToDevice, h->stream));
   if (!a22_done) {
@@ -369,6 +559,12 @@ int comm_exchange_finish(Handle* h, bool a22_done) {
 }
 
 void comm_destroy(Handle* h) {
+  for (int q = 0; q < Handle::kPeerMax; q++) {
+    if (h->peer_base[q]) { cudaIpcCloseMemHandle(h->peer_base[q]); cudaGetLastError(); }
+    h->peer_base[q] = nullptr; h->peer_recv[q] = nullptr; h->peer_cap[q] = 0;
+  }
+  h->peer_mode = -1;
+  h->peer_now = false;
   if (h->nccl_comm) {
     NcclApi* api = nccl_api();
     if (api) api->destroy(h->nccl_comm);
@@ -411,6 +607,13 @@ int emba_comm_init(emba_handle_t hh, const void* id128, int32_t rank, int32_t wo
     EMBA_CUDA(cudaMemsetAsync(h->d_flags, 0, sizeof(int32_t) * 16, h->stream));
     EMBA_TRY(comm_allreduce(h, h->d_flags, 16, 0));
     EMBA_CUDA(cudaStreamSynchronize(h->stream));
+    // peer-memory strip exchange: map every rank's receive buffer now (context creation on the peers and the IPC
+    // opens take tens of milliseconds), with a starting capacity that later windows grow on demand
+    if (peer_wanted(h)) {
+      int64_t want[Handle::kPeerMax] = {};
+      for (int q = 0; q < world; q++) want[q] = (int64_t)4 << 20;  // 32 MB
+      EMBA_TRY(peer_remap(h, want));
+    }
   }
   return EMBA_OK;
 }

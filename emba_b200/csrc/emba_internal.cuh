@@ -106,6 +106,18 @@ struct Handle {
   std::vector<int64_t> x_recv_cnt, x_send_off, x_recvbase;  // strip exchange: poses received per source rank, my
   int64_t x_gtot = 0;                                        // strip offsets at the ownership boundaries, merged total
   int64_t* d_glen = nullptr;       // [P+2] merged strip lengths
+  // peer-memory strip exchange (comm.cu): the map-side kernel stores every finished sub-strip straight into its
+  // owner's receive buffer over NVLink (CUDA IPC mapping of every rank's d_recv)
+  static constexpr int kPeerMax = 16;
+  int peer_mode = -1;                          // -1 not negotiated yet, 0 off (ncclSend/ncclRecv all-to-all), 1 on
+  bool peer_now = false;                       // this assembly's strips go through peer memory
+  double* peer_recv[kPeerMax] = {};            // every rank's receive buffer as mapped here (own entry = d_recv)
+  void* peer_base[kPeerMax] = {};              // what cudaIpcOpenMemHandle returned (closed on re-map / destroy)
+  int64_t peer_cap[kPeerMax] = {};             // capacity (doubles) of every rank's buffer, tracked identically everywhere
+  std::vector<int64_t> x_cnt;                  // [source][owner] poses of sub-strips (identical on all ranks)
+  int64_t* d_dst = nullptr;                    // [Np] destination address of every local sub-strip
+  int64_t dst_cap = 0;
+  int64_t* d_peerx = nullptr;                  // device staging of the handle all-gather
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sort0 = nullptr, ev_sort1 = nullptr;
   cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
   cudaEvent_t ev_host = nullptr;   // marks a small device->host read-back the host waits for while later launches queue

@@ -478,7 +478,7 @@ int emba_destroy(emba_handle_t hh) {
                   h->d_scan_tmp, h->d_gmask, h->d_gmask2, h->d_win64, h->d_winlo, h->d_winhi, h->d_stripoff, h->d_strip,
                   h->d_A22, h->d_b2, h->d_A11, h->d_b1, h->d_C, h->d_S, h->d_rhs, h->d_x1, h->d_x2, h->d_Spart, h->d_cg,
                   h->d_ldlt_w, h->d_win2, h->d_win_all, h->d_own_len, h->d_gwinlo, h->d_gwinhi, h->d_gstripoff,
-                  h->d_gstrip, h->d_recv};
+                  h->d_gstrip, h->d_recv, h->d_dst, h->d_peerx};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : {h->ev_fork, h->ev_join, h->ev_fork2, h->ev_join2, h->ev_sort0, h->ev_sort1, h->ev_host}) if (e) cudaEventDestroy(e);
@@ -1033,6 +1033,7 @@ extern "C" int emba_last_comm_ms(emba_handle_t hh, double* out8) {
   Handle* h = (Handle*)hh;
   if (!h || !out8) return EMBA_E_ARG;
   for (int i = 0; i < 8; i++) out8[i] = h->t_comm_ms[i];
+  out8[7] = h->peer_now ? 1.0 : 0.0;
   return EMBA_OK;
 }
 

@@ -223,7 +223,8 @@ class Engine:
     def comm_ms(self):
         out = np.zeros(8)
         self._chk(self.L.emba_last_comm_ms(self.h, ptr(out)))
-        return dict(eval_allreduce=out[0], exchange_prepare=out[1], pix_and_sends=out[2], allreduce_and_merge=out[3])
+        return dict(eval_allreduce=out[0], exchange_prepare=out[1], pix_and_sends=out[2], allreduce_and_merge=out[3],
+                    strip_exchange="peer" if out[7] == 1.0 else "nccl")
 
     def set_strict_range(self, on):
         self._chk(self.L.emba_set_strict_range(self.h, int(bool(on))))

@@ -308,7 +308,10 @@ EMBA_API int emba_get_counters(emba_handle_t h, int64_t* out8);
 /* several GPUs: device ms of the collective phases of the last pass on this rank. out[0] = histogram / cost
  * all-reduce of emba_evaluate, out[1] = window all-gather + exchange bookkeeping (before the map-side kernel),
  * out[2] = map-side kernel with the overlapped strip sends (until the last chunk has arrived), out[3] = A22 / b2
- * all-reduce + merge of the received sub-strips; the rest 0 */
+ * all-reduce + merge of the received sub-strips; out[7] = 1 if the A12 sub-strips of that pass went through peer memory
+ * (the map-side kernel stores them straight into the owner rank's receive buffer over NVLink, mapped with CUDA IPC;
+ * the default wherever every rank can map every other rank's buffer), 0 if through the ncclSend/ncclRecv all-to-all
+ * (EMBA_XCHG_PEER=0, or the mapping failed on some rank); the rest 0 */
 EMBA_API int emba_last_comm_ms(emba_handle_t h, double* out8);
 /* number of kernel launches issued by this handle so far */
 EMBA_API int emba_launch_count(emba_handle_t h, int64_t* out);

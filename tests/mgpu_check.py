@@ -35,6 +35,9 @@ def main():
         assert np.array_equal(num, ref["num_ev_map"])
         assert abs(cd - float(ref["cost_data"])) < 1e-11 * float(ref["cost_data"])
         Np = eng.form_normal_eq(5, 0, 1.0, 5.0)
+        mode = eng.comm_ms()["strip_exchange"]
+        want = os.environ.get("EMBA_EXPECT_EXCHANGE")
+        assert want is None or mode == want, (mode, want)
         A11, A12, A22, b1, b2, act = eng.get_normal_eq(True)
         assert np.array_equal(act, ref["active"])
         # A12 is pixel-sharded: every rank holds the complete columns of the pixels it owns and zeros elsewhere
@@ -64,7 +67,7 @@ def main():
         assert np.max(ang) < 1e-5 and rel(ref["Gx_final"], gx) < 1e-4
         eng.close()
         if rank == 0:
-            print(f"mgpu_check {name}: world={world} OK (M={M}, Np={Np}, LM solves={log.shape[0]})", flush=True)
+            print(f"mgpu_check {name}: world={world} OK (M={M}, Np={Np}, LM solves={log.shape[0]}, strips via {mode})", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

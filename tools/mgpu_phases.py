@@ -36,7 +36,7 @@ if rank == 0:
     A = torch.stack(allm).cpu().numpy()
     names = ["evaluate", "k_eval", "eval_allreduce", "form", "k_asm_pose", "k_pix(+sends)", "sort_side", "xchg_prepare",
              "pix_and_sends", "allreduce+merge", "solve"]
-    print(f"{name} world={world} pipeline={os.environ.get('EMBA_XCHG_PIPELINE', '1')} N={sc.n_events}  pass(max over ranks) = "
+    print(f"{name} world={world} strips via {cf['strip_exchange']} pipeline={os.environ.get('EMBA_XCHG_PIPELINE', '0')} N={sc.n_events}  pass(max over ranks) = "
           f"{(A[:, 0] + A[:, 3]).max():.3f} ms")
     for j, nm in enumerate(names):
         print(f"  {nm:18s} mean {A[:, j].mean():7.3f}  max {A[:, j].max():7.3f}  per rank {np.round(A[:, j], 2).tolist()}")
