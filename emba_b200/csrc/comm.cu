@@ -296,6 +296,11 @@ static_assert(sizeof(PeerMsg) == 80, "PeerMsg layout");
 // them on every rank. Every rank calls this with the same `want` (it follows from the all-gathered pose windows), so
 // the collectives inside line up. On any failure anywhere, ALL ranks switch to the ncclSend/ncclRecv exchange for
 // good (the decision is taken on all-gathered / all-reduced flags). The caller has synchronised the stream.
+static void peer_note(const Handle* h, const char* what, cudaError_t e) {
+  static const bool dbg = getenv("EMBA_PEER_DEBUG") && atoi(getenv("EMBA_PEER_DEBUG")) == 1;
+  if (dbg) fprintf(stderr, "[emba_b200 rank %d] peer-memory exchange: %s: %s\n", h->rank, what, cudaGetErrorString(e));
+}
+
 static int peer_remap(Handle* h, const int64_t* want) {
   NcclApi* api = nccl_api();
   const int W = h->world, r = h->rank;
@@ -315,11 +320,11 @@ static int peer_remap(Handle* h, const int64_t* want) {
   double* old = nullptr;
   if (want[r] > 0) {
     double* fresh = nullptr;
-    if (cudaMalloc((void**)&fresh, sizeof(double) * (size_t)want[r]) != cudaSuccess) { cudaGetLastError(); msg->ok = 0; }
+    if (cudaError_t e = cudaMalloc((void**)&fresh, sizeof(double) * (size_t)want[r])) { peer_note(h, "cudaMalloc", e); cudaGetLastError(); msg->ok = 0; }
     else { old = h->d_recv; h->d_recv = fresh; h->recv_cap = want[r]; }
   }
   if (msg->ok && h->d_recv) {
-    if (cudaIpcGetMemHandle(&msg->handle, h->d_recv) != cudaSuccess) { cudaGetLastError(); msg->ok = 0; }
+    if (cudaError_t e = cudaIpcGetMemHandle(&msg->handle, h->d_recv)) { peer_note(h, "cudaIpcGetMemHandle", e); cudaGetLastError(); msg->ok = 0; }
     else {
       typedef CUresult (*fn_range)(CUdeviceptr*, size_t*, CUdeviceptr);
       void* fn = nullptr;
@@ -327,7 +332,9 @@ static int peer_remap(Handle* h, const int64_t* want) {
       CUdeviceptr base = 0;
       size_t size = 0;
       if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn ||
-          ((fn_range)fn)(&base, &size, (CUdeviceptr)(uintptr_t)h->d_recv) != CUDA_SUCCESS) { cudaGetLastError(); msg->ok = 0; }
+          ((fn_range)fn)(&base, &size, (CUdeviceptr)(uintptr_t)h->d_recv) != CUDA_SUCCESS) {
+        peer_note(h, "cuMemGetAddressRange", cudaErrorUnknown); cudaGetLastError(); msg->ok = 0;
+      }
       else msg->offset = (int64_t)((uintptr_t)h->d_recv - (uintptr_t)base);
     }
   }
@@ -342,13 +349,16 @@ static int peer_remap(Handle* h, const int64_t* want) {
   // every rank unmapped the buffers that are being replaced BEFORE it contributed to that all-gather
   if (old) cudaFree(old);
   bool ok = true;
-  for (int q = 0; q < W; q++) ok = ok && all[q].ok == 1;
+  for (int q = 0; q < W; q++) {
+    ok = ok && all[q].ok == 1;
+    if (all[q].ok != 1) peer_note(h, "a rank could not publish its receive buffer", cudaErrorUnknown);
+  }
   int32_t mine = ok ? 1 : 0;
   if (ok) {
     for (int q = 0; q < W && mine; q++) {
       if (q == r || want[q] <= 0) continue;
       void* base = nullptr;
-      if (cudaIpcOpenMemHandle(&base, all[q].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); mine = 0; break; }
+      if (cudaError_t e = cudaIpcOpenMemHandle(&base, all[q].handle, cudaIpcMemLazyEnablePeerAccess)) { peer_note(h, "cudaIpcOpenMemHandle", e); cudaGetLastError(); mine = 0; break; }
       h->peer_base[q] = base;
       h->peer_recv[q] = reinterpret_cast<double*>(reinterpret_cast<char*>(base) + all[q].offset);
     }
@@ -360,6 +370,7 @@ static int peer_remap(Handle* h, const int64_t* want) {
     EMBA_CUDA(cudaMemcpyAsync(hflag, stage, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     EMBA_CUDA(cudaStreamSynchronize(h->stream));
     ok = *hflag == 1;
+    if (!ok) peer_note(h, "a rank could not map a peer's receive buffer", cudaErrorUnknown);
   }
   if (!ok) {
     for (int q = 0; q < W; q++) {
@@ -372,6 +383,7 @@ static int peer_remap(Handle* h, const int64_t* want) {
   for (int q = 0; q < W; q++) if (want[q] > 0) h->peer_cap[q] = want[q];
   h->peer_recv[r] = h->d_recv;
   h->peer_mode = 1;
+  peer_note(h, "receive buffers mapped", cudaSuccess);
   return EMBA_OK;
 }
 
