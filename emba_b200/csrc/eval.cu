@@ -136,7 +136,16 @@ __device__ __forceinline__ double rho_of(double e, double a) {
 // kernel is bound by its gathers and the counting atomic, not by the fp64 pipe, so the split only added traffic.)
 constexpr int kEvalThreads = 256;
 
-template <int COST, int MINB>
+// PF (software prefetch across the grid-stride loop; the kernel is bound by the latency of its dependent loads --
+// record -> batch entries -> knot entries -> map gather, "long scoreboard" 7 of 12.8 stall cycles per issue):
+//   bit 0: the record two iterations ahead and the two batch-table entries of the NEXT iteration's record are
+//          prefetched into L1, bit 1: into L2 instead; bit 2: both batch-table entries are requested before the first
+//          one is consumed (the 256-bit loads are volatile asm, which otherwise keeps them in source order, the second
+//          behind the first's dependent knot loads).
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <int COST, int MINB, int PF>
 __global__ void __launch_bounds__(kEvalThreads, MINB)
 k_eval(const MeasRec* __restrict__ rec, int64_t Mc, const double* __restrict__ Ktab,
        const double4* __restrict__ RotTab, const double2* __restrict__ G2, PanoCam cam, int W, int H, double C_th, double eta,
@@ -145,27 +154,53 @@ k_eval(const MeasRec* __restrict__ rec, int64_t Mc, const double* __restrict__ K
        int32_t* __restrict__ flags) {
   double cost = 0.0;
   double cnt = 0.0;
-  for (int64_t m = (int64_t)blockIdx.x * kEvalThreads + threadIdx.x; m < Mc; m += (int64_t)gridDim.x * kEvalThreads) {
+  const int64_t stride = (int64_t)gridDim.x * kEvalThreads;
+  for (int64_t m = (int64_t)blockIdx.x * kEvalThreads + threadIdx.x; m < Mc; m += stride) {
     const double4 r0 = ldg256(rec + m);
+    unsigned long long wn = 0ull;
+    bool have_next = false;
+    if (PF & 3) {
+      if (m + 2 * stride < Mc) { if (PF & 1) prefetch_l1(rec + m + 2 * stride); else prefetch_l2(rec + m + 2 * stride); }
+      have_next = m + stride < Mc;
+      if (have_next) wn = __ldg(reinterpret_cast<const unsigned long long*>(rec + m + stride) + 3);
+    }
     const double bx = r0.x, by = r0.y, bz = r0.z;
     const unsigned long long w = (unsigned long long)__double_as_longlong(r0.w);
     const uint32_t bcp = (uint32_t)w, bp = (uint32_t)(w >> 32);
     const uint32_t bc = bcp & 0x7FFFFFFFu;
     const double pol = (bcp >> 31) ? 1.0 : 0.0;
     double pcx, pcy, ppx, ppy;
-    {
-      const double4 rt = ldg256(RotTab + bc);
-      const int sk = (int)__double_as_longlong(rt.z);
+    if (PF & 4) {
+      const double4 rtc = ldg256(RotTab + bc);
+      const double4 rtp = ldg256(RotTab + bp);
       double X, Y, Z;
-      rotate_bearing_v(Ktab + (size_t)sk * kKnotStride, rt.x, rt.y, bx, by, bz, X, Y, Z);
+      // ptxas schedules loads as it likes, whatever the source order: the (always zero) high bits of the second
+      // entry's knot index enter the first one's knot address, so both entries are in flight before either is used
+      const int skc = (int)__double_as_longlong(rtc.z) + (int)(__double_as_longlong(rtp.z) >> 40);
+      rotate_bearing_v(Ktab + (size_t)skc * kKnotStride, rtc.x, rtc.y, bx, by, bz, X, Y, Z);
       project_pm_unit(cam, X, Y, Z, pcx, pcy);
-    }
-    {
-      const double4 rt = ldg256(RotTab + bp);
-      const int sk = (int)__double_as_longlong(rt.z);
-      double X, Y, Z;
-      rotate_bearing_v(Ktab + (size_t)sk * kKnotStride, rt.x, rt.y, bx, by, bz, X, Y, Z);
+      rotate_bearing_v(Ktab + (size_t)((int)__double_as_longlong(rtp.z)) * kKnotStride, rtp.x, rtp.y, bx, by, bz, X, Y, Z);
       project_pm_unit(cam, X, Y, Z, ppx, ppy);
+    } else {
+      {
+        const double4 rt = ldg256(RotTab + bc);
+        const int sk = (int)__double_as_longlong(rt.z);
+        double X, Y, Z;
+        rotate_bearing_v(Ktab + (size_t)sk * kKnotStride, rt.x, rt.y, bx, by, bz, X, Y, Z);
+        project_pm_unit(cam, X, Y, Z, pcx, pcy);
+      }
+      {
+        const double4 rt = ldg256(RotTab + bp);
+        const int sk = (int)__double_as_longlong(rt.z);
+        double X, Y, Z;
+        rotate_bearing_v(Ktab + (size_t)sk * kKnotStride, rt.x, rt.y, bx, by, bz, X, Y, Z);
+        project_pm_unit(cam, X, Y, Z, ppx, ppy);
+      }
+    }
+    if ((PF & 3) && have_next) {
+      const uint32_t nbc = (uint32_t)wn & 0x7FFFFFFFu, nbp = (uint32_t)(wn >> 32);
+      if (PF & 1) { prefetch_l1(RotTab + nbc); prefetch_l1(RotTab + nbp); }
+      else { prefetch_l2(RotTab + nbc); prefetch_l2(RotTab + nbp); }
     }
     const double dx = pcx - ppx, dy = pcy - ppy;
     // dp.norm() > 10 (model.cpp:199-200), evaluated without FMA contraction like the CPU build
@@ -335,15 +370,20 @@ int evaluate_slot(Handle* h, int slot, int cost_type, double eta, double alpha) 
     // resident CTAs per SM the kernel is compiled for: 4 (64 registers, no spills; the default), 5 (48 registers),
     // 6 (40). Measured on C4: 3.58 / 3.77 / 4.32 ms -- the spilled values cost more than the extra warps hide.
     static const int occ = getenv("EMBA_EVAL_OCC") ? atoi(getenv("EMBA_EVAL_OCC")) : 4;
-#define EMBA_EVAL_LAUNCH2(C, B)                                                                                   \
-  k_eval<C, B><<<grid, kEvalThreads, 0, h->stream>>>(h->d_rec, h->Mc, s.Ktab, s.RotTab, s.G2, cam, h->Wp, h->Hp,  \
-                                                     h->C_th, eta, s.dp, s.e, s.pix, s.slot, s.hist_loc,           \
-                                                     h->d_part, h->d_flags)
-#define EMBA_EVAL_LAUNCH(C)                        \
-  do {                                             \
-    if (occ >= 6) EMBA_EVAL_LAUNCH2(C, 6);         \
-    else if (occ == 5) EMBA_EVAL_LAUNCH2(C, 5);    \
-    else EMBA_EVAL_LAUNCH2(C, 4);                  \
+    const int pf = getenv("EMBA_EVAL_PF") ? atoi(getenv("EMBA_EVAL_PF")) : 0;  // read per call: tools/eval_variants.py switches it
+#define EMBA_EVAL_LAUNCH2(C, B, F)                                                                                   \
+  k_eval<C, B, F><<<grid, kEvalThreads, 0, h->stream>>>(h->d_rec, h->Mc, s.Ktab, s.RotTab, s.G2, cam, h->Wp, h->Hp,  \
+                                                        h->C_th, eta, s.dp, s.e, s.pix, s.slot, s.hist_loc,           \
+                                                        h->d_part, h->d_flags)
+#define EMBA_EVAL_LAUNCH(C)                           \
+  do {                                                \
+    if (occ >= 6) EMBA_EVAL_LAUNCH2(C, 6, 0);         \
+    else if (occ == 5) EMBA_EVAL_LAUNCH2(C, 5, 0);    \
+    else if (pf == 1) EMBA_EVAL_LAUNCH2(C, 4, 1);     \
+    else if (pf == 4) EMBA_EVAL_LAUNCH2(C, 4, 4);     \
+    else if (pf == 5) EMBA_EVAL_LAUNCH2(C, 4, 5);     \
+    else if (pf == 6) EMBA_EVAL_LAUNCH2(C, 4, 6);     \
+    else EMBA_EVAL_LAUNCH2(C, 4, 0);                  \
   } while (0)
     if (cost_type == EMBA_COST_QUADRATIC) EMBA_EVAL_LAUNCH(EMBA_COST_QUADRATIC);
     else if (cost_type == EMBA_COST_CAUCHY) EMBA_EVAL_LAUNCH(EMBA_COST_CAUCHY);
