@@ -113,19 +113,50 @@ constexpr int kSegRegCap = 1024;   // longest segment a single warp sorts in reg
 
 // element i = lane * K + r  (blocked: a lane's K keys are consecutive)
 // KMIN = 2: full sort. KMIN = 32 K: only the last merge (the two halves are already sorted).
-template <int K, int KMIN = 2>
-__device__ __forceinline__ void warp_bitonic(uint32_t (&a)[K], int lane) {
+// Code size matters here: fully unrolled, the six networks (K = 1 .. 32) are ~150 KB of straight-line SASS that every
+// warp streams through once per segment, and the kernel spent 17.8 of its 23.3 stall cycles per issue waiting for
+// instructions (ncu "no_instruction"). So only the in-register steps (compile-time register indices) are unrolled; the
+// merge sizes above K and their cross-lane steps are runtime loops whose bodies -- one exchange step over K registers
+// and the in-register tail -- are reused by every iteration.
+template <int K>
+__device__ __forceinline__ void bitonic_in_regs(uint32_t (&a)[K], int jtop) {  // steps j = jtop, jtop/2, .. 1 (jtop < K)
 #pragma unroll
-  for (int k = KMIN; k <= 32 * K; k <<= 1) {
-    // flip step: i <-> i ^ (k - 1)
-    if (k <= K) {
+  for (int j = K / 2; j >= 1; j >>= 1) {
+    if (j <= jtop) {
 #pragma unroll
       for (int r = 0; r < K; r++) {
-        const int q = r ^ (k - 1);
+        const int q = r ^ j;
         if (q > r) { const uint32_t lo = min(a[r], a[q]), hi = max(a[r], a[q]); a[r] = lo; a[q] = hi; }
       }
-    } else {
-      const int lm = k / K - 1;  // lane ^= lm, r -> K - 1 - r
+    }
+  }
+}
+
+template <int K, int KMIN = 2>
+__device__ __forceinline__ void warp_bitonic(uint32_t (&a)[K], int lane) {
+  // merges that stay inside a lane: compile-time network
+#pragma unroll
+  for (int k = KMIN; k <= K; k <<= 1) {
+#pragma unroll
+    for (int r = 0; r < K; r++) {  // flip step: i <-> i ^ (k - 1)
+      const int q = r ^ (k - 1);
+      if (q > r) { const uint32_t lo = min(a[r], a[q]), hi = max(a[r], a[q]); a[r] = lo; a[q] = hi; }
+    }
+#pragma unroll
+    for (int j = k >> 2; j >= 1; j >>= 1) {
+#pragma unroll
+      for (int r = 0; r < K; r++) {
+        const int q = r ^ j;
+        if (q > r) { const uint32_t lo = min(a[r], a[q]), hi = max(a[r], a[q]); a[r] = lo; a[q] = hi; }
+      }
+    }
+  }
+  // merges across lanes: runtime loops over the merge size and the cross-lane steps
+  constexpr int k0 = (KMIN > 2 * K) ? KMIN : 2 * K;
+#pragma unroll 1
+  for (int k = k0; k <= 32 * K; k <<= 1) {
+    {
+      const int lm = k / K - 1;  // flip step: lane ^= lm, r -> K - 1 - r
       const bool lower = (lane & ((lm + 1) >> 1)) == 0;  // the top flipped lane bit decides who is the lower index
       if (K == 1) {
         const uint32_t o = __shfl_xor_sync(0xffffffffu, a[0], lm);
@@ -140,24 +171,17 @@ __device__ __forceinline__ void warp_bitonic(uint32_t (&a)[K], int lane) {
         }
       }
     }
+#pragma unroll 1
+    for (int j = k >> 2; j >= K; j >>= 1) {
+      const int lm = j / K;
+      const bool lower = (lane & lm) == 0;
 #pragma unroll
-    for (int j = k >> 2; j >= 1; j >>= 1) {
-      if (j < K) {
-#pragma unroll
-        for (int r = 0; r < K; r++) {
-          const int q = r ^ j;
-          if (q > r) { const uint32_t lo = min(a[r], a[q]), hi = max(a[r], a[q]); a[r] = lo; a[q] = hi; }
-        }
-      } else {
-        const int lm = j / K;
-        const bool lower = (lane & lm) == 0;
-#pragma unroll
-        for (int r = 0; r < K; r++) {
-          const uint32_t o = __shfl_xor_sync(0xffffffffu, a[r], lm);
-          a[r] = lower ? min(a[r], o) : max(a[r], o);
-        }
+      for (int r = 0; r < K; r++) {
+        const uint32_t o = __shfl_xor_sync(0xffffffffu, a[r], lm);
+        a[r] = lower ? min(a[r], o) : max(a[r], o);
       }
     }
+    if (K > 1) bitonic_in_regs<K>(a, K / 2);
   }
 }
 

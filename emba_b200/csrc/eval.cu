@@ -370,7 +370,8 @@ int evaluate_slot(Handle* h, int slot, int cost_type, double eta, double alpha) 
     // resident CTAs per SM the kernel is compiled for: 4 (64 registers, no spills; the default), 5 (48 registers),
     // 6 (40). Measured on C4: 3.58 / 3.77 / 4.32 ms -- the spilled values cost more than the extra warps hide.
     static const int occ = getenv("EMBA_EVAL_OCC") ? atoi(getenv("EMBA_EVAL_OCC")) : 4;
-    const int pf = getenv("EMBA_EVAL_PF") ? atoi(getenv("EMBA_EVAL_PF")) : 0;  // read per call: tools/eval_variants.py switches it
+    // default 4; measured on C4 / C2 (ms): PF 0: 3.58 / 0.276, 4: 3.21 / 0.262, 5: 3.21 / 0.285, 6: 3.40 / 0.285, 1: 3.62 / 0.299
+    const int pf = getenv("EMBA_EVAL_PF") ? atoi(getenv("EMBA_EVAL_PF")) : 4;  // read per call: tools/eval_variants.py switches it
 #define EMBA_EVAL_LAUNCH2(C, B, F)                                                                                   \
   k_eval<C, B, F><<<grid, kEvalThreads, 0, h->stream>>>(h->d_rec, h->Mc, s.Ktab, s.RotTab, s.G2, cam, h->Wp, h->Hp,  \
                                                         h->C_th, eta, s.dp, s.e, s.pix, s.slot, s.hist_loc,           \
@@ -380,10 +381,10 @@ int evaluate_slot(Handle* h, int slot, int cost_type, double eta, double alpha) 
     if (occ >= 6) EMBA_EVAL_LAUNCH2(C, 6, 0);         \
     else if (occ == 5) EMBA_EVAL_LAUNCH2(C, 5, 0);    \
     else if (pf == 1) EMBA_EVAL_LAUNCH2(C, 4, 1);     \
-    else if (pf == 4) EMBA_EVAL_LAUNCH2(C, 4, 4);     \
+    else if (pf == 0) EMBA_EVAL_LAUNCH2(C, 4, 0);     \
     else if (pf == 5) EMBA_EVAL_LAUNCH2(C, 4, 5);     \
     else if (pf == 6) EMBA_EVAL_LAUNCH2(C, 4, 6);     \
-    else EMBA_EVAL_LAUNCH2(C, 4, 0);                  \
+    else EMBA_EVAL_LAUNCH2(C, 4, 4);                  \
   } while (0)
     if (cost_type == EMBA_COST_QUADRATIC) EMBA_EVAL_LAUNCH(EMBA_COST_QUADRATIC);
     else if (cost_type == EMBA_COST_CAUCHY) EMBA_EVAL_LAUNCH(EMBA_COST_CAUCHY);
