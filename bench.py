@@ -422,6 +422,20 @@ def main():
         allr = [mine]
     allr = torch.stack(allr).cpu().numpy()
 
+    # ---- per-kernel standalone durations: the same pass with the row placement / segment sort queued BEHIND the
+    # pose-side kernel instead of beside it (EMBA_SIDE_SERIAL, csrc/assemble.cu), so that every kernel's event-timed
+    # duration is its own; every rank runs the same three passes (the pass contains collectives)
+    os.environ["EMBA_SIDE_SERIAL"] = "1"
+    ser = []
+    for i in range(4):
+        _, _, _, tm_e, tm_f = one_pass()
+        if i:
+            ser.append([tm_e["eval_kernel"], tm_f["asm_pose_kernel"], tm_f["pix_kernel"], tm_f["sort"], tm_e["evaluate"] + tm_f["form"]])
+    os.environ["EMBA_SIDE_SERIAL"] = "0"
+    one_pass()
+    sync_all()
+    ser = np.mean(ser, 0)
+
     # ---- the fp64-atomic map-block path, reported beside the deterministic one (north star: "also reported")
     atomic = None
     if not args.no_extras:
@@ -660,6 +674,14 @@ def main():
                                             place_and_segment_sort_side_stream=float(allr[slow, 6]),
                                             map_side_total=float(allr[slow, 7])),
                          "kernels_alg_gbs": {k: v[1] / (v[0] * 1e-3) / 1e9 for k, v in kern.items() if v[0] > 0},
+                         "standalone_rank0": {
+                             "note": "3 passes with the placement / segment sort queued behind the pose-side kernel "
+                                     "instead of beside it: each kernel's own duration (same pass time)",
+                             "kernels_ms": {"k_eval": float(ser[0]), "k_asm_pose": float(ser[1]), "k_pix": float(ser[2]),
+                                            "place_and_segment_sort": float(ser[3])},
+                             "ms_per_step": float(ser[4]),
+                             "kernels_frac": {k: kern_ranks[0][k][1] / (t * 1e-3) / 1e9 / peak
+                                              for k, t in (("k_eval", ser[0]), ("k_asm_pose", ser[1]), ("k_pix", ser[2])) if t > 0}},
                          "kernels_frac": {k: v[1] / (v[0] * 1e-3) / 1e9 / peak for k, v in kern.items() if v[0] > 0},
                          "pass_alg_bytes": pass_bytes,
                          "pass_frac": pass_bytes / (ms_step * 1e-3) / 1e9 / (peak * world),

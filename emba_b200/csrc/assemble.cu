@@ -83,24 +83,29 @@ __global__ void k_active_fill(const int32_t* __restrict__ flag, const int32_t* _
 
 // every inlier row on an active pixel goes to its slot of the pixel's segment (a separate pass: fused into the
 // pose-side kernel the scattered 4-byte stores cost that HBM-bound kernel 2.8 ms on C4, alone they take 1.7 ms)
-constexpr int kPlaceRows = 4;  // rows per thread: the dependent gather chain pix -> rowbase[pix] -> store of four rows
-                               // is in flight at once (the one-row version issued 7 % of the time: pure latency)
+// ROWS rows per thread: the dependent gather chain pix -> rowbase[pix] -> store of all of them is in flight at once
+// (the one-row version issued 7 % of the time: pure latency). CG: the table gather and the scattered store bypass L1
+// (ld.global.cg / st.global.cg) -- neither has any reuse there.
+template <int ROWS, bool CG>
 __global__ void __launch_bounds__(256)
 k_place(int64_t Mc, const int32_t* __restrict__ pix, const int32_t* __restrict__ slot,
         const int32_t* __restrict__ rowbase, uint32_t* __restrict__ sval) {
-  const int64_t m0 = (int64_t)blockIdx.x * (256 * kPlaceRows) + threadIdx.x;
-  int32_t p[kPlaceRows], sl[kPlaceRows], base[kPlaceRows];
+  const int64_t m0 = (int64_t)blockIdx.x * (256 * ROWS) + threadIdx.x;
+  int32_t p[ROWS], sl[ROWS], base[ROWS];
 #pragma unroll
-  for (int k = 0; k < kPlaceRows; k++) {
+  for (int k = 0; k < ROWS; k++) {
     const int64_t m = m0 + k * 256;
-    p[k] = m < Mc ? pix[m] : -1;
-    sl[k] = m < Mc ? slot[m] : 0;
+    p[k] = m < Mc ? __ldcs(pix + m) : -1;
+    sl[k] = m < Mc ? __ldcs(slot + m) : 0;
   }
 #pragma unroll
-  for (int k = 0; k < kPlaceRows; k++) base[k] = p[k] >= 0 ? rowbase[p[k]] : -1;
+  for (int k = 0; k < ROWS; k++) base[k] = p[k] >= 0 ? (CG ? __ldcg(rowbase + p[k]) : rowbase[p[k]]) : -1;
 #pragma unroll
-  for (int k = 0; k < kPlaceRows; k++)
-    if (base[k] >= 0) sval[(int64_t)base[k] + sl[k]] = (uint32_t)(m0 + k * 256);
+  for (int k = 0; k < ROWS; k++)
+    if (base[k] >= 0) {
+      if (CG) __stcg(sval + (int64_t)base[k] + sl[k], (uint32_t)(m0 + k * 256));
+      else sval[(int64_t)base[k] + sl[k]] = (uint32_t)(m0 + k * 256);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -995,26 +1000,37 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
     h->launches++;
     EMBA_CUDAC(cudaGetLastError());
   }
+  EMBA_CUDAC(cudaEventRecord(h->ev[6], h->stream));  // end of the pose-side kernel
   // ---- 1b. side stream: rows -> pixel segments (k_place) and the per-segment ordering (k_seg_sort*). They need only
   // the evaluation and the segment offsets; they are submitted before the pose-side kernel and the main stream joins
   // them before the map-side kernel.
   if (!atomic_path && h->Mc > 0) {
     const int64_t Mc = h->Mc;
-    EMBA_CUDAC(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
-    EMBA_CUDAC(cudaEventRecord(h->ev_sort0, h->stream2));
-    EMBA_CUDAC(cudaMemsetAsync(h->d_longlist, 0, sizeof(int32_t), h->stream2));
-    k_place<<<ceil_div64(Mc, 256 * kPlaceRows), 256, 0, h->stream2>>>(Mc, s.pix, s.slot, d_rowbase, h->d_sval);
-    k_seg_sort<<<h->sm_count * 32, kSegWarps * 32, 0, h->stream2>>>(d_totals, h->d_segoff, h->d_segend, h->d_sval, h->d_longlist);
-    k_seg_sort_long<<<h->sm_count * 16, kSegLongWarps * 32, 0, h->stream2>>>(h->d_longlist, h->d_segoff, h->d_segend, h->d_sval);
+    // EMBA_SIDE_SERIAL=1 (read per call; bench.py's per-kernel roofline leg): the same kernels on the main stream, behind
+    // the pose-side kernel, so that every kernel's event-timed duration is its standalone one. The pass takes the same
+    // time either way: both sides are bound by the memory system, what the side stream overlaps it takes from the
+    // pose-side kernel (C4: 7.0 ms beside the side stream, 5.2 ms alone).
+    const bool side_serial = getenv("EMBA_SIDE_SERIAL") && atoi(getenv("EMBA_SIDE_SERIAL")) == 1;
+    cudaStream_t sst = side_serial ? h->stream : h->stream2;
+    EMBA_CUDAC(cudaStreamWaitEvent(sst, h->ev_fork, 0));
+    EMBA_CUDAC(cudaEventRecord(h->ev_sort0, sst));
+    EMBA_CUDAC(cudaMemsetAsync(h->d_longlist, 0, sizeof(int32_t), sst));
+    const int place_v = getenv("EMBA_PLACE_V") ? atoi(getenv("EMBA_PLACE_V")) : 0;  // read per call (tools/place_variants.py)
+    if (place_v == 1) k_place<4, true><<<ceil_div64(Mc, 256 * 4), 256, 0, sst>>>(Mc, s.pix, s.slot, d_rowbase, h->d_sval);
+    else if (place_v == 2) k_place<8, false><<<ceil_div64(Mc, 256 * 8), 256, 0, sst>>>(Mc, s.pix, s.slot, d_rowbase, h->d_sval);
+    else if (place_v == 3) k_place<8, true><<<ceil_div64(Mc, 256 * 8), 256, 0, sst>>>(Mc, s.pix, s.slot, d_rowbase, h->d_sval);
+    else if (place_v == 4) k_place<2, true><<<ceil_div64(Mc, 256 * 2), 256, 0, sst>>>(Mc, s.pix, s.slot, d_rowbase, h->d_sval);
+    else k_place<4, false><<<ceil_div64(Mc, 256 * 4), 256, 0, sst>>>(Mc, s.pix, s.slot, d_rowbase, h->d_sval);
+    k_seg_sort<<<h->sm_count * 32, kSegWarps * 32, 0, sst>>>(d_totals, h->d_segoff, h->d_segend, h->d_sval, h->d_longlist);
+    k_seg_sort_long<<<h->sm_count * 16, kSegLongWarps * 32, 0, sst>>>(h->d_longlist, h->d_segoff, h->d_segend, h->d_sval);
     const int huge_smem = 200 * 1024;
     EMBA_CUDAC(cudaFuncSetAttribute(k_seg_sort_huge, cudaFuncAttributeMaxDynamicSharedMemorySize, huge_smem));
-    k_seg_sort_huge<<<h->sm_count, 512, huge_smem, h->stream2>>>(h->d_longlist, h->d_segoff, h->d_segend, h->d_sval, huge_smem / 4);
+    k_seg_sort_huge<<<h->sm_count, 512, huge_smem, sst>>>(h->d_longlist, h->d_segoff, h->d_segend, h->d_sval, huge_smem / 4);
     h->launches += 4;
     EMBA_CUDAC(cudaGetLastError());
-    EMBA_CUDAC(cudaEventRecord(h->ev_sort1, h->stream2));
-    EMBA_CUDAC(cudaEventRecord(h->ev_join, h->stream2));
+    EMBA_CUDAC(cudaEventRecord(h->ev_sort1, sst));
+    EMBA_CUDAC(cudaEventRecord(h->ev_join, sst));
   }
-  EMBA_CUDAC(cudaEventRecord(h->ev[6], h->stream));
   EMBA_CUDAC(cudaEventSynchronize(h->ev_host));
   const int64_t Np = h->h_pin[0];
   h->Np = Np;
