@@ -361,7 +361,10 @@ int prepare_state_tables(Handle* h, StateSlot& s) {
 
 int evaluate_slot(Handle* h, int slot, int cost_type, double eta, double alpha) {
   StateSlot& s = h->st[slot];
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((h->Mc + kEvalThreads - 1) / kEvalThreads, (int64_t)h->sm_count * 8));
+  // CTAs per SM of the grid-stride kernel (4 are resident). Measured on C4 (ms): 4: 3.27, 8: 3.20, 12: 3.21, 16: 3.27,
+  // 24: 3.05, 32: 2.95 - 3.0, 48: 2.99, 64: 3.06, 128: 3.08, 256: 2.94, 1024: 3.10; C2 is flat (0.26) up to 48.
+  const int grid_mult = getenv("EMBA_EVAL_GRID") ? std::max(1, atoi(getenv("EMBA_EVAL_GRID"))) : 32;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((h->Mc + kEvalThreads - 1) / kEvalThreads, (int64_t)h->sm_count * grid_mult));
   const int rgrid = h->sm_count * 4;
   EMBA_TRY(dev_reserve(h, &h->d_part, &h->part_cap, (int64_t)2 * grid + rgrid + 16));
   EMBA_CUDA(cudaEventRecord(h->ev[0], h->stream));

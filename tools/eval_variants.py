@@ -12,8 +12,9 @@ eng.set_events(sc.x, sc.y, sc.t_ns, sc.pol)
 t0, dt = spline_base_ns(sc.t_beg, sc.dt_knots)
 eng.set_state(0, t0, dt, sc.quat_init, sc.Gx_init, sc.Gy_init)
 ref = None
-for pf in (0, 4, 5, 6, 1, 0, 5):
+for pf, gm in ((4, 32), (4, 8), (0, 32), (5, 32), (6, 32), (1, 32), (4, 32)):
     os.environ["EMBA_EVAL_PF"] = str(pf)
+    os.environ["EMBA_EVAL_GRID"] = str(gm)
     ts = []
     for i in range(10):
         cd, cr, M = eng.evaluate(0, 0, 1.0, 5.0)
@@ -23,5 +24,5 @@ for pf in (0, 4, 5, 6, 1, 0, 5):
     if ref is None:
         ref = (cd, M, num.copy())
     same = cd == ref[0] and M == ref[1] and np.array_equal(num, ref[2])
-    print(f"{name} EMBA_EVAL_PF={pf}: k_eval {np.mean(ts):.3f} ms (min {np.min(ts):.3f}); cost/M/num_ev_map identical to PF=0: {same}", flush=True)
+    print(f"{name} EMBA_EVAL_PF={pf} EMBA_EVAL_GRID={gm}: k_eval {np.mean(ts):.3f} ms (min {np.min(ts):.3f}); cost/M/num_ev_map identical to PF=0: {same}", flush=True)
 eng.close()
