@@ -61,7 +61,8 @@ __device__ __forceinline__ void cp_async_commit_s() { asm volatile("cp.async.com
 template <int N>
 __device__ __forceinline__ void cp_async_wait_s() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(kSchurThreads, 4)
+template <int MINB>
+__global__ void __launch_bounds__(kSchurThreads, MINB)
 k_schur_tiles(int64_t own0, int64_t own1, int d, int fix, int nt, int Z, const int32_t* __restrict__ winlo,
               const int32_t* __restrict__ winhi, const int64_t* __restrict__ stripoff,
               const double* __restrict__ strip, const double* __restrict__ C, const double* __restrict__ b2,
@@ -112,8 +113,15 @@ k_schur_tiles(int64_t own0, int64_t own1, int d, int fix, int nt, int Z, const i
   for (int r = 0; r < 3; r++)
 #pragma unroll
     for (int c = 0; c < 3; c++) acc[r][c][0] = acc[r][c][1] = 0.0;
-  // staging roles: 8 pixels x 2 sides x 48 rows = 768 items of 16 bytes per step, 6 per thread
-  constexpr int kStage = kSPix * kST * 2 / kSchurThreads;
+  // staging roles: a step is 8 pixels x 2 sides x 48 rows of 16 bytes. Thread t < 96 owns ONE (side, row) and copies it
+  // for the 8 pixels of the step: its row number, tile side and the right-hand-side test are fixed for the whole
+  // kernel and the per-pixel list entries are warp-uniform (broadcast) shared loads. (With the items dealt out as
+  // t + 128 q the index arithmetic of the copies was ~60 % of the kernel's instructions, 11 per DMMA.)
+  const bool stager = tid < 2 * kST;
+  const int s_side = tid / kST, s_rr = tid % kST;
+  const int s_grow = (s_side ? rowJ0 : rowI0) + s_rr;
+  const bool s_rhs = s_side && s_grow == d;   // the right-hand-side "row" of the J tile carries b2_a (plain store)
+  const bool s_in = s_grow < d;
   const double2* strip2 = reinterpret_cast<const double2*>(strip);
 
   for (int64_t base = a0; base < a1; base += kSchurThreads) {
@@ -148,24 +156,21 @@ k_schur_tiles(int64_t own0, int64_t own1, int d, int fix, int nt, int Z, const i
     __syncthreads();
     const int nl = nlist;
     auto issue = [&](int l0, int st) {
-      if (l0 < nl) {
+      if (l0 < nl && stager) {
 #pragma unroll
-        for (int q = 0; q < kStage; q++) {
-          const int e = tid + kSchurThreads * q;
-          const int pl = e / (kST * 2), side = (e % (kST * 2)) / kST, rr = e % kST;
+        for (int pl = 0; pl < kSPix; pl++) {
           const int l = l0 + pl;
-          const int grow = (side ? rowJ0 : rowI0) + rr;
-          if (side && grow == d) {  // the right-hand-side "row" of the J tile carries b2_a (plain store)
-            V[st][1][pl][rr] = l < nl ? m_b[l] : make_double2(0.0, 0.0);
+          if (s_rhs) {
+            V[st][1][pl][s_rr] = l < nl ? m_b[l] : make_double2(0.0, 0.0);
             continue;
           }
           const double2* src = strip2;
           int bytes = 0;
-          if (l < nl) {
-            const int rel = grow - m_row0[l];
-            if (grow < d && rel >= 0 && rel < m_rows[l]) { src = strip2 + m_base[l] + rel; bytes = 16; }
+          if (l < nl && s_in) {
+            const int rel = s_grow - m_row0[l];
+            if (rel >= 0 && rel < m_rows[l]) { src = strip2 + m_base[l] + rel; bytes = 16; }
           }
-          cp_async16_zfill(&V[st][side][pl][rr], src, bytes);
+          cp_async16_zfill(&V[st][s_side][pl][s_rr], src, bytes);
         }
       }
       cp_async_commit_s();
@@ -774,7 +779,17 @@ int solve_schur(Handle* h, double lambda, int fix) {
   const int order = order_env >= 0 ? order_env : (strip_mb > 96.0 ? 1 : 0);
   dim3 grid(Z, npairs);
   if (order) grid = dim3((unsigned)((int64_t)Z * npairs), 1);
-  k_schur_tiles<<<grid, kSchurThreads, 0, h->stream>>>(own0, own1, d, fix, nt, Z, h->sv_winlo, h->sv_winhi, h->sv_stripoff, h->sv_strip,
+  // resident CTAs per SM the tile kernel is compiled for (registers 108 / 92 / 78 / 72, no spills). The kernel waits on
+  // fixed-latency dependencies (smem load -> shuffle -> scale -> DMMA), so more warps pay: whole solve on C4 / C3 / C2
+  // (ms) 4: 5.28 / 5.04 / 0.826, 5: 4.85 / 4.63 / 0.797, 6: 4.65 / 4.45 / 0.777, 7: 4.77 / 4.57 / 0.82. Read per call.
+  const int schur_occ = getenv("EMBA_SCHUR_OCC") ? atoi(getenv("EMBA_SCHUR_OCC")) : 6;
+  if (schur_occ >= 7) k_schur_tiles<7><<<grid, kSchurThreads, 0, h->stream>>>(own0, own1, d, fix, nt, Z, h->sv_winlo, h->sv_winhi, h->sv_stripoff, h->sv_strip,
+                                             h->d_C, h->d_b2, h->sv_gmask, h->pose_group, h->d_Spart, order);
+  else if (schur_occ == 6) k_schur_tiles<6><<<grid, kSchurThreads, 0, h->stream>>>(own0, own1, d, fix, nt, Z, h->sv_winlo, h->sv_winhi, h->sv_stripoff, h->sv_strip,
+                                             h->d_C, h->d_b2, h->sv_gmask, h->pose_group, h->d_Spart, order);
+  else if (schur_occ == 5) k_schur_tiles<5><<<grid, kSchurThreads, 0, h->stream>>>(own0, own1, d, fix, nt, Z, h->sv_winlo, h->sv_winhi, h->sv_stripoff, h->sv_strip,
+                                             h->d_C, h->d_b2, h->sv_gmask, h->pose_group, h->d_Spart, order);
+  else k_schur_tiles<4><<<grid, kSchurThreads, 0, h->stream>>>(own0, own1, d, fix, nt, Z, h->sv_winlo, h->sv_winhi, h->sv_stripoff, h->sv_strip,
                                              h->d_C, h->d_b2, h->sv_gmask, h->pose_group, h->d_Spart, order);
   EMBA_LAUNCH_CHECK();
   const int64_t tot = (int64_t)d * (d + 1);
