@@ -91,8 +91,8 @@ with open(os.path.join(out_dir, f"{tag}_ncu_summary.txt"), "w") as f:
     f.write("Commands (each ncu pass only after the same command exited 0 without ncu, same gpurun call):\n"
             "  python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras\n"
             f"  ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv   -> {tag}_launches_bench_{wl}.csv\n"
-            "  ncu --set full --clock-control none --import-source on -k regex:\"k_eval|k_asm_pose|k_pix|k_place|k_seg_sort\" (second pass)\n"
-            "  ncu --set full --clock-control none --import-source on -k regex:\"k_schur_tiles|k_ldlt_fused|k_cg_pix\"\n"
+            "  ncu --set full --clock-control none --import-source on -k regex:\"k_eval|k_asm_pose|k_pix|k_place|k_seg_sort\" --launch-skip 14 --launch-count 7 (the third pass)\n"
+            "  ncu --set full --clock-control none --import-source on -k regex:\"k_schur_tiles|k_ldlt_fused|k_solve_x2\" --launch-skip 3 --launch-count 3\n"
             f"Default bench of the same build (python bench.py): {tag}_bench_default_{wl}.json\n")
     rf = bench["roofline"]
     f.write(f"  value {bench['value']:.4g} events/s ({bench['ms_per_step']:.3f} ms per pass), e2e {bench['e2e']['value']:.4g} events/s, "
