@@ -274,10 +274,12 @@ def run_reference(args, workload, rank, world):
         Np_window = None
         # active pixels of the whole window are not known without a full pass: scale the prefix's count by events
         Np_window = big["ref"].Np * sc.n_events / big["n_events"] if big.get("ref") is not None else 0
+        Np_window = min(Np_window, sc.pano_w * sc.pano_h)  # ... but never more than the panorama has
         lm = cpu_lm_iteration_estimate(sc, big, Np_window, 0.5)
         if lm is not None:
-            lm["note"] = ("active pixels of the window estimated as prefix count x events ratio (upper bound: revisits "
-                          "reuse pixels); accepted fraction 0.5 assumed")
+            lm["note"] = ("active pixels of the window estimated as prefix count x events ratio, capped at the panorama size "
+                          "(an upper bound: revisits reuse pixels; the emba_b200 arm's cpu_baseline.lm_iteration_ms "
+                          "uses the true count); accepted fraction 0.5 assumed")
     except Exception as ex:
         lm = {"error": str(ex)}
     out = {
