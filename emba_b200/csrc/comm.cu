@@ -618,6 +618,10 @@ int emba_comm_init(emba_handle_t hh, const void* id128, int32_t rank, int32_t wo
   if (world > 1) {
     EMBA_CUDA(cudaMemsetAsync(h->d_flags, 0, sizeof(int32_t) * 16, h->stream));
     EMBA_TRY(comm_allreduce(h, h->d_flags, 16, 0));
+    // ... and the first all-gather sets up its own connections (2 GPUs: 0.3 s inside the first emba_set_events)
+    if (!h->d_peerx) EMBA_TRY(dev_alloc(h, &h->d_peerx, (int64_t)(Handle::kPeerMax + 2) * 10));
+    if (world <= 256)
+      EMBA_TRY(comm_allgather_i32(h, h->d_flags, reinterpret_cast<int32_t*>(h->d_peerx), 1));
     EMBA_CUDA(cudaStreamSynchronize(h->stream));
     // peer-memory strip exchange: map every rank's receive buffer now (context creation on the peers and the IPC
     // opens take tens of milliseconds), with a starting capacity that later windows grow on demand
