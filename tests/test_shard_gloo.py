@@ -6,7 +6,8 @@
     num_ev_map is all-reduced BEFORE the active-pixel decision, the cost is all-reduced;
   * A11/b1/A22/b2 partials are all-reduced;
   * A12 is exchanged as per-pixel sub-strips: every rank sends, for the pixels another rank owns, only its own
-    (pose-window) sub-strip; the owner merges them -- no rank ever holds all of A12;
+    (pose-window) sub-strip; the owner merges them -- no rank ever holds all of A12; the receive layout of the
+    peer-memory exchange (every rank derives every owner's layout from the all-gathered windows) is restated too;
   * Schur: owners' partial sums all-reduced, replicated factorisation, x2 from the owners;
   * PCG: replicated vectors, partial matrix-vector products combined by one all-reduce per iteration.
 
@@ -130,6 +131,48 @@ def _worker(rank, world, port, out):
         for i, (l, blk) in enumerate(gathered[src][rank]):
             if blk is not None:
                 owned[3 * l: 3 * l + blk.shape[0], i, :] += blk
+    # (3b) the same exchange in the layout of the peer-memory path (emba_b200/csrc/comm.cu): windows all-gathered, every
+    # rank derives the SAME [source][owner] volume matrix and from it every owner's receive layout; a sender's
+    # sub-strip of pixel a goes to  base[owner][me] + stripoff_me[a] - stripoff_me[first pixel of the owner]  (what
+    # k_strip_dst computes and k_pix stores to); the owner's merge finds source s's sub-strip of its i-th pixel at the
+    # flattened exclusive scan of the [source][pixel] lengths (what k_own_len + scan_exclusive compute)
+    win = torch.from_numpy(np.stack([lo, hi], 1).astype(np.int64))
+    wins = [torch.zeros_like(win) for _ in range(world)]
+    dist.all_gather(wins, win)
+    wins = [w.numpy() for w in wins]
+    lens = [np.where(w[:, 1] >= w[:, 0], w[:, 1] - w[:, 0] + 1, 0) for w in wins]           # poses per (source, pixel)
+    owner_of = ((np.arange(Np) + 1) * world - 1) // Np                                      # comm.cu: owner_of()
+    for q in range(world):
+        qa0, qa1 = own(q)
+        assert np.all(owner_of[qa0:qa1] == q)
+    cnt = np.array([[lens[s_][owner_of == q].sum() for q in range(world)] for s_ in range(world)])  # k_cnt_matrix
+    base = np.vstack([np.zeros(world, dtype=np.int64), np.cumsum(cnt, 0)[:-1]])             # base[s][q]: poses before s's chunk
+    stripoff = np.concatenate([[0], np.cumsum(lens[rank])])                                  # my local strip offsets
+    stores = [[] for _ in range(world)]                                                     # what k_pix would store, per owner
+    for a in range(Np):
+        if lens[rank][a] == 0:
+            continue
+        q = owner_of[a]
+        dst = base[rank][q] + stripoff[a] - stripoff[own(q)[0]]
+        stores[q].append((int(dst), A12p[3 * lo[a]: 3 * (hi[a] + 1), a, :].copy()))
+    got = [None] * world
+    dist.all_gather_object(got, stores)
+    recv = np.full((int(cnt[:, rank].sum()) * 3, 2), np.nan)                                # my receive buffer, 3 rows per pose
+    for src in range(world):
+        for dst, blk in got[src][rank]:
+            assert np.all(np.isnan(recv[3 * dst: 3 * dst + blk.shape[0]]))                  # nobody else wrote here
+            recv[3 * dst: 3 * dst + blk.shape[0]] = blk
+    assert not np.isnan(recv).any()                                                         # ... and every slot was written
+    own_len = np.stack([np.r_[lens[s_][a0:a1], 0] for s_ in range(world)])                  # [source][n_own + 1], tail 0
+    own_off = (np.cumsum(own_len.reshape(-1)) - own_len.reshape(-1)).reshape(world, -1)     # flattened exclusive scan
+    owned_peer = np.zeros_like(owned)
+    for i in range(a1 - a0):
+        for s_ in range(world):                                                             # rank order: deterministic
+            L = own_len[s_, i]
+            if L:
+                l = wins[s_][a0 + i, 0]
+                owned_peer[3 * l: 3 * (l + L), i, :] += recv[3 * own_off[s_, i]: 3 * (own_off[s_, i] + L)]
+    assert np.array_equal(owned_peer, owned)
     # pose windows of different time slices overlap only at slice boundaries
     full = np.zeros((3 * n, Np, 2))
     full[:, a0:a1, :] = owned
