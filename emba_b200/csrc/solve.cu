@@ -569,18 +569,16 @@ __global__ void k_cg_a11(int d, int fix, int n, const double* __restrict__ A11, 
 // chunk): y2_a = U_a^T p1 + A22m_a p2_a by a warp reduction, and the pixel's contribution U_a p2_a to y1 is added
 // into a per-WARP accumulator in shared memory (lanes own distinct rows, pixels come in a fixed order), so the
 // summation order is fixed: warp accumulators -> CTA partial (fixed order) -> k_cg_y1 (fixed order over chunks).
-__global__ void __launch_bounds__(256)
-k_cg_pix(int64_t Np, int d, int fix, int n, int nwarps, const int32_t* __restrict__ winlo, const int32_t* __restrict__ winhi,
-         const int64_t* __restrict__ stripoff, const double* __restrict__ strip, const double* __restrict__ A22,
-         const double* __restrict__ A11, double lambda, const double* __restrict__ p, double* __restrict__ y,
-         double* __restrict__ part, int64_t own0, int64_t own1, const int* __restrict__ done) {
-  extern __shared__ double y1s[];  // [nwarps][d]
-  if (*done) return;
-  const int chunk = blockIdx.x;
+__device__ __forceinline__ void
+cg_pix_body(double* y1s, int chunk, int nchunks, int64_t Np, int d, int fix, int n, int nwarps, const int32_t* __restrict__ winlo,
+            const int32_t* __restrict__ winhi,
+            const int64_t* __restrict__ stripoff, const double* __restrict__ strip, const double* __restrict__ A22,
+            const double* __restrict__ A11, double lambda, const double* __restrict__ p, double* __restrict__ y,
+            double* __restrict__ part, int64_t own0, int64_t own1) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // y1 = A11m p1: one warp per row, rows dealt round-robin over the grid (A11 == nullptr on the ranks that do not
   // hold the pose block: their rows start from zero)
-  for (int i = chunk * 8 + warp; i < d; i += gridDim.x * 8) {
+  for (int i = chunk * 8 + warp; i < d; i += nchunks * 8) {
     double s = 0.0;
     if (A11) {
       const double* row = A11 + (size_t)(3 * fix + i) * (3 * n) + 3 * fix;
@@ -595,7 +593,7 @@ k_cg_pix(int64_t Np, int d, int fix, int n, int nwarps, const int32_t* __restric
     if (lane == 0) y[i] = s;
   }
   // chunks of the pixel range this rank owns (the map rows of the other pixels were zeroed by the caller)
-  const int64_t a0 = own0 + (own1 - own0) * chunk / gridDim.x, a1 = own0 + (own1 - own0) * (chunk + 1) / gridDim.x;
+  const int64_t a0 = own0 + (own1 - own0) * chunk / nchunks, a1 = own0 + (own1 - own0) * (chunk + 1) / nchunks;
   for (int i = threadIdx.x; i < nwarps * d; i += blockDim.x) y1s[i] = 0.0;
   __syncthreads();
   const double* p1 = p;
@@ -638,6 +636,17 @@ k_cg_pix(int64_t Np, int d, int fix, int n, int nwarps, const int32_t* __restric
     for (int w = 0; w < nwarps; w++) s += y1s[(size_t)w * d + i];
     part[(size_t)chunk * d + i] = s;
   }
+}
+
+__global__ void __launch_bounds__(256)
+k_cg_pix(int64_t Np, int d, int fix, int n, int nwarps, const int32_t* __restrict__ winlo, const int32_t* __restrict__ winhi,
+         const int64_t* __restrict__ stripoff, const double* __restrict__ strip, const double* __restrict__ A22,
+         const double* __restrict__ A11, double lambda, const double* __restrict__ p, double* __restrict__ y,
+         double* __restrict__ part, int64_t own0, int64_t own1, const int* __restrict__ done) {
+  extern __shared__ double y1s[];  // [nwarps][d]
+  if (*done) return;
+  cg_pix_body(y1s, blockIdx.x, gridDim.x, Np, d, fix, n, nwarps, winlo, winhi, stripoff, strip, A22, A11, lambda, p, y, part,
+              own0, own1);
 }
 
 // y1 += sum over the chunks' partial rows: one WARP per row (lane l takes chunks l, l + 32, ... then a fixed shuffle
@@ -921,6 +930,17 @@ __device__ __forceinline__ void cg_block_partial(double s, double* sh, double* _
   if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
 }
 
+__device__ __forceinline__ void cg_block_partial_at(double s, double* sh, double* __restrict__ part, int vb) {
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[vb] = sh[0];
+  __syncthreads();
+}
+
 // rhsNorm2 == 0 -> x = 0, 0 iterations; threshold = max(tol^2 rhsNorm2, smallest normal); residual = rhs (x0 = 0);
 // absNew = r . (M^-1 r)
 __global__ void __launch_bounds__(256) k_cg_init(const double* __restrict__ part_bb, const double* __restrict__ part_rp,
@@ -1001,6 +1021,101 @@ __global__ void k_cg_bound(CgScal* sc, int max_iter) {
   if (!sc->done && sc->iters >= max_iter) sc->done = 1;
 }
 
+// ---- the whole iteration loop as ONE cooperative kernel (single GPU): the six phases of an iteration are separated
+// by grid barriers instead of kernel boundaries. Same grids in spirit -- kCgChunks CTAs walk the pixel chunks, the first
+// kCgDotGrid of them do the vector phases -- and the same per-block partials summed in the same fixed order, so the
+// arithmetic, the stopping decision and the iteration count are bit for bit those of the multi-launch chain above
+// (which stays for several GPUs, where an all-reduce sits inside the product). Every block derives the stopping test
+// from the same partials, so all blocks leave the loop together.
+struct CgArgs {
+  int64_t Np, tot;
+  int d, fix, n, nwarps, max_iter;
+  const int32_t *winlo, *winhi;
+  const int64_t* stripoff;
+  const double *strip, *A22, *A11, *invd;
+  double lambda;
+  double *x, *r, *p, *z, *tmp, *ypart, *pa, *pb, *pc;
+  CgScal* sc;
+};
+
+__global__ void __launch_bounds__(256, 4) k_cg_persist(CgArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ double y1s[];
+  __shared__ double sh[256];
+  const int bid = blockIdx.x;
+  const int64_t tot = a.tot;
+  CgScal* sc = a.sc;
+  if (sc->done) return;  // written by k_cg_init, an earlier launch: uniform
+  const double thr = sc->thr;
+  const int nrowblk = (a.d + 7) / 8;
+  for (int k = 0;; k++) {
+    const int par = k & 1;
+    // tmp = A p
+    cg_pix_body(y1s, bid, gridDim.x, a.Np, a.d, a.fix, a.n, a.nwarps, a.winlo, a.winhi, a.stripoff, a.strip, a.A22, a.A11,
+                a.lambda, a.p, a.tmp, a.ypart, 0, a.Np);
+    grid.sync();
+    for (int vb = bid; vb < nrowblk; vb += gridDim.x) {  // k_cg_y1
+      const int i = vb * 8 + (threadIdx.x >> 5);
+      const int lane = threadIdx.x & 31;
+      if (i < a.d) {
+        double s = 0.0;
+        for (int c = lane; c < (int)gridDim.x; c += 32) s += a.ypart[(size_t)c * a.d + i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+        if (lane == 0) a.tmp[i] += s;
+      }
+    }
+    grid.sync();
+    if (bid < kCgDotGrid) {  // k_cg_dot: partials of p . tmp
+      double s = 0;
+      for (int64_t i = (int64_t)bid * 256 + threadIdx.x; i < tot; i += (int64_t)kCgDotGrid * 256) s += a.p[i] * a.tmp[i];
+      cg_block_partial_at(s, sh, a.pa, bid);
+    }
+    grid.sync();
+    if (bid < kCgDotGrid) {  // k_cg_step1
+      const double alpha = sc->absNew[par] / cg_sum_partials(a.pa, sh);
+      double s = 0;
+      for (int64_t i = (int64_t)bid * 256 + threadIdx.x; i < tot; i += (int64_t)kCgDotGrid * 256) {
+        a.x[i] += alpha * a.p[i];
+        const double ri = a.r[i] + (-alpha) * a.tmp[i];
+        a.r[i] = ri;
+        s += ri * ri;
+      }
+      cg_block_partial_at(s, sh, a.pb, bid);
+    }
+    grid.sync();
+    // k_cg_step2: every block takes the stopping decision from the same partials
+    const double rn2 = cg_sum_partials(a.pb, sh);
+    const bool stop = rn2 < thr;
+    if (bid == 0 && threadIdx.x == 0) { sc->rn2 = rn2; if (stop) sc->done = 1; }
+    if (stop) break;
+    if (bid < kCgDotGrid) {
+      double s = 0;
+      for (int64_t i = (int64_t)bid * 256 + threadIdx.x; i < tot; i += (int64_t)kCgDotGrid * 256) {
+        const double zi = a.invd[i] * a.r[i];
+        a.z[i] = zi;
+        s += a.r[i] * zi;
+      }
+      cg_block_partial_at(s, sh, a.pc, bid);
+    }
+    grid.sync();
+    if (bid < kCgDotGrid) {  // k_cg_step3
+      const double absNew = cg_sum_partials(a.pc, sh);
+      const double beta = absNew / sc->absNew[par];
+      for (int64_t i = (int64_t)bid * 256 + threadIdx.x; i < tot; i += (int64_t)kCgDotGrid * 256) a.p[i] = a.z[i] + beta * a.p[i];
+      if (bid == 0 && threadIdx.x == 0) {
+        sc->absNew[par ^ 1] = absNew;
+        sc->iters += 1;
+      }
+    }
+    if (k + 1 >= a.max_iter) {  // k_cg_bound
+      if (bid == 0 && threadIdx.x == 0) sc->done = 1;
+      break;
+    }
+    grid.sync();
+  }
+}
+
 int solve_pcg(Handle* h, double lambda, int fix, int* iters_out, double* err_out) {
   const int n = h->n;
   const int d = 3 * (n - fix);
@@ -1065,10 +1180,32 @@ int solve_pcg(Handle* h, double lambda, int fix, int* iters_out, double* err_out
   k_cg_init<<<1, 256, 0, h->stream>>>(pa, pb, sc, tol);
   h->launches += 4;
   EMBA_CUDA(cudaGetLastError());
+  // one GPU: the whole loop as one cooperative launch (k_cg_persist) when kCgChunks CTAs are co-resident
+  bool persisted = false;
+  const bool persist_env = !(getenv("EMBA_CG_PERSIST") && atoi(getenv("EMBA_CG_PERSIST")) == 0);  // read per call
+  if (W == 1 && persist_env && Np > 0) {
+    const int nwarps = std::max(1, std::min(8, (int)((48 * 1024) / (sizeof(double) * (size_t)d))));
+    const size_t shm = sizeof(double) * (size_t)d * nwarps;
+    int per_sm = 0;
+    if (shm <= 48 * 1024 &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_persist, 256, shm) == cudaSuccess &&
+        per_sm * h->sm_count >= kCgChunks) {
+      CgArgs a;
+      a.Np = Np; a.tot = tot; a.d = d; a.fix = fix; a.n = n; a.nwarps = nwarps; a.max_iter = max_iter;
+      a.winlo = h->sv_winlo; a.winhi = h->sv_winhi; a.stripoff = h->sv_stripoff; a.strip = h->sv_strip;
+      a.A22 = h->d_A22; a.A11 = h->d_A11; a.invd = invd; a.lambda = lambda;
+      a.x = x; a.r = r; a.p = p; a.z = z; a.tmp = tmp; a.ypart = ypart; a.pa = pa; a.pb = pb; a.pc = pc; a.sc = sc;
+      void* args[] = {&a};
+      EMBA_CUDA(cudaLaunchCooperativeKernel((void*)k_cg_persist, dim3(kCgChunks), dim3(256), args, shm, h->stream));
+      h->launches++;
+      persisted = true;
+    }
+    cudaGetLastError();
+  }
   // iterations: enqueued in chunks, the flag is looked at once per chunk (kernels after the stop are no-ops)
   int64_t* hflag = h->h_pin + 20;
   const int chunk = 10;
-  for (int it0 = 0; it0 < max_iter; it0 += chunk) {
+  for (int it0 = 0; it0 < max_iter && !persisted; it0 += chunk) {
     for (int k = it0; k < it0 + chunk && k < max_iter; k++) {
       EMBA_TRY(matvec(p, tmp));
       k_cg_dot<<<kCgDotGrid, 256, 0, h->stream>>>(tot, p, tmp, pa, sc, 1);
