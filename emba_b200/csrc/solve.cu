@@ -600,20 +600,58 @@ cg_pix_body(double* y1s, int chunk, int nchunks, int64_t Np, int d, int fix, int
   const double* p2 = p + d;
   if (warp < nwarps) {
     double* acc = y1s + (size_t)warp * d;
-    for (int64_t a = a0 + warp; a < a1; a += nwarps) {
-      const int lo = winlo[a], hi = winhi[a];
-      const double* sp = strip + stripoff[a] * 6;
-      const double pa = p2[2 * a], pb = p2[2 * a + 1];
-      const int rows = hi >= lo ? (hi - lo + 1) * 3 : 0;
+    // the per-pixel header (window, strip offset, p2, A22) of the NEXT pixel is requested before the current pixel's
+    // rows are walked, and the rows of a pixel are requested all at once (up to 4 x 32) before any is used: a warp
+    // walks ~15 pixels one after the other, and with everything loaded where it was used a C2 product took ~90 us
+    // for 113 MB of strips
+    int64_t a = a0 + warp;
+    int lo = 0, hi = -1;
+    int64_t so = 0;
+    double pa = 0.0, pb = 0.0, xx = 0.0, xy = 0.0, yy = 0.0;
+    auto header = [&](int64_t q) {
+      lo = winlo[q]; hi = winhi[q]; so = stripoff[q];
+      pa = p2[2 * q]; pb = p2[2 * q + 1];
+      xx = A22[3 * q]; xy = A22[3 * q + 1]; yy = A22[3 * q + 2];
+    };
+    if (a < a1) header(a);
+    while (a < a1) {
+      const int c_lo = lo, c_hi = hi;
+      const double c_pa = pa, c_pb = pb, c_xx = xx, c_xy = xy, c_yy = yy;
+      const double2* sp = reinterpret_cast<const double2*>(strip + so * 6);
+      const int64_t an = a + nwarps;
+      if (an < a1) header(an);
+      const int rows = c_hi >= c_lo ? (c_hi - c_lo + 1) * 3 : 0;
+      const int g0 = 3 * (c_lo - fix);  // row of the strip's first entry in the reduced system (negative: fixed pose)
       double t0 = 0.0, t1 = 0.0;
-      for (int rr = lane; rr < rows; rr += 32) {
-        const int grow = 3 * (lo - fix) + rr;  // row in the reduced system (negative: fixed first pose)
-        if (grow < 0) continue;
-        const double2 u = reinterpret_cast<const double2*>(sp)[rr];
-        acc[grow] += u.x * pa + u.y * pb;
-        const double x = p1[grow];
-        t0 += u.x * x;
-        t1 += u.y * x;
+      if (rows <= 128) {
+        double2 u[4];
+        double xv[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int rr = lane + 32 * k;
+          const bool ok = rr < rows && g0 + rr >= 0;
+          u[k] = ok ? sp[rr] : make_double2(0.0, 0.0);
+          xv[k] = ok ? p1[g0 + rr] : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int rr = lane + 32 * k;
+          if (rr < rows && g0 + rr >= 0) {
+            acc[g0 + rr] += u[k].x * c_pa + u[k].y * c_pb;
+            t0 += u[k].x * xv[k];
+            t1 += u[k].y * xv[k];
+          }
+        }
+      } else {
+        for (int rr = lane; rr < rows; rr += 32) {
+          const int grow = g0 + rr;
+          if (grow < 0) continue;
+          const double2 uu = sp[rr];
+          acc[grow] += uu.x * c_pa + uu.y * c_pb;
+          const double x = p1[grow];
+          t0 += uu.x * x;
+          t1 += uu.y * x;
+        }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -623,11 +661,11 @@ cg_pix_body(double* y1s, int chunk, int nchunks, int64_t Np, int d, int fix, int
       if (lane == 0) {
         // several GPUs: A22 is replicated, so only the pixel's owner adds the A22m term (the strips of the other
         // pixels are empty here and t0 = t1 = 0); the partial vectors are summed by one all-reduce
-        const double xx = A22[3 * a], xy = A22[3 * a + 1], yy = A22[3 * a + 2];
-        y[d + 2 * a] = t0 + (xx + lambda * xx) * pa + xy * pb;
-        y[d + 2 * a + 1] = t1 + xy * pa + (yy + lambda * yy) * pb;
+        y[d + 2 * a] = t0 + (c_xx + lambda * c_xx) * c_pa + c_xy * c_pb;
+        y[d + 2 * a + 1] = t1 + c_xy * c_pa + (c_yy + lambda * c_yy) * c_pb;
       }
       __syncwarp();
+      a = an;
     }
   }
   __syncthreads();
@@ -1180,9 +1218,12 @@ int solve_pcg(Handle* h, double lambda, int fix, int* iters_out, double* err_out
   k_cg_init<<<1, 256, 0, h->stream>>>(pa, pb, sc, tol);
   h->launches += 4;
   EMBA_CUDA(cudaGetLastError());
-  // one GPU: the whole loop as one cooperative launch (k_cg_persist) when kCgChunks CTAs are co-resident
+  // one GPU, EMBA_CG_PERSIST=1: the whole loop as one cooperative launch (k_cg_persist) when kCgChunks CTAs are
+  // co-resident. Measured against the chain of launches below (same arithmetic, bit-identical results, same iteration
+  // counts): C2 106 vs 108 us per iteration, C4 850 vs 711 us -- six grid barriers cost what six launches cost, so the
+  // launches are not what an iteration spends its time on and the chain stays the default.
   bool persisted = false;
-  const bool persist_env = !(getenv("EMBA_CG_PERSIST") && atoi(getenv("EMBA_CG_PERSIST")) == 0);  // read per call
+  const bool persist_env = getenv("EMBA_CG_PERSIST") && atoi(getenv("EMBA_CG_PERSIST")) == 1;  // read per call
   if (W == 1 && persist_env && Np > 0) {
     const int nwarps = std::max(1, std::min(8, (int)((48 * 1024) / (sizeof(double) * (size_t)d))));
     const size_t shm = sizeof(double) * (size_t)d * nwarps;
