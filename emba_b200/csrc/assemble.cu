@@ -1005,8 +1005,8 @@ int form_normal_eq(Handle* h, int thres, int cost_type, double eta, double alpha
   }
   EMBA_CUDAC(cudaEventRecord(h->ev[6], h->stream));  // end of the pose-side kernel
   // ---- 1b. side stream: rows -> pixel segments (k_place) and the per-segment ordering (k_seg_sort*). They need only
-  // the evaluation and the segment offsets; they are submitted before the pose-side kernel and the main stream joins
-  // them before the map-side kernel.
+  // the evaluation and the segment offsets; they are submitted BEHIND the pose-side kernel (see above) and the main
+  // stream joins them before the map-side kernel.
   if (!atomic_path && h->Mc > 0) {
     const int64_t Mc = h->Mc;
     // EMBA_SIDE_SERIAL=1 (read per call; bench.py's per-kernel roofline leg): the same kernels on the main stream, behind

@@ -543,28 +543,6 @@ __global__ void k_expand_x1(int n, int fix, const double* __restrict__ rhs_x, do
 // Jacobi-PCG on [[A11m, A12], [A12^T, A22m]] (model.cpp:794-840). Vectors are laid out [x1 (d) | x2 (2Np)].
 // ---------------------------------------------------------------------------------------------------
 constexpr int kCgChunks = 592;  // 4 CTAs per SM
-// y1 = A11m p1 (+ A12 p2 accumulated by k_cg_a12), one thread per row
-__global__ void k_cg_a11(int d, int fix, int n, const double* __restrict__ A11, double lambda,
-                         const double* __restrict__ p, double* __restrict__ y) {
-  const int i = blockIdx.x;
-  const int d3 = 3 * n;
-  const double* row = A11 + (size_t)(3 * fix + i) * d3 + 3 * fix;
-  double s = 0.0;
-  for (int j = threadIdx.x; j < d; j += blockDim.x) {
-    double a = row[j];
-    if (j == i) a += lambda * a;
-    s += a * p[j];
-  }
-  __shared__ double sh[128];
-  sh[threadIdx.x] = s;
-  __syncthreads();
-  for (int o = 64; o > 0; o >>= 1) {
-    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) y[i] = sh[0];
-}
-
 // SpMV with the strips. One warp per pixel (pixels dealt round-robin to the warps of a CTA inside a contiguous
 // chunk): y2_a = U_a^T p1 + A22m_a p2_a by a warp reduction, and the pixel's contribution U_a p2_a to y1 is added
 // into a per-WARP accumulator in shared memory (lanes own distinct rows, pixels come in a fixed order), so the
@@ -703,41 +681,6 @@ __global__ void __launch_bounds__(256) k_cg_y1(int d, int chunks, const double* 
   if (lane == 0) y[i] += s;
 }
 
-// deterministic dot products: out[0] = a.b with fixed-grid partials
-__global__ void __launch_bounds__(256) k_dot_partial(int64_t n, const double* __restrict__ a,
-                                                     const double* __restrict__ b, double* __restrict__ part) {
-  double s = 0;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) s += a[i] * b[i];
-  __shared__ double sh[256];
-  sh[threadIdx.x] = s;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
-}
-__global__ void k_dot_final(int nblk, const double* __restrict__ part, double* __restrict__ out) {
-  __shared__ double sh[256];
-  double s = 0;
-  for (int b = threadIdx.x; b < nblk; b += 256) s += part[b];
-  sh[threadIdx.x] = s;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *out = sh[0];
-}
-// y = a*x + y ; z = inv_diag .* r etc.
-__global__ void k_axpy(int64_t n, double a, const double* __restrict__ x, double* __restrict__ y) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) y[i] += a * x[i];
-}
-__global__ void k_xpby(int64_t n, const double* __restrict__ x, double b, double* __restrict__ y) {  // y = x + b*y
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) y[i] = x[i] + b * y[i];
-}
 __global__ void k_mul(int64_t n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ c) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) c[i] = a[i] * b[i];
@@ -996,7 +939,7 @@ __global__ void __launch_bounds__(256) k_cg_init(const double* __restrict__ part
   }
 }
 
-// partials of a . b (k_dot_partial's grid-stride order)
+// partials of a . b (fixed grid-stride order)
 __global__ void __launch_bounds__(256) k_cg_dot(int64_t n, const double* __restrict__ a, const double* __restrict__ b,
                                                 double* __restrict__ part, const CgScal* sc, int check) {
   __shared__ double sh[256];
