@@ -177,6 +177,29 @@ def cpu_reference_pass(sc, n_events, want_outputs=False):
     return out
 
 
+def host_info():
+    """nproc and CPU model of the box the CPU legs ran on"""
+    model = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.lower().startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return {"nproc": os.cpu_count(), "cpu_model": model}
+
+
+def _omp_set_threads(k):
+    """the compiled reference is built with -fopenmp (only Eigen's GEMM inside solveNormalEq has a parallel region)"""
+    import ctypes
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(k))
+        return True
+    except OSError:
+        return False
+
+
 def cpu_lm_iteration_estimate(sc, cpu, Np_window, accepted_frac):
     """CPU LM-iteration time of the reference ON THIS WINDOW from the three regions it instruments itself
     (solver.cpp:105-151 form, :181-222 solve, :242-294 objective), measured on the prefix `cpu` was run on (with all
@@ -188,6 +211,16 @@ def cpu_lm_iteration_estimate(sc, cpu, Np_window, accepted_frac):
     t = time.perf_counter()
     ref.solve(1e-3, False, True)
     t_solve = time.perf_counter() - t
+    # the same solve with all host threads (only Eigen's GEMM in the Schur solve has a parallel region;
+    # the single-thread figure stays the baseline of record)
+    t_solve_all, nthr = None, os.cpu_count() or 1
+    if nthr > 1 and _omp_set_threads(nthr):
+        try:
+            t = time.perf_counter()
+            ref.solve(1e-3, False, True)
+            t_solve_all = time.perf_counter() - t
+        finally:
+            _omp_set_threads(1)
     Np_p = max(1, ref.Np)
     scale_n = sc.n_events / cpu["n_events"]
     obj_ms = cpu["t_evaluate"] * scale_n * 1e3
@@ -196,7 +229,9 @@ def cpu_lm_iteration_estimate(sc, cpu, Np_window, accepted_frac):
     return {"lm_iteration_ms": solve_ms + obj_ms + accepted_frac * form_ms,
             "regions_ms_scaled_to_window": {"objective": obj_ms, "form": form_ms, "solve": solve_ms},
             "measured_on": {"events": cpu["n_events"], "control_poses": sc.n_poses, "active_pixels": int(Np_p),
-                            "objective_s": cpu["t_evaluate"], "form_s": cpu["t_form"], "solve_s": t_solve},
+                            "objective_s": cpu["t_evaluate"], "form_s": cpu["t_form"], "solve_s": t_solve,
+                            "solve_s_all_threads": t_solve_all, "threads_all": nthr},
+            "host": host_info(),
             "extrapolated": True,
             "how": "objective and form scaled linearly in events, solve linearly in active pixels; iteration = solve + "
                    "objective + accepted_fraction * form (rejected steps reuse the equations, solver.cpp:66-130)"}
@@ -289,7 +324,7 @@ def run_reference(args, workload, rank, world):
         "scaling": "weak" if args.weak else "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_of(sc, workload, world, args.weak),
-        "cpu_baseline": {"value": val, "unit": "events/s", "cores": last["cores"], "kind": last["kind"],
+        "cpu_baseline": {"value": val, "unit": "events/s", "cores": last["cores"], "kind": last["kind"], "host": host_info(),
                          "sample": f"first {n_used} events of the window per step, OMP_NUM_THREADS=1 "
                                    f"(the reference is single-threaded); ms_per_step is scaled linearly to the window"},
         "e2e": {"value": val, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -705,6 +740,7 @@ def main():
             n_cpu = min(N, 5_000_000)
             cpu = cpu_reference_pass(sc, n_cpu, want_outputs=True)
             out["cpu_baseline"] = {"value": cpu["value"], "unit": "events/s", "cores": cpu["cores"], "kind": cpu["kind"],
+                                   "host": host_info(),
                                    "sample": f"one pass over the first {cpu['n_events']} events of the same window "
                                              f"({cpu['seconds']:.1f} s, OMP_NUM_THREADS=1: the reference is single-threaded)"}
             try:

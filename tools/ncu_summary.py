@@ -71,6 +71,16 @@ for units, col, r in all_rows:
             if lab.endswith("_GB"):
                 v = v / 1e9 if u in ("byte", "B") else v / 1e3 if u in ("Mbyte", "MB") else v / 1e6 if u in ("Kbyte", "KB") else v
             d[lab] = v
+    # achieved fp64 arithmetic: thread-level DFMA (x2) + DMUL + DADD, and the tensor path's fp64 flops
+    def val(m):
+        return float(r[col[m]].replace(",", "")) if m in col and r[col[m]] not in ("", "n/a") else 0.0
+    cyc = val("sm__cycles_elapsed.max")
+    scalar = (2 * val("smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed") +
+              val("smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed") +
+              val("smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed")) * cyc
+    if d.get("time_us"):
+        d["f64_TF/s"] = scalar / (d["time_us"] * 1e-6) / 1e12
+        d["dmma_TF/s"] = val("sm__ops_path_tensor_src_fp64.sum") / (d["time_us"] * 1e-6) / 1e12
     seen[k] = d
 
 bench = json.load(open(bench_json))
@@ -106,8 +116,9 @@ with open(os.path.join(out_dir, f"{tag}_ncu_summary.txt"), "w") as f:
     if "cpu_baseline" in bench:
         cb = bench["cpu_baseline"]
         f.write(f"  CPU {cb['kind']}: {cb['value']:.4g} {cb['unit']} on {cb['cores']} core(s)\n")
-    f.write("\n== ncu --set full, one launch each (cold cache, serialised; shares matter, not absolutes) ==\n")
-    labs = [l for l, _ in want]
+    f.write("\n== ncu --set full, one launch each (cold cache, serialised; shares matter, not absolutes) ==\n"
+            "   (f64_TF/s: thread-level DFMA x2 + DMUL + DADD per second; dmma_TF/s: fp64 flops of the tensor path per second)\n")
+    labs = [l for l, _ in want] + ["f64_TF/s", "dmma_TF/s"]
     f.write(f"{'kernel':<28}" + "".join(f"{l:>11}" for l in labs) + "\n")
     for k, d in seen.items():
         f.write(f"{k.split('::')[-1][:27]:<28}" + "".join(f"{d[l]:>11.3f}" if l in d else f"{'-':>11}" for l in labs) + "\n")
