@@ -213,7 +213,7 @@ def cpu_lm_iteration_estimate(sc, cpu, Np_window, accepted_frac):
     t_solve = time.perf_counter() - t
     # the same solve with all host threads (only Eigen's GEMM in the Schur solve has a parallel region;
     # the single-thread figure stays the baseline of record)
-    t_solve_all, nthr = None, os.cpu_count() or 1
+    t_solve_all, nthr = None, min(os.cpu_count() or 1, 16)  # capped: the products are small, more threads only add overhead
     if nthr > 1 and _omp_set_threads(nthr):
         try:
             t = time.perf_counter()
